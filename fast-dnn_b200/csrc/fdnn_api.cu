@@ -1,0 +1,776 @@
+// C ABI of libfast-dnn.so (include/fdnn.h): model upload, contexts, the kernel sequence of one
+// forward pass, host↔device streaming.  Everything that computes runs on the GPU; without a usable
+// device the compute entry points fail with FDNN_ENOGPU — there is no CPU path.
+//
+// One forward pass over m frames mirrors CalculationContext::Calculate (reference
+// src/cpp/dnn.cc:162-165, 402-454) as a sequence of kernels on one stream:
+//   input_layer → qlayer(hidden) × (L−2) → qlayer(logits) → softmax
+// with u8 activations ping-ponging between two device buffers and each layer's saturation
+// corrections travelling through its correction channel (device_common.cuh).
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <array>
+#include <atomic>
+#include <cstdlib>
+#include <cstring>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/fdnn.h"
+#include "fdnn_internal.h"
+#include "kernels.h"
+
+using namespace fdnn;
+
+namespace {
+
+std::atomic<long long> g_launches{0};
+
+#define CUDA_TRY(expr)                                                                      \
+  do {                                                                                      \
+    cudaError_t e_ = (expr);                                                                \
+    if (e_ != cudaSuccess) {                                                                \
+      set_error(std::string(#expr) + ": " + cudaGetErrorString(e_));                        \
+      return FDNN_ECUDA;                                                                    \
+    }                                                                                       \
+  } while (0)
+
+int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+using EncodeTiledFn = CUresult (*)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                   const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = [] {
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+      p = nullptr;
+    return reinterpret_cast<EncodeTiledFn>(p);
+  }();
+  return fn;
+}
+
+// 2D u8/s8 matrix [rows][K] row-major → TMA map with a (128-byte × box_rows) box, 128B swizzle.
+int make_tmap(CUtensorMap *map, const void *base, int rows, int K, int box_rows) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (!fn) {
+    set_error("cuTensorMapEncodeTiled is not available from this driver");
+    return FDNN_ECUDA;
+  }
+  cuuint64_t dims[2] = {cuuint64_t(K), cuuint64_t(rows)};
+  cuuint64_t strides[1] = {cuuint64_t(K)};
+  cuuint32_t box[2] = {128u, cuuint32_t(box_rows)};
+  cuuint32_t estr[2] = {1u, 1u};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with CUresult " + std::to_string(int(r)));
+    return FDNN_ECUDA;
+  }
+  return FDNN_OK;
+}
+
+struct DeviceGuard {
+  int prev = -1;
+  bool ok = false;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    ok = cudaSetDevice(dev) == cudaSuccess;
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+int usable_device(int device, int *out) {
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count <= 0) {
+    cudaGetLastError();
+    set_error("no usable CUDA device (this library has no CPU path)");
+    return FDNN_ENOGPU;
+  }
+  if (device < 0) {
+    if (cudaGetDevice(&device) != cudaSuccess) device = 0;
+  }
+  if (device >= count) {
+    set_error("CUDA device " + std::to_string(device) + " does not exist");
+    return FDNN_EINVAL;
+  }
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess || prop.major != 10) {
+    cudaGetLastError();
+    set_error("CUDA device " + std::to_string(device) + " is not an sm_100 (Blackwell B200) part; the kernels are built for sm_100a only");
+    return FDNN_ENOGPU;
+  }
+  *out = device;
+  return FDNN_OK;
+}
+
+}  // namespace
+
+// ---- handles ----------------------------------------------------------------------------------------
+
+struct fdnn_model {
+  int device = 0;
+  int num_sms = 0;
+  uint8_t *d_blob = nullptr;
+  size_t blob_size = 0;
+  BlobHeader hdr{};
+  std::vector<BlobQLayer> q;
+  std::vector<std::array<CUtensorMap, 3>> wmaps;  // per int8 layer, box rows 64 / 128 / 256
+  std::vector<bool> tc_ok;
+  bool force_simt = false;
+  // contexts cached for fdnn_calculate
+  std::mutex pool_mu;
+  std::vector<fdnn_ctx *> pool;
+
+  template <class T>
+  const T *at(uint64_t off) const {
+    return reinterpret_cast<const T *>(d_blob + off);
+  }
+};
+
+struct fdnn_ctx {
+  fdnn_model *model = nullptr;
+  int cap = 0;  // frames
+  float *d_in = nullptr;      // [cap][I]
+  uint8_t *d_act[2] = {nullptr, nullptr};  // [cap][H]
+  float *d_logits = nullptr;  // [cap][O]
+  int8_t *d_masks = nullptr;  // [cap][O], allocated on first lazy use
+  float *d_row = nullptr;     // [O] scratch for single-row lazy output
+  float *d_lazy = nullptr;    // [cap][O] masked softmax rows, allocated on first batched lazy use
+  CorrChannel chan[3]{};      // A, B (hidden-sized), C (output-sized)
+  CUtensorMap amap[2];
+  bool amap_ok = false;
+  cudaStream_t stream = nullptr;
+  bool trace = false;
+  uint8_t *d_trace = nullptr;  // [n_qlayers][cap][H]
+  int last_frames = 0;
+  bool have_logits = false;
+};
+
+namespace {
+
+void destroy_ctx(fdnn_ctx *c) {
+  if (!c) return;
+  DeviceGuard g(c->model->device);
+  cudaFree(c->d_in);
+  cudaFree(c->d_act[0]);
+  cudaFree(c->d_act[1]);
+  cudaFree(c->d_logits);
+  cudaFree(c->d_masks);
+  cudaFree(c->d_row);
+  cudaFree(c->d_lazy);
+  for (auto &ch : c->chan) {
+    cudaFree(ch.corr);
+    cudaFree(ch.flags);
+  }
+  cudaFree(c->d_trace);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+int alloc_channel(CorrChannel &ch, int rows, int nodes) {
+  ch.ld = round_up(nodes, 32);
+  ch.rows_cap = rows;
+  size_t corr_bytes = size_t(rows) * size_t(ch.ld) * 4, flag_bytes = size_t(ch.ld / 32) * size_t(rows);
+  CUDA_TRY(cudaMalloc(&ch.corr, corr_bytes));
+  CUDA_TRY(cudaMalloc(&ch.flags, flag_bytes));
+  CUDA_TRY(cudaMemset(ch.corr, 0, corr_bytes));
+  CUDA_TRY(cudaMemset(ch.flags, 0, flag_bytes));
+  return FDNN_OK;
+}
+
+int create_ctx(fdnn_model *m, int n, fdnn_ctx **out) {
+  if (n <= 0) {
+    set_error("a context needs at least one frame");
+    return FDNN_EINVAL;
+  }
+  const int I = m->hdr.in_dim, H = m->hdr.hidden, O = m->hdr.out_dim;
+  // ≈ (4I + 2H + 12·pad32(H) + 8·pad32(O)) bytes of device memory per frame
+  const double per_frame = 4.0 * I + 2.0 * H + 8.0 * round_up(H, 32) + 8.0 * round_up(O, 32) + 64;
+  size_t free_b = 0, total_b = 0;
+  DeviceGuard g(m->device);
+  if (!g.ok) {
+    set_error("cudaSetDevice failed");
+    return FDNN_ECUDA;
+  }
+  if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && per_frame * n > 0.9 * double(free_b)) {
+    set_error("context for " + std::to_string(n) + " frames does not fit in device memory");
+    return FDNN_ENOMEM;
+  }
+  std::unique_ptr<fdnn_ctx, void (*)(fdnn_ctx *)> c(new fdnn_ctx, destroy_ctx);
+  c->model = m;
+  c->cap = n;
+  CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  CUDA_TRY(cudaMalloc(&c->d_in, size_t(n) * I * 4));
+  // activations are read by TMA in 128-row boxes; rows past `n` are never stored, but keep the
+  // buffers whole tiles long so box reads stay inside the allocation's pages
+  const size_t act_bytes = size_t(round_up(n, 128)) * H;
+  CUDA_TRY(cudaMalloc(&c->d_act[0], act_bytes));
+  CUDA_TRY(cudaMalloc(&c->d_act[1], act_bytes));
+  CUDA_TRY(cudaMemset(c->d_act[0], 0, act_bytes));
+  CUDA_TRY(cudaMemset(c->d_act[1], 0, act_bytes));
+  CUDA_TRY(cudaMalloc(&c->d_logits, size_t(n) * O * 4));
+  CUDA_TRY(cudaMalloc(&c->d_row, size_t(O) * 4));
+  if (int rc = alloc_channel(c->chan[0], n, H)) return rc;
+  if (int rc = alloc_channel(c->chan[1], n, H)) return rc;
+  if (int rc = alloc_channel(c->chan[2], n, O)) return rc;
+  if (H % 128 == 0 && !m->force_simt) {
+    if (int rc = make_tmap(&c->amap[0], c->d_act[0], n, H, 128)) return rc;
+    if (int rc = make_tmap(&c->amap[1], c->d_act[1], n, H, 128)) return rc;
+    c->amap_ok = true;
+  }
+  CUDA_TRY(cudaDeviceSynchronize());  // the memsets above ran on the legacy stream; ours does not wait for it
+  *out = c.release();
+  return FDNN_OK;
+}
+
+// Enqueue one forward pass over frames [0, m) of `d_in` on `stream`.  Logits (lin + bias of the
+// output layer) go to `d_logits` with row pitch O.
+int enqueue_until_logits(fdnn_ctx *c, const float *d_in, int m, float *d_logits, cudaStream_t stream) {
+  fdnn_model *mod = c->model;
+  const BlobHeader &h = mod->hdr;
+  const int nq = h.n_qlayers;
+  auto fix_of = [&](int layer) {
+    FixList f;
+    f.ptr = mod->at<uint32_t>(mod->q[size_t(layer)].off_fix_ptr);
+    f.ent = mod->at<FixEntry>(mod->q[size_t(layer)].off_fix_ent);
+    return f;
+  };
+  auto chan_of = [&](int layer) -> const CorrChannel & { return layer == nq - 1 ? c->chan[2] : c->chan[layer & 1]; };
+
+  InputLayerArgs ia{};
+  ia.in = d_in;
+  ia.shift = mod->at<float>(h.off_shift);
+  ia.scale = mod->at<float>(h.off_scale);
+  ia.w0 = mod->at<float>(h.off_w0);
+  ia.bias0 = mod->at<float>(h.off_bias0);
+  ia.lut = mod->at<uint8_t>(h.off_lut);
+  ia.out_u8 = c->d_act[0];
+  ia.M = m;
+  ia.I = h.in_dim;
+  ia.H = h.hidden;
+  ia.next_fix = fix_of(0);
+  ia.next = chan_of(0);
+  CUDA_TRY(launch_input_layer(ia, stream));
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  const size_t act_bytes = size_t(m) * size_t(h.hidden);
+  if (c->trace) CUDA_TRY(cudaMemcpyAsync(c->d_trace, c->d_act[0], act_bytes, cudaMemcpyDeviceToDevice, stream));
+
+  for (int j = 0; j < nq; ++j) {
+    const BlobQLayer &ql = mod->q[size_t(j)];
+    const bool logits = j == nq - 1;
+    QLayerArgs a{};
+    a.act = c->d_act[j & 1];
+    a.w = mod->at<int8_t>(ql.off_w);
+    a.bias = mod->at<float>(ql.off_bias);
+    a.lut = mod->at<uint8_t>(h.off_lut);
+    a.coeff = ql.coeff;
+    a.rcp = ql.rcp_coeff;
+    a.fast_div = int(ql.fast_div);
+    a.M = m;
+    a.N = ql.nodes;
+    a.K = ql.inputs;
+    a.self = chan_of(j);
+    if (logits) {
+      a.out_f32 = d_logits;
+      a.out_ld = ql.nodes;
+    } else {
+      a.out_u8 = c->d_act[(j + 1) & 1];
+      a.next_fix = fix_of(j + 1);
+      a.next = chan_of(j + 1);
+    }
+    if (mod->tc_ok[size_t(j)] && c->amap_ok) {
+      const int bn = qlayer_tc_block_n(m, ql.nodes, mod->num_sms);
+      const int which = bn == 64 ? 0 : (bn == 128 ? 1 : 2);
+      CUDA_TRY(launch_qlayer_tc(c->amap[j & 1], mod->wmaps[size_t(j)][size_t(which)], a, logits, bn, mod->num_sms, stream));
+    } else {
+      CUDA_TRY(launch_qlayer_simt(a, logits, stream));
+    }
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    if (c->trace && !logits)
+      CUDA_TRY(cudaMemcpyAsync(c->d_trace + size_t(j + 1) * size_t(c->cap) * size_t(h.hidden), c->d_act[(j + 1) & 1], act_bytes,
+                               cudaMemcpyDeviceToDevice, stream));
+  }
+  c->last_frames = m;
+  return FDNN_OK;
+}
+
+int enqueue_softmax(fdnn_ctx *c, const float *d_logits, const int8_t *d_masks, int rows, float *d_out, cudaStream_t stream) {
+  const int O = c->model->hdr.out_dim;
+  SoftmaxArgs s{};
+  s.logits = d_logits;
+  s.mask = d_masks;
+  s.out = d_out;
+  s.rows = rows;
+  s.O = O;
+  s.ld = O;
+  s.mask_ld = O;
+  s.out_ld = O;
+  CUDA_TRY(launch_softmax(s, stream));
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return FDNN_OK;
+}
+
+int upload_model(const uint8_t *host_view, const void *src, bool src_on_device, size_t size, int device, fdnn_model **out) {
+  std::unique_ptr<fdnn_model> m(new fdnn_model);
+  std::memcpy(&m->hdr, host_view, sizeof(BlobHeader));
+  m->q.resize(size_t(m->hdr.n_qlayers));
+  std::memcpy(m->q.data(), host_view + m->hdr.off_qlayers, sizeof(BlobQLayer) * m->q.size());
+  m->device = device;
+  m->blob_size = size;
+  const char *env = std::getenv("FDNN_FORCE_SIMT");
+  m->force_simt = env && env[0] == '1';
+  DeviceGuard g(device);
+  if (!g.ok) {
+    set_error("cudaSetDevice failed");
+    return FDNN_ECUDA;
+  }
+  CUDA_TRY(cudaDeviceGetAttribute(&m->num_sms, cudaDevAttrMultiProcessorCount, device));
+  CUDA_TRY(cudaMalloc(&m->d_blob, size));
+  cudaError_t e = cudaMemcpy(m->d_blob, src, size, src_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) {
+    cudaFree(m->d_blob);
+    set_error(std::string("model upload: ") + cudaGetErrorString(e));
+    return FDNN_ECUDA;
+  }
+  auto fail = [&](int rc) {
+    cudaFree(m->d_blob);
+    return rc;
+  };
+  if (cudaError_t ce = input_layer_configure(); ce != cudaSuccess) {
+    set_error(std::string("input_layer_configure: ") + cudaGetErrorString(ce));
+    return fail(FDNN_ECUDA);
+  }
+  if (cudaError_t ce = qlayer_tc_configure(); ce != cudaSuccess) {
+    set_error(std::string("qlayer_tc_configure: ") + cudaGetErrorString(ce));
+    return fail(FDNN_ECUDA);
+  }
+  if (cudaError_t ce = softmax_configure(); ce != cudaSuccess) {
+    set_error(std::string("softmax_configure: ") + cudaGetErrorString(ce));
+    return fail(FDNN_ECUDA);
+  }
+  m->wmaps.resize(m->q.size());
+  m->tc_ok.assign(m->q.size(), false);
+  for (size_t j = 0; j < m->q.size(); ++j) {
+    const BlobQLayer &ql = m->q[j];
+    const bool logits = j + 1 == m->q.size();
+    if (m->force_simt || !qlayer_tc_supported(ql.nodes, ql.inputs, logits)) continue;
+    const int boxes[3] = {64, 128, 256};
+    for (int b = 0; b < 3; ++b)
+      if (int rc = make_tmap(&m->wmaps[j][size_t(b)], m->d_blob + ql.off_w, ql.nodes, ql.inputs, boxes[b])) return fail(rc);
+    m->tc_ok[j] = true;
+  }
+  *out = m.release();
+  return FDNN_OK;
+}
+
+}  // namespace
+
+// ---- exported C ABI ---------------------------------------------------------------------------------
+
+extern "C" {
+
+const char *fdnn_last_error(void) { return get_error(); }
+const char *fdnn_version(void) { return "fast-dnn-b200 0.1 (sm_100a)"; }
+
+int fdnn_pack(const char *path, float cutoff, void **blob, size_t *size) {
+  if (!blob || !size) {
+    set_error("null output pointer");
+    return FDNN_EINVAL;
+  }
+  std::vector<uint8_t> v;
+  if (int rc = pack_model(path, cutoff, v)) return rc;
+  void *p = std::malloc(v.size());
+  if (!p) {
+    set_error("out of host memory");
+    return FDNN_ENOMEM;
+  }
+  std::memcpy(p, v.data(), v.size());
+  *blob = p;
+  *size = v.size();
+  return FDNN_OK;
+}
+
+void fdnn_blob_free(void *blob) { std::free(blob); }
+
+int fdnn_load_blob(const void *blob, size_t size, int device, fdnn_model **out) {
+  if (!blob || !out) {
+    set_error("null argument");
+    return FDNN_EINVAL;
+  }
+  int dev = 0;
+  if (int rc = usable_device(device, &dev)) return rc;
+  cudaPointerAttributes attr{};
+  bool on_device = cudaPointerGetAttributes(&attr, blob) == cudaSuccess && attr.type == cudaMemoryTypeDevice;
+  cudaGetLastError();
+  std::vector<uint8_t> host_copy;
+  const uint8_t *view = static_cast<const uint8_t *>(blob);
+  if (on_device) {
+    // validation needs the index sections on the host; weights stay on the device
+    host_copy.resize(size);
+    DeviceGuard g(dev);
+    CUDA_TRY(cudaMemcpy(host_copy.data(), blob, size, cudaMemcpyDeviceToHost));
+    view = host_copy.data();
+  }
+  if (int rc = validate_blob(view, size)) return rc;
+  return upload_model(view, blob, on_device, size, dev, out);
+}
+
+int fdnn_load(const char *path, float cutoff, int device, fdnn_model **out) {
+  if (!out) {
+    set_error("null output pointer");
+    return FDNN_EINVAL;
+  }
+  int dev = 0;
+  if (int rc = usable_device(device, &dev)) return rc;
+  std::vector<uint8_t> v;
+  if (int rc = pack_model(path, cutoff, v)) return rc;
+  return upload_model(v.data(), v.data(), false, v.size(), dev, out);
+}
+
+int fdnn_free(fdnn_model *model) {
+  if (!model) return FDNN_OK;
+  for (fdnn_ctx *c : model->pool) destroy_ctx(c);
+  DeviceGuard g(model->device);
+  cudaFree(model->d_blob);
+  delete model;
+  return FDNN_OK;
+}
+
+int fdnn_input_dim(const fdnn_model *m) { return m ? m->hdr.in_dim : FDNN_EINVAL; }
+int fdnn_output_dim(const fdnn_model *m) { return m ? m->hdr.out_dim : FDNN_EINVAL; }
+int fdnn_hidden_dim(const fdnn_model *m) { return m ? m->hdr.hidden : FDNN_EINVAL; }
+int fdnn_device(const fdnn_model *m) { return m ? m->device : FDNN_EINVAL; }
+int fdnn_layer_count(const fdnn_model *m) { return m ? m->hdr.n_qlayers + 1 : FDNN_EINVAL; }
+
+int fdnn_layer_dim(const fdnn_model *m, int i) {
+  if (!m) return FDNN_EINVAL;
+  if (i == 0) return m->hdr.hidden;
+  // jni_dnn.cc:135-148 indexes the int8 layer vector with i itself: valid for 1 ≤ i < n_qlayers,
+  // −1 past it (and where the reference would read out of bounds, i == n_qlayers)
+  if (i < 0 || i >= m->hdr.n_qlayers) return -1;
+  return m->q[size_t(i)].nodes;
+}
+
+int fdnn_model_qlayer(const fdnn_model *m, int i, int *nodes, int *inputs, float *multiplier, int8_t *weights, float *bias) {
+  if (!m || i < 0 || i >= m->hdr.n_qlayers) {
+    set_error("bad layer index");
+    return FDNN_EINVAL;
+  }
+  const BlobQLayer &q = m->q[size_t(i)];
+  if (nodes) *nodes = q.nodes;
+  if (inputs) *inputs = q.inputs;
+  if (multiplier) *multiplier = q.multiplier;
+  DeviceGuard g(m->device);
+  if (weights) CUDA_TRY(cudaMemcpy(weights, m->d_blob + q.off_w, size_t(q.nodes) * size_t(q.inputs), cudaMemcpyDeviceToHost));
+  if (bias) CUDA_TRY(cudaMemcpy(bias, m->d_blob + q.off_bias, size_t(q.nodes) * 4, cudaMemcpyDeviceToHost));
+  return FDNN_OK;
+}
+
+int fdnn_model_fixup_count(const fdnn_model *m, int i) {
+  if (!m || i < 0 || i >= m->hdr.n_qlayers) return FDNN_EINVAL;
+  return int(m->q[size_t(i)].n_fix);
+}
+
+int fdnn_model_fast_div(const fdnn_model *m, int i) {
+  if (!m || i < 0 || i >= m->hdr.n_qlayers) return FDNN_EINVAL;
+  return int(m->q[size_t(i)].fast_div);
+}
+
+int fdnn_model_uses_tensor_cores(const fdnn_model *m, int i) {
+  if (!m || i < 0 || i >= m->hdr.n_qlayers) return FDNN_EINVAL;
+  return m->tc_ok[size_t(i)] ? 1 : 0;
+}
+
+int fdnn_sigmoid_lut(uint8_t out[1280]) {
+  if (!out) return FDNN_EINVAL;
+  build_reference_lut(out);
+  return FDNN_OK;
+}
+
+// ---- contexts -----------------------------------------------------------------------------------------
+
+int fdnn_ctx_new(fdnn_model *model, int n, int batch_hint, fdnn_ctx **out) {
+  (void) batch_hint;
+  if (!model || !out) {
+    set_error("null argument");
+    return FDNN_EINVAL;
+  }
+  return create_ctx(model, n, out);
+}
+
+int fdnn_ctx_free(fdnn_ctx *ctx) {
+  destroy_ctx(ctx);
+  return FDNN_OK;
+}
+
+int fdnn_ctx_frames(const fdnn_ctx *ctx) { return ctx ? ctx->cap : FDNN_EINVAL; }
+int fdnn_ctx_output_dim(const fdnn_ctx *ctx) { return ctx ? ctx->model->hdr.out_dim : FDNN_EINVAL; }
+
+int fdnn_ctx_set_trace(fdnn_ctx *ctx, int enable) {
+  if (!ctx) return FDNN_EINVAL;
+  DeviceGuard g(ctx->model->device);
+  if (enable && !ctx->d_trace)
+    CUDA_TRY(cudaMalloc(&ctx->d_trace, size_t(ctx->model->hdr.n_qlayers) * size_t(ctx->cap) * size_t(ctx->model->hdr.hidden)));
+  ctx->trace = enable != 0;
+  return FDNN_OK;
+}
+
+int fdnn_ctx_until_output_device(fdnn_ctx *ctx, const float *d_in, int n_frames, void *stream) {
+  if (!ctx || !d_in || n_frames < 0 || n_frames > ctx->cap) {
+    set_error("bad argument to fdnn_ctx_until_output_device");
+    return FDNN_EINVAL;
+  }
+  DeviceGuard g(ctx->model->device);
+  if (int rc = enqueue_until_logits(ctx, d_in, n_frames, ctx->d_logits, static_cast<cudaStream_t>(stream))) return rc;
+  ctx->have_logits = true;
+  return FDNN_OK;
+}
+
+int fdnn_ctx_forward_device(fdnn_ctx *ctx, const float *d_in, int n_frames, float *d_out, void *stream) {
+  if (!ctx || !d_in || !d_out || n_frames < 0 || n_frames > ctx->cap) {
+    set_error("bad argument to fdnn_ctx_forward_device");
+    return FDNN_EINVAL;
+  }
+  DeviceGuard g(ctx->model->device);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (int rc = enqueue_until_logits(ctx, d_in, n_frames, d_out, s)) return rc;
+  ctx->have_logits = false;  // logits were produced straight into the caller's buffer
+  return enqueue_softmax(ctx, d_out, nullptr, n_frames, d_out, s);
+}
+
+int fdnn_ctx_lazy_batch_device(fdnn_ctx *ctx, const int8_t *d_masks, int n_frames, float *d_out, void *stream) {
+  if (!ctx || !d_masks || !d_out || n_frames < 0 || n_frames > ctx->last_frames) {
+    set_error("bad argument to fdnn_ctx_lazy_batch_device");
+    return FDNN_EINVAL;
+  }
+  if (!ctx->have_logits) {
+    set_error("calculateUntilOutput has not been run on this context");
+    return FDNN_EINVAL;
+  }
+  DeviceGuard g(ctx->model->device);
+  return enqueue_softmax(ctx, ctx->d_logits, d_masks, n_frames, d_out, static_cast<cudaStream_t>(stream));
+}
+
+int fdnn_ctx_until_output(fdnn_ctx *ctx, const float *in) {
+  if (!ctx || !in) {
+    set_error("null argument");
+    return FDNN_EINVAL;
+  }
+  DeviceGuard g(ctx->model->device);
+  const size_t bytes = size_t(ctx->cap) * size_t(ctx->model->hdr.in_dim) * 4;
+  CUDA_TRY(cudaMemcpyAsync(ctx->d_in, in, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  if (int rc = enqueue_until_logits(ctx, ctx->d_in, ctx->cap, ctx->d_logits, ctx->stream)) return rc;
+  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  ctx->have_logits = true;
+  return FDNN_OK;
+}
+
+int fdnn_ctx_lazy(fdnn_ctx *ctx, int idx, const int8_t *mask, float *out) {
+  if (!ctx || !mask || !out) {
+    set_error("null argument");
+    return FDNN_EINVAL;
+  }
+  if (!ctx->have_logits) {
+    set_error("calculateUntilOutput has not been run on this context");
+    return FDNN_EINVAL;
+  }
+  if (idx < 0 || idx >= ctx->last_frames) {
+    set_error("frame index out of range");
+    return FDNN_EINVAL;
+  }
+  DeviceGuard g(ctx->model->device);
+  const int O = ctx->model->hdr.out_dim;
+  if (!ctx->d_masks) CUDA_TRY(cudaMalloc(&ctx->d_masks, size_t(ctx->cap) * size_t(O)));
+  CUDA_TRY(cudaMemcpyAsync(ctx->d_masks, mask, size_t(O), cudaMemcpyHostToDevice, ctx->stream));
+  if (int rc = enqueue_softmax(ctx, ctx->d_logits + size_t(idx) * size_t(O), ctx->d_masks, 1, ctx->d_row, ctx->stream)) return rc;
+  CUDA_TRY(cudaMemcpyAsync(out, ctx->d_row, size_t(O) * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  return FDNN_OK;
+}
+
+int fdnn_ctx_lazy_batch(fdnn_ctx *ctx, const int8_t *masks, float *out) {
+  if (!ctx || !masks || !out) {
+    set_error("null argument");
+    return FDNN_EINVAL;
+  }
+  if (!ctx->have_logits) {
+    set_error("calculateUntilOutput has not been run on this context");
+    return FDNN_EINVAL;
+  }
+  DeviceGuard g(ctx->model->device);
+  const int O = ctx->model->hdr.out_dim, n = ctx->last_frames;
+  if (!ctx->d_masks) CUDA_TRY(cudaMalloc(&ctx->d_masks, size_t(ctx->cap) * size_t(O)));
+  CUDA_TRY(cudaMemcpyAsync(ctx->d_masks, masks, size_t(n) * size_t(O), cudaMemcpyHostToDevice, ctx->stream));
+  // the masked softmax must not overwrite the resident logits (later lazy calls need them)
+  if (!ctx->d_lazy) CUDA_TRY(cudaMalloc(&ctx->d_lazy, size_t(ctx->cap) * size_t(O) * 4));
+  if (int rc = enqueue_softmax(ctx, ctx->d_logits, ctx->d_masks, n, ctx->d_lazy, ctx->stream)) return rc;
+  CUDA_TRY(cudaMemcpyAsync(out, ctx->d_lazy, size_t(n) * size_t(O) * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  return FDNN_OK;
+}
+
+int fdnn_ctx_hidden(fdnn_ctx *ctx, int layer, int n_frames, uint8_t *out) {
+  if (!ctx || !out) return FDNN_EINVAL;
+  const int nq = ctx->model->hdr.n_qlayers, H = ctx->model->hdr.hidden;
+  if (layer < 0 || layer > nq - 1 || n_frames < 0 || n_frames > ctx->last_frames) {
+    set_error("bad layer or frame count");
+    return FDNN_EINVAL;
+  }
+  DeviceGuard g(ctx->model->device);
+  const uint8_t *src = nullptr;
+  if (layer == nq - 1)
+    src = ctx->d_act[(nq - 1) & 1];
+  else if (ctx->trace && ctx->d_trace)
+    src = ctx->d_trace + size_t(layer) * size_t(ctx->cap) * size_t(H);
+  else {
+    set_error("only the last hidden layer is retained unless trace mode was enabled before the forward pass");
+    return FDNN_EINVAL;
+  }
+  CUDA_TRY(cudaMemcpy(out, src, size_t(n_frames) * size_t(H), cudaMemcpyDeviceToHost));
+  return FDNN_OK;
+}
+
+int fdnn_ctx_logits(fdnn_ctx *ctx, int n_frames, float *out) {
+  if (!ctx || !out || n_frames < 0 || n_frames > ctx->last_frames || !ctx->have_logits) {
+    set_error("no resident logits for that many frames");
+    return FDNN_EINVAL;
+  }
+  DeviceGuard g(ctx->model->device);
+  CUDA_TRY(cudaMemcpy(out, ctx->d_logits, size_t(n_frames) * size_t(ctx->model->hdr.out_dim) * 4, cudaMemcpyDeviceToHost));
+  return FDNN_OK;
+}
+
+// ---- full forward over host buffers -------------------------------------------------------------
+
+namespace {
+
+int chunk_frames() {
+  static int v = [] {
+    const char *e = std::getenv("FDNN_CHUNK_FRAMES");
+    int c = e ? std::atoi(e) : 0;
+    return c > 0 ? c : 4096;
+  }();
+  return v;
+}
+
+fdnn_ctx *pool_take(fdnn_model *m, int cap) {
+  std::lock_guard<std::mutex> lk(m->pool_mu);
+  for (size_t i = 0; i < m->pool.size(); ++i)
+    if (m->pool[i]->cap == cap) {
+      fdnn_ctx *c = m->pool[i];
+      m->pool.erase(m->pool.begin() + long(i));
+      return c;
+    }
+  return nullptr;
+}
+
+void pool_give(fdnn_model *m, fdnn_ctx *c) {
+  fdnn_ctx *evict = nullptr;
+  {
+    std::lock_guard<std::mutex> lk(m->pool_mu);
+    m->pool.push_back(c);
+    if (m->pool.size() > 8) {
+      evict = m->pool.front();
+      m->pool.erase(m->pool.begin());
+    }
+  }
+  destroy_ctx(evict);
+}
+
+}  // namespace
+
+int fdnn_calculate(fdnn_model *model, const float *in, int n, int dim, int batch_hint, float *out) {
+  (void) batch_hint;
+  if (!model || n < 0) {
+    set_error("bad argument to fdnn_calculate");
+    return FDNN_EINVAL;
+  }
+  if (dim != model->hdr.in_dim) {  // QuantizedDnn.java:157-161
+    set_error("input dimension " + std::to_string(dim) + " does not match the network's " + std::to_string(model->hdr.in_dim));
+    return FDNN_EINVAL;
+  }
+  if (n == 0) return FDNN_OK;  // QuantizedDnn.java:154-156
+  if (!in || !out) {
+    set_error("null buffer");
+    return FDNN_EINVAL;
+  }
+  DeviceGuard g(model->device);
+  if (!g.ok) {
+    set_error("cudaSetDevice failed");
+    return FDNN_ECUDA;
+  }
+  const int I = model->hdr.in_dim, O = model->hdr.out_dim;
+  const int cap = std::min(n, chunk_frames());
+  const int n_chunks = (n + cap - 1) / cap;
+  const int n_slots = n_chunks > 1 ? 2 : 1;
+  fdnn_ctx *slot[2] = {nullptr, nullptr};
+  int rc = FDNN_OK;
+  for (int s = 0; s < n_slots && rc == FDNN_OK; ++s) {
+    slot[s] = pool_take(model, cap);
+    if (!slot[s]) rc = create_ctx(model, cap, &slot[s]);
+  }
+  // Two contexts on two streams: while one chunk computes, the other's input goes up and the
+  // previous result comes down.  Softmax runs in place in the context's logits buffer.
+  for (int c = 0; c < n_chunks && rc == FDNN_OK; ++c) {
+    fdnn_ctx *x = slot[c % n_slots];
+    const int f0 = c * cap, m = std::min(cap, n - f0);
+    cudaError_t e = cudaMemcpyAsync(x->d_in, in + size_t(f0) * size_t(I), size_t(m) * size_t(I) * 4, cudaMemcpyHostToDevice, x->stream);
+    if (e == cudaSuccess) {
+      rc = enqueue_until_logits(x, x->d_in, m, x->d_logits, x->stream);
+      if (rc == FDNN_OK) rc = enqueue_softmax(x, x->d_logits, nullptr, m, x->d_logits, x->stream);
+      x->have_logits = false;
+      if (rc == FDNN_OK)
+        e = cudaMemcpyAsync(out + size_t(f0) * size_t(O), x->d_logits, size_t(m) * size_t(O) * 4, cudaMemcpyDeviceToHost, x->stream);
+    }
+    if (e != cudaSuccess) {
+      set_error(std::string("fdnn_calculate copy: ") + cudaGetErrorString(e));
+      rc = FDNN_ECUDA;
+    }
+  }
+  for (int s = 0; s < n_slots; ++s)
+    if (slot[s]) {
+      cudaError_t e = cudaStreamSynchronize(slot[s]->stream);
+      if (e != cudaSuccess && rc == FDNN_OK) {
+        set_error(std::string("fdnn_calculate: ") + cudaGetErrorString(e));
+        rc = FDNN_ECUDA;
+      }
+    }
+  for (int s = 0; s < n_slots; ++s)
+    if (slot[s]) {
+      if (rc == FDNN_OK)
+        pool_give(model, slot[s]);
+      else
+        destroy_ctx(slot[s]);
+    }
+  return rc;
+}
+
+// ---- misc ---------------------------------------------------------------------------------------------
+
+int fdnn_host_alloc(void **ptr, size_t bytes) {
+  if (!ptr) return FDNN_EINVAL;
+  int dev = 0;
+  if (int rc = usable_device(-1, &dev)) return rc;
+  CUDA_TRY(cudaHostAlloc(ptr, bytes, cudaHostAllocPortable));
+  return FDNN_OK;
+}
+
+int fdnn_host_free(void *ptr) {
+  if (ptr) CUDA_TRY(cudaFreeHost(ptr));
+  return FDNN_OK;
+}
+
+long long fdnn_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+}  // extern "C"

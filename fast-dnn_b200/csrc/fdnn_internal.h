@@ -1,0 +1,89 @@
+// Internal declarations shared by the host core (model_host.cc), the C ABI (fdnn_api.cu) and the
+// kernels.  Not part of the public boundary (include/fdnn.h).
+#pragma once
+
+#include <cstddef>
+#include <cstdint>
+#include <string>
+#include <vector>
+
+namespace fdnn {
+
+// Sigmoid LUT domain.  The reference's table covers k ∈ [−640, 640) with k ≤ −640 → 0 and
+// k ≥ 640 → 255 handled by branches (dnn.h:35-42).  We extend the table by the clamp values
+// so that a single clamp of round(x·100) to [−641, 641] followed by one lookup is equivalent:
+//   ext[k + 641]:  k = −641, −640 → 0;  k ∈ (−640, 640) → lut[k + 640];  k = 640, 641 → 255.
+constexpr int kLutHalf = 640;
+constexpr int kLutExt = 2 * kLutHalf + 3;  // k ∈ [−641, 641]
+constexpr int kLutExtPadded = 1284;        // multiple of 4 bytes
+
+constexpr uint32_t kBlobMagic = 0x424E4446u;  // "FDNB"
+constexpr uint32_t kBlobVersion = 3;
+constexpr size_t kBlobAlign = 256;
+
+// Width (in layer inputs) of one saturation-scan chunk: a producer that has just written u8
+// activations for 32 consecutive nodes scans the consumer layer's risk entries of that chunk.
+constexpr int kFixChunk = 32;
+
+// pmaddubsw (dnn.cc:337-340) clamps every adjacent-pair sum a[2p]·w[2p] + a[2p+1]·w[2p+1] to int16.
+// A tensor-core contraction does not.  With a ≤ 255 the clamp can only fire for weight pairs whose
+// same-sign magnitudes add up to ≥ 129; those (node, pair) entries are listed per layer, grouped
+// by the INPUT pair index so that the kernel which PRODUCES the layer's input activations can
+// evaluate them while it still holds the two bytes, and post the (rare) difference
+// clamp(v) − v to the consumer's correction buffer.
+struct FixEntry {
+  uint32_t pair_w;  // pair index p (bits 0-15) | (uint8)w[2p] << 16 | (uint8)w[2p+1] << 24
+  uint32_t node;    // consumer node n
+};
+
+// One int8 layer inside the blob; all offsets are from the start of the blob, 256-byte aligned.
+struct BlobQLayer {
+  int32_t nodes;      // N
+  int32_t inputs;     // K (multiple of 16)
+  float multiplier;   // round(127/max)                      dnn.cc:479
+  float coeff;        // multiplier * 255.0f (fp32 product)  dnn.cc:297-298
+  float rcp_coeff;    // RN(1 / coeff)
+  uint32_t n_fix;     // saturation fix-up entries
+  uint32_t fast_div;  // 1: q=s·rcp; r=fma(−q,coeff,s); q+=r·rcp verified == s/coeff for every reachable s
+  uint32_t n_chunks;  // ceil(K / kFixChunk)
+  uint64_t off_w;     // int8  [N][K] row-major (K-major)
+  uint64_t off_bias;  // fp32  [N]
+  uint64_t off_fix_ptr;  // uint32 [n_chunks+1]: entries of input chunk c are [ptr[c], ptr[c+1])
+  uint64_t off_fix_ent;  // FixEntry [n_fix], sorted by pair index
+};
+
+struct BlobHeader {
+  uint32_t magic, version;
+  uint64_t total_size;
+  int32_t in_dim;       // padded to ×4
+  int32_t in_dim_file;  // as stored
+  int32_t hidden;       // H
+  int32_t out_dim;      // O
+  int32_t n_qlayers;
+  float cutoff;
+  uint64_t off_w0;     // fp32 [H][in_dim]
+  uint64_t off_bias0;  // fp32 [H]
+  uint64_t off_shift;  // fp32 [in_dim]
+  uint64_t off_scale;  // fp32 [in_dim]
+  uint64_t off_lut;    // u8 [kLutExtPadded], index k+641
+  uint64_t off_qlayers;  // BlobQLayer[n_qlayers]
+};
+
+// Thread-local error text behind fdnn_last_error().
+void set_error(const std::string &msg);
+const char *get_error();
+
+// Parse dnn.bin + quantize + build LUT and fix-up lists into a relocatable blob.
+// Returns FDNN_OK or a negative code (include/fdnn.h).
+int pack_model(const char *path, float cutoff, std::vector<uint8_t> &blob);
+// Structural validation of a blob (bounds, magic, constraints).
+int validate_blob(const uint8_t *blob, size_t size);
+// Reference LUT (1280 entries, dnn.cc:100-115).
+void build_reference_lut(uint8_t out[1280]);
+
+inline const BlobHeader *blob_header(const uint8_t *blob) { return reinterpret_cast<const BlobHeader *>(blob); }
+inline const BlobQLayer *blob_qlayers(const uint8_t *blob) {
+  return reinterpret_cast<const BlobQLayer *>(blob + blob_header(blob)->off_qlayers);
+}
+
+}  // namespace fdnn

@@ -1,0 +1,162 @@
+// The reference's JNI surface, re-pointed at the C ABI (include/fdnn.h).  Symbol names and JNI
+// signatures are exactly those of /root/reference/src/cpp/suskun_nn_QuantizedDnn.h:15-96, so the
+// unmodified Java class suskun.nn.QuantizedDnn (src/java/suskun/nn/QuantizedDnn.java:109-127)
+// binds to this library when it is packaged as /resources/libfast-dnn.so (QuantizedDnn.java:31).
+// Each function mirrors its counterpart in /root/reference/src/cpp/jni_dnn.cc (lines cited).
+//
+// Difference in failure behaviour: the reference crashes or exit(3)s; here a failed call throws
+// java.lang.IllegalStateException carrying fdnn_last_error() and returns 0 / null.
+
+#include <cstdlib>
+#include <cstring>
+
+#include "../../include/fdnn.h"
+#include "jni_min.h"
+
+namespace {
+
+template <class Fn>
+Fn slot(JNIEnvPtr env, int index) {
+  return reinterpret_cast<Fn>(const_cast<void *>((*env)[index]));
+}
+
+void throw_state(JNIEnvPtr env, const char *what) {
+  auto find = slot<jclass (*)(JNIEnvPtr, const char *)>(env, kJniFindClass);
+  auto thrw = slot<jint (*)(JNIEnvPtr, jclass, const char *)>(env, kJniThrowNew);
+  jclass cls = find(env, "java/lang/IllegalStateException");
+  if (cls) thrw(env, cls, what);
+}
+
+jfloatArray to_java(JNIEnvPtr env, const float *data, jsize len) {
+  auto mk = slot<jfloatArray (*)(JNIEnvPtr, jsize)>(env, kJniNewFloatArray);
+  auto set = slot<void (*)(JNIEnvPtr, jfloatArray, jsize, jsize, const jfloat *)>(env, kJniSetFloatArrayRegion);
+  jfloatArray arr = mk(env, len);
+  if (arr) set(env, arr, 0, len, data);
+  return arr;
+}
+
+}  // namespace
+
+extern "C" {
+
+// jni_dnn.cc:7-18
+FDNN_JNIEXPORT jlong Java_suskun_nn_QuantizedDnn_initialize(JNIEnvPtr env, jobject, jstring path, jfloat cutoff) {
+  auto get = slot<const char *(*) (JNIEnvPtr, jstring, jboolean *)>(env, kJniGetStringUTFChars);
+  auto rel = slot<void (*)(JNIEnvPtr, jstring, const char *)>(env, kJniReleaseStringUTFChars);
+  const char *chars = get(env, path, nullptr);
+  fdnn_model *model = nullptr;
+  int rc = fdnn_load(chars, cutoff, -1, &model);
+  rel(env, path, chars);
+  if (rc != FDNN_OK) {
+    throw_state(env, fdnn_last_error());
+    return 0;
+  }
+  return reinterpret_cast<jlong>(model);
+}
+
+// jni_dnn.cc:20-25
+FDNN_JNIEXPORT jint Java_suskun_nn_QuantizedDnn_inputDimension(JNIEnvPtr, jobject, jlong handle) {
+  return fdnn_input_dim(reinterpret_cast<fdnn_model *>(handle));
+}
+
+// jni_dnn.cc:27-33
+FDNN_JNIEXPORT jint Java_suskun_nn_QuantizedDnn_outputDimension(JNIEnvPtr, jobject, jlong handle) {
+  return fdnn_output_dim(reinterpret_cast<fdnn_model *>(handle));
+}
+
+// jni_dnn.cc:35-62: the Java array is read, never written back (JNI_ABORT)
+FDNN_JNIEXPORT jfloatArray Java_suskun_nn_QuantizedDnn_calculate(JNIEnvPtr env, jobject, jlong handle, jfloatArray input, jint count, jint dim,
+                                                                 jint batch) {
+  auto get = slot<jfloat *(*) (JNIEnvPtr, jfloatArray, jboolean *)>(env, kJniGetFloatArrayElements);
+  auto rel = slot<void (*)(JNIEnvPtr, jfloatArray, jfloat *, jint)>(env, kJniReleaseFloatArrayElements);
+  fdnn_model *model = reinterpret_cast<fdnn_model *>(handle);
+  const int O = fdnn_output_dim(model);
+  if (count < 0 || O <= 0) {
+    throw_state(env, "bad handle or frame count");
+    return nullptr;
+  }
+  const size_t len = size_t(count) * size_t(O);
+  float *out = static_cast<float *>(std::malloc(len ? len * sizeof(float) : 1));
+  if (!out) {
+    throw_state(env, "out of host memory");
+    return nullptr;
+  }
+  jfloat *elements = get(env, input, nullptr);
+  int rc = fdnn_calculate(model, elements, count, dim, batch, out);
+  rel(env, input, elements, JNI_ABORT_MODE);
+  jfloatArray result = nullptr;
+  if (rc == FDNN_OK)
+    result = to_java(env, out, jsize(len));
+  else
+    throw_state(env, fdnn_last_error());
+  std::free(out);
+  return result;
+}
+
+// jni_dnn.cc:64-77
+FDNN_JNIEXPORT jlong Java_suskun_nn_QuantizedDnn_getContext(JNIEnvPtr env, jobject, jlong handle, jint count, jint batch) {
+  fdnn_ctx *ctx = nullptr;
+  if (fdnn_ctx_new(reinterpret_cast<fdnn_model *>(handle), count, batch, &ctx) != FDNN_OK) {
+    throw_state(env, fdnn_last_error());
+    return 0;
+  }
+  return reinterpret_cast<jlong>(ctx);
+}
+
+// jni_dnn.cc:79-95
+FDNN_JNIEXPORT void Java_suskun_nn_QuantizedDnn_calculateUntilOutput(JNIEnvPtr env, jobject, jlong handle, jfloatArray input) {
+  auto get = slot<jfloat *(*) (JNIEnvPtr, jfloatArray, jboolean *)>(env, kJniGetFloatArrayElements);
+  auto rel = slot<void (*)(JNIEnvPtr, jfloatArray, jfloat *, jint)>(env, kJniReleaseFloatArrayElements);
+  jfloat *elements = get(env, input, nullptr);
+  int rc = fdnn_ctx_until_output(reinterpret_cast<fdnn_ctx *>(handle), elements);
+  rel(env, input, elements, JNI_ABORT_MODE);
+  if (rc != FDNN_OK) throw_state(env, fdnn_last_error());
+}
+
+// jni_dnn.cc:97-117: result length = mask length
+FDNN_JNIEXPORT jfloatArray Java_suskun_nn_QuantizedDnn_calculateLazy(JNIEnvPtr env, jobject, jlong handle, jint index, jbyteArray mask) {
+  auto get = slot<jbyte *(*) (JNIEnvPtr, jbyteArray, jboolean *)>(env, kJniGetByteArrayElements);
+  auto rel = slot<void (*)(JNIEnvPtr, jbyteArray, jbyte *, jint)>(env, kJniReleaseByteArrayElements);
+  auto length = slot<jsize (*)(JNIEnvPtr, jarray)>(env, kJniGetArrayLength);
+  fdnn_ctx *ctx = reinterpret_cast<fdnn_ctx *>(handle);
+  const jsize len = length(env, mask);
+  if (len != fdnn_ctx_output_dim(ctx)) {  // the reference trusts the caller here and reads past a short mask
+    throw_state(env, "mask length must equal the network's output dimension");
+    return nullptr;
+  }
+  float *out = static_cast<float *>(std::malloc(len > 0 ? size_t(len) * sizeof(float) : 1));
+  if (!out) {
+    throw_state(env, "out of host memory");
+    return nullptr;
+  }
+  jbyte *bytes = get(env, mask, nullptr);
+  int rc = fdnn_ctx_lazy(ctx, index, bytes, out);
+  rel(env, mask, bytes, JNI_ABORT_MODE);
+  jfloatArray result = nullptr;
+  if (rc == FDNN_OK)
+    result = to_java(env, out, len);
+  else
+    throw_state(env, fdnn_last_error());
+  std::free(out);
+  return result;
+}
+
+// jni_dnn.cc:119-126
+FDNN_JNIEXPORT void Java_suskun_nn_QuantizedDnn_deleteLazyContext(JNIEnvPtr, jobject, jlong handle) {
+  fdnn_ctx_free(reinterpret_cast<fdnn_ctx *>(handle));
+}
+
+// jni_dnn.cc:128-133
+FDNN_JNIEXPORT void Java_suskun_nn_QuantizedDnn_delete(JNIEnvPtr, jobject, jlong handle) { fdnn_free(reinterpret_cast<fdnn_model *>(handle)); }
+
+// jni_dnn.cc:135-148
+FDNN_JNIEXPORT jint Java_suskun_nn_QuantizedDnn_layerDimension(JNIEnvPtr, jobject, jlong handle, jint index) {
+  return fdnn_layer_dim(reinterpret_cast<fdnn_model *>(handle), index);
+}
+
+// jni_dnn.cc:150-156
+FDNN_JNIEXPORT jint Java_suskun_nn_QuantizedDnn_layerCount(JNIEnvPtr, jobject, jlong handle) {
+  return fdnn_layer_count(reinterpret_cast<fdnn_model *>(handle));
+}
+
+}  // extern "C"

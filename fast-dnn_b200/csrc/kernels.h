@@ -1,0 +1,50 @@
+// Launch interface of the CUDA kernels (host side).  One kernel per stage of the reference's
+// forward pass; every launcher enqueues on `stream` and returns the launch status only.
+#pragma once
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include "device_common.cuh"
+
+namespace fdnn {
+
+// ---- fp32 input layer (input_layer.cu) ---------------------------------------------------------
+struct InputLayerArgs {
+  const float *in;     // [M][I] raw frames (not modified)
+  const float *shift;  // [I]
+  const float *scale;  // [I]
+  const float *w0;     // [H][I]
+  const float *bias0;  // [H]
+  const uint8_t *lut;
+  uint8_t *out_u8;  // [M][H]
+  int M, I, H;
+  FixList next_fix;  // risk list of int8 layer 0
+  CorrChannel next;
+};
+cudaError_t input_layer_configure();
+cudaError_t launch_input_layer(const InputLayerArgs &a, cudaStream_t stream);
+
+// ---- int8 layers -------------------------------------------------------------------------------
+// tcgen05 path (qlayer_tc.cu): needs K a multiple of 128 and, for hidden layers, N a multiple of 32.
+cudaError_t qlayer_tc_configure();
+bool qlayer_tc_supported(int N, int K, bool logits);
+int qlayer_tc_block_n(int M, int N, int num_sms);
+cudaError_t launch_qlayer_tc(const CUtensorMap &tmap_act, const CUtensorMap &tmap_w, const QLayerArgs &a, bool logits, int block_n,
+                             int num_sms, cudaStream_t stream);
+// dp4a path (qlayer_simt.cu): any legal network (K a multiple of 16); used for narrow layers.
+cudaError_t launch_qlayer_simt(const QLayerArgs &a, bool logits, cudaStream_t stream);
+
+// ---- softmax over output rows (softmax.cu) -----------------------------------------------------
+// out[r][:] = softmax(mask ? (mask[r][i] ? logits[r][i] : 0) : logits[r][i]) without max
+// subtraction (dnn.cc:534-544, 355-392).  logits and out may alias.
+struct SoftmaxArgs {
+  const float *logits;  // [rows][ld]
+  const int8_t *mask;   // [rows][mask_ld] or nullptr
+  float *out;           // [rows][out_ld]
+  int rows, O, ld, mask_ld, out_ld;
+};
+cudaError_t softmax_configure();
+cudaError_t launch_softmax(const SoftmaxArgs &a, cudaStream_t stream);
+
+}  // namespace fdnn

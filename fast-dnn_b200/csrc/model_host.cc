@@ -1,0 +1,420 @@
+// Host half of model loading: dnn.bin → one relocatable blob that is uploaded (or NCCL-broadcast)
+// as is.  No CUDA in this file; it works without a GPU (fdnn_pack).
+//
+// Follows the behaviour of the reference loader and quantizer (paths under /root/reference):
+//   file layout / byte order      src/cpp/float_dnn.cc:18-69, 166-212 (4-byte big-endian words)
+//   layer-0 input padding to ×4   src/cpp/float_dnn.cc:32-33, 61-66, 76-83
+//   int8 weight quantization      src/cpp/dnn.cc:460-509 (+ absMax :148-160)
+//   sigmoid lookup table          src/cpp/dnn.cc:100-115, src/cpp/dnn.h:35-42
+// including its quirks: the multiplier is an integer-valued float, only the lower clip is live,
+// and the float→char conversion wraps modulo 256 the way x86 cvttss2si + truncation does.
+
+#include "fdnn_internal.h"
+
+#include <algorithm>
+#include <climits>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+
+#include "../../include/fdnn.h"
+
+namespace fdnn {
+
+namespace {
+
+thread_local std::string g_error;
+
+struct FileBytes {
+  std::vector<uint8_t> data;
+  size_t pos = 0;
+  bool short_read = false;
+
+  uint32_t word() {
+    if (pos + 4 > data.size()) {
+      short_read = true;
+      return 0;
+    }
+    const uint8_t *b = data.data() + pos;
+    pos += 4;
+    return (uint32_t(b[0]) << 24) | (uint32_t(b[1]) << 16) | (uint32_t(b[2]) << 8) | uint32_t(b[3]);
+  }
+  // bulk big-endian fp32 → native
+  bool floats(float *dst, size_t count) {
+    if (count > (data.size() - pos) / 4) {
+      short_read = true;
+      return false;
+    }
+    const uint8_t *b = data.data() + pos;
+    for (size_t i = 0; i < count; ++i, b += 4) {
+      uint32_t u = (uint32_t(b[0]) << 24) | (uint32_t(b[1]) << 16) | (uint32_t(b[2]) << 8) | uint32_t(b[3]);
+      std::memcpy(dst + i, &u, 4);
+    }
+    pos += count * 4;
+    return true;
+  }
+};
+
+int read_file(const char *path, std::vector<uint8_t> &out) {
+  FILE *f = std::fopen(path, "rb");
+  if (!f) {
+    set_error(std::string("cannot open ") + path);
+    return FDNN_EIO;
+  }
+  std::fseek(f, 0, SEEK_END);
+  long size = std::ftell(f);
+  std::rewind(f);
+  if (size < 0) {
+    std::fclose(f);
+    set_error(std::string("cannot size ") + path);
+    return FDNN_EIO;
+  }
+  out.resize(size_t(size));
+  size_t got = size ? std::fread(out.data(), 1, size_t(size), f) : 0;
+  std::fclose(f);
+  if (got != size_t(size)) {
+    set_error(std::string("short read on ") + path);
+    return FDNN_EIO;
+  }
+  return FDNN_OK;
+}
+
+inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// What static_cast<int>(float) does on x86-64 (cvttss2si): values outside int32 and NaN give
+// INT_MIN.  The reference reaches this through static_cast<char>(round(f·mult)) (dnn.cc:499).
+inline int x86_float_to_int(float v) {
+  if (!(v > -2147483904.0f && v < 2147483648.0f)) return INT_MIN;
+  return int(v);
+}
+
+struct FloatLayer {
+  int in = 0, out = 0, in_padded = 0;
+  std::vector<float> w;  // [out][in_padded]
+  std::vector<float> bias;
+};
+
+// Largest |w| after clipping to ±cutoff over the whole layer (dnn.cc:148-160, 469-476).
+float clipped_abs_max(const FloatLayer &l, float cutoff) {
+  float best = -3.402823466e+38f;
+  for (float v : l.w) {
+    if (v < -cutoff) v = -cutoff;
+    if (v > cutoff) v = cutoff;
+    float a = std::fabs(v);
+    if (a > best) best = a;
+  }
+  return best;
+}
+
+// The 3-instruction division q = s·r; e = fma(−q, c, s); q' = fma(e, r, q) with r = RN(1/c) is
+// checked against IEEE s / c for every numerator the layer can produce (|s| ≤ K/2 · 32768, as a
+// float) — cheap because numerators are integers.  Needs hardware fma on the host to be exact
+// and fast; without it the layer simply keeps the IEEE division on the device.
+__attribute__((target("fma"))) bool verify_fast_div_fma(float coeff, float rcp, int K) {
+  const int64_t limit = int64_t(K / 2) * 32768;
+  auto same = [&](float s) {
+    float q = s * rcp;
+    float e = __builtin_fmaf(-q, coeff, s);
+    float q2 = __builtin_fmaf(e, rcp, q);
+    float ref = s / coeff;
+    return std::memcmp(&q2, &ref, 4) == 0;
+  };
+  // every float value that (float)int32 can take in [0, limit]; the negative side is symmetric
+  int64_t s = 0;
+  while (s <= limit) {
+    if (!same(float(s))) return false;
+    int64_t step = 1;
+    if (s >= (int64_t(1) << 24)) step = 2;
+    if (s >= (int64_t(1) << 25)) step = 4;
+    if (s >= (int64_t(1) << 26)) step = 8;
+    if (s >= (int64_t(1) << 27)) step = 16;
+    s += step;
+  }
+  return true;
+}
+
+bool verify_fast_div(float coeff, float rcp, int K) {
+  if (!__builtin_cpu_supports("fma")) return false;
+  struct Memo {
+    float coeff;
+    int K;
+    bool ok;
+  };
+  static thread_local std::vector<Memo> memo;
+  for (const Memo &m : memo)
+    if (m.coeff == coeff && m.K == K) return m.ok;
+  bool ok = verify_fast_div_fma(coeff, rcp, K);
+  memo.push_back({coeff, K, ok});
+  return ok;
+}
+
+}  // namespace
+
+void set_error(const std::string &msg) { g_error = msg; }
+const char *get_error() { return g_error.c_str(); }
+
+void build_reference_lut(uint8_t out[1280]) {
+  for (int i = -kLutHalf; i < kLutHalf; ++i) {
+    float k = float(i) / 100.0f;
+    float s = 1.0f / (1 + expf(-k));
+    out[i + kLutHalf] = uint8_t(x86_float_to_int(roundf(s * 255.0f)));
+  }
+}
+
+int pack_model(const char *path, float cutoff, std::vector<uint8_t> &blob) {
+  if (!path) {
+    set_error("null path");
+    return FDNN_EINVAL;
+  }
+  if (!(cutoff > 0)) {  // QuantizedDnn.java:55-57 rejects these before going native
+    set_error("weight cutoff must be positive");
+    return FDNN_EINVAL;
+  }
+  FileBytes fb;
+  if (int rc = read_file(path, fb.data)) return rc;
+
+  const int layer_count = int(fb.word());
+  if (fb.short_read || layer_count < 3 || layer_count > 4096) {
+    set_error("not a usable dnn.bin: need at least 3 layers (one fp32 input layer and two int8 layers)");
+    return FDNN_EFORMAT;
+  }
+  std::vector<FloatLayer> layers(size_t(layer_count), FloatLayer{});
+  for (int j = 0; j < layer_count; ++j) {
+    FloatLayer &l = layers[size_t(j)];
+    l.in = int(fb.word());
+    l.out = int(fb.word());
+    if (fb.short_read || l.in <= 0 || l.out <= 0 || size_t(l.in) > fb.data.size() || size_t(l.out) > fb.data.size()) {
+      set_error("dnn.bin: bad layer header at layer " + std::to_string(j));
+      return fb.short_read ? FDNN_EIO : FDNN_EFORMAT;
+    }
+    l.in_padded = j == 0 ? round_up(l.in, 4) : l.in;
+    if (size_t(l.in) * size_t(l.out) > (fb.data.size() - fb.pos) / 4) {
+      set_error("dnn.bin truncated inside layer " + std::to_string(j));
+      return FDNN_EIO;
+    }
+    l.w.assign(size_t(l.out) * size_t(l.in_padded), 0.0f);
+    for (int o = 0; o < l.out; ++o) fb.floats(l.w.data() + size_t(o) * size_t(l.in_padded), size_t(l.in));
+    l.bias.resize(size_t(l.out));
+    if (!fb.floats(l.bias.data(), size_t(l.out))) {
+      set_error("dnn.bin truncated inside layer " + std::to_string(j));
+      return FDNN_EIO;
+    }
+  }
+  const int in_file = layers[0].in, in_dim = layers[0].in_padded, H = layers[0].out;
+  std::vector<float> shift(size_t(in_dim), 0.0f), scale(size_t(in_dim), 0.0f);
+  if (!fb.floats(shift.data(), size_t(in_file)) || !fb.floats(scale.data(), size_t(in_file))) {
+    set_error("dnn.bin truncated in shift/scale");
+    return FDNN_EIO;
+  }
+
+  // Constraints the reference relies on without checking (dnn.cc:199, 254, 331; README.md:10,69).
+  if (H % 16 != 0) {
+    set_error("hidden width must be a multiple of 16");
+    return FDNN_EFORMAT;
+  }
+  for (int j = 1; j < layer_count; ++j) {
+    if (layers[size_t(j)].in != layers[size_t(j - 1)].out) {
+      set_error("layer " + std::to_string(j) + " input width does not match previous layer");
+      return FDNN_EFORMAT;
+    }
+    if (j < layer_count - 1 && layers[size_t(j)].out != H) {
+      set_error("all hidden layers must have the same width");
+      return FDNN_EFORMAT;
+    }
+  }
+  if (H / 2 > 65536) {
+    set_error("hidden width too large");
+    return FDNN_EFORMAT;
+  }
+
+  const int nq = layer_count - 1;
+  std::vector<BlobQLayer> qmeta(size_t(nq), BlobQLayer{});
+  std::vector<std::vector<int8_t>> qw(size_t(nq), std::vector<int8_t>{});
+  std::vector<std::vector<FixEntry>> fix(size_t(nq), std::vector<FixEntry>{});
+  std::vector<std::vector<uint32_t>> fix_ptr(size_t(nq), std::vector<uint32_t>{});
+
+  for (int q = 0; q < nq; ++q) {
+    const FloatLayer &l = layers[size_t(q + 1)];
+    BlobQLayer &m = qmeta[size_t(q)];
+    m.nodes = l.out;
+    m.inputs = l.in;
+    const float max = clipped_abs_max(l, cutoff);
+    m.multiplier = roundf(127.0f / max);
+    m.coeff = m.multiplier * 255.0f;
+    m.rcp_coeff = 1.0f / m.coeff;
+    std::vector<int8_t> &w8 = qw[size_t(q)];
+    w8.resize(l.w.size());
+    const float lo = -cutoff;
+    for (size_t i = 0; i < l.w.size(); ++i) {
+      float f = l.w[i];
+      if (f < lo) f = lo;  // only the lower clip is live in the reference (dnn.cc:493-498)
+      w8[i] = int8_t(uint8_t(x86_float_to_int(roundf(f * m.multiplier)) & 0xff));
+    }
+    m.fast_div = (std::isfinite(m.coeff) && m.coeff != 0.0f && verify_fast_div(m.coeff, m.rcp_coeff, l.in)) ? 1u : 0u;
+
+    // saturation risk list, grouped by input pair
+    const int K = l.in, pairs = K / 2;
+    m.n_chunks = uint32_t((K + kFixChunk - 1) / kFixChunk);
+    std::vector<uint32_t> count(size_t(pairs) + 1, 0u);
+    for (int n = 0; n < l.out; ++n) {
+      const int8_t *row = w8.data() + size_t(n) * size_t(K);
+      for (int p = 0; p < pairs; ++p) {
+        int a = row[2 * p], b = row[2 * p + 1];
+        int pos = (a > 0 ? a : 0) + (b > 0 ? b : 0), neg = (a < 0 ? a : 0) + (b < 0 ? b : 0);
+        if (pos >= 129 || neg <= -129) ++count[size_t(p)];
+      }
+    }
+    std::vector<uint32_t> start(size_t(pairs) + 1, 0u);
+    for (int p = 0; p < pairs; ++p) start[size_t(p) + 1] = start[size_t(p)] + count[size_t(p)];
+    std::vector<FixEntry> &ent = fix[size_t(q)];
+    ent.resize(start[size_t(pairs)]);
+    std::vector<uint32_t> cursor(start.begin(), start.end() - 1);
+    for (int n = 0; n < l.out; ++n) {
+      const int8_t *row = w8.data() + size_t(n) * size_t(K);
+      for (int p = 0; p < pairs; ++p) {
+        int a = row[2 * p], b = row[2 * p + 1];
+        int pos = (a > 0 ? a : 0) + (b > 0 ? b : 0), neg = (a < 0 ? a : 0) + (b < 0 ? b : 0);
+        if (pos >= 129 || neg <= -129) {
+          FixEntry e;
+          e.pair_w = uint32_t(p) | (uint32_t(uint8_t(a)) << 16) | (uint32_t(uint8_t(b)) << 24);
+          e.node = uint32_t(n);
+          ent[cursor[size_t(p)]++] = e;
+        }
+      }
+    }
+    m.n_fix = uint32_t(ent.size());
+    std::vector<uint32_t> &ptr = fix_ptr[size_t(q)];
+    ptr.resize(size_t(m.n_chunks) + 1);
+    for (uint32_t c = 0; c <= m.n_chunks; ++c) {
+      int p = std::min(pairs, int(c) * (kFixChunk / 2));
+      ptr[c] = start[size_t(p)];
+    }
+  }
+
+  // ---- lay the blob out ----------------------------------------------------------------------
+  size_t off = align_up(sizeof(BlobHeader), kBlobAlign);
+  BlobHeader hdr{};
+  hdr.magic = kBlobMagic;
+  hdr.version = kBlobVersion;
+  hdr.in_dim = in_dim;
+  hdr.in_dim_file = in_file;
+  hdr.hidden = H;
+  hdr.out_dim = layers.back().out;
+  hdr.n_qlayers = nq;
+  hdr.cutoff = cutoff;
+  auto reserve = [&](size_t bytes) {
+    size_t at = off;
+    off = align_up(off + bytes, kBlobAlign);
+    return uint64_t(at);
+  };
+  hdr.off_qlayers = reserve(sizeof(BlobQLayer) * size_t(nq));
+  hdr.off_lut = reserve(kLutExtPadded);
+  hdr.off_shift = reserve(sizeof(float) * size_t(in_dim));
+  hdr.off_scale = reserve(sizeof(float) * size_t(in_dim));
+  hdr.off_bias0 = reserve(sizeof(float) * size_t(H));
+  hdr.off_w0 = reserve(sizeof(float) * layers[0].w.size());
+  for (int q = 0; q < nq; ++q) {
+    BlobQLayer &m = qmeta[size_t(q)];
+    m.off_bias = reserve(sizeof(float) * size_t(m.nodes));
+    m.off_fix_ptr = reserve(sizeof(uint32_t) * fix_ptr[size_t(q)].size());
+    m.off_fix_ent = reserve(sizeof(FixEntry) * std::max<size_t>(fix[size_t(q)].size(), 1));
+    m.off_w = reserve(qw[size_t(q)].size());
+  }
+  hdr.total_size = off;
+
+  blob.assign(off, 0);
+  uint8_t *base = blob.data();
+  std::memcpy(base, &hdr, sizeof(hdr));
+  std::memcpy(base + hdr.off_qlayers, qmeta.data(), sizeof(BlobQLayer) * size_t(nq));
+  {
+    uint8_t lut[1280];
+    build_reference_lut(lut);
+    uint8_t *ext = base + hdr.off_lut;
+    ext[0] = 0;  // k = −641
+    ext[1] = 0;  // k = −640 (dnn.h:37: k ≤ −640 → 0)
+    for (int k = -kLutHalf + 1; k < kLutHalf; ++k) ext[k + 641] = lut[k + kLutHalf];
+    ext[1281] = 255;  // k = 640 (dnn.h:38-40)
+    ext[1282] = 255;  // k = 641
+    ext[1283] = 255;
+  }
+  std::memcpy(base + hdr.off_shift, shift.data(), sizeof(float) * shift.size());
+  std::memcpy(base + hdr.off_scale, scale.data(), sizeof(float) * scale.size());
+  std::memcpy(base + hdr.off_bias0, layers[0].bias.data(), sizeof(float) * size_t(H));
+  std::memcpy(base + hdr.off_w0, layers[0].w.data(), sizeof(float) * layers[0].w.size());
+  for (int q = 0; q < nq; ++q) {
+    const BlobQLayer &m = qmeta[size_t(q)];
+    std::memcpy(base + m.off_bias, layers[size_t(q + 1)].bias.data(), sizeof(float) * size_t(m.nodes));
+    std::memcpy(base + m.off_fix_ptr, fix_ptr[size_t(q)].data(), sizeof(uint32_t) * fix_ptr[size_t(q)].size());
+    if (!fix[size_t(q)].empty())
+      std::memcpy(base + m.off_fix_ent, fix[size_t(q)].data(), sizeof(FixEntry) * fix[size_t(q)].size());
+    std::memcpy(base + m.off_w, qw[size_t(q)].data(), qw[size_t(q)].size());
+  }
+  return FDNN_OK;
+}
+
+int validate_blob(const uint8_t *blob, size_t size) {
+  if (!blob || size < sizeof(BlobHeader)) {
+    set_error("blob too small");
+    return FDNN_EFORMAT;
+  }
+  BlobHeader h;
+  std::memcpy(&h, blob, sizeof(h));
+  if (h.magic != kBlobMagic || h.version != kBlobVersion) {
+    set_error("not a fast-dnn model blob (magic/version mismatch)");
+    return FDNN_EFORMAT;
+  }
+  if (h.total_size != size) {
+    set_error("blob size does not match its header");
+    return FDNN_EFORMAT;
+  }
+  auto inside = [&](uint64_t off, uint64_t bytes) { return off % kBlobAlign == 0 && off <= size && bytes <= size - off; };
+  if (h.in_dim <= 0 || h.in_dim % 4 || h.hidden <= 0 || h.hidden % 16 || h.out_dim <= 0 || h.n_qlayers < 2) {
+    set_error("blob header holds an unusable topology");
+    return FDNN_EFORMAT;
+  }
+  if (!inside(h.off_qlayers, sizeof(BlobQLayer) * uint64_t(h.n_qlayers)) || !inside(h.off_lut, kLutExtPadded) ||
+      !inside(h.off_shift, 4ull * uint64_t(h.in_dim)) || !inside(h.off_scale, 4ull * uint64_t(h.in_dim)) ||
+      !inside(h.off_bias0, 4ull * uint64_t(h.hidden)) || !inside(h.off_w0, 4ull * uint64_t(h.hidden) * uint64_t(h.in_dim))) {
+    set_error("blob section out of bounds");
+    return FDNN_EFORMAT;
+  }
+  std::vector<BlobQLayer> q(size_t(h.n_qlayers), BlobQLayer{});
+  std::memcpy(q.data(), blob + h.off_qlayers, sizeof(BlobQLayer) * q.size());
+  int expect_in = h.hidden;
+  for (int i = 0; i < h.n_qlayers; ++i) {
+    const BlobQLayer &m = q[size_t(i)];
+    bool last = i == h.n_qlayers - 1;
+    if (m.inputs != expect_in || m.nodes <= 0 || (!last && m.nodes != h.hidden) || (last && m.nodes != h.out_dim) ||
+        m.n_chunks != uint32_t((m.inputs + kFixChunk - 1) / kFixChunk)) {
+      set_error("blob int8 layer " + std::to_string(i) + " has inconsistent dimensions");
+      return FDNN_EFORMAT;
+    }
+    if (!inside(m.off_w, uint64_t(m.nodes) * uint64_t(m.inputs)) || !inside(m.off_bias, 4ull * uint64_t(m.nodes)) ||
+        !inside(m.off_fix_ptr, 4ull * (uint64_t(m.n_chunks) + 1)) || !inside(m.off_fix_ent, sizeof(FixEntry) * uint64_t(m.n_fix))) {
+      set_error("blob int8 layer " + std::to_string(i) + " section out of bounds");
+      return FDNN_EFORMAT;
+    }
+    const uint32_t *ptr = reinterpret_cast<const uint32_t *>(blob + m.off_fix_ptr);
+    if (ptr[0] != 0 || ptr[m.n_chunks] != m.n_fix) {
+      set_error("blob int8 layer " + std::to_string(i) + " has a corrupt fix-up index");
+      return FDNN_EFORMAT;
+    }
+    for (uint32_t c = 0; c < m.n_chunks; ++c)
+      if (ptr[c] > ptr[c + 1]) {
+        set_error("blob int8 layer " + std::to_string(i) + " has a corrupt fix-up index");
+        return FDNN_EFORMAT;
+      }
+    const FixEntry *ent = reinterpret_cast<const FixEntry *>(blob + m.off_fix_ent);
+    for (uint32_t e = 0; e < m.n_fix; ++e)
+      if (int(ent[e].pair_w & 0xffffu) >= m.inputs / 2 || ent[e].node >= uint32_t(m.nodes)) {
+        set_error("blob int8 layer " + std::to_string(i) + " has a corrupt fix-up entry");
+        return FDNN_EFORMAT;
+      }
+    expect_in = m.nodes;
+  }
+  return FDNN_OK;
+}
+
+}  // namespace fdnn

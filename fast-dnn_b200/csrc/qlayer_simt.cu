@@ -1,0 +1,71 @@
+// Int8 layer on the CUDA cores (dp4a, u8 × s8 → s32) for layers the tensor-core path does not
+// take: inputs narrower than one 128-byte K block or not a multiple of it, and hidden widths that
+// are not a multiple of 32 (the reference only asks for multiples of 16, dnn.cc:331).  Same
+// arithmetic contract and the same epilogue as qlayer_tc.cu; see that file for the references.
+//
+// One thread owns one frame and one aligned chunk of 32 nodes, so the epilogue (and the
+// saturation-correction channel, which works in 32-node chunks per frame) is shared verbatim.
+
+#include <cuda_runtime.h>
+
+#include "device_common.cuh"
+#include "kernels.h"
+
+namespace fdnn {
+
+namespace {
+
+constexpr int kRowsPerBlock = 128;
+
+__device__ __forceinline__ int dp4a_u8s8(uint32_t a, uint32_t b, int c) {
+  int d;
+  asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+}
+
+template <bool kLogits>
+__global__ void __launch_bounds__(kRowsPerBlock) qlayer_simt_kernel(const QLayerArgs args) {
+  __shared__ __align__(16) uint8_t s_scan[kRowsPerBlock * kFixChunk];
+  const int row = int(blockIdx.x) * kRowsPerBlock + int(threadIdx.x);
+  const int col = int(blockIdx.y) * 32;
+  if (row >= args.M) return;
+  const int K = args.K, N = args.N;
+  const int cols = min(32, N - col);
+  int32_t s[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) s[i] = 0;
+  const uint4 *a_row = reinterpret_cast<const uint4 *>(args.act + size_t(row) * size_t(K));
+  for (int k = 0; k < K / 16; ++k) {
+    const uint4 a = a_row[k];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      if (i < cols) {  // warp-uniform
+        const uint4 w = __ldg(reinterpret_cast<const uint4 *>(args.w + size_t(col + i) * size_t(K)) + k);
+        int acc = s[i];
+        acc = dp4a_u8s8(a.x, w.x, acc);
+        acc = dp4a_u8s8(a.y, w.y, acc);
+        acc = dp4a_u8s8(a.z, w.z, acc);
+        acc = dp4a_u8s8(a.w, w.w, acc);
+        s[i] = acc;
+      }
+    }
+  }
+  float bias32[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) bias32[i] = i < cols ? __ldg(args.bias + col + i) : 0.0f;
+  epilogue_chunk<kLogits>(s, row, col, args, bias32, args.lut, s_scan + int(threadIdx.x) * kFixChunk);
+}
+
+}  // namespace
+
+cudaError_t launch_qlayer_simt(const QLayerArgs &a, bool logits, cudaStream_t stream) {
+  if (a.M <= 0) return cudaSuccess;
+  dim3 grid((a.M + kRowsPerBlock - 1) / kRowsPerBlock, (a.N + 31) / 32);
+  if (logits)
+    qlayer_simt_kernel<true><<<grid, kRowsPerBlock, 0, stream>>>(a);
+  else
+    qlayer_simt_kernel<false><<<grid, kRowsPerBlock, 0, stream>>>(a);
+  return cudaGetLastError();
+}
+
+}  // namespace fdnn

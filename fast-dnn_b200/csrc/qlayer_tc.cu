@@ -1,0 +1,259 @@
+// Int8 layer on the 5th-generation tensor cores:  u8 activations [M×K] · s8 weights [N×K]ᵀ → s32
+// in tensor memory, then the reference's per-element tail in the epilogue.
+//
+// Replaces, for one whole layer and all frames at once (paths under /root/reference):
+//   quantizedNodeSum            src/cpp/dnn.cc:323-349   (the pmaddubsw dot product)
+//   QuantizedLayerActivations   src/cpp/dnn.cc:289-318   (sum / (multiplier·255))
+//   AddBias + QuantizedSigmoid  src/cpp/dnn.cc:250-286   (hidden mode: + bias, LUT → u8)
+//   CalculateOutput's "+= bias" src/cpp/dnn.cc:442-447   (logits mode: fp32 lin + bias)
+//
+// Both operands are already K-major in the reference's own row-major layouts, so TMA copies
+// 128-row × 128-byte boxes straight into 128B-swizzled shared memory and tcgen05.mma kind::i8
+// (A unsigned, B signed) consumes them through shared-memory descriptors; no transposes.
+//
+// Persistent, warp-specialised: warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM
+// allocator, warps 4-7 = epilogue (one TMEM lane quarter each).  Two accumulator stages in TMEM
+// let the epilogue of tile i overlap the contraction of tile i+1.
+//
+// pmaddubsw's int16 pair saturation is not reproduced by the tensor core; the (rare) differences
+// arrive through the layer's correction channel (device_common.cuh) and are added to the raw
+// sums before dequantisation, which makes the sums bit-identical to the reference's.
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include "device_common.cuh"
+#include "kernels.h"
+#include "ptx.cuh"
+
+namespace fdnn {
+
+namespace {
+
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 128;  // bytes of K per pipeline stage = one 128B swizzle atom
+constexpr int kUmmaK = 32;    // K per tcgen05.mma for 8-bit operands
+constexpr int kThreads = 256;
+constexpr int kEpilogueThreads = 128;
+constexpr int kAccStages = 2;
+
+template <int BN>
+struct TcConfig {
+  static constexpr int kABytes = kBlockM * kBlockK;
+  static constexpr int kBBytes = BN * kBlockK;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = BN == 256 ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int kTmemCols = kAccStages * BN;  // 128, 256 or 512: powers of two
+  static constexpr int kBiasBytes = kAccStages * BN * 4;
+  static constexpr int kScanBytes = kEpilogueThreads * kFixChunk;
+  static constexpr int kBarBytes = (2 * kStages + 2 * kAccStages) * 8 + 16;
+  static constexpr int kSmemBytes = 1024 /*alignment slack*/ + kStages * kStageBytes + kBiasBytes + kLutExtPadded + 12 /*pad*/ +
+                                    kScanBytes + kBarBytes;
+};
+
+template <int BN, bool kLogits>
+__global__ void __launch_bounds__(kThreads, 1)
+qlayer_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_constant__ CUtensorMap tmap_w, const QLayerArgs args) {
+  using Cfg = TcConfig<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t *tiles = smem;
+  float *s_bias = reinterpret_cast<float *>(smem + Cfg::kStages * Cfg::kStageBytes);
+  uint8_t *s_lut = reinterpret_cast<uint8_t *>(s_bias) + Cfg::kBiasBytes;
+  uint8_t *s_scan = s_lut + kLutExtPadded + 12;  // 16-byte aligned
+  uint64_t *full_bar = reinterpret_cast<uint64_t *>(s_scan + Cfg::kScanBytes);
+  uint64_t *empty_bar = full_bar + Cfg::kStages;
+  uint64_t *tmem_full_bar = empty_bar + Cfg::kStages;
+  uint64_t *tmem_empty_bar = tmem_full_bar + kAccStages;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_empty_bar + kAccStages);
+
+  const int warp = int(threadIdx.x) / 32, lane = int(threadIdx.x) % 32;
+  const int M = args.M, N = args.N, K = args.K;
+  const int m_blocks = (M + kBlockM - 1) / kBlockM, n_blocks = (N + BN - 1) / BN;
+  const int tiles_total = m_blocks * n_blocks;
+  const int k_blocks = (K + kBlockK - 1) / kBlockK;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tensormap(&tmap_act);
+    ptx::prefetch_tensormap(&tmap_w);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < Cfg::kStages; ++i) {
+      ptx::mbar_init(full_bar + i, 1);
+      ptx::mbar_init(empty_bar + i, 1);
+    }
+    for (int i = 0; i < kAccStages; ++i) {
+      ptx::mbar_init(tmem_full_bar + i, 1);
+      ptx::mbar_init(tmem_empty_bar + i, kEpilogueThreads);
+    }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 2) ptx::tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+  if (warp >= 4) {
+    for (int i = int(threadIdx.x) - 128; i < kLutExtPadded / 4; i += kEpilogueThreads)
+      reinterpret_cast<uint32_t *>(s_lut)[i] = __ldg(reinterpret_cast<const uint32_t *>(args.lut) + i);
+  }
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  ptx::tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = int(blockIdx.x); t < tiles_total; t += int(gridDim.x)) {
+        const int m_blk = t / n_blocks, n_blk = t % n_blocks;
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          ptx::mbar_wait(empty_bar + stage, phase ^ 1);
+          uint8_t *sa = tiles + stage * Cfg::kStageBytes;
+          ptx::mbar_arrive_expect_tx(full_bar + stage, Cfg::kStageBytes);
+          ptx::tma_load_2d(&tmap_act, full_bar + stage, sa, kb * kBlockK, m_blk * kBlockM);
+          ptx::tma_load_2d(&tmap_w, full_bar + stage, sa + Cfg::kABytes, kb * kBlockK, n_blk * BN);
+          if (++stage == Cfg::kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer (one fixed lane issues and commits) =====
+    constexpr uint32_t idesc = ptx::idesc_i8_u8s8(BN);
+    int stage = 0, acc = 0;
+    uint32_t phase = 0, acc_phase = 0;
+    for (int t = int(blockIdx.x); t < tiles_total; t += int(gridDim.x)) {
+      ptx::mbar_wait(tmem_empty_bar + acc, acc_phase ^ 1);
+      ptx::tc_fence_after_sync();
+      const uint32_t d_tmem = tmem_base + uint32_t(acc * BN);
+      for (int kb = 0; kb < k_blocks; ++kb) {
+        ptx::mbar_wait(full_bar + stage, phase);
+        ptx::tc_fence_after_sync();
+        if (lane == 0) {
+          const uint32_t a_addr = ptx::smem_u32(tiles + stage * Cfg::kStageBytes);
+          const uint64_t da = ptx::smem_desc_k_sw128(a_addr), db = ptx::smem_desc_k_sw128(a_addr + Cfg::kABytes);
+#pragma unroll
+          for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+            // advancing K inside the swizzle atom = advancing the start address (16-byte units)
+            ptx::mma_i8_ss(d_tmem, da + uint64_t(k * (kUmmaK / 16)), db + uint64_t(k * (kUmmaK / 16)), idesc, uint32_t((kb | k) != 0));
+          }
+          ptx::mma_commit(empty_bar + stage);
+          if (kb == k_blocks - 1) ptx::mma_commit(tmem_full_bar + acc);
+        }
+        __syncwarp();
+        if (++stage == Cfg::kStages) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+      if (++acc == kAccStages) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+  } else if (warp >= 4) {
+    // ===== epilogue: TMEM → registers → reference tail → global =====
+    const int et = int(threadIdx.x) - 128;
+    const int quarter = warp - 4;  // == warp % 4: the TMEM lane quarter this warp may read
+    uint8_t *my_scan = s_scan + et * kFixChunk;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int t = int(blockIdx.x); t < tiles_total; t += int(gridDim.x)) {
+      const int m_blk = t / n_blocks, n_blk = t % n_blocks;
+      const int n0 = n_blk * BN;
+      float *bias_s = s_bias + acc * BN;
+      for (int i = et; i < BN; i += kEpilogueThreads) bias_s[i] = (n0 + i < N) ? __ldg(args.bias + n0 + i) : 0.0f;
+      ptx::named_bar_sync(1, kEpilogueThreads);
+      ptx::mbar_wait(tmem_full_bar + acc, acc_phase);
+      ptx::tc_fence_after_sync();
+      const int row = m_blk * kBlockM + quarter * 32 + lane;
+      const bool row_ok = row < M;
+      const uint32_t t_addr = tmem_base + uint32_t(acc * BN) + (uint32_t(quarter * 32) << 16);
+      const int chunks = min(BN / 32, (N - n0 + 31) / 32);
+      for (int j = 0; j < chunks; ++j) {
+        uint32_t raw[32];
+        ptx::tmem_ld_32x32(t_addr + uint32_t(j * 32), raw);
+        ptx::tmem_ld_wait();
+        if (j == chunks - 1) {
+          // accumulator stage fully read: hand it back to the MMA warp before doing the math
+          ptx::tc_fence_before_sync();
+          ptx::mbar_arrive(tmem_empty_bar + acc);
+        }
+        if (!row_ok) continue;
+        int32_t s[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) s[i] = int32_t(raw[i]);
+        epilogue_chunk<kLogits>(s, row, n0 + j * 32, args, bias_s + j * 32, s_lut, my_scan);
+      }
+      if (++acc == kAccStages) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+  }
+
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 2) {
+    ptx::tc_fence_after_sync();
+    ptx::tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+  }
+}
+
+template <int BN, bool kLogits>
+cudaError_t launch_one(const CUtensorMap &ta, const CUtensorMap &tw, const QLayerArgs &a, int num_sms, cudaStream_t stream) {
+  using Cfg = TcConfig<BN>;
+  const int tiles = ((a.M + kBlockM - 1) / kBlockM) * ((a.N + BN - 1) / BN);
+  const int grid = tiles < num_sms ? tiles : num_sms;
+  qlayer_tc_kernel<BN, kLogits><<<grid, kThreads, Cfg::kSmemBytes, stream>>>(ta, tw, a);
+  return cudaGetLastError();
+}
+
+template <int BN>
+cudaError_t configure_one() {
+  cudaError_t e = cudaFuncSetAttribute(qlayer_tc_kernel<BN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcConfig<BN>::kSmemBytes);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(qlayer_tc_kernel<BN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcConfig<BN>::kSmemBytes);
+}
+
+}  // namespace
+
+// Opt in to the large dynamic shared memory carve-out on the current device (once per device).
+cudaError_t qlayer_tc_configure() {
+  cudaError_t e = configure_one<64>();
+  if (e == cudaSuccess) e = configure_one<128>();
+  if (e == cudaSuccess) e = configure_one<256>();
+  return e;
+}
+
+bool qlayer_tc_supported(int N, int K, bool logits) {
+  if (K < kBlockK || K % kBlockK != 0) return false;
+  if (!logits && N % 32 != 0) return false;
+  return true;
+}
+
+int qlayer_tc_block_n(int M, int N, int num_sms) {
+  // Largest tile that still gives every SM work; small batches trade tile size for parallelism.
+  const int m_blocks = (M + kBlockM - 1) / kBlockM;
+  if (m_blocks * ((N + 255) / 256) >= 2 * num_sms) return 256;
+  if (m_blocks * ((N + 127) / 128) >= num_sms) return 128;
+  return 64;
+}
+
+cudaError_t launch_qlayer_tc(const CUtensorMap &tmap_act, const CUtensorMap &tmap_w, const QLayerArgs &a, bool logits, int block_n,
+                             int num_sms, cudaStream_t stream) {
+  if (a.M <= 0) return cudaSuccess;
+  switch (block_n) {
+    case 64:
+      return logits ? launch_one<64, true>(tmap_act, tmap_w, a, num_sms, stream) : launch_one<64, false>(tmap_act, tmap_w, a, num_sms, stream);
+    case 128:
+      return logits ? launch_one<128, true>(tmap_act, tmap_w, a, num_sms, stream) : launch_one<128, false>(tmap_act, tmap_w, a, num_sms, stream);
+    case 256:
+      return logits ? launch_one<256, true>(tmap_act, tmap_w, a, num_sms, stream) : launch_one<256, false>(tmap_act, tmap_w, a, num_sms, stream);
+    default:
+      return cudaErrorInvalidValue;
+  }
+}
+
+}  // namespace fdnn

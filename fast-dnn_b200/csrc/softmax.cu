@@ -1,0 +1,120 @@
+// Row softmax of the output layer, as the reference computes it (paths under /root/reference):
+//   SoftMax::apply           src/cpp/dnn.cc:534-544   e = exp(x); total = Σ e; e / total — no max subtraction
+//   LazyOutputActivations    src/cpp/dnn.cc:355-392   masked-out nodes enter as logit 0 (e = 1) and
+//                                                     come back as 1/total, not 0
+// The reference adds the exponentials sequentially in fp32 and uses glibc's expf; here the sum is a
+// fixed-shape tree (deterministic) and expf is CUDA's (≤ 2 ulp), which is where the stated float
+// tolerance of the softmax scores comes from (tests/test_gpu_parity.py).  One CTA per row; the
+// exponentials are kept in shared memory between the two passes.
+
+#include <cuda_runtime.h>
+
+#include "kernels.h"
+
+namespace fdnn {
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kMaxSmemFloats = 56 * 1024;  // 224 KB of exponentials; wider rows recompute instead
+
+__device__ __forceinline__ float block_sum(float v, float *s_red) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = __fadd_rn(v, __shfl_xor_sync(0xffffffffu, v, o));
+  const int warp = int(threadIdx.x) / 32, lane = int(threadIdx.x) % 32;
+  if (lane == 0) s_red[warp] = v;
+  __syncthreads();
+  float t = lane < kThreads / 32 ? s_red[lane] : 0.0f;
+#pragma unroll
+  for (int o = 4; o > 0; o >>= 1) t = __fadd_rn(t, __shfl_xor_sync(0xffffffffu, t, o));
+  return __shfl_sync(0xffffffffu, t, 0);
+}
+
+template <bool kCache>
+__global__ void __launch_bounds__(kThreads) softmax_kernel(const SoftmaxArgs a) {
+  extern __shared__ __align__(16) float s_e[];
+  __shared__ float s_red[kThreads / 32];
+  const int row = int(blockIdx.x);
+  const int tid = int(threadIdx.x), O = a.O;
+  const float *x = a.logits + size_t(row) * size_t(a.ld);
+  const int8_t *m = a.mask ? a.mask + size_t(row) * size_t(a.mask_ld) : nullptr;
+  float *y = a.out + size_t(row) * size_t(a.out_ld);
+  const bool vec = (O % 4 == 0) && (a.ld % 4 == 0) && (a.out_ld % 4 == 0) && (m == nullptr || a.mask_ld % 4 == 0);
+
+  float part = 0.0f;
+  if (vec) {
+    for (int i = tid; i < O / 4; i += kThreads) {
+      float4 v = reinterpret_cast<const float4 *>(x)[i];
+      if (m) {
+        const char4 k = reinterpret_cast<const char4 *>(m)[i];
+        v.x = k.x ? v.x : 0.0f;
+        v.y = k.y ? v.y : 0.0f;
+        v.z = k.z ? v.z : 0.0f;
+        v.w = k.w ? v.w : 0.0f;
+      }
+      float4 e = make_float4(expf(v.x), expf(v.y), expf(v.z), expf(v.w));
+      if (kCache) reinterpret_cast<float4 *>(s_e)[i] = e;
+      part = __fadd_rn(part, __fadd_rn(__fadd_rn(e.x, e.y), __fadd_rn(e.z, e.w)));
+    }
+  } else {
+    for (int i = tid; i < O; i += kThreads) {
+      float v = x[i];
+      if (m && m[i] == 0) v = 0.0f;
+      const float e = expf(v);
+      if (kCache) s_e[i] = e;
+      part = __fadd_rn(part, e);
+    }
+  }
+  const float total = block_sum(part, s_red);  // contains the barrier that orders s_e writes/reads
+  if (vec) {
+    for (int i = tid; i < O / 4; i += kThreads) {
+      float4 e;
+      if (kCache) {
+        e = reinterpret_cast<const float4 *>(s_e)[i];
+      } else {
+        float4 v = reinterpret_cast<const float4 *>(x)[i];
+        if (m) {
+          const char4 k = reinterpret_cast<const char4 *>(m)[i];
+          v.x = k.x ? v.x : 0.0f;
+          v.y = k.y ? v.y : 0.0f;
+          v.z = k.z ? v.z : 0.0f;
+          v.w = k.w ? v.w : 0.0f;
+        }
+        e = make_float4(expf(v.x), expf(v.y), expf(v.z), expf(v.w));
+      }
+      reinterpret_cast<float4 *>(y)[i] = make_float4(__fdiv_rn(e.x, total), __fdiv_rn(e.y, total), __fdiv_rn(e.z, total), __fdiv_rn(e.w, total));
+    }
+  } else {
+    for (int i = tid; i < O; i += kThreads) {
+      float e;
+      if (kCache) {
+        e = s_e[i];
+      } else {
+        float v = x[i];
+        if (m && m[i] == 0) v = 0.0f;
+        e = expf(v);
+      }
+      y[i] = __fdiv_rn(e, total);
+    }
+  }
+}
+
+}  // namespace
+
+cudaError_t softmax_configure() {
+  return cudaFuncSetAttribute(softmax_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmemFloats * 4);
+}
+
+cudaError_t launch_softmax(const SoftmaxArgs &a, cudaStream_t stream) {
+  if (a.rows <= 0) return cudaSuccess;
+  // the uncached variant re-reads its input in the second pass, so it cannot run in place
+  const bool cache = a.O <= kMaxSmemFloats;
+  if (!cache && a.logits == a.out) return cudaErrorInvalidValue;
+  if (cache)
+    softmax_kernel<true><<<a.rows, kThreads, size_t(a.O) * 4, stream>>>(a);
+  else
+    softmax_kernel<false><<<a.rows, kThreads, 0, stream>>>(a);
+  return cudaGetLastError();
+}
+
+}  // namespace fdnn

@@ -1,0 +1,139 @@
+/* fdnn.h — C ABI of libfast-dnn.so, the B200-native drop-in for fast-dnn's quantized inference path.
+ *
+ * This is the boundary the reference's JNI layer binds.  The eleven
+ * Java_suskun_nn_QuantizedDnn_* symbols exported by the same library (csrc/jni_shim.cc) are thin
+ * wrappers over these entry points; INTEGRATION.md shows the binding.  Every entry point cites the
+ * reference interface it replaces (paths relative to /root/reference).
+ *
+ * Conventions: plain pointers and sizes only; every function returns FDNN_OK (0) or a negative
+ * FDNN_E* code and never throws or exits across the ABI (the reference crashes or exit(3)s on
+ * failure, float_dnn.cc:171-188); fdnn_last_error() returns a thread-local message.  Caller input
+ * buffers are never modified (the reference scales its private copy in place, dnn.cc:175-192,
+ * jni_dnn.cc:44,58).  A model handle is immutable and may be shared by any number of host threads
+ * (test/java/suskun/nn/MultiThreadedStressTest.java:48-67); a context belongs to one thread at a time.
+ *
+ * There is no CPU fallback: entry points that compute return FDNN_ENOGPU when no CUDA device is
+ * usable.  fdnn_pack / fdnn_blob_* are host-only and work without a GPU.
+ */
+#ifndef FDNN_H
+#define FDNN_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FDNN_OK 0
+#define FDNN_EINVAL (-1)  /* bad argument */
+#define FDNN_EIO (-2)     /* file missing / unreadable / truncated */
+#define FDNN_EFORMAT (-3) /* not a usable dnn.bin (see constraints below) */
+#define FDNN_ENOGPU (-4)  /* no usable CUDA device; there is no CPU fallback */
+#define FDNN_ECUDA (-5)   /* CUDA runtime error, text in fdnn_last_error() */
+#define FDNN_ENOMEM (-6)
+
+typedef struct fdnn_model fdnn_model; /* replaces dnn::QuantizedDnn*        (src/cpp/dnn.h:106-142) */
+typedef struct fdnn_ctx fdnn_ctx;     /* replaces dnn::CalculationContext*  (src/cpp/dnn.h:144-208) */
+
+const char *fdnn_last_error(void);
+const char *fdnn_version(void);
+
+/* ---- load (one-time) ------------------------------------------------------------------------
+ * Network constraints inherited from the reference (dnn.cc:199,254,331; README.md:10,69): at least
+ * two int8 layers (≥3 layers in the file), all hidden layers the same width, hidden width a
+ * multiple of 16, any number of outputs.  Layer-0 input is zero-padded to a multiple of 4. */
+
+/* Java_suskun_nn_QuantizedDnn_initialize (src/cpp/jni_dnn.cc:7-18): parse dnn.bin
+ * (float_dnn.cc:18-69), quantize layers 1.. to int8 (dnn.cc:460-509), upload to CUDA `device`
+ * (−1 = the calling thread's current device). */
+int fdnn_load(const char *path, float cutoff, int device, fdnn_model **out);
+
+/* Host-only half of fdnn_load: parse + quantize into one relocatable blob (weights, biases,
+ * multipliers, sigmoid LUT, saturation fix-up lists).  In a multi-GPU job rank 0 packs, the blob
+ * is broadcast once (NCCL), and every rank calls fdnn_load_blob — SURVEY.md §8e. */
+int fdnn_pack(const char *path, float cutoff, void **blob, size_t *size);
+void fdnn_blob_free(void *blob);
+/* `blob` may be a host pointer or a device pointer on `device` (e.g. an NCCL receive buffer). */
+int fdnn_load_blob(const void *blob, size_t size, int device, fdnn_model **out);
+
+/* Java_suskun_nn_QuantizedDnn_delete (jni_dnn.cc:128-133) */
+int fdnn_free(fdnn_model *model);
+
+/* inputDimension / outputDimension (jni_dnn.cc:20-33): padded input width, output width */
+int fdnn_input_dim(const fdnn_model *model);
+int fdnn_output_dim(const fdnn_model *model);
+/* layerCount (jni_dnn.cc:150-156): number of layers in the file */
+int fdnn_layer_count(const fdnn_model *model);
+/* layerDimension (jni_dnn.cc:135-148): i==0 → nodes of file layer 0; i≥1 → nodes of file layer
+ * i+1 (the reference indexes its int8 layer vector with i); −1 where the reference returns −1 or
+ * reads out of bounds. */
+int fdnn_layer_dim(const fdnn_model *model, int i);
+int fdnn_hidden_dim(const fdnn_model *model);
+int fdnn_device(const fdnn_model *model);
+
+/* ---- full forward ---------------------------------------------------------------------------
+ * Java_suskun_nn_QuantizedDnn_calculate (jni_dnn.cc:35-62) = CalculationContext::Calculate
+ * (dnn.cc:162-165).  in: host [n × dim] fp32 row-major, dim must equal fdnn_input_dim; out: host
+ * [n × output_dim] fp32 softmax rows.  Host pointers may be pageable or pinned (fdnn_host_alloc);
+ * frames are streamed through the GPU in chunks with copies overlapped.  batch_hint is the
+ * reference's CPU cache-blocking batchSize; results do not depend on it and it is ignored.
+ * Re-entrant: concurrent calls on one model each use a private workspace. n == 0 is a no-op. */
+int fdnn_calculate(fdnn_model *model, const float *in, int n, int dim, int batch_hint, float *out);
+
+/* ---- contexts: lazy output + device-resident pipelines --------------------------------------
+ * Java_suskun_nn_QuantizedDnn_getContext (jni_dnn.cc:64-77): workspace for exactly n frames. */
+int fdnn_ctx_new(fdnn_model *model, int n, int batch_hint, fdnn_ctx **out);
+/* deleteLazyContext (jni_dnn.cc:119-126) */
+int fdnn_ctx_free(fdnn_ctx *ctx);
+int fdnn_ctx_frames(const fdnn_ctx *ctx);
+int fdnn_ctx_output_dim(const fdnn_ctx *ctx);
+
+/* calculateUntilOutput (jni_dnn.cc:79-95) = CalculateUntilLastHiddenLayer (dnn.cc:402-424).
+ * in: host [ctx.n × input_dim].  Also computes the dense output-layer logits on the device so
+ * that every later fdnn_ctx_lazy call is a masked softmax over resident data. */
+int fdnn_ctx_until_output(fdnn_ctx *ctx, const float *in);
+/* calculateLazy (jni_dnn.cc:97-117) = LazyOutputActivations (dnn.cc:355-392): mask[O], nonzero =
+ * active; inactive logits are 0 and still enter the softmax denominator.  out: host [O]. */
+int fdnn_ctx_lazy(fdnn_ctx *ctx, int idx, const int8_t *mask, float *out);
+/* All ctx.n frames at once: masks host [n × O], out host [n × O] (BASELINE config 3). */
+int fdnn_ctx_lazy_batch(fdnn_ctx *ctx, const int8_t *masks, float *out);
+
+/* Device-resident variants: pointers are device memory on the model's device, work is enqueued on
+ * `stream` (a cudaStream_t; NULL = the legacy default stream) and NOT synchronised.  n_frames ≤
+ * ctx.n.  These are what a GPU-side pipeline calls and what bench.py times for `value`. */
+int fdnn_ctx_forward_device(fdnn_ctx *ctx, const float *d_in, int n_frames, float *d_out, void *stream);
+int fdnn_ctx_until_output_device(fdnn_ctx *ctx, const float *d_in, int n_frames, void *stream);
+int fdnn_ctx_lazy_batch_device(fdnn_ctx *ctx, const int8_t *d_masks, int n_frames, float *d_out, void *stream);
+
+/* ---- inspection (stage-level parity tests; not on the hot path) ------------------------------ */
+/* u8 activations after hidden layer `layer` (0 = fp32 input layer … qlayers−2 = last hidden) of
+ * the most recent forward on this context; host out [n_frames × H]. Only the last hidden layer
+ * is retained unless the context was put in trace mode before the forward. */
+int fdnn_ctx_set_trace(fdnn_ctx *ctx, int enable);
+int fdnn_ctx_hidden(fdnn_ctx *ctx, int layer, int n_frames, uint8_t *out);
+/* dense output logits (dequantized + bias, before softmax) of the most recent until_output */
+int fdnn_ctx_logits(fdnn_ctx *ctx, int n_frames, float *out);
+/* quantized layer i (0-based among int8 layers): any of the out pointers may be NULL */
+int fdnn_model_qlayer(const fdnn_model *model, int i, int *nodes, int *inputs, float *multiplier,
+                      int8_t *weights, float *bias);
+/* number of weight pairs per int8 layer that can trip pmaddubsw's int16 saturation (dnn.cc:337-340) */
+int fdnn_model_fixup_count(const fdnn_model *model, int i);
+/* 1 if layer i's epilogue uses the 3-op division that was exhaustively verified against IEEE
+ * division for this layer's divisor at load, 0 if it uses __fdiv_rn */
+int fdnn_model_fast_div(const fdnn_model *model, int i);
+/* 1 if int8 layer i runs on the tcgen05 tensor-core kernel, 0 if on the dp4a kernel (narrow layers) */
+int fdnn_model_uses_tensor_cores(const fdnn_model *model, int i);
+int fdnn_sigmoid_lut(uint8_t out[1280]);
+
+/* ---- pinned host memory for callers that want zero staging ---------------------------------- */
+int fdnn_host_alloc(void **ptr, size_t bytes);
+int fdnn_host_free(void *ptr);
+
+/* number of kernel launches issued by this library since load (bench.py's gpu_launches) */
+long long fdnn_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FDNN_H */

@@ -1,0 +1,228 @@
+"""GPU parity: the CUDA path, called through the C ABI (libfast-dnn.so), against the CPU oracle on
+the same seeded inputs.  Bit-exact for every integer/byte stage (quantized weights, u8 activations
+of every layer) and for the fp32 logits; stated tolerance for the softmax scores."""
+import os
+import threading
+
+import numpy as np
+import pytest
+
+from conftest import softmax_close
+from fast_dnn_b200 import quantized_dnn as qd
+from fast_dnn_b200 import synth
+import oracle_py
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def loaded(net_file):
+    cache = {}
+
+    def get(shape, stress=False):
+        key = (shape, stress)
+        if key not in cache:
+            path = net_file(shape, stress=stress)
+            cache[key] = (qd.QuantizedDnn.load_from_file(path), oracle_py.Port(path))
+        return cache[key]
+
+    yield get
+    for dnn, _ in cache.values():
+        dnn.delete()
+
+
+def stage_parity(dnn, port, frames):
+    """every stage of one forward pass, via a traced context"""
+    n = frames.shape[0]
+    ctx = dnn.get_new_lazy_context(n)
+    try:
+        ctx.set_trace(True)
+        ctx.calculate_until_output(frames)
+        want = port.hidden_trace(frames)  # [qlayers][n][H]; slot j = after hidden layer j
+        for layer in range(port.qlayer_count):
+            got = ctx.hidden(layer)
+            diff = np.flatnonzero(got != want[layer])
+            assert diff.size == 0, f"u8 activations after hidden layer {layer}: {diff.size} of {got.size} differ"
+        lin = port.output_linear(want[-1])
+        _, bias, _ = port.qlayer(port.qlayer_count - 1)
+        logits = ctx.logits()
+        assert np.array_equal(logits.view(np.uint32), (lin + bias).astype(np.float32).view(np.uint32)), "logits not bit-exact"
+        return logits
+    finally:
+        ctx.delete()
+
+
+@pytest.mark.parametrize("shape,n", [("tiny", 1), ("tiny", 37), ("ragged", 130), ("S", 128), ("P", 100)])
+def test_stages_bit_exact(loaded, shape, n):
+    dnn, port = loaded(shape)
+    frames = synth.make_frames(n, dnn.input_dimension(), seed=7)
+    stage_parity(dnn, port, frames)
+
+
+@pytest.mark.parametrize("shape,n", [("tiny", 33), ("S", 70)])
+def test_stress_network_bit_exact(loaded, shape, n):
+    """heavy-tailed weights: int8 wrap-around in the quantizer and dense pmaddubsw saturation"""
+    dnn, port = loaded(shape, stress=True)
+    assert sum(dnn.fixup_count(i) for i in range(port.qlayer_count)) > 0
+    frames = synth.make_frames(n, dnn.input_dimension(), seed=9)
+    stage_parity(dnn, port, frames)
+
+
+def test_saturation_actually_fires(loaded):
+    """the fix-up path is exercised: without the int16 clamp the sums would differ"""
+    dnn, port = loaded("S", stress=True)
+    frames = synth.make_frames(16, dnn.input_dimension(), seed=9)
+    trace = port.hidden_trace(frames)
+    w, _, _ = port.qlayer(1)
+    events = 0
+    for f in range(4):
+        for node in range(0, w.shape[0], 37):
+            events += oracle_py.Port.node_sum(trace[0][f], w[node]) != oracle_py.Port.node_sum(trace[0][f], w[node], saturate=False)
+    assert events > 0
+
+
+@pytest.mark.parametrize("shape,n", [("tiny", 5), ("ragged", 64), ("S", 128), ("P", 100)])
+def test_calculate_matches_oracle(loaded, shape, n):
+    dnn, port = loaded(shape)
+    frames = synth.make_frames(n, dnn.input_dimension(), seed=3)
+    before = frames.copy()
+    got = dnn.calculate(frames)
+    assert np.array_equal(frames, before), "caller's input buffer was modified"
+    want = port.calculate(frames)
+    softmax_close(got, want)
+    assert np.array_equal(np.argmax(got, axis=1), np.argmax(want, axis=1))
+    np.testing.assert_allclose(got.sum(axis=1), 1.0, atol=2e-5)
+
+
+def test_calculate_batch_hint_irrelevant_and_empty(loaded):
+    dnn, _ = loaded("tiny")
+    frames = synth.make_frames(19, dnn.input_dimension(), seed=5)
+    a, b = dnn.calculate(frames, 1), dnn.calculate(frames, 512)
+    assert np.array_equal(a, b)
+    assert dnn.calculate(np.zeros((0, dnn.input_dimension()), np.float32)).shape == (0, 0)
+    with pytest.raises(ValueError):
+        dnn.calculate(np.zeros((3, dnn.input_dimension() + 4), np.float32))
+
+
+def test_chunked_streaming_equals_single_pass(loaded, monkeypatch):
+    """n larger than the streaming chunk: two contexts on two streams, ragged last chunk"""
+    dnn, port = loaded("S")
+    n = 4096 + 4096 + 300  # default chunk is 4096 frames
+    frames = synth.make_frames(n, dnn.input_dimension(), seed=21)
+    got = dnn.calculate(frames)
+    idx = np.r_[0:40, 4090:4110, 8180:8200, n - 20:n]
+    want = port.calculate(frames[idx])
+    softmax_close(got[idx], want)
+    ctx = dnn.get_new_lazy_context(n)
+    try:
+        ctx.calculate_until_output(frames)
+        assert np.array_equal(ctx.hidden(), port.until_output(frames))
+    finally:
+        ctx.delete()
+
+
+def test_lazy_context_matches_oracle(loaded):
+    dnn, port = loaded("S")
+    n = 24
+    frames = synth.make_frames(n, dnn.input_dimension(), seed=13)
+    masks = synth.make_masks(n, dnn.output_dimension(), ratio=0.40, drift=0.03, seed=11)
+    masks[3][masks[3] != 0] = 7  # any non-zero byte is "active" (dnn.cc:369)
+    hidden = port.until_output(frames)
+    ctx = dnn.get_new_lazy_context(n)
+    try:
+        ctx.calculate_until_output(frames)
+        assert np.array_equal(ctx.hidden(), hidden)
+        rows = [ctx.calculate_for_output_nodes(masks[i]) for i in range(n)]
+        batch = ctx.calculate_for_output_nodes_batch(masks)
+    finally:
+        ctx.delete()
+    for i in range(n):
+        want = port.lazy(hidden[i], masks[i])
+        softmax_close(rows[i], want)
+        assert np.array_equal(rows[i], batch[i])
+        inactive = masks[i] == 0
+        # inactive outputs come back as 1/total, not 0 (dnn.cc:367-370 + 534-544)
+        assert np.all(rows[i][inactive] == rows[i][inactive][0]) and rows[i][inactive][0] > 0
+        active = np.flatnonzero(~inactive)
+        assert np.array_equal(np.argsort(-rows[i][active], kind="stable")[:10], np.argsort(-want[active], kind="stable")[:10])
+
+
+def test_tensor_core_and_dp4a_kernels_agree(net_file):
+    """same layer through tcgen05 and through the dp4a kernel: identical bytes"""
+    path = net_file("S")
+    frames = synth.make_frames(200, 440, seed=2)
+    outs = []
+    for force in ("0", "1"):
+        os.environ["FDNN_FORCE_SIMT"] = force
+        try:
+            dnn = qd.QuantizedDnn.load_from_file(path)
+        finally:
+            os.environ.pop("FDNN_FORCE_SIMT", None)
+        assert dnn.uses_tensor_cores(0) == (force == "0")
+        ctx = dnn.get_new_lazy_context(200)
+        ctx.calculate_until_output(frames)
+        outs.append((ctx.hidden(), ctx.logits()))
+        ctx.delete()
+        dnn.delete()
+    assert np.array_equal(outs[0][0], outs[1][0])
+    assert np.array_equal(outs[0][1].view(np.uint32), outs[1][1].view(np.uint32))
+
+
+def test_model_accessors(loaded):
+    dnn, port = loaded("S")
+    assert (dnn.input_dimension(), dnn.output_dimension(), dnn.layer_count()) == (440, 2000, 5)
+    # layerDimension (jni_dnn.cc:135-148): 0 → layer-0 nodes; i ≥ 1 → nodes of file layer i+1
+    assert [dnn.layer_dimension(i) for i in range(6)] == [512, 512, 512, 2000, -1, -1]
+    for i in range(port.qlayer_count):
+        w, b, m = dnn.qlayer(i)
+        w2, b2, m2 = port.qlayer(i)
+        assert np.array_equal(w, w2) and np.array_equal(b, b2) and m == m2
+
+
+def test_shared_model_many_threads(loaded):
+    """MultiThreadedStressTest.java:48-67: one immutable model, concurrent calculate() calls"""
+    dnn, port = loaded("S")
+    frames = synth.make_frames(96, dnn.input_dimension(), seed=17)
+    want = dnn.calculate(frames)
+    errors = []
+
+    def work(seed):
+        rng = np.random.default_rng(seed)
+        for _ in range(6):
+            perm = rng.permutation(96)[: int(rng.integers(1, 96))]
+            got = dnn.calculate(frames[perm], 10)
+            if not np.array_equal(got, want[perm]):
+                errors.append(seed)
+
+    threads = [threading.Thread(target=work, args=(s,)) for s in range(8)]
+    [t.start() for t in threads]
+    [t.join() for t in threads]
+    assert not errors
+
+
+def test_headline_network_batch512(loaded):
+    """BASELINE configs[2]: 7×2048 hidden, 8000 outputs, batch 512 — last-hidden bytes and logits
+    bit-exact against the oracle, scores within tolerance, plus size-independent properties."""
+    dnn, port = loaded("L")
+    frames = synth.make_frames(512, 440, seed=7)
+    ctx = dnn.get_new_lazy_context(512)
+    try:
+        ctx.calculate_until_output(frames)
+        hidden = ctx.hidden()
+        want_hidden = port.until_output(frames, threads=os.cpu_count() or 8)
+        assert np.array_equal(hidden, want_hidden)
+        rows = np.r_[0:24, 500:512]
+        lin = port.output_linear(want_hidden[rows])
+        _, bias, _ = port.qlayer(port.qlayer_count - 1)
+        assert np.array_equal(ctx.logits()[rows].view(np.uint32), (lin + bias).astype(np.float32).view(np.uint32))
+        masks = synth.make_masks(512, 8000, seed=11)
+        lazy = ctx.calculate_for_output_nodes_batch(masks)
+        for r in (0, 255, 511):
+            softmax_close(lazy[r], port.lazy(want_hidden[r], masks[r]))
+    finally:
+        ctx.delete()
+    got = dnn.calculate(frames)
+    np.testing.assert_allclose(got.sum(axis=1), 1.0, atol=5e-5)
+    # a frame's result does not depend on its neighbours or its position in the batch
+    again = dnn.calculate(frames[::-1].copy())
+    assert np.array_equal(again[::-1], got)
