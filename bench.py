@@ -1,0 +1,347 @@
+#!/usr/bin/env python
+"""bench.py — frames/sec of the quantized inference hot path (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]            our CUDA path
+  python bench.py --impl reference [--gpus N] [--steps K] ...     the reference's own SSE4.1 CPU path
+  (N > 1: launched by torchrun, one rank per GPU)
+
+A step = one pass of the hot path over one batch of synthetic frames: the 7×2048-hidden /
+8000-output / 440-input network of BASELINE.json configs[2] at batch 512 (per GPU; weak scaling).
+Prints ONE JSON line (rank 0).  See DESIGN.md §Measurement for what every field means.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "frames/sec (7x2048 hidden, 8000 out)"
+SHAPE = "L"            # 440-[2048x7]-8000, SURVEY.md §8d
+BATCH = 512
+I_DIM, H_DIM, O_DIM, N_HIDDEN = 440, 2048, 8000, 7
+INT8_OPS_PER_FRAME = 2 * ((N_HIDDEN - 1) * H_DIM * H_DIM + O_DIM * H_DIM)  # 83 099 648 − layer 0 is fp32
+
+
+def env_int(name, default):
+    try:
+        return int(os.environ.get(name, default))
+    except ValueError:
+        return default
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return d, "measured (MEASURED_PEAKS.json)"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """SM clock / throttle reasons of one GPU sampled through NVML while the timed loops run."""
+
+    REASONS = {
+        0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x10: "sync_boost",
+        0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown", 0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting",
+    }
+
+    def __init__(self, index: int):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thread = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(visible.split(",")[index]) if visible and visible.split(",")[index].isdigit() else index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                self.samples.append(int(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                mask = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                for bit, name in self.REASONS.items():
+                    if mask & bit and name != "gpu_idle":
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.004)
+
+    def start(self):
+        if self.nv:
+            self._stop.clear()
+            self._thread = threading.Thread(target=self._run, daemon=True)
+            self._thread.start()
+
+    def stop(self):
+        if self._thread:
+            self._stop.set()
+            self._thread.join()
+            self._thread = None
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+# ---------------------------------------------------------------------------------------------------
+# reference arm: the unmodified reference C++ (oracle/_ref) on the host cores
+# ---------------------------------------------------------------------------------------------------
+def load_cpu_reference(path):
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle_py  # the one place besides tests/ and smoke() where the checker is executed
+    if oracle_py.have_ref():
+        return oracle_py.Ref(path), "reference"
+    return oracle_py.Port(path), "port"
+
+
+def time_cpu(model, kind, frames, threads):
+    """wall seconds for `frames` split over `threads` host threads (one context each, one shared
+    model — the MultiThreadedStressTest.java:48-61 pattern; timed region = what JNI calculate does)"""
+    if kind == "reference":
+        return model.time_calculate(frames, batch=10, threads=threads)
+    return model.time_calculate(frames, threads=threads)
+
+
+def run_reference_arm(args):
+    rank = env_int("RANK", 0)
+    if rank != 0:
+        return
+    from fast_dnn_b200 import synth
+    path = synth.network_file(SHAPE)
+    model, kind = load_cpu_reference(path)
+    cores = os.cpu_count() or 1
+    n = BATCH * max(1, args.gpus)
+    frames = synth.make_frames(n, I_DIM, seed=7)
+    for _ in range(max(args.warmup, 1)):
+        time_cpu(model, kind, frames, cores)
+    t = [time_cpu(model, kind, frames, cores) for _ in range(args.steps)]
+    total = float(np.sum(t))
+    value = n * args.steps / total
+    sample = f"{args.steps} steps x {n} frames (one batch of {BATCH} per GPU of the GPU arm) split over {cores} threads"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "int8 weights x uint8 activations (SSE4.1 pmaddubsw), fp32 input layer", "data": "synthetic",
+        "config": {"workload": f"440-7x2048-8000 synthetic network, batch {BATCH} synthetic frames per step and GPU, "
+                               "reference C++ (dnn.cc) compiled -O2 -msse4.1, batchSize 10"},
+        "cpu_baseline": {"value": value, "unit": "frames/s", "cores": cores, "kind": kind, "sample": sample},
+        "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+# ---------------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------------
+def run_gpu_arm(args):
+    import torch
+    import torch.distributed as dist
+    from fast_dnn_b200 import quantized_dnn as qd, synth
+
+    world = env_int("WORLD_SIZE", 1)
+    rank = env_int("RANK", 0)
+    local = env_int("LOCAL_RANK", 0)
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the hot path has no CPU implementation (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    # ---- load: rank 0 parses + quantizes, ONE broadcast of the packed blob, every rank uploads ----
+    path = synth.network_file(SHAPE)
+    if world > 1:
+        if rank == 0:
+            blob_np = qd.pack(path)
+            size = torch.tensor([blob_np.nbytes], dtype=torch.int64, device=dev)
+        else:
+            size = torch.zeros(1, dtype=torch.int64, device=dev)
+        dist.broadcast(size, 0)
+        blob = torch.from_numpy(blob_np).to(dev) if rank == 0 else torch.empty(int(size.item()), dtype=torch.uint8, device=dev)
+        dist.broadcast(blob, 0)
+        dnn = qd.QuantizedDnn.load_from_blob(blob.data_ptr(), device=local, size=blob.numel())
+        del blob
+    else:
+        dnn = qd.QuantizedDnn.load_from_file(path, device=local)
+    n_layers = dnn.layer_count()
+    assert all(dnn.uses_tensor_cores(i) for i in range(n_layers - 1)), "tcgen05 path not selected"
+
+    # ---- device-resident pool: inputs + outputs rotate over more than the L2 (126 MB) -------------
+    pool = 16
+    seeds = 1000 + rank * pool
+    d_in = [torch.from_numpy(synth.make_frames(BATCH, I_DIM, seed=seeds + i)).to(dev) for i in range(pool)]
+    d_out = [torch.empty(BATCH, O_DIM, dtype=torch.float32, device=dev) for _ in range(pool)]
+    ctx = dnn.get_new_lazy_context(BATCH)
+    stream = torch.cuda.current_stream()
+    sampler = ClockSampler(local)
+
+    def step(i):
+        ctx.forward_device(d_in[i % pool].data_ptr(), BATCH, d_out[i % pool].data_ptr(), stream.cuda_stream)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for i in range(max(args.warmup, 3)):
+        step(i)
+    barrier()
+    sampler.start()
+    launches0 = qd.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    for i in range(args.steps):
+        step(i)
+    ev1.record(stream)
+    torch.cuda.synchronize()
+    launches = qd.launch_count() - launches0
+    ms_total = ev0.elapsed_time(ev1)
+    if world > 1:
+        t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    barrier()
+    value = world * BATCH * args.steps / (ms_total * 1e-3)
+
+    # keep the device busy with the same loop long enough for NVML to see clocks under load
+    t_end = time.time() + 1.0
+    i = 0
+    while time.time() < t_end:
+        step(i)
+        i += 1
+        if i % 64 == 0:
+            torch.cuda.synchronize()
+    torch.cuda.synchronize()
+
+    # ---- per-kernel times (CUDA events on the launching stream) → roofline of the hidden kernel --
+    stage_ms = ctx.profile_stages(d_in[0].data_ptr(), BATCH, d_out[0].data_ptr(), iters=max(args.steps, 20))
+    hidden_ms = [float(x) for x in stage_ms[1:n_layers - 1]]
+    hid_avg = float(np.mean(hidden_ms))
+    peaks, peak_src = measured_peaks()
+    int8_peak = 2.0 * float(peaks["bf16_tflops"])  # dense int8 tensor rate = 2 × bf16 on sm_100 (4.5 vs 2.25 P nominal)
+    hid_ops = 2.0 * BATCH * H_DIM * H_DIM
+    achieved = hid_ops / (hid_avg * 1e-3) / 1e12
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "hidden_kernel_traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            traffic = json.load(f).get("dram_bytes_per_launch")
+    total_stage = float(np.sum(stage_ms))
+    roofline = {
+        "kernel": "qlayer_tc_kernel<hidden> (tcgen05 kind::i8, one 2048x2048 layer over 512 frames)", "bound": "tensor",
+        "achieved": achieved, "peak": int8_peak, "unit": "TOP/s (int8, 2*M*N*K per launch)", "frac": achieved / int8_peak,
+        "traffic": traffic, "peak_source": f"2 x bf16_tflops {peak_src}; the file has no int8 entry, nominal dense int8 is 4500",
+        "avg_launch_ms": hid_avg, "share_of_step": float(np.sum(hidden_ms)) / total_stage,
+    }
+    stages = {"input_fp32_ms": float(stage_ms[0]), "hidden_int8_ms": hidden_ms, "output_int8_ms": float(stage_ms[n_layers - 1]),
+              "softmax_ms": float(stage_ms[n_layers]), "sum_ms": total_stage,
+              "output_plus_softmax_hbm_gbs": (BATCH * O_DIM * 4 * 3 + O_DIM * H_DIM) / ((stage_ms[n_layers - 1] + stage_ms[n_layers]) * 1e-3) / 1e9}
+
+    # ---- end to end through the public call (fdnn_calculate): pinned HOST buffers, H2D + D2H inside
+    e2e_threads = 3
+    e2e_pool = 2
+    h_in = [[qd.PinnedArray((BATCH, I_DIM), np.float32) for _ in range(e2e_pool)] for _ in range(e2e_threads)]
+    h_out = [[qd.PinnedArray((BATCH, O_DIM), np.float32) for _ in range(e2e_pool)] for _ in range(e2e_threads)]
+    for t_ in range(e2e_threads):
+        for j in range(e2e_pool):
+            h_in[t_][j].array[:] = synth.make_frames(BATCH, I_DIM, seed=5000 + rank * 100 + t_ * 10 + j)
+    e2e_steps = max(args.steps, 30)
+    per_thread = [e2e_steps // e2e_threads + (1 if t_ < e2e_steps % e2e_threads else 0) for t_ in range(e2e_threads)]
+
+    def e2e_worker(t_, count):
+        torch.cuda.set_device(local)
+        for k in range(count):
+            dnn.calculate(h_in[t_][k % e2e_pool].array, 10, out=h_out[t_][k % e2e_pool].array)
+
+    for t_ in range(e2e_threads):  # warm-up: creates the pooled contexts
+        e2e_worker(t_, 3)
+    barrier()
+    t0 = time.perf_counter()
+    workers = [threading.Thread(target=e2e_worker, args=(t_, per_thread[t_])) for t_ in range(e2e_threads)]
+    [w.start() for w in workers]
+    [w.join() for w in workers]
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    # single-caller latency for reference
+    t0 = time.perf_counter()
+    for k in range(10):
+        dnn.calculate(h_in[0][k % e2e_pool].array, 10, out=h_out[0][k % e2e_pool].array)
+    e2e_serial_ms = (time.perf_counter() - t0) / 10 * 1e3
+    sampler.stop()
+    e2e = {"value": world * BATCH * e2e_steps / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": BATCH * I_DIM * 4,
+           "d2h_bytes_per_step": BATCH * O_DIM * 4, "steps": e2e_steps,
+           "mode": f"QuantizedDnn.calculate (fdnn_calculate) on pinned host buffers, {e2e_threads} host threads sharing one model "
+                   "(MultiThreadedStressTest pattern) so copies overlap compute; wall clock",
+           "single_caller_ms_per_step": e2e_serial_ms}
+
+    # ---- CPU baseline on this box's host cores (rank 0, N = 1 only; bounded sample) ------------------
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        model, kind = load_cpu_reference(path)
+        cores = os.cpu_count() or 1
+        frames = synth.make_frames(BATCH, I_DIM, seed=7)
+        per = max(8, min(BATCH, 4096 // cores))  # ≈ 4096 frames ≈ 12 CPU-seconds in total
+        big = np.concatenate([frames] * ((per * cores + BATCH - 1) // BATCH))[: per * cores]
+        time_cpu(model, kind, big[: cores * 4], cores)
+        secs = time_cpu(model, kind, big, cores)
+        cpu_baseline = {"value": per * cores / secs, "unit": "frames/s", "cores": cores, "kind": kind,
+                        "sample": f"{per * cores} frames of the same workload, {per} per thread on {cores} threads, one pass, "
+                                  f"{secs:.2f} s wall; batchSize 10"}
+
+    if rank == 0:
+        print(json.dumps({
+            "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u8 activations x s8 weights -> s32 (tcgen05 kind::i8); fp32 input layer and softmax", "data": "synthetic",
+            "config": {"workload": f"BASELINE configs[2]: 440-7x2048-8000 synthetic network, batch {BATCH} synthetic frames per step and GPU",
+                       "l2": f"inputs and outputs rotate over a {pool}-deep pool ({pool * BATCH * (I_DIM + O_DIM) * 4 / 1e6:.0f} MB > 126 MB L2); "
+                             "the 45 MB of weights stay L2-resident as in steady-state serving",
+                       "parallelism": f"frames sharded over {world} GPU(s), one NCCL broadcast of the weight blob at load, no per-frame collective"},
+            "e2e": e2e, "gpu_launches": int(launches), "clocks": sampler.summary(), "roofline": roofline, "stages": stages,
+            "cpu_baseline": cpu_baseline,
+        }))
+    ctx.delete()
+    dnn.delete()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -16,6 +16,7 @@
 #include <atomic>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <memory>
 #include <mutex>
 #include <string>
@@ -236,7 +237,8 @@ int create_ctx(fdnn_model *m, int n, fdnn_ctx **out) {
 
 // Enqueue one forward pass over frames [0, m) of `d_in` on `stream`.  Logits (lin + bias of the
 // output layer) go to `d_logits` with row pitch O.
-int enqueue_until_logits(fdnn_ctx *c, const float *d_in, int m, float *d_logits, cudaStream_t stream) {
+int enqueue_until_logits(fdnn_ctx *c, const float *d_in, int m, float *d_logits, cudaStream_t stream,
+                         const std::function<void(int)> &after_stage = nullptr) {
   fdnn_model *mod = c->model;
   const BlobHeader &h = mod->hdr;
   const int nq = h.n_qlayers;
@@ -263,6 +265,7 @@ int enqueue_until_logits(fdnn_ctx *c, const float *d_in, int m, float *d_logits,
   ia.next = chan_of(0);
   CUDA_TRY(launch_input_layer(ia, stream));
   g_launches.fetch_add(1, std::memory_order_relaxed);
+  if (after_stage) after_stage(0);
   const size_t act_bytes = size_t(m) * size_t(h.hidden);
   if (c->trace) CUDA_TRY(cudaMemcpyAsync(c->d_trace, c->d_act[0], act_bytes, cudaMemcpyDeviceToDevice, stream));
 
@@ -297,6 +300,7 @@ int enqueue_until_logits(fdnn_ctx *c, const float *d_in, int m, float *d_logits,
       CUDA_TRY(launch_qlayer_simt(a, logits, stream));
     }
     g_launches.fetch_add(1, std::memory_order_relaxed);
+    if (after_stage) after_stage(j + 1);
     if (c->trace && !logits)
       CUDA_TRY(cudaMemcpyAsync(c->d_trace + size_t(j + 1) * size_t(c->cap) * size_t(h.hidden), c->d_act[(j + 1) & 1], act_bytes,
                                cudaMemcpyDeviceToDevice, stream));
@@ -649,6 +653,42 @@ int fdnn_ctx_logits(fdnn_ctx *ctx, int n_frames, float *out) {
   DeviceGuard g(ctx->model->device);
   CUDA_TRY(cudaMemcpy(out, ctx->d_logits, size_t(n_frames) * size_t(ctx->model->hdr.out_dim) * 4, cudaMemcpyDeviceToHost));
   return FDNN_OK;
+}
+
+// Bench/profiling aid: `iters` forward passes over device-resident input with CUDA events between
+// the kernels.  ms[0] = input layer, ms[1 .. nq−1] = hidden int8 layers, ms[nq] = output int8
+// layer, ms[nq+1] = softmax (averages, milliseconds).  Event pairs between back-to-back kernels
+// include the inter-kernel launch gap.
+int fdnn_ctx_profile_stages(fdnn_ctx *ctx, const float *d_in, int n_frames, float *d_out, int iters, float *ms) {
+  if (!ctx || !d_in || !d_out || !ms || iters <= 0 || n_frames <= 0 || n_frames > ctx->cap) {
+    set_error("bad argument to fdnn_ctx_profile_stages");
+    return FDNN_EINVAL;
+  }
+  DeviceGuard g(ctx->model->device);
+  const int stages = ctx->model->hdr.n_qlayers + 2;
+  std::vector<cudaEvent_t> ev(size_t(stages) + 1);
+  for (auto &e : ev) CUDA_TRY(cudaEventCreate(&e));
+  std::vector<double> total(size_t(stages), 0.0);
+  int rc = FDNN_OK;
+  for (int it = 0; it < iters && rc == FDNN_OK; ++it) {
+    cudaEventRecord(ev[0], ctx->stream);
+    rc = enqueue_until_logits(ctx, d_in, n_frames, d_out, ctx->stream, [&](int stage) { cudaEventRecord(ev[size_t(stage) + 1], ctx->stream); });
+    if (rc == FDNN_OK) rc = enqueue_softmax(ctx, d_out, nullptr, n_frames, d_out, ctx->stream);
+    cudaEventRecord(ev[size_t(stages)], ctx->stream);
+    if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
+      set_error("profile_stages: stream synchronize failed");
+      rc = FDNN_ECUDA;
+    }
+    for (int s = 0; s < stages && rc == FDNN_OK; ++s) {
+      float t = 0;
+      cudaEventElapsedTime(&t, ev[size_t(s)], ev[size_t(s) + 1]);
+      total[size_t(s)] += t;
+    }
+  }
+  ctx->have_logits = false;
+  for (auto &e : ev) cudaEventDestroy(e);
+  for (int s = 0; s < stages; ++s) ms[s] = float(total[size_t(s)] / iters);
+  return rc;
 }
 
 // ---- full forward over host buffers -------------------------------------------------------------

@@ -60,6 +60,7 @@ SIGNATURES = {
     "fdnn_ctx_forward_device": (_I, [_P, _P, _I, _P, _P]),
     "fdnn_ctx_until_output_device": (_I, [_P, _P, _I, _P]),
     "fdnn_ctx_lazy_batch_device": (_I, [_P, _P, _I, _P, _P]),
+    "fdnn_ctx_profile_stages": (_I, [_P, _P, _I, _P, _I, _P]),
     "fdnn_ctx_set_trace": (_I, [_P, _I]),
     "fdnn_ctx_hidden": (_I, [_P, _I, _I, _P]),
     "fdnn_ctx_logits": (_I, [_P, _I, _P]),
@@ -311,6 +312,12 @@ class LazyContext:
 
     def lazy_batch_device(self, d_masks: int, n_frames: int, d_out: int, stream: int = 0) -> None:
         _check(lib().fdnn_ctx_lazy_batch_device(self._h, C.c_void_p(d_masks), n_frames, C.c_void_p(d_out), C.c_void_p(stream)))
+
+    def profile_stages(self, d_in: int, n_frames: int, d_out: int, iters: int = 20) -> np.ndarray:
+        """per-kernel milliseconds of one forward pass (bench aid): [input, int8 layers…, softmax]"""
+        ms = np.zeros(self.dnn.layer_count() + 1, dtype=np.float32)
+        _check(lib().fdnn_ctx_profile_stages(self._h, C.c_void_p(d_in), n_frames, C.c_void_p(d_out), iters, _ptr(ms)))
+        return ms
 
     def delete(self) -> None:
         """delete() — :95-97."""

@@ -126,6 +126,12 @@ int fdnn_model_fast_div(const fdnn_model *model, int i);
 int fdnn_model_uses_tensor_cores(const fdnn_model *model, int i);
 int fdnn_sigmoid_lut(uint8_t out[1280]);
 
+/* Bench/profiling aid (not on the hot path): `iters` forward passes over device-resident input on
+ * the context's own stream with CUDA events between the kernels.  ms[0] = fp32 input layer,
+ * ms[1..L-2] = hidden int8 layers, ms[L-1] = output int8 layer, ms[L] = softmax (L = layer count);
+ * averages in milliseconds, synchronised on return. */
+int fdnn_ctx_profile_stages(fdnn_ctx *ctx, const float *d_in, int n_frames, float *d_out, int iters, float *ms);
+
 /* ---- pinned host memory for callers that want zero staging ---------------------------------- */
 int fdnn_host_alloc(void **ptr, size_t bytes);
 int fdnn_host_free(void *ptr);
