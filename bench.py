@@ -169,14 +169,8 @@ def run_gpu_arm(args):
     # ---- load: rank 0 parses + quantizes, ONE broadcast of the packed blob, every rank uploads ----
     path = synth.network_file(SHAPE)
     if world > 1:
-        if rank == 0:
-            blob_np = qd.pack(path)
-            size = torch.tensor([blob_np.nbytes], dtype=torch.int64, device=dev)
-        else:
-            size = torch.zeros(1, dtype=torch.int64, device=dev)
-        dist.broadcast(size, 0)
-        blob = torch.from_numpy(blob_np).to(dev) if rank == 0 else torch.empty(int(size.item()), dtype=torch.uint8, device=dev)
-        dist.broadcast(blob, 0)
+        from fast_dnn_b200 import sharding
+        blob = sharding.broadcast_blob(qd.pack(path) if rank == 0 else None, src=0, device=dev)
         dnn = qd.QuantizedDnn.load_from_blob(blob.data_ptr(), device=local, size=blob.numel())
         del blob
     else:
@@ -312,6 +306,11 @@ def run_gpu_arm(args):
                                   f"{secs:.2f} s wall; batchSize 10"}
 
     if rank == 0:
+        def plain(o):
+            if isinstance(o, (np.floating, np.integer)):
+                return o.item()
+            raise TypeError(type(o).__name__)
+
         print(json.dumps({
             "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -322,7 +321,7 @@ def run_gpu_arm(args):
                        "parallelism": f"frames sharded over {world} GPU(s), one NCCL broadcast of the weight blob at load, no per-frame collective"},
             "e2e": e2e, "gpu_launches": int(launches), "clocks": sampler.summary(), "roofline": roofline, "stages": stages,
             "cpu_baseline": cpu_baseline,
-        }))
+        }, default=plain))
     ctx.delete()
     dnn.delete()
     if world > 1:

@@ -1,0 +1,91 @@
+// Hardware probes that decide kernel design (run under gpurun; see DESIGN.md §Measured hardware facts):
+//   1. fp32 issue rate: separately rounded mul+add as scalar FMUL/FADD vs packed mul.f32x2/add.f32x2
+//   2. L2-resident read bandwidth with 128-bit loads (what feeds the TMA pipelines when weights are L2-hot)
+// nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o microbench microbench.cu
+#include <cstdio>
+#include <cstdint>
+#include <cuda_runtime.h>
+
+constexpr int kChains = 16;
+
+__global__ void __launch_bounds__(256) scalar_kernel(float *out, float a, float b, int iters) {
+  float acc[kChains], x[kChains];
+#pragma unroll
+  for (int i = 0; i < kChains; ++i) { acc[i] = float(threadIdx.x + i); x[i] = a + float(i); }
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < kChains; ++i) acc[i] = __fadd_rn(acc[i], __fmul_rn(x[i], b));
+#pragma unroll
+    for (int i = 0; i < kChains; ++i) x[i] = __fadd_rn(x[i], a);  // keep products loop-variant (1 extra add per chain)
+  }
+  float s = 0;
+#pragma unroll
+  for (int i = 0; i < kChains; ++i) s += acc[i];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) { uint64_t d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) { uint64_t d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ uint64_t pack2(float lo, float hi) { return (uint64_t(__float_as_uint(hi)) << 32) | __float_as_uint(lo); }
+
+__global__ void __launch_bounds__(256) packed_kernel(float *out, float a, float b, int iters) {
+  uint64_t acc[kChains / 2], x[kChains / 2];
+  const uint64_t bb = pack2(b, b), aa = pack2(a, a);
+#pragma unroll
+  for (int i = 0; i < kChains / 2; ++i) { acc[i] = pack2(float(threadIdx.x + 2 * i), float(threadIdx.x + 2 * i + 1)); x[i] = pack2(a + float(2 * i), a + float(2 * i + 1)); }
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < kChains / 2; ++i) acc[i] = add2(acc[i], mul2(x[i], bb));
+#pragma unroll
+    for (int i = 0; i < kChains / 2; ++i) x[i] = add2(x[i], aa);
+  }
+  float s = 0;
+#pragma unroll
+  for (int i = 0; i < kChains / 2; ++i) s += __uint_as_float(uint32_t(acc[i])) + __uint_as_float(uint32_t(acc[i] >> 32));
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+__global__ void __launch_bounds__(256) l2_read_kernel(const uint4 *buf, size_t n_vec, uint32_t *out, int passes) {
+  uint32_t acc = 0;
+  const size_t stride = size_t(gridDim.x) * blockDim.x;
+  for (int p = 0; p < passes; ++p)
+    for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n_vec; i += stride * 4) {
+      uint4 v0 = buf[i], v1 = (i + stride < n_vec) ? buf[i + stride] : v0, v2 = (i + 2 * stride < n_vec) ? buf[i + 2 * stride] : v0,
+            v3 = (i + 3 * stride < n_vec) ? buf[i + 3 * stride] : v0;
+      acc += v0.x ^ v1.y ^ v2.z ^ v3.w;
+    }
+  if (acc == 0x12345678u) out[0] = acc;
+}
+
+template <class F> float time_ms(F f, int reps) {
+  cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+  f();
+  cudaEventRecord(e0);
+  for (int i = 0; i < reps; ++i) f();
+  cudaEventRecord(e1); cudaEventSynchronize(e1);
+  float ms; cudaEventElapsedTime(&ms, e0, e1); return ms / reps;
+}
+
+int main() {
+  int sms = 0; cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
+  float *out; cudaMalloc(&out, sizeof(float) * sms * 8 * 256);
+  const int iters = 4096;
+  for (int ctas_per_sm : {2, 4, 8}) {
+    const int grid = sms * ctas_per_sm;
+    float ms_s = time_ms([&] { scalar_kernel<<<grid, 256>>>(out, 1.0001f, 0.9999f, iters); }, 5);
+    float ms_p = time_ms([&] { packed_kernel<<<grid, 256>>>(out, 1.0001f, 0.9999f, iters); }, 5);
+    const double lane_ops = double(grid) * 256 * iters * kChains * 3;  // mul + add + add per chain per iteration
+    printf("fp32 probe, %d CTAs/SM: scalar %.3f ms = %.1f Gop/s (%.1f lane-ops/clk/SM @1.965GHz) | packed f32x2 %.3f ms = %.1f Gop/s (%.1f)\n",
+           ctas_per_sm, ms_s, lane_ops / ms_s / 1e6, lane_ops / (ms_s * 1e-3) / sms / 1.965e9, ms_p, lane_ops / ms_p / 1e6,
+           lane_ops / (ms_p * 1e-3) / sms / 1.965e9);
+  }
+  for (size_t mb : {32, 64, 96, 512}) {
+    size_t bytes = mb << 20; uint4 *buf; cudaMalloc(&buf, bytes); cudaMemset(buf, 1, bytes);
+    uint32_t *o; cudaMalloc(&o, 4);
+    float ms = time_ms([&] { l2_read_kernel<<<sms * 8, 256>>>(buf, bytes / 16, o, 4); }, 5);
+    printf("read probe, %zu MB buffer x4 passes: %.3f ms = %.0f GB/s\n", mb, ms, 4.0 * bytes / ms / 1e6);
+    cudaFree(buf); cudaFree(o);
+  }
+  printf("%s\n", cudaGetErrorString(cudaDeviceSynchronize()));
+  return 0;
+}
