@@ -6,8 +6,8 @@ from __future__ import annotations
 import numpy as np
 
 MAGIC = 0x424E4446
-VERSION = 3
-FIX_CHUNK = 32
+VERSION = 4
+FIX_CHUNK = 16
 
 HEADER = np.dtype([
     ("magic", "<u4"), ("version", "<u4"), ("total_size", "<u8"),
@@ -53,9 +53,10 @@ class Blob:
         return (self._f32(self.header["off_w0"], H * I).reshape(H, I), self._f32(self.header["off_bias0"], H),
                 self._f32(self.header["off_shift"], I), self._f32(self.header["off_scale"], I))
 
-    def lut_ext(self):
+    def lut2(self):
+        """doubled sigmoid table: index trunc(2*clamp(x*100, -641, 641)) + 1282"""
         o = int(self.header["off_lut"])
-        return self.data[o:o + 1283]
+        return self.data[o:o + 2565]
 
     def qlayer(self, i):
         q = self.qlayers[i]

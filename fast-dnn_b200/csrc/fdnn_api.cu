@@ -180,9 +180,9 @@ void destroy_ctx(fdnn_ctx *c) {
 }
 
 int alloc_channel(CorrChannel &ch, int rows, int nodes) {
-  ch.ld = round_up(nodes, 32);
+  ch.ld = round_up(nodes, kFixChunk);
   ch.rows_cap = rows;
-  size_t corr_bytes = size_t(rows) * size_t(ch.ld) * 4, flag_bytes = size_t(ch.ld / 32) * size_t(rows);
+  size_t corr_bytes = size_t(rows) * size_t(ch.ld) * 4, flag_bytes = size_t(ch.ld / kFixChunk) * size_t(rows);
   CUDA_TRY(cudaMalloc(&ch.corr, corr_bytes));
   CUDA_TRY(cudaMalloc(&ch.flags, flag_bytes));
   CUDA_TRY(cudaMemset(ch.corr, 0, corr_bytes));
@@ -197,7 +197,7 @@ int create_ctx(fdnn_model *m, int n, fdnn_ctx **out) {
   }
   const int I = m->hdr.in_dim, H = m->hdr.hidden, O = m->hdr.out_dim;
   // ≈ (4I + 2H + 12·pad32(H) + 8·pad32(O)) bytes of device memory per frame
-  const double per_frame = 4.0 * I + 2.0 * H + 8.0 * round_up(H, 32) + 8.0 * round_up(O, 32) + 64;
+  const double per_frame = 4.0 * I + 2.0 * H + 8.0 * round_up(H, 16) + 8.0 * round_up(O, 16) + 64;
   size_t free_b = 0, total_b = 0;
   DeviceGuard g(m->device);
   if (!g.ok) {

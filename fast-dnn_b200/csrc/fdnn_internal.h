@@ -10,20 +10,23 @@
 namespace fdnn {
 
 // Sigmoid LUT domain.  The reference's table covers k ∈ [−640, 640) with k ≤ −640 → 0 and
-// k ≥ 640 → 255 handled by branches (dnn.h:35-42).  We extend the table by the clamp values
-// so that a single clamp of round(x·100) to [−641, 641] followed by one lookup is equivalent:
-//   ext[k + 641]:  k = −641, −640 → 0;  k ∈ (−640, 640) → lut[k + 640];  k = 640, 641 → 255.
+// k ≥ 640 → 255 handled by branches (dnn.h:35-42), where k = (int)round(x·100), round half away
+// from zero.  The device table folds the rounding and both clamps into one lookup: with
+// c = clamp(x·100, −641, 641) and v = trunc(2c) ∈ [−1282, 1282] (2c is exact),
+//   |k| = (|v| + 1) >> 1,   lut2[v + 1282] = (k ≤ −640 ? 0 : k ≥ 640 ? 255 : lut[k + 640]).
 constexpr int kLutHalf = 640;
-constexpr int kLutExt = 2 * kLutHalf + 3;  // k ∈ [−641, 641]
-constexpr int kLutExtPadded = 1284;        // multiple of 4 bytes
+constexpr int kLut2Center = 1282;
+constexpr int kLut2Size = 2 * kLut2Center + 1;  // 2565
+constexpr int kLut2Padded = 2576;               // multiple of 16 bytes
 
 constexpr uint32_t kBlobMagic = 0x424E4446u;  // "FDNB"
-constexpr uint32_t kBlobVersion = 3;
+constexpr uint32_t kBlobVersion = 4;
 constexpr size_t kBlobAlign = 256;
 
-// Width (in layer inputs) of one saturation-scan chunk: a producer that has just written u8
-// activations for 32 consecutive nodes scans the consumer layer's risk entries of that chunk.
-constexpr int kFixChunk = 32;
+// Granularity of the saturation-correction machinery, in nodes: a producer thread that has just
+// written u8 activations for 16 consecutive nodes scans the consumer layer's risk entries of that
+// input chunk, and a consumer thread owns the corrections of 16 consecutive output nodes of a row.
+constexpr int kFixChunk = 16;
 
 // pmaddubsw (dnn.cc:337-340) clamps every adjacent-pair sum a[2p]·w[2p] + a[2p+1]·w[2p+1] to int16.
 // A tensor-core contraction does not.  With a ≤ 255 the clamp can only fire for weight pairs whose
@@ -65,7 +68,7 @@ struct BlobHeader {
   uint64_t off_bias0;  // fp32 [H]
   uint64_t off_shift;  // fp32 [in_dim]
   uint64_t off_scale;  // fp32 [in_dim]
-  uint64_t off_lut;    // u8 [kLutExtPadded], index k+641
+  uint64_t off_lut;    // u8 [kLut2Padded], index trunc(2·clamp(x·100)) + 1282
   uint64_t off_qlayers;  // BlobQLayer[n_qlayers]
 };
 

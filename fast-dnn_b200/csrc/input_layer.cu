@@ -6,12 +6,17 @@
 //   QuantizedSigmoid     src/cpp/dnn.cc:267-286, src/cpp/dnn.h:35-42   LUT → u8
 //
 // The summation order is part of the result, so this is CUDA-core work: every product and every
-// add is a separately rounded fp32 operation (__fmul_rn / __fadd_rn, never contracted to FMA) and
-// each thread keeps the four SSE lanes of every (frame, node) it owns as four accumulators.
+// add is a separately rounded fp32 operation, never contracted to FMA, and each thread keeps the
+// four SSE lanes of every (frame, node) it owns as four accumulators.  Products are scalar FMUL;
+// the lane pairs are accumulated with Blackwell's packed add.rn.f32x2 (two independent IEEE adds
+// per instruction, fewer issue slots).  NOTE: ptxas 12.9 contracts mul.rn.f32x2 + add.rn.f32x2
+// into a fused FFMA2 even with --fmad=false, which would change results, so the multiply must
+// stay scalar (checked in SASS: the main loop holds FMUL + FADD2 and no FFMA2).
 //
-// Tiling: a CTA computes 64 frames × 128 nodes; a thread 8 frames × 4 nodes (nodes strided by 32
-// so that 128-bit shared-memory reads of the weight rows are conflict-free with a 44-float row
-// pitch; frame reads are warp-wide broadcasts).  K is streamed in 40-float chunks, double
+// Tiling: a CTA (16 warps) computes 64 frames × 128 nodes; a warp 16 frames × 32 nodes; a thread
+// 4 frames × 4 nodes, strided (frames fg + 4i, nodes ng + 8j with lane = 8·fg + ng) so that every
+// 128-bit shared-memory read is either a broadcast or conflict-free with the 44-float row pitch —
+// 8 wavefronts per 64 packed math instructions.  K is streamed in 40-float chunks, double
 // buffered: weights by cp.async, frames through registers so shift/scale is applied on the way in.
 
 #include <cuda_runtime.h>
@@ -26,11 +31,11 @@ namespace {
 constexpr int kTileF = 64;    // frames per CTA
 constexpr int kTileN = 128;   // nodes per CTA
 constexpr int kChunk = 40;    // floats of K per stage
-constexpr int kPitch = 44;    // smem row pitch in floats (≡ 12 mod 32 → conflict-free LDS.128)
-constexpr int kThreads = 256;
-constexpr int kTF = 8, kTN = 4;
+constexpr int kPitch = 44;    // smem row pitch in floats (≡ 12 mod 32 → conflict-free LDS.128 over consecutive rows)
+constexpr int kThreads = 512;
+constexpr int kTF = 4, kTN = 4;
 constexpr int kStageFloats = (kTileF + kTileN) * kPitch;
-constexpr int kSmemBytes = 2 * kStageFloats * 4 + kLutExtPadded + 12;
+constexpr int kSmemBytes = 2 * kStageFloats * 4 + kLut2Padded;
 static_assert(kTileF * kTileN <= 2 * kStageFloats * 4, "u8 output tile must fit in the pipeline buffers");
 
 __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src) {
@@ -39,21 +44,32 @@ __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src)
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
+// two independent round-to-nearest fp32 operations on the halves of a 64-bit register pair
+__device__ __forceinline__ uint64_t pack2(float lo, float hi) { return (uint64_t(__float_as_uint(hi)) << 32) | __float_as_uint(lo); }
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ float lo_f(uint64_t v) { return __uint_as_float(uint32_t(v)); }
+__device__ __forceinline__ float hi_f(uint64_t v) { return __uint_as_float(uint32_t(v >> 32)); }
+
 __global__ void __launch_bounds__(kThreads, 1) input_layer_kernel(const InputLayerArgs args) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   float *stage_buf = reinterpret_cast<float *>(smem_raw);
   uint8_t *s_lut = smem_raw + 2 * kStageFloats * 4;
 
   const int tid = int(threadIdx.x);
-  const int tx = tid % 32, ty = tid / 32;  // tx → nodes tx + 32·j, ty → frames 8·ty + i
+  const int warp = tid / 32, lane = tid % 32;
+  const int fg = lane / 8, ng = lane % 8;
+  const int wf = (warp / 4) * 16, wn = (warp % 4) * 32;  // warp tile origin inside the CTA tile
   const int f0 = int(blockIdx.y) * kTileF, n0 = int(blockIdx.x) * kTileN;
   const int M = args.M, I = args.I, H = args.H;
   const int n_chunks = (I + kChunk - 1) / kChunk;
 
-  for (int i = tid; i < kLutExtPadded / 4; i += kThreads)
-    reinterpret_cast<uint32_t *>(s_lut)[i] = __ldg(reinterpret_cast<const uint32_t *>(args.lut) + i);
+  for (int i = tid; i < kLut2Padded / 16; i += kThreads) reinterpret_cast<uint4 *>(s_lut)[i] = __ldg(reinterpret_cast<const uint4 *>(args.lut) + i);
 
-  // Frame elements this thread moves per chunk: kTileF rows × (kChunk/4) float4 = 640 → ≤ 3 per thread.
+  // Frame elements this thread moves per chunk: kTileF rows × (kChunk/4) float4 = 640 vectors.
   constexpr int kXVecs = kTileF * (kChunk / 4);
   constexpr int kXPerThread = (kXVecs + kThreads - 1) / kThreads;
   float4 xr[kXPerThread];
@@ -102,11 +118,12 @@ __global__ void __launch_bounds__(kThreads, 1) input_layer_kernel(const InputLay
     cp_async_commit();
   };
 
-  float4 acc[kTF][kTN];
+  // acc[i][j][0] = SSE lanes (0,1), acc[i][j][1] = lanes (2,3) of frame fg+4i, node ng+8j
+  uint64_t acc[kTF][kTN][2];
 #pragma unroll
   for (int i = 0; i < kTF; ++i)
 #pragma unroll
-    for (int j = 0; j < kTN; ++j) acc[i][j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int j = 0; j < kTN; ++j) acc[i][j][0] = acc[i][j][1] = 0ull;
 
   load_x_regs(0);
   issue_w(0, 0);
@@ -121,24 +138,22 @@ __global__ void __launch_bounds__(kThreads, 1) input_layer_kernel(const InputLay
       issue_w(c + 1, buf ^ 1);
       load_x_regs(c + 1);
     }
-    const float *xs = stage_buf + buf * kStageFloats + (ty * kTF) * kPitch;
-    const float *ws = stage_buf + buf * kStageFloats + kTileF * kPitch + tx * kPitch;
+    const float *xs = stage_buf + buf * kStageFloats + (wf + fg) * kPitch;
+    const float *ws = stage_buf + buf * kStageFloats + (kTileF + wn + ng) * kPitch;
     const int kc4 = (min(kChunk, I - c * kChunk)) / 4;
 #pragma unroll 2
     for (int q = 0; q < kc4; ++q) {
       float4 xv[kTF], wv[kTN];
 #pragma unroll
-      for (int i = 0; i < kTF; ++i) xv[i] = *reinterpret_cast<const float4 *>(xs + i * kPitch + 4 * q);
+      for (int i = 0; i < kTF; ++i) xv[i] = *reinterpret_cast<const float4 *>(xs + (4 * i) * kPitch + 4 * q);
 #pragma unroll
-      for (int j = 0; j < kTN; ++j) wv[j] = *reinterpret_cast<const float4 *>(ws + j * 32 * kPitch + 4 * q);
+      for (int j = 0; j < kTN; ++j) wv[j] = *reinterpret_cast<const float4 *>(ws + (8 * j) * kPitch + 4 * q);
 #pragma unroll
       for (int i = 0; i < kTF; ++i)
 #pragma unroll
         for (int j = 0; j < kTN; ++j) {
-          acc[i][j].x = __fadd_rn(acc[i][j].x, __fmul_rn(xv[i].x, wv[j].x));
-          acc[i][j].y = __fadd_rn(acc[i][j].y, __fmul_rn(xv[i].y, wv[j].y));
-          acc[i][j].z = __fadd_rn(acc[i][j].z, __fmul_rn(xv[i].z, wv[j].z));
-          acc[i][j].w = __fadd_rn(acc[i][j].w, __fmul_rn(xv[i].w, wv[j].w));
+          acc[i][j][0] = add2(acc[i][j][0], pack2(__fmul_rn(xv[i].x, wv[j].x), __fmul_rn(xv[i].y, wv[j].y)));
+          acc[i][j][1] = add2(acc[i][j][1], pack2(__fmul_rn(xv[i].z, wv[j].z), __fmul_rn(xv[i].w, wv[j].w)));
         }
     }
     if (more) store_x_regs(buf ^ 1);
@@ -150,26 +165,29 @@ __global__ void __launch_bounds__(kThreads, 1) input_layer_kernel(const InputLay
   uint8_t *s_out = smem_raw;  // [kTileF][kTileN], pipeline buffers are free after the last barrier
   float bias[kTN];
 #pragma unroll
-  for (int j = 0; j < kTN; ++j) bias[j] = (n0 + tx + 32 * j < H) ? __ldg(args.bias0 + n0 + tx + 32 * j) : 0.0f;
+  for (int j = 0; j < kTN; ++j) bias[j] = (n0 + wn + ng + 8 * j < H) ? __ldg(args.bias0 + n0 + wn + ng + 8 * j) : 0.0f;
 #pragma unroll
   for (int i = 0; i < kTF; ++i)
 #pragma unroll
     for (int j = 0; j < kTN; ++j) {
-      const float h = __fadd_rn(__fadd_rn(acc[i][j].x, acc[i][j].y), __fadd_rn(acc[i][j].z, acc[i][j].w));
-      s_out[(ty * kTF + i) * kTileN + tx + 32 * j] = s_lut[qsig_index(__fadd_rn(h, bias[j]))];
+      const float h = __fadd_rn(__fadd_rn(lo_f(acc[i][j][0]), hi_f(acc[i][j][0])), __fadd_rn(lo_f(acc[i][j][1]), hi_f(acc[i][j][1])));
+      s_out[(wf + fg + 4 * i) * kTileN + wn + ng + 8 * j] = s_lut[qsig_slot(__fadd_rn(h, bias[j]))];
     }
   __syncthreads();
 
   const int cols = min(kTileN, H - n0);  // multiple of 16
   for (int v = tid; v < kTileF * (kTileN / 16); v += kThreads) {
     const int r = v / (kTileN / 16), q = v % (kTileN / 16);
-    if (f0 + r < M && 16 * q < cols)
-      *reinterpret_cast<uint4 *>(args.out_u8 + size_t(f0 + r) * size_t(H) + n0 + 16 * q) = *reinterpret_cast<const uint4 *>(s_out + r * kTileN + 16 * q);
-  }
-  // saturation corrections for the first int8 layer: one (frame, 32-node chunk) per thread
-  if (args.next_fix.ptr != nullptr) {
-    const int r = tid / (kTileN / kFixChunk), ch = tid % (kTileN / kFixChunk);
-    if (f0 + r < M && ch * kFixChunk < cols) post_saturation(s_out + r * kTileN + ch * kFixChunk, (n0 >> 5) + ch, f0 + r, args.next_fix, args.next);
+    if (f0 + r < M && 16 * q < cols) {
+      const uint8_t *src = s_out + r * kTileN + 16 * q;
+      *reinterpret_cast<uint4 *>(args.out_u8 + size_t(f0 + r) * size_t(H) + n0 + 16 * q) = *reinterpret_cast<const uint4 *>(src);
+      // saturation corrections for the first int8 layer: this (frame, 16-node chunk)
+      if (args.next_fix.ptr != nullptr) {
+        const int chunk = (n0 >> 4) + q;
+        const uint32_t e0 = __ldg(args.next_fix.ptr + chunk), e1 = __ldg(args.next_fix.ptr + chunk + 1);
+        post_saturation(src, chunk, f0 + r, args.next_fix.ent, 0u, e0, e1, args.next);
+      }
+    }
   }
 }
 

@@ -310,7 +310,7 @@ int pack_model(const char *path, float cutoff, std::vector<uint8_t> &blob) {
     return uint64_t(at);
   };
   hdr.off_qlayers = reserve(sizeof(BlobQLayer) * size_t(nq));
-  hdr.off_lut = reserve(kLutExtPadded);
+  hdr.off_lut = reserve(kLut2Padded);
   hdr.off_shift = reserve(sizeof(float) * size_t(in_dim));
   hdr.off_scale = reserve(sizeof(float) * size_t(in_dim));
   hdr.off_bias0 = reserve(sizeof(float) * size_t(H));
@@ -331,13 +331,12 @@ int pack_model(const char *path, float cutoff, std::vector<uint8_t> &blob) {
   {
     uint8_t lut[1280];
     build_reference_lut(lut);
-    uint8_t *ext = base + hdr.off_lut;
-    ext[0] = 0;  // k = −641
-    ext[1] = 0;  // k = −640 (dnn.h:37: k ≤ −640 → 0)
-    for (int k = -kLutHalf + 1; k < kLutHalf; ++k) ext[k + 641] = lut[k + kLutHalf];
-    ext[1281] = 255;  // k = 640 (dnn.h:38-40)
-    ext[1282] = 255;  // k = 641
-    ext[1283] = 255;
+    uint8_t *lut2 = base + hdr.off_lut;
+    for (int v = -kLut2Center; v <= kLut2Center; ++v) {
+      const int mag = ((v < 0 ? -v : v) + 1) >> 1;
+      const int k = v < 0 ? -mag : mag;
+      lut2[v + kLut2Center] = k <= -kLutHalf ? uint8_t(0) : (k >= kLutHalf ? uint8_t(255) : lut[k + kLutHalf]);  // dnn.h:35-42
+    }
   }
   std::memcpy(base + hdr.off_shift, shift.data(), sizeof(float) * shift.size());
   std::memcpy(base + hdr.off_scale, scale.data(), sizeof(float) * scale.size());
@@ -374,7 +373,7 @@ int validate_blob(const uint8_t *blob, size_t size) {
     set_error("blob header holds an unusable topology");
     return FDNN_EFORMAT;
   }
-  if (!inside(h.off_qlayers, sizeof(BlobQLayer) * uint64_t(h.n_qlayers)) || !inside(h.off_lut, kLutExtPadded) ||
+  if (!inside(h.off_qlayers, sizeof(BlobQLayer) * uint64_t(h.n_qlayers)) || !inside(h.off_lut, kLut2Padded) ||
       !inside(h.off_shift, 4ull * uint64_t(h.in_dim)) || !inside(h.off_scale, 4ull * uint64_t(h.in_dim)) ||
       !inside(h.off_bias0, 4ull * uint64_t(h.hidden)) || !inside(h.off_w0, 4ull * uint64_t(h.hidden) * uint64_t(h.in_dim))) {
     set_error("blob section out of bounds");

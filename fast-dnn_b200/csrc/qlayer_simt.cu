@@ -3,8 +3,8 @@
 // are not a multiple of 32 (the reference only asks for multiples of 16, dnn.cc:331).  Same
 // arithmetic contract and the same epilogue as qlayer_tc.cu; see that file for the references.
 //
-// One thread owns one frame and one aligned chunk of 32 nodes, so the epilogue (and the
-// saturation-correction channel, which works in 32-node chunks per frame) is shared verbatim.
+// One thread owns one frame and one aligned chunk of 16 nodes, so the epilogue (and the
+// saturation-correction channel, which works in 16-node chunks per frame) is shared verbatim.
 
 #include <cuda_runtime.h>
 
@@ -27,18 +27,19 @@ template <bool kLogits>
 __global__ void __launch_bounds__(kRowsPerBlock) qlayer_simt_kernel(const QLayerArgs args) {
   __shared__ __align__(16) uint8_t s_scan[kRowsPerBlock * kFixChunk];
   const int row = int(blockIdx.x) * kRowsPerBlock + int(threadIdx.x);
-  const int col = int(blockIdx.y) * 32;
+  const int col = int(blockIdx.y) * kFixChunk;
   if (row >= args.M) return;
   const int K = args.K, N = args.N;
-  const int cols = min(32, N - col);
-  int32_t s[32];
+  const int cols = min(kFixChunk, N - col);
+  const uint8_t flag = load_flag(args.self, col >> 4, row);
+  int32_t s[16];
 #pragma unroll
-  for (int i = 0; i < 32; ++i) s[i] = 0;
+  for (int i = 0; i < 16; ++i) s[i] = 0;
   const uint4 *a_row = reinterpret_cast<const uint4 *>(args.act + size_t(row) * size_t(K));
   for (int k = 0; k < K / 16; ++k) {
     const uint4 a = a_row[k];
 #pragma unroll
-    for (int i = 0; i < 32; ++i) {
+    for (int i = 0; i < 16; ++i) {
       if (i < cols) {  // warp-uniform
         const uint4 w = __ldg(reinterpret_cast<const uint4 *>(args.w + size_t(col + i) * size_t(K)) + k);
         int acc = s[i];
@@ -50,17 +51,26 @@ __global__ void __launch_bounds__(kRowsPerBlock) qlayer_simt_kernel(const QLayer
       }
     }
   }
-  float bias32[32];
+  float bias16[16];
 #pragma unroll
-  for (int i = 0; i < 32; ++i) bias32[i] = i < cols ? __ldg(args.bias + col + i) : 0.0f;
-  epilogue_chunk<kLogits>(s, row, col, args, bias32, args.lut, s_scan + int(threadIdx.x) * kFixChunk);
+  for (int i = 0; i < 16; ++i) bias16[i] = i < cols ? __ldg(args.bias + col + i) : 0.0f;
+  take_corrections(s, flag, col >> 4, row, args.self);
+  const uint4 bytes = finish_chunk<kLogits>(s, row, col, args, bias16, args.lut);
+  if constexpr (!kLogits) {
+    if (args.next_fix.ptr != nullptr) {
+      uint8_t *scan = s_scan + int(threadIdx.x) * kFixChunk;
+      *reinterpret_cast<uint4 *>(scan) = bytes;
+      const uint32_t e0 = __ldg(args.next_fix.ptr + (col >> 4)), e1 = __ldg(args.next_fix.ptr + (col >> 4) + 1);
+      post_saturation(scan, col >> 4, row, args.next_fix.ent, 0u, e0, e1, args.next);
+    }
+  }
 }
 
 }  // namespace
 
 cudaError_t launch_qlayer_simt(const QLayerArgs &a, bool logits, cudaStream_t stream) {
   if (a.M <= 0) return cudaSuccess;
-  dim3 grid((a.M + kRowsPerBlock - 1) / kRowsPerBlock, (a.N + 31) / 32);
+  dim3 grid((a.M + kRowsPerBlock - 1) / kRowsPerBlock, (a.N + kFixChunk - 1) / kFixChunk);
   if (logits)
     qlayer_simt_kernel<true><<<grid, kRowsPerBlock, 0, stream>>>(a);
   else

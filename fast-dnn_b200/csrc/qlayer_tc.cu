@@ -12,8 +12,10 @@
 // (A unsigned, B signed) consumes them through shared-memory descriptors; no transposes.
 //
 // Persistent, warp-specialised: warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM
-// allocator, warps 4-7 = epilogue (one TMEM lane quarter each).  Two accumulator stages in TMEM
-// let the epilogue of tile i overlap the contraction of tile i+1.
+// allocator, warps 4-19 = epilogue (four warps per TMEM lane quarter, each a quarter of the tile's
+// columns, 16 columns at a time — the tail is ≈15 instructions per element, so it needs the
+// issue slots of many warps).  Two accumulator stages in TMEM let the epilogue of tile i overlap
+// the contraction of tile i+1.
 //
 // pmaddubsw's int16 pair saturation is not reproduced by the tensor core; the (rare) differences
 // arrive through the layer's correction channel (device_common.cuh) and are added to the raw
@@ -33,9 +35,11 @@ namespace {
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 128;  // bytes of K per pipeline stage = one 128B swizzle atom
 constexpr int kUmmaK = 32;    // K per tcgen05.mma for 8-bit operands
-constexpr int kThreads = 256;
-constexpr int kEpilogueThreads = 128;
+constexpr int kEpilogueWarps = 16;  // four per TMEM lane quarter, each owning a quarter of the tile's columns
+constexpr int kEpilogueThreads = kEpilogueWarps * 32;
+constexpr int kThreads = 128 + kEpilogueThreads;
 constexpr int kAccStages = 2;
+constexpr int kEntCap = 640;  // risk entries of the next layer staged in shared memory per tile
 
 template <int BN>
 struct TcConfig {
@@ -44,11 +48,18 @@ struct TcConfig {
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kStages = BN == 256 ? 4 : (BN == 128 ? 6 : 8);
   static constexpr int kTmemCols = kAccStages * BN;  // 128, 256 or 512: powers of two
+  static constexpr int kColsPerWarp = BN / 4;
+  static constexpr int kChunks = kColsPerWarp / kFixChunk;  // 16-column chunks per epilogue thread
+  static constexpr int kPtrSlots = 20;                       // ≥ BN/16 + 1, per accumulator stage
   static constexpr int kBiasBytes = kAccStages * BN * 4;
+  static constexpr int kEntBytes = kAccStages * kEntCap * 8;
+  static constexpr int kPtrBytes = kAccStages * kPtrSlots * 4;
   static constexpr int kScanBytes = kEpilogueThreads * kFixChunk;
   static constexpr int kBarBytes = (2 * kStages + 2 * kAccStages) * 8 + 16;
-  static constexpr int kSmemBytes = 1024 /*alignment slack*/ + kStages * kStageBytes + kBiasBytes + kLutExtPadded + 12 /*pad*/ +
-                                    kScanBytes + kBarBytes;
+  static constexpr int kSmemBytes =
+      1024 /*alignment slack*/ + kStages * kStageBytes + kBiasBytes + kLut2Padded + kEntBytes + kPtrBytes + kScanBytes + kBarBytes;
+  static_assert(BN / kFixChunk + 1 <= kPtrSlots, "pointer slots");
+  static_assert(kSmemBytes <= 232448, "shared memory budget");
 };
 
 template <int BN, bool kLogits>
@@ -60,7 +71,9 @@ qlayer_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_cons
   uint8_t *tiles = smem;
   float *s_bias = reinterpret_cast<float *>(smem + Cfg::kStages * Cfg::kStageBytes);
   uint8_t *s_lut = reinterpret_cast<uint8_t *>(s_bias) + Cfg::kBiasBytes;
-  uint8_t *s_scan = s_lut + kLutExtPadded + 12;  // 16-byte aligned
+  FixEntry *s_ent = reinterpret_cast<FixEntry *>(s_lut + kLut2Padded);
+  uint32_t *s_ptr = reinterpret_cast<uint32_t *>(reinterpret_cast<uint8_t *>(s_ent) + Cfg::kEntBytes);
+  uint8_t *s_scan = reinterpret_cast<uint8_t *>(s_ptr) + Cfg::kPtrBytes;
   uint64_t *full_bar = reinterpret_cast<uint64_t *>(s_scan + Cfg::kScanBytes);
   uint64_t *empty_bar = full_bar + Cfg::kStages;
   uint64_t *tmem_full_bar = empty_bar + Cfg::kStages;
@@ -89,9 +102,9 @@ qlayer_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_cons
     ptx::fence_barrier_init();
   }
   if (warp == 2) ptx::tmem_alloc<Cfg::kTmemCols>(tmem_slot);
-  if (warp >= 4) {
-    for (int i = int(threadIdx.x) - 128; i < kLutExtPadded / 4; i += kEpilogueThreads)
-      reinterpret_cast<uint32_t *>(s_lut)[i] = __ldg(reinterpret_cast<const uint32_t *>(args.lut) + i);
+  if (warp >= 4 && !kLogits) {
+    for (int i = int(threadIdx.x) - 128; i < kLut2Padded / 16; i += kEpilogueThreads)
+      reinterpret_cast<uint4 *>(s_lut)[i] = __ldg(reinterpret_cast<const uint4 *>(args.lut) + i);
   }
   ptx::tc_fence_before_sync();
   __syncthreads();
@@ -154,37 +167,81 @@ qlayer_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_cons
     }
   } else if (warp >= 4) {
     // ===== epilogue: TMEM → registers → reference tail → global =====
+    // 16 warps: warp % 4 selects the TMEM lane quarter (rows), (warp − 4) / 4 the column quarter.
     const int et = int(threadIdx.x) - 128;
-    const int quarter = warp - 4;  // == warp % 4: the TMEM lane quarter this warp may read
+    const int quarter = warp & 3;
+    const int col_group = (warp - 4) >> 2;
     uint8_t *my_scan = s_scan + et * kFixChunk;
+    const int next_chunks = kLogits ? 0 : (N + kFixChunk - 1) / kFixChunk;  // input chunks of the next layer = our output chunks
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int t = int(blockIdx.x); t < tiles_total; t += int(gridDim.x)) {
       const int m_blk = t / n_blocks, n_blk = t % n_blocks;
       const int n0 = n_blk * BN;
-      float *bias_s = s_bias + acc * BN;
-      for (int i = et; i < BN; i += kEpilogueThreads) bias_s[i] = (n0 + i < N) ? __ldg(args.bias + n0 + i) : 0.0f;
-      ptx::named_bar_sync(1, kEpilogueThreads);
-      ptx::mbar_wait(tmem_full_bar + acc, acc_phase);
-      ptx::tc_fence_after_sync();
       const int row = m_blk * kBlockM + quarter * 32 + lane;
       const bool row_ok = row < M;
-      const uint32_t t_addr = tmem_base + uint32_t(acc * BN) + (uint32_t(quarter * 32) << 16);
-      const int chunks = min(BN / 32, (N - n0 + 31) / 32);
-      for (int j = 0; j < chunks; ++j) {
-        uint32_t raw[32];
-        ptx::tmem_ld_32x32(t_addr + uint32_t(j * 32), raw);
-        ptx::tmem_ld_wait();
-        if (j == chunks - 1) {
-          // accumulator stage fully read: hand it back to the MMA warp before doing the math
-          ptx::tc_fence_before_sync();
-          ptx::mbar_arrive(tmem_empty_bar + acc);
+      const int col0 = n0 + col_group * Cfg::kColsPerWarp;  // first column of this thread
+      const int n_valid = max(0, min(Cfg::kChunks, (N - col0 + kFixChunk - 1) / kFixChunk));  // warp-uniform
+
+      // -- stage what the tail needs while the tensor core works on this tile ---------------------
+      float *bias_s = s_bias + acc * BN;
+      for (int i = et; i < BN; i += kEpilogueThreads) bias_s[i] = (n0 + i < N) ? __ldg(args.bias + n0 + i) : 0.0f;
+      uint32_t ent_begin = 0;
+      const FixEntry *ent_s = s_ent + acc * kEntCap;
+      uint32_t *ptr_s = s_ptr + acc * Cfg::kPtrSlots;
+      if constexpr (!kLogits) {
+        if (args.next_fix.ptr != nullptr) {
+          const int c0 = n0 / kFixChunk;
+          ent_begin = __ldg(args.next_fix.ptr + min(c0, next_chunks));
+          const uint32_t ent_end = __ldg(args.next_fix.ptr + min(c0 + BN / kFixChunk, next_chunks));
+          if (et <= BN / kFixChunk) ptr_s[et] = __ldg(args.next_fix.ptr + min(c0 + et, next_chunks));
+          const uint32_t staged = min(ent_end - ent_begin, uint32_t(kEntCap));
+          for (uint32_t i = uint32_t(et); i < staged; i += kEpilogueThreads)
+            reinterpret_cast<uint2 *>(s_ent + acc * kEntCap)[i] = __ldg(reinterpret_cast<const uint2 *>(args.next_fix.ent) + ent_begin + i);
         }
-        if (!row_ok) continue;
-        int32_t s[32];
+      }
+      uint8_t flag[Cfg::kChunks];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) s[i] = int32_t(raw[i]);
-        epilogue_chunk<kLogits>(s, row, n0 + j * 32, args, bias_s + j * 32, s_lut, my_scan);
+      for (int j = 0; j < Cfg::kChunks; ++j) flag[j] = (row_ok && j < n_valid) ? load_flag(args.self, (col0 >> 4) + j, row) : uint8_t(0);
+      ptx::named_bar_sync(1, kEpilogueThreads);
+
+      ptx::mbar_wait(tmem_full_bar + acc, acc_phase);
+      ptx::tc_fence_after_sync();
+      const uint32_t t_addr = tmem_base + uint32_t(acc * BN + col_group * Cfg::kColsPerWarp) + (uint32_t(quarter * 32) << 16);
+      if (n_valid == 0) {
+        ptx::tc_fence_before_sync();
+        ptx::mbar_arrive(tmem_empty_bar + acc);
+      }
+#pragma unroll
+      for (int j = 0; j < Cfg::kChunks; ++j) {
+        if (j < n_valid) {
+          uint32_t raw[16];
+          ptx::tmem_ld_32x16(t_addr + uint32_t(j * kFixChunk), raw);
+          ptx::tmem_ld_wait();
+          if (j == n_valid - 1) {
+            // this thread is done with the accumulator stage: hand it back before doing the math
+            ptx::tc_fence_before_sync();
+            ptx::mbar_arrive(tmem_empty_bar + acc);
+          }
+          if (row_ok) {
+            int32_t s[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) s[i] = int32_t(raw[i]);
+            const int col = col0 + j * kFixChunk;
+            take_corrections(s, flag[j], col >> 4, row, args.self);
+            const uint4 bytes = finish_chunk<kLogits>(s, row, col, args, bias_s + (col - n0), s_lut);
+            if constexpr (!kLogits) {
+              if (args.next_fix.ptr != nullptr) {
+                *reinterpret_cast<uint4 *>(my_scan) = bytes;
+                const int lc = (col - n0) >> 4;
+                const uint32_t p0 = ptr_s[lc], p1 = ptr_s[lc + 1];
+                const uint32_t split = min(p1, ent_begin + uint32_t(kEntCap));
+                post_saturation(my_scan, col >> 4, row, ent_s, ent_begin, p0, min(p1, split), args.next);
+                if (p1 > split) post_saturation(my_scan, col >> 4, row, args.next_fix.ent, 0u, max(p0, split), p1, args.next);
+              }
+            }
+          }
+        }
       }
       if (++acc == kAccStages) {
         acc = 0;
@@ -229,7 +286,7 @@ cudaError_t qlayer_tc_configure() {
 
 bool qlayer_tc_supported(int N, int K, bool logits) {
   if (K < kBlockK || K % kBlockK != 0) return false;
-  if (!logits && N % 32 != 0) return false;
+  if (!logits && N % 16 != 0) return false;
   return true;
 }
 

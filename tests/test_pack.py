@@ -21,9 +21,12 @@ def test_blob_matches_oracle(shape, stress, net_file):
     assert (b.in_dim, b.hidden, b.out_dim, len(b.qlayers)) == (port.input_dim, port.hidden_dim, port.output_dim, port.qlayer_count)
     for got, want in zip(b.input_layer(), port.input_layer()):
         assert np.array_equal(got, want)
+    # doubled LUT: slot v + 1282 with v = trunc(2c) holds QuantizedSigmoid::get for every c that truncates to v
+    lut2 = b.lut2()
+    ks = (np.abs(np.arange(-1282, 1283)) + 1) // 2 * np.sign(np.arange(-1282, 1283))
     lut = oracle_py.Port.sigmoid_lut()
-    ext = b.lut_ext()
-    assert ext[0] == 0 and ext[1] == 0 and np.array_equal(ext[2:1281], lut[1:]) and ext[1281] == 255 and ext[1282] == 255
+    want = np.where(ks <= -640, 0, np.where(ks >= 640, 255, lut[np.clip(ks + 640, 0, 1279)]))
+    assert np.array_equal(lut2, want.astype(np.uint8))
     for i in range(port.qlayer_count):
         w, bias, mult = b.qlayer(i)
         w2, b2, m2 = port.qlayer(i)
@@ -44,7 +47,7 @@ def test_blob_matches_oracle(shape, stress, net_file):
         assert np.all(np.diff(pair.astype(np.int64)) >= 0)
         for c in range(int(q["n_chunks"])):
             seg = pair[ptr[c]:ptr[c + 1]]
-            assert np.all((seg >= 16 * c) & (seg < 16 * (c + 1)))
+            assert np.all((seg >= 8 * c) & (seg < 8 * (c + 1)))  # 16 inputs = 8 pairs per chunk
         assert ptr[0] == 0 and ptr[-1] == len(pair)
 
 
@@ -141,3 +144,27 @@ def test_blob_validation_rejects_corruption(net_file):
     assert rc in (qd.FDNN_EFORMAT, qd.FDNN_ENOGPU)
     rc = lib.fdnn_load_blob(blob.ctypes.data_as(C.c_void_p), blob.nbytes - 256, -1, C.byref(h))
     assert rc in (qd.FDNN_EFORMAT, qd.FDNN_ENOGPU)
+
+
+def test_doubled_lut_trick_equals_reference_rounding(net_file):
+    """numpy float32 emulation of device qsig_slot() (csrc/device_common.cuh): one clamp, one exact
+    doubling, one truncation, one lookup == QuantizedSigmoid::get (round half away, two clamps)"""
+    lut2 = B.Blob(qd.pack(net_file("tiny"))).lut2()
+    rng = np.random.default_rng(1)
+    xs = np.concatenate([
+        rng.normal(0, 3, 20000).astype(np.float32),
+        (np.arange(-1300, 1301, dtype=np.float32) / np.float32(200.0)),           # every half-step of k
+        np.nextafter(np.arange(-1300, 1301, dtype=np.float32) / np.float32(200.0), np.float32(np.inf)),
+        np.nextafter(np.arange(-1300, 1301, dtype=np.float32) / np.float32(200.0), np.float32(-np.inf)),
+        np.float32([0.004999999888241291, 0.005, 0.0049999995, -0.005, 6.4, -6.4, 6.395, 6.3949995, 1e9, -1e9, 2.2e7, 2.1474836e7,
+                    np.inf, -np.inf, np.nan, 0.0, -0.0, 1e-40]),
+    ])
+    with np.errstate(invalid="ignore", over="ignore"):
+        t = (xs * np.float32(100.0)).astype(np.float32)
+        c = np.minimum(np.maximum(t, np.float32(-641.0)), np.float32(641.0))
+        c = np.where(np.isnan(t), np.float32(-641.0), c)
+        c = np.where(~(t < np.float32(2147483648.0)), np.float32(-641.0), c)
+        v = np.trunc((c + c).astype(np.float32)).astype(np.int64)
+    got = lut2[v + 1282]
+    want = np.array([oracle_py.Port.qsigmoid(float(x)) for x in xs], dtype=np.uint8)
+    assert np.array_equal(got, want), np.flatnonzero(got != want)[:10]
