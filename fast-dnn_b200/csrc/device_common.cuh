@@ -41,7 +41,13 @@ struct QLayerArgs {
   // logits mode: lin + bias, fp32 [M][out_ld]
   float *out_f32;
   int out_ld;
+  // optional per-CTA phase timestamps (SM clock), 8 slots per CTA; nullptr in normal operation
+  unsigned long long *timeline;
 };
+
+__device__ __forceinline__ void stamp(unsigned long long *timeline, int slot) {
+  if (timeline != nullptr) timeline[size_t(blockIdx.x) * 8 + slot] = clock64();
+}
 
 // (float)sum / (multiplier·255)  — dnn.cc:296-311.  IEEE division, or the 3-op form proven equal
 // to it for every reachable sum when the model was packed (model_host.cc: verify_fast_div).

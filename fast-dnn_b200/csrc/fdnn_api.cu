@@ -154,6 +154,7 @@ struct fdnn_ctx {
   cudaStream_t stream = nullptr;
   bool trace = false;
   uint8_t *d_trace = nullptr;  // [n_qlayers][cap][H]
+  unsigned long long *d_timeline = nullptr;  // optional [n_qlayers][1024 CTAs][8] phase stamps (profiling aid)
   int last_frames = 0;
   bool have_logits = false;
 };
@@ -175,6 +176,7 @@ void destroy_ctx(fdnn_ctx *c) {
     cudaFree(ch.flags);
   }
   cudaFree(c->d_trace);
+  cudaFree(c->d_timeline);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -284,6 +286,7 @@ int enqueue_until_logits(fdnn_ctx *c, const float *d_in, int m, float *d_logits,
     a.N = ql.nodes;
     a.K = ql.inputs;
     a.self = chan_of(j);
+    a.timeline = c->d_timeline ? c->d_timeline + size_t(j) * 1024 * 8 : nullptr;
     if (logits) {
       a.out_f32 = d_logits;
       a.out_ld = ql.nodes;
@@ -520,6 +523,28 @@ int fdnn_ctx_free(fdnn_ctx *ctx) {
 
 int fdnn_ctx_frames(const fdnn_ctx *ctx) { return ctx ? ctx->cap : FDNN_EINVAL; }
 int fdnn_ctx_output_dim(const fdnn_ctx *ctx) { return ctx ? ctx->model->hdr.out_dim : FDNN_EINVAL; }
+
+// Profiling aid: per-CTA phase timestamps (SM clocks) of the tensor-core layer kernels of the NEXT
+// forward pass.  out = [n_qlayers][1024][8] uint64 (host); slots: 0 entry, 1 setup done, 2 first
+// operands landed, 3 last MMA committed, 4 epilogue staging done, 5 accumulator ready, 6 tile done,
+// 7 exit.  enable = 1 arms, enable = 0 copies the stamps out and disarms.
+int fdnn_ctx_timeline(fdnn_ctx *ctx, int enable, unsigned long long *out) {
+  if (!ctx) return FDNN_EINVAL;
+  DeviceGuard g(ctx->model->device);
+  const size_t bytes = size_t(ctx->model->hdr.n_qlayers) * 1024 * 8 * sizeof(unsigned long long);
+  if (enable) {
+    if (!ctx->d_timeline) CUDA_TRY(cudaMalloc(&ctx->d_timeline, bytes));
+    CUDA_TRY(cudaMemset(ctx->d_timeline, 0, bytes));
+    CUDA_TRY(cudaDeviceSynchronize());
+    return FDNN_OK;
+  }
+  if (!ctx->d_timeline || !out) return FDNN_EINVAL;
+  CUDA_TRY(cudaDeviceSynchronize());
+  CUDA_TRY(cudaMemcpy(out, ctx->d_timeline, bytes, cudaMemcpyDeviceToHost));
+  cudaFree(ctx->d_timeline);
+  ctx->d_timeline = nullptr;
+  return FDNN_OK;
+}
 
 int fdnn_ctx_set_trace(fdnn_ctx *ctx, int enable) {
   if (!ctx) return FDNN_EINVAL;

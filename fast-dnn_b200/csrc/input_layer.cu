@@ -7,16 +7,15 @@
 //
 // The summation order is part of the result, so this is CUDA-core work: every product and every
 // add is a separately rounded fp32 operation, never contracted to FMA, and each thread keeps the
-// four SSE lanes of every (frame, node) it owns as four accumulators.  Products are scalar FMUL;
-// the lane pairs are accumulated with Blackwell's packed add.rn.f32x2 (two independent IEEE adds
-// per instruction, fewer issue slots).  NOTE: ptxas 12.9 contracts mul.rn.f32x2 + add.rn.f32x2
-// into a fused FFMA2 even with --fmad=false, which would change results, so the multiply must
-// stay scalar (checked in SASS: the main loop holds FMUL + FADD2 and no FFMA2).
+// four SSE lanes of every (frame, node) it owns as four accumulators (scalar FMUL + FADD: measured
+// on B200, the packed add.rn.f32x2 is slower than two scalar FADDs, and ptxas 12.9 contracts
+// mul.rn.f32x2 + add.rn.f32x2 into a fused FFMA2 even with --fmad=false, which would change
+// results — tools/microbench.cu, DESIGN.md §Measured hardware facts).
 //
 // Tiling: a CTA (16 warps) computes 64 frames × 128 nodes; a warp 16 frames × 32 nodes; a thread
 // 4 frames × 4 nodes, strided (frames fg + 4i, nodes ng + 8j with lane = 8·fg + ng) so that every
 // 128-bit shared-memory read is either a broadcast or conflict-free with the 44-float row pitch —
-// 8 wavefronts per 64 packed math instructions.  K is streamed in 40-float chunks, double
+// 8 wavefronts per 128 math instructions.  K is streamed in 40-float chunks, double
 // buffered: weights by cp.async, frames through registers so shift/scale is applied on the way in.
 
 #include <cuda_runtime.h>
@@ -43,16 +42,6 @@ __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src)
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
-
-// two independent round-to-nearest fp32 operations on the halves of a 64-bit register pair
-__device__ __forceinline__ uint64_t pack2(float lo, float hi) { return (uint64_t(__float_as_uint(hi)) << 32) | __float_as_uint(lo); }
-__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
-  uint64_t d;
-  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-  return d;
-}
-__device__ __forceinline__ float lo_f(uint64_t v) { return __uint_as_float(uint32_t(v)); }
-__device__ __forceinline__ float hi_f(uint64_t v) { return __uint_as_float(uint32_t(v >> 32)); }
 
 __global__ void __launch_bounds__(kThreads, 1) input_layer_kernel(const InputLayerArgs args) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
@@ -118,12 +107,12 @@ __global__ void __launch_bounds__(kThreads, 1) input_layer_kernel(const InputLay
     cp_async_commit();
   };
 
-  // acc[i][j][0] = SSE lanes (0,1), acc[i][j][1] = lanes (2,3) of frame fg+4i, node ng+8j
-  uint64_t acc[kTF][kTN][2];
+  // acc[i][j] = the four SSE lanes of frame fg+4i, node ng+8j
+  float4 acc[kTF][kTN];
 #pragma unroll
   for (int i = 0; i < kTF; ++i)
 #pragma unroll
-    for (int j = 0; j < kTN; ++j) acc[i][j][0] = acc[i][j][1] = 0ull;
+    for (int j = 0; j < kTN; ++j) acc[i][j] = make_float4(0.f, 0.f, 0.f, 0.f);
 
   load_x_regs(0);
   issue_w(0, 0);
@@ -152,8 +141,10 @@ __global__ void __launch_bounds__(kThreads, 1) input_layer_kernel(const InputLay
       for (int i = 0; i < kTF; ++i)
 #pragma unroll
         for (int j = 0; j < kTN; ++j) {
-          acc[i][j][0] = add2(acc[i][j][0], pack2(__fmul_rn(xv[i].x, wv[j].x), __fmul_rn(xv[i].y, wv[j].y)));
-          acc[i][j][1] = add2(acc[i][j][1], pack2(__fmul_rn(xv[i].z, wv[j].z), __fmul_rn(xv[i].w, wv[j].w)));
+          acc[i][j].x = __fadd_rn(acc[i][j].x, __fmul_rn(xv[i].x, wv[j].x));
+          acc[i][j].y = __fadd_rn(acc[i][j].y, __fmul_rn(xv[i].y, wv[j].y));
+          acc[i][j].z = __fadd_rn(acc[i][j].z, __fmul_rn(xv[i].z, wv[j].z));
+          acc[i][j].w = __fadd_rn(acc[i][j].w, __fmul_rn(xv[i].w, wv[j].w));
         }
     }
     if (more) store_x_regs(buf ^ 1);
@@ -170,7 +161,7 @@ __global__ void __launch_bounds__(kThreads, 1) input_layer_kernel(const InputLay
   for (int i = 0; i < kTF; ++i)
 #pragma unroll
     for (int j = 0; j < kTN; ++j) {
-      const float h = __fadd_rn(__fadd_rn(lo_f(acc[i][j][0]), hi_f(acc[i][j][0])), __fadd_rn(lo_f(acc[i][j][1]), hi_f(acc[i][j][1])));
+      const float h = __fadd_rn(__fadd_rn(acc[i][j].x, acc[i][j].y), __fadd_rn(acc[i][j].z, acc[i][j].w));
       s_out[(wf + fg + 4 * i) * kTileN + wn + ng + 8 * j] = s_lut[qsig_slot(__fadd_rn(h, bias[j]))];
     }
   __syncthreads();

@@ -81,6 +81,7 @@ qlayer_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_cons
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_empty_bar + kAccStages);
 
   const int warp = int(threadIdx.x) / 32, lane = int(threadIdx.x) % 32;
+  if (threadIdx.x == 0) stamp(args.timeline, 0);
   const int M = args.M, N = args.N, K = args.K;
   const int m_blocks = (M + kBlockM - 1) / kBlockM, n_blocks = (N + BN - 1) / BN;
   const int tiles_total = m_blocks * n_blocks;
@@ -110,6 +111,7 @@ qlayer_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_cons
   __syncthreads();
   ptx::tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) stamp(args.timeline, 1);
 
   if (warp == 0) {
     // ===== TMA producer =====
@@ -144,6 +146,7 @@ qlayer_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_cons
         ptx::mbar_wait(full_bar + stage, phase);
         ptx::tc_fence_after_sync();
         if (lane == 0) {
+          if (kb == 0) stamp(args.timeline, 2);
           const uint32_t a_addr = ptx::smem_u32(tiles + stage * Cfg::kStageBytes);
           const uint64_t da = ptx::smem_desc_k_sw128(a_addr), db = ptx::smem_desc_k_sw128(a_addr + Cfg::kABytes);
 #pragma unroll
@@ -152,7 +155,10 @@ qlayer_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_cons
             ptx::mma_i8_ss(d_tmem, da + uint64_t(k * (kUmmaK / 16)), db + uint64_t(k * (kUmmaK / 16)), idesc, uint32_t((kb | k) != 0));
           }
           ptx::mma_commit(empty_bar + stage);
-          if (kb == k_blocks - 1) ptx::mma_commit(tmem_full_bar + acc);
+          if (kb == k_blocks - 1) {
+            ptx::mma_commit(tmem_full_bar + acc);
+            stamp(args.timeline, 3);
+          }
         }
         __syncwarp();
         if (++stage == Cfg::kStages) {
@@ -204,9 +210,11 @@ qlayer_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_cons
 #pragma unroll
       for (int j = 0; j < Cfg::kChunks; ++j) flag[j] = (row_ok && j < n_valid) ? load_flag(args.self, (col0 >> 4) + j, row) : uint8_t(0);
       ptx::named_bar_sync(1, kEpilogueThreads);
+      if (et == 0) stamp(args.timeline, 4);
 
       ptx::mbar_wait(tmem_full_bar + acc, acc_phase);
       ptx::tc_fence_after_sync();
+      if (et == 0) stamp(args.timeline, 5);
       const uint32_t t_addr = tmem_base + uint32_t(acc * BN + col_group * Cfg::kColsPerWarp) + (uint32_t(quarter * 32) << 16);
       if (n_valid == 0) {
         ptx::tc_fence_before_sync();
@@ -243,6 +251,7 @@ qlayer_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_cons
           }
         }
       }
+      if (et == 0) stamp(args.timeline, 6);
       if (++acc == kAccStages) {
         acc = 0;
         acc_phase ^= 1;
@@ -252,6 +261,7 @@ qlayer_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_cons
 
   ptx::tc_fence_before_sync();
   __syncthreads();
+  if (threadIdx.x == 0) stamp(args.timeline, 7);
   if (warp == 2) {
     ptx::tc_fence_after_sync();
     ptx::tmem_dealloc<Cfg::kTmemCols>(tmem_base);

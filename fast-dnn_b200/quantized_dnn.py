@@ -61,6 +61,7 @@ SIGNATURES = {
     "fdnn_ctx_until_output_device": (_I, [_P, _P, _I, _P]),
     "fdnn_ctx_lazy_batch_device": (_I, [_P, _P, _I, _P, _P]),
     "fdnn_ctx_profile_stages": (_I, [_P, _P, _I, _P, _I, _P]),
+    "fdnn_ctx_timeline": (_I, [_P, _I, _P]),
     "fdnn_ctx_set_trace": (_I, [_P, _I]),
     "fdnn_ctx_hidden": (_I, [_P, _I, _I, _P]),
     "fdnn_ctx_logits": (_I, [_P, _I, _P]),
@@ -312,6 +313,15 @@ class LazyContext:
 
     def lazy_batch_device(self, d_masks: int, n_frames: int, d_out: int, stream: int = 0) -> None:
         _check(lib().fdnn_ctx_lazy_batch_device(self._h, C.c_void_p(d_masks), n_frames, C.c_void_p(d_out), C.c_void_p(stream)))
+
+    def timeline(self, enable: bool):
+        """arm (True) / read back (False) per-CTA phase stamps of the tensor-core layer kernels"""
+        if enable:
+            _check(lib().fdnn_ctx_timeline(self._h, 1, None))
+            return None
+        out = np.zeros((self.dnn.layer_count() - 1, 1024, 8), dtype=np.uint64)
+        _check(lib().fdnn_ctx_timeline(self._h, 0, _ptr(out)))
+        return out
 
     def profile_stages(self, d_in: int, n_frames: int, d_out: int, iters: int = 20) -> np.ndarray:
         """per-kernel milliseconds of one forward pass (bench aid): [input, int8 layers…, softmax]"""

@@ -132,6 +132,10 @@ int fdnn_sigmoid_lut(uint8_t out[1280]);
  * averages in milliseconds, synchronised on return. */
 int fdnn_ctx_profile_stages(fdnn_ctx *ctx, const float *d_in, int n_frames, float *d_out, int iters, float *ms);
 
+/* Profiling aid: per-CTA phase timestamps of the tensor-core layer kernels.  enable=1 arms the
+ * next forward pass; enable=0 copies [layers-1][1024][8] uint64 SM-clock stamps to `out` and disarms. */
+int fdnn_ctx_timeline(fdnn_ctx *ctx, int enable, unsigned long long *out);
+
 /* ---- pinned host memory for callers that want zero staging ---------------------------------- */
 int fdnn_host_alloc(void **ptr, size_t bytes);
 int fdnn_host_free(void *ptr);
