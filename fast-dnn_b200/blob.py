@@ -6,8 +6,9 @@ from __future__ import annotations
 import numpy as np
 
 MAGIC = 0x424E4446
-VERSION = 4
-FIX_CHUNK = 16
+VERSION = 5
+FIX_GROUP = 64
+FIX_KBLOCK = 128
 
 HEADER = np.dtype([
     ("magic", "<u4"), ("version", "<u4"), ("total_size", "<u8"),
@@ -18,10 +19,10 @@ HEADER = np.dtype([
 ])
 QLAYER = np.dtype([
     ("nodes", "<i4"), ("inputs", "<i4"), ("multiplier", "<f4"), ("coeff", "<f4"), ("rcp_coeff", "<f4"),
-    ("n_fix", "<u4"), ("fast_div", "<u4"), ("n_chunks", "<u4"),
+    ("n_fix", "<u4"), ("fast_div", "<u4"), ("n_groups", "<u4"), ("k_blocks", "<u4"), ("pad_", "<u4"),
     ("off_w", "<u8"), ("off_bias", "<u8"), ("off_fix_ptr", "<u8"), ("off_fix_ent", "<u8"),
 ])
-assert HEADER.itemsize == 88 and QLAYER.itemsize == 64
+assert HEADER.itemsize == 88 and QLAYER.itemsize == 72
 
 
 class Blob:
@@ -65,9 +66,10 @@ class Blob:
         return w, self._f32(q["off_bias"], n), float(q["multiplier"])
 
     def fix_list(self, i):
-        """→ (chunk_ptr uint32 [n_chunks+1], pair uint32 [n_fix], w0 int8, w1 int8, node uint32)."""
+        """→ (ptr uint32 [n_groups*k_blocks+1], pair uint32 [n_fix], w0 int8, w1 int8, node uint32);
+        entries are ordered by (node // 64, pair // 64, node, pair)."""
         q = self.qlayers[i]
-        nc, nf = int(q["n_chunks"]), int(q["n_fix"])
+        nc, nf = int(q["n_groups"]) * int(q["k_blocks"]), int(q["n_fix"])
         ptr = self.data[int(q["off_fix_ptr"]):int(q["off_fix_ptr"]) + 4 * (nc + 1)].view("<u4")
         ent = self.data[int(q["off_fix_ent"]):int(q["off_fix_ent"]) + 8 * nf].view("<u4").reshape(nf, 2)
         pair = ent[:, 0] & 0xFFFF

@@ -1,5 +1,5 @@
-// Device-side pieces shared by all kernels: the exact scalar arithmetic of the reference's
-// per-element stages, and the producer/consumer halves of the pmaddubsw-saturation correction.
+// Device-side pieces shared by the kernels: the exact scalar arithmetic of the reference's
+// per-element stages and the evaluation of pmaddubsw-saturation risk entries.
 #pragma once
 
 #include <cstdint>
@@ -8,21 +8,11 @@
 
 namespace fdnn {
 
-// Correction channel of one int8 layer.  Producers (the kernel writing the layer's INPUT
-// activations) post clamp(v) − v for the few weight pairs that can saturate; the layer's own
-// kernel adds them to its raw tensor-core sums.  `corr` is kept all-zero between uses: whoever
-// consumes a non-zero flag re-zeroes what it read.  Granularity: kFixChunk (16) nodes per flag.
-struct CorrChannel {
-  int32_t *corr;   // [rows][ld] int32
-  uint8_t *flags;  // [ld/16][rows_cap]: non-zero ⇒ corr[row][16c .. 16c+15] holds something
-  int ld;          // corr row pitch (elements, multiple of 16)
-  int rows_cap;    // flag pitch
-};
-
-// Risk list of the consumer layer, seen from the producer (BlobQLayer::off_fix_*).
+// Risk list of one int8 layer (BlobQLayer::off_fix_*; order described in fdnn_internal.h).
 struct FixList {
-  const uint32_t *ptr;  // [n_chunks + 1], chunk = 16 consecutive inputs of the consumer
+  const uint32_t *ptr;  // [n_groups · k_blocks + 1]
   const FixEntry *ent;
+  int k_blocks;
 };
 
 struct QLayerArgs {
@@ -33,13 +23,9 @@ struct QLayerArgs {
   float coeff, rcp;
   int fast_div;
   int M, N, K;
-  CorrChannel self;   // corrections addressed to this layer
-  // hidden mode: u8 activations out + corrections for the next layer
-  uint8_t *out_u8;  // [M][N]
-  FixList next_fix;
-  CorrChannel next;
-  // logits mode: lin + bias, fp32 [M][out_ld]
-  float *out_f32;
+  FixList fix;      // this layer's saturation risk entries
+  uint8_t *out_u8;  // hidden mode: u8 activations [M][N]
+  float *out_f32;   // logits mode: lin + bias, fp32 [M][out_ld]
   int out_ld;
   // optional per-CTA phase timestamps (SM clock), 8 slots per CTA; nullptr in normal operation
   unsigned long long *timeline;
@@ -72,52 +58,38 @@ __device__ __forceinline__ int qsig_slot(float x) {
   return __float2int_rz(__fadd_rn(c, c)) + kLut2Center;
 }
 
-// Producer half: `a` points at this row's 16 freshly written activations of input chunk `chunk`
-// (shared memory); evaluates entries [e0, e1) of the consumer's risk list.  `ent` may point to
-// shared or global memory; entry e lives at ent[e − ent_base].
-__device__ __forceinline__ void post_saturation(const uint8_t *a, int chunk, int row, const FixEntry *ent, uint32_t ent_base, uint32_t e0,
-                                                uint32_t e1, const CorrChannel &ch) {
+// clamp(v) − v for one pair sum v = a0·w0 + a1·w1 (what pmaddubsw's int16 saturation changes)
+__device__ __forceinline__ int saturation_delta(uint32_t a01, uint32_t pair_w) {
+  const int w0 = int(int8_t(pair_w >> 16)), w1 = int(int8_t(pair_w >> 24));
+  const int v = int(a01 & 0xffu) * w0 + int(a01 >> 8) * w1;
+  return max(min(v, 32767), -32768) - v;
+}
+
+// Slow, self-contained evaluation of every risk entry that touches nodes [col, col+16) of `row`,
+// reading the activation bytes from global memory.  Used by the dp4a kernel and as the overflow
+// path of the tensor-core kernel.
+__device__ __forceinline__ void brute_force_corrections(int32_t (&s)[16], int row, int col, const QLayerArgs &args) {
+  const int kb_n = args.fix.k_blocks;
+  const int sg = col / kFixGroup;
+  const uint32_t e0 = __ldg(args.fix.ptr + size_t(sg) * kb_n), e1 = __ldg(args.fix.ptr + size_t(sg + 1) * kb_n);
+  const uint8_t *a_row = args.act + size_t(row) * size_t(args.K);
   for (uint32_t e = e0; e < e1; ++e) {
-    const uint2 fe = *reinterpret_cast<const uint2 *>(ent + (e - ent_base));
-    const int off = 2 * int(fe.x & 0xffffu) - kFixChunk * chunk;
-    const int w0 = int(int8_t(fe.x >> 16)), w1 = int(int8_t(fe.x >> 24));
-    const int v = int(a[off]) * w0 + int(a[off + 1]) * w1;
-    const int d = max(min(v, 32767), -32768) - v;
-    if (d != 0) {
-      atomicAdd(ch.corr + size_t(row) * size_t(ch.ld) + fe.y, d);
-      ch.flags[size_t(fe.y >> 4) * size_t(ch.rows_cap) + size_t(row)] = 1;
-    }
-  }
-}
-
-__device__ __forceinline__ uint8_t load_flag(const CorrChannel &ch, int node_chunk, int row) {
-  return ch.flags[size_t(node_chunk) * size_t(ch.rows_cap) + size_t(row)];
-}
-
-// Consumer half for one row and one aligned chunk of 16 nodes held in registers; `flag` is the
-// (possibly prefetched) flag byte of that (chunk, row).
-__device__ __forceinline__ void take_corrections(int32_t (&s)[16], uint8_t flag, int node_chunk, int row, const CorrChannel &ch) {
-  if (flag) {
-    int4 *c = reinterpret_cast<int4 *>(ch.corr + size_t(row) * size_t(ch.ld) + size_t(node_chunk) * kFixChunk);
+    const uint2 fe = __ldg(reinterpret_cast<const uint2 *>(args.fix.ent) + e);
+    const uint32_t rel = fe.y - uint32_t(col);
+    if (rel < 16u) {
+      const uint32_t a01 = *reinterpret_cast<const uint16_t *>(a_row + 2 * (fe.x & 0xffffu));
+      const int d = saturation_delta(a01, fe.x);
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      int4 v = c[j];
-      s[4 * j + 0] += v.x;
-      s[4 * j + 1] += v.y;
-      s[4 * j + 2] += v.z;
-      s[4 * j + 3] += v.w;
-      c[j] = make_int4(0, 0, 0, 0);
+      for (int i = 0; i < 16; ++i) s[i] += (rel == uint32_t(i)) ? d : 0;
     }
-    ch.flags[size_t(node_chunk) * size_t(ch.rows_cap) + size_t(row)] = 0;
   }
 }
 
-// The reference's per-element tail for one row and one aligned chunk of 16 nodes whose corrected
-// sums are in `s`: dequantise → + bias → {LUT → u8 | fp32 logits} → global memory.  Returns the
-// 16 packed bytes in hidden mode (for the saturation scan of the next layer).
+// The reference's per-element tail for one row and one aligned chunk of 16 nodes whose exact
+// (saturation-corrected) sums are in `s`: dequantise → + bias → {LUT → u8 | fp32 logits} → global.
 template <bool kLogits>
-__device__ __forceinline__ uint4 finish_chunk(const int32_t (&s)[16], int row, int col, const QLayerArgs &args, const float *bias16,
-                                              const uint8_t *lut) {
+__device__ __forceinline__ void finish_chunk(const int32_t (&s)[16], int row, int col, const QLayerArgs &args, const float *bias16,
+                                             const uint8_t *lut) {
   const int N = args.N;
   if constexpr (kLogits) {
     float v[16];
@@ -132,7 +104,6 @@ __device__ __forceinline__ uint4 finish_chunk(const int32_t (&s)[16], int row, i
       for (int i = 0; i < 16; ++i)
         if (col + i < N) dst[i] = v[i];
     }
-    return make_uint4(0, 0, 0, 0);
   } else {
     uint32_t packed[4];
 #pragma unroll
@@ -145,10 +116,8 @@ __device__ __forceinline__ uint4 finish_chunk(const int32_t (&s)[16], int row, i
       }
       packed[i] = w;
     }
-    const uint4 out = make_uint4(packed[0], packed[1], packed[2], packed[3]);
     // hidden widths are multiples of 16 (dnn.cc:331), so a chunk is always whole and 16-byte aligned
-    *reinterpret_cast<uint4 *>(args.out_u8 + size_t(row) * size_t(N) + col) = out;
-    return out;
+    *reinterpret_cast<uint4 *>(args.out_u8 + size_t(row) * size_t(N) + col) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
   }
 }
 

@@ -148,7 +148,6 @@ struct fdnn_ctx {
   int8_t *d_masks = nullptr;  // [cap][O], allocated on first lazy use
   float *d_row = nullptr;     // [O] scratch for single-row lazy output
   float *d_lazy = nullptr;    // [cap][O] masked softmax rows, allocated on first batched lazy use
-  CorrChannel chan[3]{};      // A, B (hidden-sized), C (output-sized)
   CUtensorMap amap[2];
   bool amap_ok = false;
   cudaStream_t stream = nullptr;
@@ -171,25 +170,10 @@ void destroy_ctx(fdnn_ctx *c) {
   cudaFree(c->d_masks);
   cudaFree(c->d_row);
   cudaFree(c->d_lazy);
-  for (auto &ch : c->chan) {
-    cudaFree(ch.corr);
-    cudaFree(ch.flags);
-  }
   cudaFree(c->d_trace);
   cudaFree(c->d_timeline);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
-}
-
-int alloc_channel(CorrChannel &ch, int rows, int nodes) {
-  ch.ld = round_up(nodes, kFixChunk);
-  ch.rows_cap = rows;
-  size_t corr_bytes = size_t(rows) * size_t(ch.ld) * 4, flag_bytes = size_t(ch.ld / kFixChunk) * size_t(rows);
-  CUDA_TRY(cudaMalloc(&ch.corr, corr_bytes));
-  CUDA_TRY(cudaMalloc(&ch.flags, flag_bytes));
-  CUDA_TRY(cudaMemset(ch.corr, 0, corr_bytes));
-  CUDA_TRY(cudaMemset(ch.flags, 0, flag_bytes));
-  return FDNN_OK;
 }
 
 int create_ctx(fdnn_model *m, int n, fdnn_ctx **out) {
@@ -198,8 +182,8 @@ int create_ctx(fdnn_model *m, int n, fdnn_ctx **out) {
     return FDNN_EINVAL;
   }
   const int I = m->hdr.in_dim, H = m->hdr.hidden, O = m->hdr.out_dim;
-  // ≈ (4I + 2H + 12·pad32(H) + 8·pad32(O)) bytes of device memory per frame
-  const double per_frame = 4.0 * I + 2.0 * H + 8.0 * round_up(H, 16) + 8.0 * round_up(O, 16) + 64;
+  // ≈ (4I + 2H + 4O) bytes of device memory per frame (+ masks and a second [n][O] buffer on lazy use)
+  const double per_frame = 4.0 * I + 2.0 * H + 4.0 * O + 64;
   size_t free_b = 0, total_b = 0;
   DeviceGuard g(m->device);
   if (!g.ok) {
@@ -224,9 +208,6 @@ int create_ctx(fdnn_model *m, int n, fdnn_ctx **out) {
   CUDA_TRY(cudaMemset(c->d_act[1], 0, act_bytes));
   CUDA_TRY(cudaMalloc(&c->d_logits, size_t(n) * O * 4));
   CUDA_TRY(cudaMalloc(&c->d_row, size_t(O) * 4));
-  if (int rc = alloc_channel(c->chan[0], n, H)) return rc;
-  if (int rc = alloc_channel(c->chan[1], n, H)) return rc;
-  if (int rc = alloc_channel(c->chan[2], n, O)) return rc;
   if (H % 128 == 0 && !m->force_simt) {
     if (int rc = make_tmap(&c->amap[0], c->d_act[0], n, H, 128)) return rc;
     if (int rc = make_tmap(&c->amap[1], c->d_act[1], n, H, 128)) return rc;
@@ -248,9 +229,9 @@ int enqueue_until_logits(fdnn_ctx *c, const float *d_in, int m, float *d_logits,
     FixList f;
     f.ptr = mod->at<uint32_t>(mod->q[size_t(layer)].off_fix_ptr);
     f.ent = mod->at<FixEntry>(mod->q[size_t(layer)].off_fix_ent);
+    f.k_blocks = int(mod->q[size_t(layer)].k_blocks);
     return f;
   };
-  auto chan_of = [&](int layer) -> const CorrChannel & { return layer == nq - 1 ? c->chan[2] : c->chan[layer & 1]; };
 
   InputLayerArgs ia{};
   ia.in = d_in;
@@ -263,8 +244,6 @@ int enqueue_until_logits(fdnn_ctx *c, const float *d_in, int m, float *d_logits,
   ia.M = m;
   ia.I = h.in_dim;
   ia.H = h.hidden;
-  ia.next_fix = fix_of(0);
-  ia.next = chan_of(0);
   CUDA_TRY(launch_input_layer(ia, stream));
   g_launches.fetch_add(1, std::memory_order_relaxed);
   if (after_stage) after_stage(0);
@@ -285,15 +264,13 @@ int enqueue_until_logits(fdnn_ctx *c, const float *d_in, int m, float *d_logits,
     a.M = m;
     a.N = ql.nodes;
     a.K = ql.inputs;
-    a.self = chan_of(j);
+    a.fix = fix_of(j);
     a.timeline = c->d_timeline ? c->d_timeline + size_t(j) * 1024 * 8 : nullptr;
     if (logits) {
       a.out_f32 = d_logits;
       a.out_ld = ql.nodes;
     } else {
       a.out_u8 = c->d_act[(j + 1) & 1];
-      a.next_fix = fix_of(j + 1);
-      a.next = chan_of(j + 1);
     }
     if (mod->tc_ok[size_t(j)] && c->amap_ok) {
       const int bn = qlayer_tc_block_n(m, ql.nodes, mod->num_sms);

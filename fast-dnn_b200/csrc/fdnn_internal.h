@@ -20,23 +20,24 @@ constexpr int kLut2Size = 2 * kLut2Center + 1;  // 2565
 constexpr int kLut2Padded = 2576;               // multiple of 16 bytes
 
 constexpr uint32_t kBlobMagic = 0x424E4446u;  // "FDNB"
-constexpr uint32_t kBlobVersion = 4;
+constexpr uint32_t kBlobVersion = 5;
 constexpr size_t kBlobAlign = 256;
-
-// Granularity of the saturation-correction machinery, in nodes: a producer thread that has just
-// written u8 activations for 16 consecutive nodes scans the consumer layer's risk entries of that
-// input chunk, and a consumer thread owns the corrections of 16 consecutive output nodes of a row.
-constexpr int kFixChunk = 16;
 
 // pmaddubsw (dnn.cc:337-340) clamps every adjacent-pair sum a[2p]·w[2p] + a[2p+1]·w[2p+1] to int16.
 // A tensor-core contraction does not.  With a ≤ 255 the clamp can only fire for weight pairs whose
-// same-sign magnitudes add up to ≥ 129; those (node, pair) entries are listed per layer, grouped
-// by the INPUT pair index so that the kernel which PRODUCES the layer's input activations can
-// evaluate them while it still holds the two bytes, and post the (rare) difference
-// clamp(v) − v to the consumer's correction buffer.
+// same-sign magnitudes add up to ≥ 129; those (node, pair) "risk entries" are listed per layer.
+// The layer kernel evaluates them against the activation tiles it is streaming anyway and adds
+// clamp(v) − v to the raw tensor-core sums, which makes the sums bit-identical to the reference's.
+//
+// Order: by node supergroup (kFixGroup = 64 consecutive nodes, the smallest N tile), then by the
+// 128-byte K block the pair lives in (the pipeline stage that carries its two activation bytes),
+// then by node and pair.  ptr[sg · k_blocks + kb] .. ptr[sg · k_blocks + kb + 1] delimits the
+// entries of supergroup sg whose pair is in K block kb; ptr has n_groups · k_blocks + 1 elements.
+constexpr int kFixGroup = 64;
+constexpr int kFixKBlock = 128;  // bytes of K per block (= 64 pairs)
 struct FixEntry {
   uint32_t pair_w;  // pair index p (bits 0-15) | (uint8)w[2p] << 16 | (uint8)w[2p+1] << 24
-  uint32_t node;    // consumer node n
+  uint32_t node;    // node n
 };
 
 // One int8 layer inside the blob; all offsets are from the start of the blob, 256-byte aligned.
@@ -46,13 +47,15 @@ struct BlobQLayer {
   float multiplier;   // round(127/max)                      dnn.cc:479
   float coeff;        // multiplier * 255.0f (fp32 product)  dnn.cc:297-298
   float rcp_coeff;    // RN(1 / coeff)
-  uint32_t n_fix;     // saturation fix-up entries
+  uint32_t n_fix;     // saturation risk entries
   uint32_t fast_div;  // 1: q=s·rcp; r=fma(−q,coeff,s); q+=r·rcp verified == s/coeff for every reachable s
-  uint32_t n_chunks;  // ceil(K / kFixChunk)
+  uint32_t n_groups;  // ceil(N / kFixGroup)
+  uint32_t k_blocks;  // ceil(K / kFixKBlock)
+  uint32_t pad_;
   uint64_t off_w;     // int8  [N][K] row-major (K-major)
   uint64_t off_bias;  // fp32  [N]
-  uint64_t off_fix_ptr;  // uint32 [n_chunks+1]: entries of input chunk c are [ptr[c], ptr[c+1])
-  uint64_t off_fix_ent;  // FixEntry [n_fix], sorted by pair index
+  uint64_t off_fix_ptr;  // uint32 [n_groups·k_blocks + 1]
+  uint64_t off_fix_ent;  // FixEntry [n_fix], sorted by (supergroup, K block, node, pair)
 };
 
 struct BlobHeader {

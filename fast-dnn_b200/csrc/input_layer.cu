@@ -170,14 +170,7 @@ __global__ void __launch_bounds__(kThreads, 1) input_layer_kernel(const InputLay
   for (int v = tid; v < kTileF * (kTileN / 16); v += kThreads) {
     const int r = v / (kTileN / 16), q = v % (kTileN / 16);
     if (f0 + r < M && 16 * q < cols) {
-      const uint8_t *src = s_out + r * kTileN + 16 * q;
-      *reinterpret_cast<uint4 *>(args.out_u8 + size_t(f0 + r) * size_t(H) + n0 + 16 * q) = *reinterpret_cast<const uint4 *>(src);
-      // saturation corrections for the first int8 layer: this (frame, 16-node chunk)
-      if (args.next_fix.ptr != nullptr) {
-        const int chunk = (n0 >> 4) + q;
-        const uint32_t e0 = __ldg(args.next_fix.ptr + chunk), e1 = __ldg(args.next_fix.ptr + chunk + 1);
-        post_saturation(src, chunk, f0 + r, args.next_fix.ent, 0u, e0, e1, args.next);
-      }
+      *reinterpret_cast<uint4 *>(args.out_u8 + size_t(f0 + r) * size_t(H) + n0 + 16 * q) = *reinterpret_cast<const uint4 *>(s_out + r * kTileN + 16 * q);
     }
   }
 }

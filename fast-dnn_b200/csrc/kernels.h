@@ -19,8 +19,6 @@ struct InputLayerArgs {
   const uint8_t *lut;
   uint8_t *out_u8;  // [M][H]
   int M, I, H;
-  FixList next_fix;  // risk list of int8 layer 0
-  CorrChannel next;
 };
 cudaError_t input_layer_configure();
 cudaError_t launch_input_layer(const InputLayerArgs &a, cudaStream_t stream);

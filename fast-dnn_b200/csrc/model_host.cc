@@ -254,43 +254,39 @@ int pack_model(const char *path, float cutoff, std::vector<uint8_t> &blob) {
     }
     m.fast_div = (std::isfinite(m.coeff) && m.coeff != 0.0f && verify_fast_div(m.coeff, m.rcp_coeff, l.in)) ? 1u : 0u;
 
-    // saturation risk list, grouped by input pair
+    // saturation risk list, ordered by (node supergroup, K block, node, pair)
     const int K = l.in, pairs = K / 2;
-    m.n_chunks = uint32_t((K + kFixChunk - 1) / kFixChunk);
-    std::vector<uint32_t> count(size_t(pairs) + 1, 0u);
+    m.n_groups = uint32_t((l.out + kFixGroup - 1) / kFixGroup);
+    m.k_blocks = uint32_t((K + kFixKBlock - 1) / kFixKBlock);
+    const size_t buckets = size_t(m.n_groups) * size_t(m.k_blocks);
+    auto risky = [](int a, int b) {
+      int pos = (a > 0 ? a : 0) + (b > 0 ? b : 0), neg = (a < 0 ? a : 0) + (b < 0 ? b : 0);
+      return pos >= 129 || neg <= -129;
+    };
+    std::vector<uint32_t> &ptr = fix_ptr[size_t(q)];
+    ptr.assign(buckets + 1, 0u);
     for (int n = 0; n < l.out; ++n) {
       const int8_t *row = w8.data() + size_t(n) * size_t(K);
-      for (int p = 0; p < pairs; ++p) {
-        int a = row[2 * p], b = row[2 * p + 1];
-        int pos = (a > 0 ? a : 0) + (b > 0 ? b : 0), neg = (a < 0 ? a : 0) + (b < 0 ? b : 0);
-        if (pos >= 129 || neg <= -129) ++count[size_t(p)];
-      }
+      for (int p = 0; p < pairs; ++p)
+        if (risky(row[2 * p], row[2 * p + 1])) ++ptr[size_t(n / kFixGroup) * m.k_blocks + size_t(2 * p / kFixKBlock) + 1];
     }
-    std::vector<uint32_t> start(size_t(pairs) + 1, 0u);
-    for (int p = 0; p < pairs; ++p) start[size_t(p) + 1] = start[size_t(p)] + count[size_t(p)];
+    for (size_t i = 0; i < buckets; ++i) ptr[i + 1] += ptr[i];
     std::vector<FixEntry> &ent = fix[size_t(q)];
-    ent.resize(start[size_t(pairs)]);
-    std::vector<uint32_t> cursor(start.begin(), start.end() - 1);
-    for (int n = 0; n < l.out; ++n) {
+    ent.resize(ptr[buckets]);
+    std::vector<uint32_t> cursor(ptr.begin(), ptr.end() - 1);
+    for (int n = 0; n < l.out; ++n) {  // node-major fill keeps (node, pair) order inside every bucket
       const int8_t *row = w8.data() + size_t(n) * size_t(K);
       for (int p = 0; p < pairs; ++p) {
-        int a = row[2 * p], b = row[2 * p + 1];
-        int pos = (a > 0 ? a : 0) + (b > 0 ? b : 0), neg = (a < 0 ? a : 0) + (b < 0 ? b : 0);
-        if (pos >= 129 || neg <= -129) {
+        const int a = row[2 * p], b = row[2 * p + 1];
+        if (risky(a, b)) {
           FixEntry e;
           e.pair_w = uint32_t(p) | (uint32_t(uint8_t(a)) << 16) | (uint32_t(uint8_t(b)) << 24);
           e.node = uint32_t(n);
-          ent[cursor[size_t(p)]++] = e;
+          ent[cursor[size_t(n / kFixGroup) * m.k_blocks + size_t(2 * p / kFixKBlock)]++] = e;
         }
       }
     }
     m.n_fix = uint32_t(ent.size());
-    std::vector<uint32_t> &ptr = fix_ptr[size_t(q)];
-    ptr.resize(size_t(m.n_chunks) + 1);
-    for (uint32_t c = 0; c <= m.n_chunks; ++c) {
-      int p = std::min(pairs, int(c) * (kFixChunk / 2));
-      ptr[c] = start[size_t(p)];
-    }
   }
 
   // ---- lay the blob out ----------------------------------------------------------------------
@@ -386,31 +382,36 @@ int validate_blob(const uint8_t *blob, size_t size) {
     const BlobQLayer &m = q[size_t(i)];
     bool last = i == h.n_qlayers - 1;
     if (m.inputs != expect_in || m.nodes <= 0 || (!last && m.nodes != h.hidden) || (last && m.nodes != h.out_dim) ||
-        m.n_chunks != uint32_t((m.inputs + kFixChunk - 1) / kFixChunk)) {
+        m.n_groups != uint32_t((m.nodes + kFixGroup - 1) / kFixGroup) || m.k_blocks != uint32_t((m.inputs + kFixKBlock - 1) / kFixKBlock)) {
       set_error("blob int8 layer " + std::to_string(i) + " has inconsistent dimensions");
       return FDNN_EFORMAT;
     }
     if (!inside(m.off_w, uint64_t(m.nodes) * uint64_t(m.inputs)) || !inside(m.off_bias, 4ull * uint64_t(m.nodes)) ||
-        !inside(m.off_fix_ptr, 4ull * (uint64_t(m.n_chunks) + 1)) || !inside(m.off_fix_ent, sizeof(FixEntry) * uint64_t(m.n_fix))) {
+        !inside(m.off_fix_ptr, 4ull * (uint64_t(m.n_groups) * uint64_t(m.k_blocks) + 1)) || !inside(m.off_fix_ent, sizeof(FixEntry) * uint64_t(m.n_fix))) {
       set_error("blob int8 layer " + std::to_string(i) + " section out of bounds");
       return FDNN_EFORMAT;
     }
     const uint32_t *ptr = reinterpret_cast<const uint32_t *>(blob + m.off_fix_ptr);
-    if (ptr[0] != 0 || ptr[m.n_chunks] != m.n_fix) {
-      set_error("blob int8 layer " + std::to_string(i) + " has a corrupt fix-up index");
+    const uint64_t buckets = uint64_t(m.n_groups) * uint64_t(m.k_blocks);
+    if (ptr[0] != 0 || ptr[buckets] != m.n_fix) {
+      set_error("blob int8 layer " + std::to_string(i) + " has a corrupt risk index");
       return FDNN_EFORMAT;
     }
-    for (uint32_t c = 0; c < m.n_chunks; ++c)
-      if (ptr[c] > ptr[c + 1]) {
-        set_error("blob int8 layer " + std::to_string(i) + " has a corrupt fix-up index");
-        return FDNN_EFORMAT;
-      }
     const FixEntry *ent = reinterpret_cast<const FixEntry *>(blob + m.off_fix_ent);
-    for (uint32_t e = 0; e < m.n_fix; ++e)
-      if (int(ent[e].pair_w & 0xffffu) >= m.inputs / 2 || ent[e].node >= uint32_t(m.nodes)) {
-        set_error("blob int8 layer " + std::to_string(i) + " has a corrupt fix-up entry");
+    for (uint64_t bkt = 0; bkt < buckets; ++bkt) {
+      if (ptr[bkt] > ptr[bkt + 1]) {
+        set_error("blob int8 layer " + std::to_string(i) + " has a corrupt risk index");
         return FDNN_EFORMAT;
       }
+      const uint32_t sg = uint32_t(bkt / m.k_blocks), kb = uint32_t(bkt % m.k_blocks);
+      for (uint32_t e = ptr[bkt]; e < ptr[bkt + 1]; ++e) {
+        const uint32_t p = ent[e].pair_w & 0xffffu;
+        if (ent[e].node >= uint32_t(m.nodes) || ent[e].node / kFixGroup != sg || int(p) >= m.inputs / 2 || 2 * p / kFixKBlock != kb) {
+          set_error("blob int8 layer " + std::to_string(i) + " has a corrupt risk entry");
+          return FDNN_EFORMAT;
+        }
+      }
+    }
     expect_in = m.nodes;
   }
   return FDNN_OK;

@@ -53,6 +53,21 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
   }
 }
 
+// Same, for waits that are expected to be long (epilogue waiting for a whole tile): back off so the
+// polling warps do not take issue slots from the warps that are working.
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t *bar, uint32_t parity) {
+  uint32_t polls = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    __nanosleep(128);
+    if (++polls > (1u << 22)) __trap();
+  }
+}
+__device__ __forceinline__ uint32_t lds_u16(uint32_t smem_addr) {
+  uint16_t v;
+  asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(smem_addr));
+  return v;
+}
+
 // ---- TMA ---------------------------------------------------------------------------------------
 __device__ __forceinline__ void prefetch_tensormap(const CUtensorMap *map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");

@@ -3,8 +3,8 @@
 // are not a multiple of 32 (the reference only asks for multiples of 16, dnn.cc:331).  Same
 // arithmetic contract and the same epilogue as qlayer_tc.cu; see that file for the references.
 //
-// One thread owns one frame and one aligned chunk of 16 nodes, so the epilogue (and the
-// saturation-correction channel, which works in 16-node chunks per frame) is shared verbatim.
+// One thread owns one frame and one aligned chunk of 16 nodes, so the per-element tail is shared
+// verbatim; saturation corrections are recomputed per thread from the layer's risk list.
 
 #include <cuda_runtime.h>
 
@@ -25,13 +25,11 @@ __device__ __forceinline__ int dp4a_u8s8(uint32_t a, uint32_t b, int c) {
 
 template <bool kLogits>
 __global__ void __launch_bounds__(kRowsPerBlock) qlayer_simt_kernel(const QLayerArgs args) {
-  __shared__ __align__(16) uint8_t s_scan[kRowsPerBlock * kFixChunk];
   const int row = int(blockIdx.x) * kRowsPerBlock + int(threadIdx.x);
-  const int col = int(blockIdx.y) * kFixChunk;
+  const int col = int(blockIdx.y) * 16;
   if (row >= args.M) return;
   const int K = args.K, N = args.N;
-  const int cols = min(kFixChunk, N - col);
-  const uint8_t flag = load_flag(args.self, col >> 4, row);
+  const int cols = min(16, N - col);
   int32_t s[16];
 #pragma unroll
   for (int i = 0; i < 16; ++i) s[i] = 0;
@@ -51,26 +49,18 @@ __global__ void __launch_bounds__(kRowsPerBlock) qlayer_simt_kernel(const QLayer
       }
     }
   }
+  brute_force_corrections(s, row, col, args);  // dp4a does not saturate pair sums either
   float bias16[16];
 #pragma unroll
   for (int i = 0; i < 16; ++i) bias16[i] = i < cols ? __ldg(args.bias + col + i) : 0.0f;
-  take_corrections(s, flag, col >> 4, row, args.self);
-  const uint4 bytes = finish_chunk<kLogits>(s, row, col, args, bias16, args.lut);
-  if constexpr (!kLogits) {
-    if (args.next_fix.ptr != nullptr) {
-      uint8_t *scan = s_scan + int(threadIdx.x) * kFixChunk;
-      *reinterpret_cast<uint4 *>(scan) = bytes;
-      const uint32_t e0 = __ldg(args.next_fix.ptr + (col >> 4)), e1 = __ldg(args.next_fix.ptr + (col >> 4) + 1);
-      post_saturation(scan, col >> 4, row, args.next_fix.ent, 0u, e0, e1, args.next);
-    }
-  }
+  finish_chunk<kLogits>(s, row, col, args, bias16, args.lut);
 }
 
 }  // namespace
 
 cudaError_t launch_qlayer_simt(const QLayerArgs &a, bool logits, cudaStream_t stream) {
   if (a.M <= 0) return cudaSuccess;
-  dim3 grid((a.M + kRowsPerBlock - 1) / kRowsPerBlock, (a.N + kFixChunk - 1) / kFixChunk);
+  dim3 grid((a.M + kRowsPerBlock - 1) / kRowsPerBlock, (a.N + 15) / 16);
   if (logits)
     qlayer_simt_kernel<true><<<grid, kRowsPerBlock, 0, stream>>>(a);
   else

@@ -11,15 +11,17 @@
 // 128-row × 128-byte boxes straight into 128B-swizzled shared memory and tcgen05.mma kind::i8
 // (A unsigned, B signed) consumes them through shared-memory descriptors; no transposes.
 //
-// Persistent, warp-specialised: warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 = TMEM
-// allocator, warps 4-19 = epilogue (four warps per TMEM lane quarter, each a quarter of the tile's
-// columns, 16 columns at a time — the tail is ≈15 instructions per element, so it needs the
-// issue slots of many warps).  Two accumulator stages in TMEM let the epilogue of tile i overlap
-// the contraction of tile i+1.
+// Persistent, warp-specialised (24 warps): warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 =
+// TMEM allocator, warps 4-7 = saturation scan, warps 8-23 = epilogue (four warps per TMEM lane
+// quarter, each a quarter of the tile's columns, 16 columns at a time — the tail is ≈20
+// instructions per element, so it needs the issue slots of many warps).  Two accumulator stages
+// in TMEM let the epilogue of tile i overlap the contraction of tile i+1.
 //
-// pmaddubsw's int16 pair saturation is not reproduced by the tensor core; the (rare) differences
-// arrive through the layer's correction channel (device_common.cuh) and are added to the raw
-// sums before dequantisation, which makes the sums bit-identical to the reference's.
+// pmaddubsw's int16 pair saturation is not reproduced by the tensor core.  The scan warps (one
+// thread per tile row) walk the layer's risk entries K block by K block, read the two activation
+// bytes of each entry from the very A tile that TMA staged for the MMA, and record the rare
+// non-zero clamp(v) − v as per-row events in shared memory; the epilogue adds them to the raw sums
+// before dequantisation, which makes the sums bit-identical to the reference's.
 
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -35,11 +37,18 @@ namespace {
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 128;  // bytes of K per pipeline stage = one 128B swizzle atom
 constexpr int kUmmaK = 32;    // K per tcgen05.mma for 8-bit operands
+constexpr int kScanWarps = 4;       // one thread per tile row: evaluates saturation risk entries on the staged A tiles
 constexpr int kEpilogueWarps = 16;  // four per TMEM lane quarter, each owning a quarter of the tile's columns
+constexpr int kScanThreads = kScanWarps * 32;
 constexpr int kEpilogueThreads = kEpilogueWarps * 32;
-constexpr int kThreads = 128 + kEpilogueThreads;
+constexpr int kFirstScanWarp = 4, kFirstEpilogueWarp = 8;
+constexpr int kThreads = (kFirstEpilogueWarp + kEpilogueWarps) * 32;  // 768
 constexpr int kAccStages = 2;
-constexpr int kEntCap = 640;  // risk entries of the next layer staged in shared memory per tile
+constexpr int kEntCap = 1024;   // risk entries of the tile staged in shared memory (the rest is read from global)
+constexpr int kPtrSlots = 132;  // ≥ (BN/64)·k_blocks + 1 → K ≤ 4096 at BN = 256
+constexpr int kRowEvents = 8;   // saturation events kept per tile row; more → that row recomputes from global memory
+
+static_assert(kBlockK == kFixKBlock && kFixGroup == 64, "risk-list order is tied to the tiling");
 
 template <int BN>
 struct TcConfig {
@@ -49,16 +58,15 @@ struct TcConfig {
   static constexpr int kStages = BN == 256 ? 4 : (BN == 128 ? 6 : 8);
   static constexpr int kTmemCols = kAccStages * BN;  // 128, 256 or 512: powers of two
   static constexpr int kColsPerWarp = BN / 4;
-  static constexpr int kChunks = kColsPerWarp / kFixChunk;  // 16-column chunks per epilogue thread
-  static constexpr int kPtrSlots = 20;                       // ≥ BN/16 + 1, per accumulator stage
+  static constexpr int kChunks = kColsPerWarp / 16;  // 16-column chunks per epilogue thread
   static constexpr int kBiasBytes = kAccStages * BN * 4;
   static constexpr int kEntBytes = kAccStages * kEntCap * 8;
   static constexpr int kPtrBytes = kAccStages * kPtrSlots * 4;
-  static constexpr int kScanBytes = kEpilogueThreads * kFixChunk;
-  static constexpr int kBarBytes = (2 * kStages + 2 * kAccStages) * 8 + 16;
-  static constexpr int kSmemBytes =
-      1024 /*alignment slack*/ + kStages * kStageBytes + kBiasBytes + kLut2Padded + kEntBytes + kPtrBytes + kScanBytes + kBarBytes;
-  static_assert(BN / kFixChunk + 1 <= kPtrSlots, "pointer slots");
+  static constexpr int kEvBytes = kAccStages * kBlockM * kRowEvents * 4;
+  static constexpr int kCntBytes = kAccStages * kBlockM * 4;
+  static constexpr int kBarBytes = (2 * kStages + 3 * kAccStages) * 8 + 16;
+  static constexpr int kSmemBytes = 1024 /*alignment slack*/ + kStages * kStageBytes + kBiasBytes + kLut2Padded + kEntBytes + kPtrBytes +
+                                    kEvBytes + kCntBytes + kBarBytes;
   static_assert(kSmemBytes <= 232448, "shared memory budget");
 };
 
@@ -71,14 +79,16 @@ qlayer_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_cons
   uint8_t *tiles = smem;
   float *s_bias = reinterpret_cast<float *>(smem + Cfg::kStages * Cfg::kStageBytes);
   uint8_t *s_lut = reinterpret_cast<uint8_t *>(s_bias) + Cfg::kBiasBytes;
-  FixEntry *s_ent = reinterpret_cast<FixEntry *>(s_lut + kLut2Padded);
+  uint2 *s_ent = reinterpret_cast<uint2 *>(s_lut + kLut2Padded);
   uint32_t *s_ptr = reinterpret_cast<uint32_t *>(reinterpret_cast<uint8_t *>(s_ent) + Cfg::kEntBytes);
-  uint8_t *s_scan = reinterpret_cast<uint8_t *>(s_ptr) + Cfg::kPtrBytes;
-  uint64_t *full_bar = reinterpret_cast<uint64_t *>(s_scan + Cfg::kScanBytes);
+  uint32_t *s_rowev = reinterpret_cast<uint32_t *>(reinterpret_cast<uint8_t *>(s_ptr) + Cfg::kPtrBytes);
+  uint32_t *s_rowcnt = reinterpret_cast<uint32_t *>(reinterpret_cast<uint8_t *>(s_rowev) + Cfg::kEvBytes);
+  uint64_t *full_bar = reinterpret_cast<uint64_t *>(reinterpret_cast<uint8_t *>(s_rowcnt) + Cfg::kCntBytes);
   uint64_t *empty_bar = full_bar + Cfg::kStages;
   uint64_t *tmem_full_bar = empty_bar + Cfg::kStages;
   uint64_t *tmem_empty_bar = tmem_full_bar + kAccStages;
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_empty_bar + kAccStages);
+  uint64_t *scan_done_bar = tmem_empty_bar + kAccStages;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(scan_done_bar + kAccStages);
 
   const int warp = int(threadIdx.x) / 32, lane = int(threadIdx.x) % 32;
   if (threadIdx.x == 0) stamp(args.timeline, 0);
@@ -94,17 +104,18 @@ qlayer_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_cons
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < Cfg::kStages; ++i) {
       ptx::mbar_init(full_bar + i, 1);
-      ptx::mbar_init(empty_bar + i, 1);
+      ptx::mbar_init(empty_bar + i, 1 + kScanWarps);  // MMA commit + one arrival per scan warp
     }
     for (int i = 0; i < kAccStages; ++i) {
       ptx::mbar_init(tmem_full_bar + i, 1);
       ptx::mbar_init(tmem_empty_bar + i, kEpilogueThreads);
+      ptx::mbar_init(scan_done_bar + i, kScanThreads);
     }
     ptx::fence_barrier_init();
   }
   if (warp == 2) ptx::tmem_alloc<Cfg::kTmemCols>(tmem_slot);
-  if (warp >= 4 && !kLogits) {
-    for (int i = int(threadIdx.x) - 128; i < kLut2Padded / 16; i += kEpilogueThreads)
+  if (warp >= kFirstEpilogueWarp && !kLogits) {
+    for (int i = int(threadIdx.x) - kFirstEpilogueWarp * 32; i < kLut2Padded / 16; i += kEpilogueThreads)
       reinterpret_cast<uint4 *>(s_lut)[i] = __ldg(reinterpret_cast<const uint4 *>(args.lut) + i);
   }
   ptx::tc_fence_before_sync();
@@ -171,50 +182,93 @@ qlayer_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_cons
         acc_phase ^= 1;
       }
     }
-  } else if (warp >= 4) {
-    // ===== epilogue: TMEM → registers → reference tail → global =====
-    // 16 warps: warp % 4 selects the TMEM lane quarter (rows), (warp − 4) / 4 the column quarter.
-    const int et = int(threadIdx.x) - 128;
+  } else if (warp >= kFirstScanWarp && warp < kFirstEpilogueWarp) {
+    // ===== saturation scan: thread = tile row, reads its two activation bytes per risk entry =====
+    // straight from the 128B-swizzled A tile TMA staged for the tensor core (row r, byte b of the
+    // 128-byte K block lives at r·128 + ((b/16 ^ r%8)·16 + b%16)).
+    const int st = int(threadIdx.x) - kFirstScanWarp * 32;
+    const uint32_t swz = uint32_t(st & 7) << 4;
+    const int kbn = args.fix.k_blocks;
+    const int groups_total = (N + kFixGroup - 1) / kFixGroup;
+    int stage = 0, acc = 0;
+    uint32_t phase = 0, acc_phase = 0;
+    for (int t = int(blockIdx.x); t < tiles_total; t += int(gridDim.x)) {
+      const int n_blk = t % n_blocks;
+      const int n0 = n_blk * BN;
+      const int sg0 = n0 / kFixGroup;
+      const int nsg = min(BN / kFixGroup, groups_total - sg0);
+      const uint32_t *gp = args.fix.ptr + size_t(sg0) * kbn;
+      uint32_t *P = s_ptr + acc * kPtrSlots;
+      uint2 *E = s_ent + acc * kEntCap;
+      // the event slots of this accumulator stage are free once its previous tile has been drained
+      ptx::mbar_wait(tmem_empty_bar + acc, acc_phase ^ 1);
+      const int nptr = nsg * kbn + 1;
+      for (int i = st; i < nptr; i += kScanThreads) P[i] = __ldg(gp + i);
+      const uint32_t ent_begin = __ldg(gp), ent_end = __ldg(gp + nsg * kbn);
+      const uint32_t staged = min(ent_end - ent_begin, uint32_t(kEntCap));
+      for (uint32_t i = uint32_t(st); i < staged; i += kScanThreads) E[i] = __ldg(reinterpret_cast<const uint2 *>(args.fix.ent) + ent_begin + i);
+      ptx::named_bar_sync(2, kScanThreads);
+      uint32_t *my_ev = s_rowev + (acc * kBlockM + st) * kRowEvents;
+      uint32_t cnt = 0;
+      for (int kb = 0; kb < k_blocks; ++kb) {
+        ptx::mbar_wait(full_bar + stage, phase);
+        const uint32_t a_row = ptx::smem_u32(tiles + stage * Cfg::kStageBytes) + uint32_t(st) * 128u;
+        for (int g = 0; g < nsg; ++g) {
+          const uint32_t e0 = P[g * kbn + kb], e1 = P[g * kbn + kb + 1];
+          for (uint32_t e = e0; e < e1; ++e) {
+            const uint32_t rel = e - ent_begin;
+            const uint2 fe = rel < uint32_t(kEntCap) ? E[rel] : __ldg(reinterpret_cast<const uint2 *>(args.fix.ent) + e);
+            const uint32_t b = (2u * (fe.x & 0xffffu)) & 127u;
+            const uint32_t a01 = ptx::lds_u16(a_row + (((b & 0x70u) ^ swz) | (b & 15u)));
+            const int d = saturation_delta(a01, fe.x);
+            if (d != 0) {
+              if (cnt < uint32_t(kRowEvents)) my_ev[cnt] = ((fe.y - uint32_t(n0)) << 24) | (uint32_t(d) & 0xffffffu);
+              ++cnt;
+            }
+          }
+        }
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(empty_bar + stage);
+        if (++stage == Cfg::kStages) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+      s_rowcnt[acc * kBlockM + st] = cnt;
+      ptx::mbar_arrive(scan_done_bar + acc);
+      if (++acc == kAccStages) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+  } else if (warp >= kFirstEpilogueWarp) {
+    // ===== epilogue: TMEM → registers → + saturation events → reference tail → global =====
+    // 16 warps: warp % 4 selects the TMEM lane quarter (rows), (warp − 8) / 4 the column quarter.
+    const int et = int(threadIdx.x) - kFirstEpilogueWarp * 32;
     const int quarter = warp & 3;
-    const int col_group = (warp - 4) >> 2;
-    uint8_t *my_scan = s_scan + et * kFixChunk;
-    const int next_chunks = kLogits ? 0 : (N + kFixChunk - 1) / kFixChunk;  // input chunks of the next layer = our output chunks
+    const int col_group = (warp - kFirstEpilogueWarp) >> 2;
+    const int row_local = quarter * 32 + lane;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int t = int(blockIdx.x); t < tiles_total; t += int(gridDim.x)) {
       const int m_blk = t / n_blocks, n_blk = t % n_blocks;
       const int n0 = n_blk * BN;
-      const int row = m_blk * kBlockM + quarter * 32 + lane;
+      const int row = m_blk * kBlockM + row_local;
       const bool row_ok = row < M;
       const int col0 = n0 + col_group * Cfg::kColsPerWarp;  // first column of this thread
-      const int n_valid = max(0, min(Cfg::kChunks, (N - col0 + kFixChunk - 1) / kFixChunk));  // warp-uniform
+      const int n_valid = max(0, min(Cfg::kChunks, (N - col0 + 15) / 16));  // warp-uniform
 
-      // -- stage what the tail needs while the tensor core works on this tile ---------------------
       float *bias_s = s_bias + acc * BN;
       for (int i = et; i < BN; i += kEpilogueThreads) bias_s[i] = (n0 + i < N) ? __ldg(args.bias + n0 + i) : 0.0f;
-      uint32_t ent_begin = 0;
-      const FixEntry *ent_s = s_ent + acc * kEntCap;
-      uint32_t *ptr_s = s_ptr + acc * Cfg::kPtrSlots;
-      if constexpr (!kLogits) {
-        if (args.next_fix.ptr != nullptr) {
-          const int c0 = n0 / kFixChunk;
-          ent_begin = __ldg(args.next_fix.ptr + min(c0, next_chunks));
-          const uint32_t ent_end = __ldg(args.next_fix.ptr + min(c0 + BN / kFixChunk, next_chunks));
-          if (et <= BN / kFixChunk) ptr_s[et] = __ldg(args.next_fix.ptr + min(c0 + et, next_chunks));
-          const uint32_t staged = min(ent_end - ent_begin, uint32_t(kEntCap));
-          for (uint32_t i = uint32_t(et); i < staged; i += kEpilogueThreads)
-            reinterpret_cast<uint2 *>(s_ent + acc * kEntCap)[i] = __ldg(reinterpret_cast<const uint2 *>(args.next_fix.ent) + ent_begin + i);
-        }
-      }
-      uint8_t flag[Cfg::kChunks];
-#pragma unroll
-      for (int j = 0; j < Cfg::kChunks; ++j) flag[j] = (row_ok && j < n_valid) ? load_flag(args.self, (col0 >> 4) + j, row) : uint8_t(0);
       ptx::named_bar_sync(1, kEpilogueThreads);
       if (et == 0) stamp(args.timeline, 4);
 
-      ptx::mbar_wait(tmem_full_bar + acc, acc_phase);
+      ptx::mbar_wait_relaxed(tmem_full_bar + acc, acc_phase);
+      ptx::mbar_wait(scan_done_bar + acc, acc_phase);
       ptx::tc_fence_after_sync();
       if (et == 0) stamp(args.timeline, 5);
+      const uint32_t n_ev = s_rowcnt[acc * kBlockM + row_local];
+      const uint32_t *ev = s_rowev + (acc * kBlockM + row_local) * kRowEvents;
       const uint32_t t_addr = tmem_base + uint32_t(acc * BN + col_group * Cfg::kColsPerWarp) + (uint32_t(quarter * 32) << 16);
       if (n_valid == 0) {
         ptx::tc_fence_before_sync();
@@ -224,31 +278,31 @@ qlayer_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_cons
       for (int j = 0; j < Cfg::kChunks; ++j) {
         if (j < n_valid) {
           uint32_t raw[16];
-          ptx::tmem_ld_32x16(t_addr + uint32_t(j * kFixChunk), raw);
+          ptx::tmem_ld_32x16(t_addr + uint32_t(j * 16), raw);
           ptx::tmem_ld_wait();
+          int32_t s[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) s[i] = int32_t(raw[i]);
+          const int col = col0 + j * 16;
+          if (n_ev != 0 && row_ok) {
+            if (n_ev <= uint32_t(kRowEvents)) {
+              for (uint32_t k = 0; k < n_ev; ++k) {
+                const uint32_t e = ev[k];
+                const uint32_t rel = (e >> 24) - uint32_t(col - n0);
+                const int d = int(e << 8) >> 8;
+#pragma unroll
+                for (int i = 0; i < 16; ++i) s[i] += (rel == uint32_t(i)) ? d : 0;
+              }
+            } else {
+              brute_force_corrections(s, row, col, args);  // more events than slots in this row: recompute them
+            }
+          }
           if (j == n_valid - 1) {
-            // this thread is done with the accumulator stage: hand it back before doing the math
+            // accumulator stage and its event slots fully read: hand both back before doing the math
             ptx::tc_fence_before_sync();
             ptx::mbar_arrive(tmem_empty_bar + acc);
           }
-          if (row_ok) {
-            int32_t s[16];
-#pragma unroll
-            for (int i = 0; i < 16; ++i) s[i] = int32_t(raw[i]);
-            const int col = col0 + j * kFixChunk;
-            take_corrections(s, flag[j], col >> 4, row, args.self);
-            const uint4 bytes = finish_chunk<kLogits>(s, row, col, args, bias_s + (col - n0), s_lut);
-            if constexpr (!kLogits) {
-              if (args.next_fix.ptr != nullptr) {
-                *reinterpret_cast<uint4 *>(my_scan) = bytes;
-                const int lc = (col - n0) >> 4;
-                const uint32_t p0 = ptr_s[lc], p1 = ptr_s[lc + 1];
-                const uint32_t split = min(p1, ent_begin + uint32_t(kEntCap));
-                post_saturation(my_scan, col >> 4, row, ent_s, ent_begin, p0, min(p1, split), args.next);
-                if (p1 > split) post_saturation(my_scan, col >> 4, row, args.next_fix.ent, 0u, max(p0, split), p1, args.next);
-              }
-            }
-          }
+          if (row_ok) finish_chunk<kLogits>(s, row, col, args, bias_s + (col - n0), s_lut);
         }
       }
       if (et == 0) stamp(args.timeline, 6);
@@ -296,6 +350,7 @@ cudaError_t qlayer_tc_configure() {
 
 bool qlayer_tc_supported(int N, int K, bool logits) {
   if (K < kBlockK || K % kBlockK != 0) return false;
+  if (4 * (K / kBlockK) + 1 > kPtrSlots || K / 2 > 65536) return false;
   if (!logits && N % 16 != 0) return false;
   return true;
 }

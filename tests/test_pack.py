@@ -44,11 +44,13 @@ def test_blob_matches_oracle(shape, stress, net_file):
         want = set(zip(pairs.tolist(), nodes.tolist()))
         assert set(zip(pair.tolist(), node.tolist())) == want
         assert np.array_equal(w0, w[node, 2 * pair]) and np.array_equal(w1, w[node, 2 * pair + 1])
-        assert np.all(np.diff(pair.astype(np.int64)) >= 0)
-        for c in range(int(q["n_chunks"])):
-            seg = pair[ptr[c]:ptr[c + 1]]
-            assert np.all((seg >= 8 * c) & (seg < 8 * (c + 1)))  # 16 inputs = 8 pairs per chunk
-        assert ptr[0] == 0 and ptr[-1] == len(pair)
+        # ordered by (node // 64, K block of the pair, node, pair); ptr delimits (supergroup, K block) buckets
+        ng, kb = int(q["n_groups"]), int(q["k_blocks"])
+        assert ng == -(-w.shape[0] // 64) and kb == -(-w.shape[1] // 128)
+        key = (node.astype(np.int64) // 64) * kb + (2 * pair.astype(np.int64)) // 128
+        assert np.all(np.diff(key) >= 0)
+        assert ptr[0] == 0 and ptr[-1] == len(pair) and len(ptr) == ng * kb + 1
+        assert np.array_equal(np.searchsorted(key, np.arange(ng * kb + 1)), ptr)
 
 
 def test_stress_network_hits_quantizer_quirks(net_file):
