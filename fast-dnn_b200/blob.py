@@ -6,8 +6,8 @@ from __future__ import annotations
 import numpy as np
 
 MAGIC = 0x424E4446
-VERSION = 5
-FIX_GROUP = 64
+VERSION = 6
+FIX_GROUPS = (64, 128, 256)
 FIX_KBLOCK = 128
 
 HEADER = np.dtype([
@@ -19,10 +19,10 @@ HEADER = np.dtype([
 ])
 QLAYER = np.dtype([
     ("nodes", "<i4"), ("inputs", "<i4"), ("multiplier", "<f4"), ("coeff", "<f4"), ("rcp_coeff", "<f4"),
-    ("n_fix", "<u4"), ("fast_div", "<u4"), ("n_groups", "<u4"), ("k_blocks", "<u4"), ("pad_", "<u4"),
-    ("off_w", "<u8"), ("off_bias", "<u8"), ("off_fix_ptr", "<u8"), ("off_fix_ent", "<u8"),
+    ("n_fix", "<u4"), ("fast_div", "<u4"), ("k_blocks", "<u4"),
+    ("off_w", "<u8"), ("off_bias", "<u8"), ("off_fix_ptr", "<u8", (3,)), ("off_fix_ent", "<u8", (3,)),
 ])
-assert HEADER.itemsize == 88 and QLAYER.itemsize == 72
+assert HEADER.itemsize == 88 and QLAYER.itemsize == 96
 
 
 class Blob:
@@ -65,13 +65,15 @@ class Blob:
         w = self.data[int(q["off_w"]):int(q["off_w"]) + n * k].view(np.int8).reshape(n, k)
         return w, self._f32(q["off_bias"], n), float(q["multiplier"])
 
-    def fix_list(self, i):
-        """→ (ptr uint32 [n_groups*k_blocks+1], pair uint32 [n_fix], w0 int8, w1 int8, node uint32);
-        entries are ordered by (node // 64, pair // 64, node, pair)."""
+    def fix_list(self, i, variant=0):
+        """→ (ptr uint32 [groups*k_blocks+1], pair uint32 [n_fix], w0 int8, w1 int8, node uint32) of the
+        risk list grouped by FIX_GROUPS[variant] nodes; ordered by (node // G, pair // 64, node, pair)."""
         q = self.qlayers[i]
-        nc, nf = int(q["n_groups"]) * int(q["k_blocks"]), int(q["n_fix"])
-        ptr = self.data[int(q["off_fix_ptr"]):int(q["off_fix_ptr"]) + 4 * (nc + 1)].view("<u4")
-        ent = self.data[int(q["off_fix_ent"]):int(q["off_fix_ent"]) + 8 * nf].view("<u4").reshape(nf, 2)
+        G = FIX_GROUPS[variant]
+        nc, nf = -(-int(q["nodes"]) // G) * int(q["k_blocks"]), int(q["n_fix"])
+        o_ptr, o_ent = int(q["off_fix_ptr"][variant]), int(q["off_fix_ent"][variant])
+        ptr = self.data[o_ptr:o_ptr + 4 * (nc + 1)].view("<u4")
+        ent = self.data[o_ent:o_ent + 8 * nf].view("<u4").reshape(nf, 2)
         pair = ent[:, 0] & 0xFFFF
         w0 = ((ent[:, 0] >> 16) & 0xFF).astype(np.uint8).view(np.int8)
         w1 = ((ent[:, 0] >> 24) & 0xFF).astype(np.uint8).view(np.int8)

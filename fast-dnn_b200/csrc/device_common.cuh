@@ -8,11 +8,13 @@
 
 namespace fdnn {
 
-// Risk list of one int8 layer (BlobQLayer::off_fix_*; order described in fdnn_internal.h).
+// Risk list of one int8 layer, in the variant grouped by `group` nodes (BlobQLayer::off_fix_*;
+// order described in fdnn_internal.h).
 struct FixList {
-  const uint32_t *ptr;  // [n_groups · k_blocks + 1]
+  const uint32_t *ptr;  // [ceil(N/group) · k_blocks + 1]
   const FixEntry *ent;
   int k_blocks;
+  int group;  // 64, 128 or 256
 };
 
 struct QLayerArgs {
@@ -70,7 +72,7 @@ __device__ __forceinline__ int saturation_delta(uint32_t a01, uint32_t pair_w) {
 // path of the tensor-core kernel.
 __device__ __forceinline__ void brute_force_corrections(int32_t (&s)[16], int row, int col, const QLayerArgs &args) {
   const int kb_n = args.fix.k_blocks;
-  const int sg = col / kFixGroup;
+  const int sg = col / args.fix.group;
   const uint32_t e0 = __ldg(args.fix.ptr + size_t(sg) * kb_n), e1 = __ldg(args.fix.ptr + size_t(sg + 1) * kb_n);
   const uint8_t *a_row = args.act + size_t(row) * size_t(args.K);
   for (uint32_t e = e0; e < e1; ++e) {

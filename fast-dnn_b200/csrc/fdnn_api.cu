@@ -225,11 +225,12 @@ int enqueue_until_logits(fdnn_ctx *c, const float *d_in, int m, float *d_logits,
   fdnn_model *mod = c->model;
   const BlobHeader &h = mod->hdr;
   const int nq = h.n_qlayers;
-  auto fix_of = [&](int layer) {
+  auto fix_of = [&](int layer, int variant) {
     FixList f;
-    f.ptr = mod->at<uint32_t>(mod->q[size_t(layer)].off_fix_ptr);
-    f.ent = mod->at<FixEntry>(mod->q[size_t(layer)].off_fix_ent);
+    f.ptr = mod->at<uint32_t>(mod->q[size_t(layer)].off_fix_ptr[variant]);
+    f.ent = mod->at<FixEntry>(mod->q[size_t(layer)].off_fix_ent[variant]);
     f.k_blocks = int(mod->q[size_t(layer)].k_blocks);
+    f.group = kFixGroups[variant];
     return f;
   };
 
@@ -264,7 +265,7 @@ int enqueue_until_logits(fdnn_ctx *c, const float *d_in, int m, float *d_logits,
     a.M = m;
     a.N = ql.nodes;
     a.K = ql.inputs;
-    a.fix = fix_of(j);
+    a.fix = fix_of(j, 0);
     a.timeline = c->d_timeline ? c->d_timeline + size_t(j) * 1024 * 8 : nullptr;
     if (logits) {
       a.out_f32 = d_logits;
@@ -275,6 +276,7 @@ int enqueue_until_logits(fdnn_ctx *c, const float *d_in, int m, float *d_logits,
     if (mod->tc_ok[size_t(j)] && c->amap_ok) {
       const int bn = qlayer_tc_block_n(m, ql.nodes, mod->num_sms);
       const int which = bn == 64 ? 0 : (bn == 128 ? 1 : 2);
+      a.fix = fix_of(j, which);
       CUDA_TRY(launch_qlayer_tc(c->amap[j & 1], mod->wmaps[size_t(j)][size_t(which)], a, logits, bn, mod->num_sms, stream));
     } else {
       CUDA_TRY(launch_qlayer_simt(a, logits, stream));

@@ -20,7 +20,7 @@ constexpr int kLut2Size = 2 * kLut2Center + 1;  // 2565
 constexpr int kLut2Padded = 2576;               // multiple of 16 bytes
 
 constexpr uint32_t kBlobMagic = 0x424E4446u;  // "FDNB"
-constexpr uint32_t kBlobVersion = 5;
+constexpr uint32_t kBlobVersion = 6;
 constexpr size_t kBlobAlign = 256;
 
 // pmaddubsw (dnn.cc:337-340) clamps every adjacent-pair sum a[2p]·w[2p] + a[2p+1]·w[2p+1] to int16.
@@ -29,11 +29,13 @@ constexpr size_t kBlobAlign = 256;
 // The layer kernel evaluates them against the activation tiles it is streaming anyway and adds
 // clamp(v) − v to the raw tensor-core sums, which makes the sums bit-identical to the reference's.
 //
-// Order: by node supergroup (kFixGroup = 64 consecutive nodes, the smallest N tile), then by the
-// 128-byte K block the pair lives in (the pipeline stage that carries its two activation bytes),
-// then by node and pair.  ptr[sg · k_blocks + kb] .. ptr[sg · k_blocks + kb + 1] delimits the
-// entries of supergroup sg whose pair is in K block kb; ptr has n_groups · k_blocks + 1 elements.
-constexpr int kFixGroup = 64;
+// The list is stored three times, once per N-tile width G the tensor-core kernel can use
+// (kFixGroups = 64, 128, 256), each ordered by (node / G, 128-byte K block of the pair, node, pair):
+// a tile's entries are then one contiguous run, already in the order the K pipeline delivers the
+// activation bytes.  ptr[g · k_blocks + kb] .. ptr[g · k_blocks + kb + 1] delimits the entries of
+// node group g whose pair is in K block kb; ptr has n_groups · k_blocks + 1 elements.
+constexpr int kFixVariants = 3;
+constexpr int kFixGroups[kFixVariants] = {64, 128, 256};
 constexpr int kFixKBlock = 128;  // bytes of K per block (= 64 pairs)
 struct FixEntry {
   uint32_t pair_w;  // pair index p (bits 0-15) | (uint8)w[2p] << 16 | (uint8)w[2p+1] << 24
@@ -49,13 +51,11 @@ struct BlobQLayer {
   float rcp_coeff;    // RN(1 / coeff)
   uint32_t n_fix;     // saturation risk entries
   uint32_t fast_div;  // 1: q=s·rcp; r=fma(−q,coeff,s); q+=r·rcp verified == s/coeff for every reachable s
-  uint32_t n_groups;  // ceil(N / kFixGroup)
   uint32_t k_blocks;  // ceil(K / kFixKBlock)
-  uint32_t pad_;
   uint64_t off_w;     // int8  [N][K] row-major (K-major)
   uint64_t off_bias;  // fp32  [N]
-  uint64_t off_fix_ptr;  // uint32 [n_groups·k_blocks + 1]
-  uint64_t off_fix_ent;  // FixEntry [n_fix], sorted by (supergroup, K block, node, pair)
+  uint64_t off_fix_ptr[kFixVariants];  // uint32 [ceil(N/G)·k_blocks + 1] for G = 64, 128, 256
+  uint64_t off_fix_ent[kFixVariants];  // FixEntry [n_fix], sorted by (node/G, K block, node, pair)
 };
 
 struct BlobHeader {

@@ -12,6 +12,7 @@
 #include "fdnn_internal.h"
 
 #include <algorithm>
+#include <array>
 #include <climits>
 #include <cmath>
 #include <cstdio>
@@ -232,8 +233,10 @@ int pack_model(const char *path, float cutoff, std::vector<uint8_t> &blob) {
   const int nq = layer_count - 1;
   std::vector<BlobQLayer> qmeta(size_t(nq), BlobQLayer{});
   std::vector<std::vector<int8_t>> qw(size_t(nq), std::vector<int8_t>{});
-  std::vector<std::vector<FixEntry>> fix(size_t(nq), std::vector<FixEntry>{});
-  std::vector<std::vector<uint32_t>> fix_ptr(size_t(nq), std::vector<uint32_t>{});
+  using FixVariants = std::array<std::vector<FixEntry>, kFixVariants>;
+  using PtrVariants = std::array<std::vector<uint32_t>, kFixVariants>;
+  std::vector<FixVariants> fix(size_t(nq), FixVariants{});
+  std::vector<PtrVariants> fix_ptr(size_t(nq), PtrVariants{});
 
   for (int q = 0; q < nq; ++q) {
     const FloatLayer &l = layers[size_t(q + 1)];
@@ -254,39 +257,35 @@ int pack_model(const char *path, float cutoff, std::vector<uint8_t> &blob) {
     }
     m.fast_div = (std::isfinite(m.coeff) && m.coeff != 0.0f && verify_fast_div(m.coeff, m.rcp_coeff, l.in)) ? 1u : 0u;
 
-    // saturation risk list, ordered by (node supergroup, K block, node, pair)
+    // saturation risk lists, one per tile width G, ordered by (node / G, K block, node, pair)
     const int K = l.in, pairs = K / 2;
-    m.n_groups = uint32_t((l.out + kFixGroup - 1) / kFixGroup);
     m.k_blocks = uint32_t((K + kFixKBlock - 1) / kFixKBlock);
-    const size_t buckets = size_t(m.n_groups) * size_t(m.k_blocks);
     auto risky = [](int a, int b) {
       int pos = (a > 0 ? a : 0) + (b > 0 ? b : 0), neg = (a < 0 ? a : 0) + (b < 0 ? b : 0);
       return pos >= 129 || neg <= -129;
     };
-    std::vector<uint32_t> &ptr = fix_ptr[size_t(q)];
-    ptr.assign(buckets + 1, 0u);
+    std::vector<FixEntry> all;  // node-major
     for (int n = 0; n < l.out; ++n) {
-      const int8_t *row = w8.data() + size_t(n) * size_t(K);
-      for (int p = 0; p < pairs; ++p)
-        if (risky(row[2 * p], row[2 * p + 1])) ++ptr[size_t(n / kFixGroup) * m.k_blocks + size_t(2 * p / kFixKBlock) + 1];
-    }
-    for (size_t i = 0; i < buckets; ++i) ptr[i + 1] += ptr[i];
-    std::vector<FixEntry> &ent = fix[size_t(q)];
-    ent.resize(ptr[buckets]);
-    std::vector<uint32_t> cursor(ptr.begin(), ptr.end() - 1);
-    for (int n = 0; n < l.out; ++n) {  // node-major fill keeps (node, pair) order inside every bucket
       const int8_t *row = w8.data() + size_t(n) * size_t(K);
       for (int p = 0; p < pairs; ++p) {
         const int a = row[2 * p], b = row[2 * p + 1];
-        if (risky(a, b)) {
-          FixEntry e;
-          e.pair_w = uint32_t(p) | (uint32_t(uint8_t(a)) << 16) | (uint32_t(uint8_t(b)) << 24);
-          e.node = uint32_t(n);
-          ent[cursor[size_t(n / kFixGroup) * m.k_blocks + size_t(2 * p / kFixKBlock)]++] = e;
-        }
+        if (risky(a, b)) all.push_back(FixEntry{uint32_t(p) | (uint32_t(uint8_t(a)) << 16) | (uint32_t(uint8_t(b)) << 24), uint32_t(n)});
       }
     }
-    m.n_fix = uint32_t(ent.size());
+    m.n_fix = uint32_t(all.size());
+    for (int v = 0; v < kFixVariants; ++v) {
+      const int G = kFixGroups[v];
+      const size_t buckets = size_t((l.out + G - 1) / G) * size_t(m.k_blocks);
+      auto bucket_of = [&](const FixEntry &e) { return size_t(e.node / uint32_t(G)) * m.k_blocks + size_t(2 * (e.pair_w & 0xffffu) / kFixKBlock); };
+      std::vector<uint32_t> &ptr = fix_ptr[size_t(q)][size_t(v)];
+      ptr.assign(buckets + 1, 0u);
+      for (const FixEntry &e : all) ++ptr[bucket_of(e) + 1];
+      for (size_t i = 0; i < buckets; ++i) ptr[i + 1] += ptr[i];
+      std::vector<uint32_t> cursor(ptr.begin(), ptr.end() - 1);
+      std::vector<FixEntry> &ent = fix[size_t(q)][size_t(v)];
+      ent.resize(all.size());
+      for (const FixEntry &e : all) ent[cursor[bucket_of(e)]++] = e;  // stable: keeps (node, pair) order inside a bucket
+    }
   }
 
   // ---- lay the blob out ----------------------------------------------------------------------
@@ -314,8 +313,10 @@ int pack_model(const char *path, float cutoff, std::vector<uint8_t> &blob) {
   for (int q = 0; q < nq; ++q) {
     BlobQLayer &m = qmeta[size_t(q)];
     m.off_bias = reserve(sizeof(float) * size_t(m.nodes));
-    m.off_fix_ptr = reserve(sizeof(uint32_t) * fix_ptr[size_t(q)].size());
-    m.off_fix_ent = reserve(sizeof(FixEntry) * std::max<size_t>(fix[size_t(q)].size(), 1));
+    for (int v = 0; v < kFixVariants; ++v) {
+      m.off_fix_ptr[v] = reserve(sizeof(uint32_t) * fix_ptr[size_t(q)][size_t(v)].size());
+      m.off_fix_ent[v] = reserve(sizeof(FixEntry) * std::max<size_t>(fix[size_t(q)][size_t(v)].size(), 1));
+    }
     m.off_w = reserve(qw[size_t(q)].size());
   }
   hdr.total_size = off;
@@ -341,9 +342,12 @@ int pack_model(const char *path, float cutoff, std::vector<uint8_t> &blob) {
   for (int q = 0; q < nq; ++q) {
     const BlobQLayer &m = qmeta[size_t(q)];
     std::memcpy(base + m.off_bias, layers[size_t(q + 1)].bias.data(), sizeof(float) * size_t(m.nodes));
-    std::memcpy(base + m.off_fix_ptr, fix_ptr[size_t(q)].data(), sizeof(uint32_t) * fix_ptr[size_t(q)].size());
-    if (!fix[size_t(q)].empty())
-      std::memcpy(base + m.off_fix_ent, fix[size_t(q)].data(), sizeof(FixEntry) * fix[size_t(q)].size());
+    for (int v = 0; v < kFixVariants; ++v) {
+      const auto &ptr = fix_ptr[size_t(q)][size_t(v)];
+      const auto &ent = fix[size_t(q)][size_t(v)];
+      std::memcpy(base + m.off_fix_ptr[v], ptr.data(), sizeof(uint32_t) * ptr.size());
+      if (!ent.empty()) std::memcpy(base + m.off_fix_ent[v], ent.data(), sizeof(FixEntry) * ent.size());
+    }
     std::memcpy(base + m.off_w, qw[size_t(q)].data(), qw[size_t(q)].size());
   }
   return FDNN_OK;
@@ -382,34 +386,35 @@ int validate_blob(const uint8_t *blob, size_t size) {
     const BlobQLayer &m = q[size_t(i)];
     bool last = i == h.n_qlayers - 1;
     if (m.inputs != expect_in || m.nodes <= 0 || (!last && m.nodes != h.hidden) || (last && m.nodes != h.out_dim) ||
-        m.n_groups != uint32_t((m.nodes + kFixGroup - 1) / kFixGroup) || m.k_blocks != uint32_t((m.inputs + kFixKBlock - 1) / kFixKBlock)) {
+        m.k_blocks != uint32_t((m.inputs + kFixKBlock - 1) / kFixKBlock)) {
       set_error("blob int8 layer " + std::to_string(i) + " has inconsistent dimensions");
       return FDNN_EFORMAT;
     }
-    if (!inside(m.off_w, uint64_t(m.nodes) * uint64_t(m.inputs)) || !inside(m.off_bias, 4ull * uint64_t(m.nodes)) ||
-        !inside(m.off_fix_ptr, 4ull * (uint64_t(m.n_groups) * uint64_t(m.k_blocks) + 1)) || !inside(m.off_fix_ent, sizeof(FixEntry) * uint64_t(m.n_fix))) {
+    if (!inside(m.off_w, uint64_t(m.nodes) * uint64_t(m.inputs)) || !inside(m.off_bias, 4ull * uint64_t(m.nodes))) {
       set_error("blob int8 layer " + std::to_string(i) + " section out of bounds");
       return FDNN_EFORMAT;
     }
-    const uint32_t *ptr = reinterpret_cast<const uint32_t *>(blob + m.off_fix_ptr);
-    const uint64_t buckets = uint64_t(m.n_groups) * uint64_t(m.k_blocks);
-    if (ptr[0] != 0 || ptr[buckets] != m.n_fix) {
-      set_error("blob int8 layer " + std::to_string(i) + " has a corrupt risk index");
-      return FDNN_EFORMAT;
-    }
-    const FixEntry *ent = reinterpret_cast<const FixEntry *>(blob + m.off_fix_ent);
-    for (uint64_t bkt = 0; bkt < buckets; ++bkt) {
-      if (ptr[bkt] > ptr[bkt + 1]) {
-        set_error("blob int8 layer " + std::to_string(i) + " has a corrupt risk index");
+    for (int v = 0; v < kFixVariants; ++v) {
+      const uint32_t G = uint32_t(kFixGroups[v]);
+      const uint64_t buckets = uint64_t((uint32_t(m.nodes) + G - 1) / G) * uint64_t(m.k_blocks);
+      if (!inside(m.off_fix_ptr[v], 4ull * (buckets + 1)) || !inside(m.off_fix_ent[v], sizeof(FixEntry) * uint64_t(m.n_fix))) {
+        set_error("blob int8 layer " + std::to_string(i) + " risk list out of bounds");
         return FDNN_EFORMAT;
       }
-      const uint32_t sg = uint32_t(bkt / m.k_blocks), kb = uint32_t(bkt % m.k_blocks);
-      for (uint32_t e = ptr[bkt]; e < ptr[bkt + 1]; ++e) {
-        const uint32_t p = ent[e].pair_w & 0xffffu;
-        if (ent[e].node >= uint32_t(m.nodes) || ent[e].node / kFixGroup != sg || int(p) >= m.inputs / 2 || 2 * p / kFixKBlock != kb) {
-          set_error("blob int8 layer " + std::to_string(i) + " has a corrupt risk entry");
-          return FDNN_EFORMAT;
+      const uint32_t *ptr = reinterpret_cast<const uint32_t *>(blob + m.off_fix_ptr[v]);
+      const FixEntry *ent = reinterpret_cast<const FixEntry *>(blob + m.off_fix_ent[v]);
+      bool ok = ptr[0] == 0 && ptr[buckets] == m.n_fix;
+      for (uint64_t bkt = 0; ok && bkt < buckets; ++bkt) {
+        ok = ptr[bkt] <= ptr[bkt + 1] && ptr[bkt + 1] <= m.n_fix;
+        const uint32_t g = uint32_t(bkt / m.k_blocks), kb = uint32_t(bkt % m.k_blocks);
+        for (uint32_t e = ptr[bkt]; ok && e < ptr[bkt + 1]; ++e) {
+          const uint32_t p = ent[e].pair_w & 0xffffu;
+          ok = ent[e].node < uint32_t(m.nodes) && ent[e].node / G == g && int(p) < m.inputs / 2 && 2 * p / kFixKBlock == kb;
         }
+      }
+      if (!ok) {
+        set_error("blob int8 layer " + std::to_string(i) + " has a corrupt risk list");
+        return FDNN_EFORMAT;
       }
     }
     expect_in = m.nodes;

@@ -44,11 +44,17 @@ constexpr int kEpilogueThreads = kEpilogueWarps * 32;
 constexpr int kFirstScanWarp = 4, kFirstEpilogueWarp = 8;
 constexpr int kThreads = (kFirstEpilogueWarp + kEpilogueWarps) * 32;  // 768
 constexpr int kAccStages = 2;
-constexpr int kEntCap = 1024;   // risk entries of the tile staged in shared memory (the rest is read from global)
-constexpr int kPtrSlots = 132;  // ≥ (BN/64)·k_blocks + 1 → K ≤ 4096 at BN = 256
+constexpr int kEntCap = 2048;   // risk entries of the tile staged (packed) in shared memory; the rest is read from global
+constexpr int kPtrSlots = 132;  // ≥ k_blocks + 1 → K ≤ 16768
 constexpr int kRowEvents = 8;   // saturation events kept per tile row; more → that row recomputes from global memory
 
-static_assert(kBlockK == kFixKBlock && kFixGroup == 64, "risk-list order is tied to the tiling");
+static_assert(kBlockK == kFixKBlock && kFixGroups[0] == 64 && kFixGroups[1] == 128 && kFixGroups[2] == 256, "risk-list order is tied to the tiling");
+
+__device__ __forceinline__ int dp4a_u8s8(uint32_t a, uint32_t b, int c) {
+  int d;
+  asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+}
 
 template <int BN>
 struct TcConfig {
@@ -60,12 +66,12 @@ struct TcConfig {
   static constexpr int kColsPerWarp = BN / 4;
   static constexpr int kChunks = kColsPerWarp / 16;  // 16-column chunks per epilogue thread
   static constexpr int kBiasBytes = kAccStages * BN * 4;
-  static constexpr int kEntBytes = kAccStages * kEntCap * 8;
+  static constexpr int kEntBytes = kAccStages * kEntCap * 4;
   static constexpr int kPtrBytes = kAccStages * kPtrSlots * 4;
   static constexpr int kEvBytes = kAccStages * kBlockM * kRowEvents * 4;
   static constexpr int kCntBytes = kAccStages * kBlockM * 4;
   static constexpr int kBarBytes = (2 * kStages + 3 * kAccStages) * 8 + 16;
-  static constexpr int kSmemBytes = 1024 /*alignment slack*/ + kStages * kStageBytes + kBiasBytes + kLut2Padded + kEntBytes + kPtrBytes +
+  static constexpr int kSmemBytes = kStages * kStageBytes + kBiasBytes + kLut2Padded + kEntBytes + kPtrBytes +
                                     kEvBytes + kCntBytes + kBarBytes;
   static_assert(kSmemBytes <= 232448, "shared memory budget");
 };
@@ -74,12 +80,15 @@ template <int BN, bool kLogits>
 __global__ void __launch_bounds__(kThreads, 1)
 qlayer_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_constant__ CUtensorMap tmap_w, const QLayerArgs args) {
   using Cfg = TcConfig<BN>;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 128B-swizzled tiles need 1024-byte alignment.  Dynamic shared memory starts at the base of the
+  // CTA's window (this kernel has no static shared memory); keeping the pointers derived from the
+  // array itself (no integer round-trip) lets the compiler emit LDS/STS instead of generic accesses.
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((ptx::smem_u32(smem) & 1023u) != 0u) __trap();
   uint8_t *tiles = smem;
   float *s_bias = reinterpret_cast<float *>(smem + Cfg::kStages * Cfg::kStageBytes);
   uint8_t *s_lut = reinterpret_cast<uint8_t *>(s_bias) + Cfg::kBiasBytes;
-  uint2 *s_ent = reinterpret_cast<uint2 *>(s_lut + kLut2Padded);
+  uint32_t *s_ent = reinterpret_cast<uint32_t *>(s_lut + kLut2Padded);
   uint32_t *s_ptr = reinterpret_cast<uint32_t *>(reinterpret_cast<uint8_t *>(s_ent) + Cfg::kEntBytes);
   uint32_t *s_rowev = reinterpret_cast<uint32_t *>(reinterpret_cast<uint8_t *>(s_ptr) + Cfg::kPtrBytes);
   uint32_t *s_rowcnt = reinterpret_cast<uint32_t *>(reinterpret_cast<uint8_t *>(s_rowev) + Cfg::kEvBytes);
@@ -188,47 +197,77 @@ qlayer_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_cons
     // 128-byte K block lives at r·128 + ((b/16 ^ r%8)·16 + b%16)).
     const int st = int(threadIdx.x) - kFirstScanWarp * 32;
     const uint32_t swz = uint32_t(st & 7) << 4;
-    const int kbn = args.fix.k_blocks;
-    const int groups_total = (N + kFixGroup - 1) / kFixGroup;
+    const int kbn = args.fix.k_blocks;  // == k_blocks; the list variant is the one grouped by BN nodes
     int stage = 0, acc = 0;
     uint32_t phase = 0, acc_phase = 0;
     for (int t = int(blockIdx.x); t < tiles_total; t += int(gridDim.x)) {
       const int n_blk = t % n_blocks;
-      const int n0 = n_blk * BN;
-      const int sg0 = n0 / kFixGroup;
-      const int nsg = min(BN / kFixGroup, groups_total - sg0);
-      const uint32_t *gp = args.fix.ptr + size_t(sg0) * kbn;
-      uint32_t *P = s_ptr + acc * kPtrSlots;
-      uint2 *E = s_ent + acc * kEntCap;
+      const uint32_t *gp = args.fix.ptr + size_t(n_blk) * kbn;
+      uint32_t *P = s_ptr + acc * kPtrSlots;  // K-block offsets of this tile's entries, relative to its first one
+      uint32_t *E = s_ent + acc * kEntCap;
       // the event slots of this accumulator stage are free once its previous tile has been drained
       ptx::mbar_wait(tmem_empty_bar + acc, acc_phase ^ 1);
-      const int nptr = nsg * kbn + 1;
-      for (int i = st; i < nptr; i += kScanThreads) P[i] = __ldg(gp + i);
-      const uint32_t ent_begin = __ldg(gp), ent_end = __ldg(gp + nsg * kbn);
-      const uint32_t staged = min(ent_end - ent_begin, uint32_t(kEntCap));
-      for (uint32_t i = uint32_t(st); i < staged; i += kScanThreads) E[i] = __ldg(reinterpret_cast<const uint2 *>(args.fix.ent) + ent_begin + i);
+      const uint32_t ent_begin = __ldg(gp);
+      for (int i = st; i <= kbn; i += kScanThreads) P[i] = __ldg(gp + i) - ent_begin;
+      const uint32_t n_ent = __ldg(gp + kbn) - ent_begin;
+      const uint32_t staged = min(n_ent, uint32_t(kEntCap));
+      // staged form, one word per entry: w0 | w1 << 8 | (node − n0) << 16 | (byte offset of the pair
+      // inside its 128-byte K block) << 24 — dp4a of that word with the zero-extended activation
+      // pair is exactly a0·w0 + a1·w1
+      const uint2 *gent = reinterpret_cast<const uint2 *>(args.fix.ent) + ent_begin;
+      for (uint32_t e = uint32_t(st); e < staged; e += kScanThreads) {
+        const uint2 fe = __ldg(gent + e);
+        E[e] = (fe.x >> 16) | ((fe.y - uint32_t(n_blk * BN)) << 16) | (((2u * (fe.x & 0xffffu)) & 127u) << 24);
+      }
       ptx::named_bar_sync(2, kScanThreads);
       uint32_t *my_ev = s_rowev + (acc * kBlockM + st) * kRowEvents;
       uint32_t cnt = 0;
+      auto record = [&](int v, uint32_t node_local) {
+        const int d = max(min(v, 32767), -32768) - v;
+        if (cnt < uint32_t(kRowEvents)) my_ev[cnt] = (node_local << 24) | (uint32_t(d) & 0xffffffu);
+        ++cnt;
+      };
+      // Entry words are fetched one K block ahead: they do not depend on the data TMA is bringing,
+      // so after the barrier only activation load → dp4a → range check remains on the critical path.
+      uint32_t w[8];
+      auto fetch = [&](uint32_t r0, uint32_t r_end) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) w[i] = E[min(r0 + uint32_t(i), max(r_end, 1u) - 1u)];
+      };
+      uint32_t r0 = P[0], r1 = P[1];
+      fetch(r0, min(r1, staged));
       for (int kb = 0; kb < k_blocks; ++kb) {
         ptx::mbar_wait(full_bar + stage, phase);
         const uint32_t a_row = ptx::smem_u32(tiles + stage * Cfg::kStageBytes) + uint32_t(st) * 128u;
-        for (int g = 0; g < nsg; ++g) {
-          const uint32_t e0 = P[g * kbn + kb], e1 = P[g * kbn + kb + 1];
-          for (uint32_t e = e0; e < e1; ++e) {
-            const uint32_t rel = e - ent_begin;
-            const uint2 fe = rel < uint32_t(kEntCap) ? E[rel] : __ldg(reinterpret_cast<const uint2 *>(args.fix.ent) + e);
-            const uint32_t b = (2u * (fe.x & 0xffffu)) & 127u;
-            const uint32_t a01 = ptx::lds_u16(a_row + (((b & 0x70u) ^ swz) | (b & 15u)));
-            const int d = saturation_delta(a01, fe.x);
-            if (d != 0) {
-              if (cnt < uint32_t(kRowEvents)) my_ev[cnt] = ((fe.y - uint32_t(n0)) << 24) | (uint32_t(d) & 0xffffffu);
-              ++cnt;
-            }
+        const uint32_t fast_end = min(r1, staged);
+        for (uint32_t e = r0; e < fast_end; e += 8) {
+          if (e != r0) fetch(e, fast_end);
+          uint32_t a01[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const uint32_t b = w[i] >> 24;
+            a01[i] = ptx::lds_u16(a_row + (((b & 0x70u) ^ swz) | (b & 15u)));
           }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int v = dp4a_u8s8(a01[i], w[i], 0);
+            if (uint32_t(v + 32768) > 65535u && e + uint32_t(i) < fast_end) record(v, (w[i] >> 16) & 0xffu);
+          }
+        }
+        for (uint32_t e = max(r0, staged); e < r1; ++e) {  // beyond the staging capacity (dense risk lists)
+          const uint2 fe = __ldg(gent + e);
+          const uint32_t b = (2u * (fe.x & 0xffffu)) & 127u;
+          const uint32_t a01s = ptx::lds_u16(a_row + (((b & 0x70u) ^ swz) | (b & 15u)));
+          const int v = dp4a_u8s8(a01s, fe.x >> 16, 0);
+          if (uint32_t(v + 32768) > 65535u) record(v, fe.y - uint32_t(n_blk * BN));
         }
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(empty_bar + stage);
+        if (kb + 1 < k_blocks) {
+          r0 = r1;
+          r1 = P[kb + 2];
+          fetch(r0, min(r1, staged));
+        }
         if (++stage == Cfg::kStages) {
           stage = 0;
           phase ^= 1;
@@ -350,7 +389,7 @@ cudaError_t qlayer_tc_configure() {
 
 bool qlayer_tc_supported(int N, int K, bool logits) {
   if (K < kBlockK || K % kBlockK != 0) return false;
-  if (4 * (K / kBlockK) + 1 > kPtrSlots || K / 2 > 65536) return false;
+  if (K / kBlockK + 1 > kPtrSlots || K / 2 > 65536) return false;
   if (!logits && N % 16 != 0) return false;
   return true;
 }

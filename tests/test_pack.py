@@ -39,18 +39,20 @@ def test_blob_matches_oracle(shape, stress, net_file):
         pos = np.maximum(wi[:, 0::2], 0) + np.maximum(wi[:, 1::2], 0)
         neg = np.minimum(wi[:, 0::2], 0) + np.minimum(wi[:, 1::2], 0)
         nodes, pairs = np.nonzero((pos >= 129) | (neg <= -129))
-        ptr, pair, w0, w1, node = b.fix_list(i)
-        assert len(pair) == len(nodes) == int(q["n_fix"])
         want = set(zip(pairs.tolist(), nodes.tolist()))
-        assert set(zip(pair.tolist(), node.tolist())) == want
-        assert np.array_equal(w0, w[node, 2 * pair]) and np.array_equal(w1, w[node, 2 * pair + 1])
-        # ordered by (node // 64, K block of the pair, node, pair); ptr delimits (supergroup, K block) buckets
-        ng, kb = int(q["n_groups"]), int(q["k_blocks"])
-        assert ng == -(-w.shape[0] // 64) and kb == -(-w.shape[1] // 128)
-        key = (node.astype(np.int64) // 64) * kb + (2 * pair.astype(np.int64)) // 128
-        assert np.all(np.diff(key) >= 0)
-        assert ptr[0] == 0 and ptr[-1] == len(pair) and len(ptr) == ng * kb + 1
-        assert np.array_equal(np.searchsorted(key, np.arange(ng * kb + 1)), ptr)
+        assert int(q["n_fix"]) == len(want)
+        kb = int(q["k_blocks"])
+        assert kb == -(-w.shape[1] // 128)
+        for variant, G in enumerate(B.FIX_GROUPS):
+            # one copy per tile width G, ordered by (node // G, K block of the pair, node, pair)
+            ptr, pair, w0, w1, node = b.fix_list(i, variant)
+            assert len(pair) == len(want) and set(zip(pair.tolist(), node.tolist())) == want
+            assert np.array_equal(w0, w[node, 2 * pair]) and np.array_equal(w1, w[node, 2 * pair + 1])
+            ng = -(-w.shape[0] // G)
+            key = (node.astype(np.int64) // G) * kb + (2 * pair.astype(np.int64)) // 128
+            assert np.all(np.diff(key) >= 0)
+            assert ptr[0] == 0 and ptr[-1] == len(pair) and len(ptr) == ng * kb + 1
+            assert np.array_equal(np.searchsorted(key, np.arange(ng * kb + 1)), ptr)
 
 
 def test_stress_network_hits_quantizer_quirks(net_file):
