@@ -43,6 +43,12 @@ std::atomic<long long> g_launches{0};
 
 int round_up(int v, int m) { return (v + m - 1) / m * m; }
 
+bool env_flag(const char *name, bool dflt) {
+  const char *e = std::getenv(name);
+  if (!e || !e[0]) return dflt;
+  return e[0] != '0';
+}
+
 using EncodeTiledFn = CUresult (*)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
                                    const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -117,6 +123,13 @@ int usable_device(int device, int *out) {
 
 }  // namespace
 
+namespace fdnn {
+bool pdl_enabled() {
+  static const bool on = env_flag("FDNN_PDL", true);
+  return on;
+}
+}  // namespace fdnn
+
 // ---- handles ----------------------------------------------------------------------------------------
 
 struct fdnn_model {
@@ -156,6 +169,16 @@ struct fdnn_ctx {
   unsigned long long *d_timeline = nullptr;  // optional [n_qlayers][1024 CTAs][8] phase stamps (profiling aid)
   int last_frames = 0;
   bool have_logits = false;
+  // One forward pass is 9 small kernels: replayed as a CUDA graph (captured on first use per
+  // distinct (input, output, frames, softmax) combination) to keep launch overhead off the GPU.
+  struct PassGraph {
+    const float *d_in;
+    float *d_out;
+    int m;
+    bool softmax;
+    cudaGraphExec_t exec;
+  };
+  std::vector<PassGraph> graphs;
 };
 
 namespace {
@@ -172,6 +195,7 @@ void destroy_ctx(fdnn_ctx *c) {
   cudaFree(c->d_lazy);
   cudaFree(c->d_trace);
   cudaFree(c->d_timeline);
+  for (auto &g : c->graphs) cudaGraphExecDestroy(g.exec);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -304,6 +328,55 @@ int enqueue_softmax(fdnn_ctx *c, const float *d_logits, const int8_t *d_masks, i
   s.out_ld = O;
   CUDA_TRY(launch_softmax(s, stream));
   g_launches.fetch_add(1, std::memory_order_relaxed);
+  return FDNN_OK;
+}
+
+// One whole pass (input layer … output layer [→ softmax in place]) on `stream`, replayed from a
+// cached CUDA graph when possible.
+int run_pass(fdnn_ctx *c, const float *d_in, int m, float *d_out, bool softmax, cudaStream_t stream) {
+  static const bool use_graphs = env_flag("FDNN_GRAPHS", true);
+  const int kernels = c->model->hdr.n_qlayers + 1 + (softmax ? 1 : 0);
+  if (!use_graphs || c->trace || c->d_timeline != nullptr || m <= 0) {
+    if (int rc = enqueue_until_logits(c, d_in, m, d_out, stream)) return rc;
+    return softmax ? enqueue_softmax(c, d_out, nullptr, m, d_out, stream) : FDNN_OK;
+  }
+  for (auto &g : c->graphs)
+    if (g.d_in == d_in && g.d_out == d_out && g.m == m && g.softmax == softmax) {
+      CUDA_TRY(cudaGraphLaunch(g.exec, stream));
+      g_launches.fetch_add(kernels, std::memory_order_relaxed);
+      c->last_frames = m;
+      return FDNN_OK;
+    }
+  // capture on the context's own stream (thread-local mode: other threads keep using CUDA freely)
+  const long long before = g_launches.load(std::memory_order_relaxed);
+  CUDA_TRY(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+  int rc = enqueue_until_logits(c, d_in, m, d_out, c->stream);
+  if (rc == FDNN_OK && softmax) rc = enqueue_softmax(c, d_out, nullptr, m, d_out, c->stream);
+  cudaGraph_t graph = nullptr;
+  cudaError_t e = cudaStreamEndCapture(c->stream, &graph);
+  g_launches.store(before, std::memory_order_relaxed);  // capturing is not launching
+  if (rc != FDNN_OK) {
+    if (graph) cudaGraphDestroy(graph);
+    return rc;
+  }
+  if (e != cudaSuccess) {
+    set_error(std::string("graph capture: ") + cudaGetErrorString(e));
+    return FDNN_ECUDA;
+  }
+  cudaGraphExec_t exec = nullptr;
+  e = cudaGraphInstantiate(&exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (e != cudaSuccess) {
+    set_error(std::string("graph instantiate: ") + cudaGetErrorString(e));
+    return FDNN_ECUDA;
+  }
+  if (c->graphs.size() >= 64) {
+    cudaGraphExecDestroy(c->graphs.front().exec);
+    c->graphs.erase(c->graphs.begin());
+  }
+  c->graphs.push_back({d_in, d_out, m, softmax, exec});
+  CUDA_TRY(cudaGraphLaunch(exec, stream));
+  g_launches.fetch_add(kernels, std::memory_order_relaxed);
   return FDNN_OK;
 }
 
@@ -540,7 +613,7 @@ int fdnn_ctx_until_output_device(fdnn_ctx *ctx, const float *d_in, int n_frames,
     return FDNN_EINVAL;
   }
   DeviceGuard g(ctx->model->device);
-  if (int rc = enqueue_until_logits(ctx, d_in, n_frames, ctx->d_logits, static_cast<cudaStream_t>(stream))) return rc;
+  if (int rc = run_pass(ctx, d_in, n_frames, ctx->d_logits, false, static_cast<cudaStream_t>(stream))) return rc;
   ctx->have_logits = true;
   return FDNN_OK;
 }
@@ -551,10 +624,8 @@ int fdnn_ctx_forward_device(fdnn_ctx *ctx, const float *d_in, int n_frames, floa
     return FDNN_EINVAL;
   }
   DeviceGuard g(ctx->model->device);
-  cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (int rc = enqueue_until_logits(ctx, d_in, n_frames, d_out, s)) return rc;
-  ctx->have_logits = false;  // logits were produced straight into the caller's buffer
-  return enqueue_softmax(ctx, d_out, nullptr, n_frames, d_out, s);
+  ctx->have_logits = false;  // logits are produced straight into the caller's buffer and normalised in place
+  return run_pass(ctx, d_in, n_frames, d_out, true, static_cast<cudaStream_t>(stream));
 }
 
 int fdnn_ctx_lazy_batch_device(fdnn_ctx *ctx, const int8_t *d_masks, int n_frames, float *d_out, void *stream) {
@@ -578,7 +649,7 @@ int fdnn_ctx_until_output(fdnn_ctx *ctx, const float *in) {
   DeviceGuard g(ctx->model->device);
   const size_t bytes = size_t(ctx->cap) * size_t(ctx->model->hdr.in_dim) * 4;
   CUDA_TRY(cudaMemcpyAsync(ctx->d_in, in, bytes, cudaMemcpyHostToDevice, ctx->stream));
-  if (int rc = enqueue_until_logits(ctx, ctx->d_in, ctx->cap, ctx->d_logits, ctx->stream)) return rc;
+  if (int rc = run_pass(ctx, ctx->d_in, ctx->cap, ctx->d_logits, false, ctx->stream)) return rc;
   CUDA_TRY(cudaStreamSynchronize(ctx->stream));
   ctx->have_logits = true;
   return FDNN_OK;
@@ -771,8 +842,7 @@ int fdnn_calculate(fdnn_model *model, const float *in, int n, int dim, int batch
     const int f0 = c * cap, m = std::min(cap, n - f0);
     cudaError_t e = cudaMemcpyAsync(x->d_in, in + size_t(f0) * size_t(I), size_t(m) * size_t(I) * 4, cudaMemcpyHostToDevice, x->stream);
     if (e == cudaSuccess) {
-      rc = enqueue_until_logits(x, x->d_in, m, x->d_logits, x->stream);
-      if (rc == FDNN_OK) rc = enqueue_softmax(x, x->d_logits, nullptr, m, x->d_logits, x->stream);
+      rc = run_pass(x, x->d_in, m, x->d_logits, true, x->stream);
       x->have_logits = false;
       if (rc == FDNN_OK)
         e = cudaMemcpyAsync(out + size_t(f0) * size_t(O), x->d_logits, size_t(m) * size_t(O) * 4, cudaMemcpyDeviceToHost, x->stream);

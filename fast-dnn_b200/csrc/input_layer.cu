@@ -22,6 +22,7 @@
 
 #include "device_common.cuh"
 #include "kernels.h"
+#include "ptx.cuh"
 
 namespace fdnn {
 
@@ -57,6 +58,8 @@ __global__ void __launch_bounds__(kThreads, 1) input_layer_kernel(const InputLay
   const int n_chunks = (I + kChunk - 1) / kChunk;
 
   for (int i = tid; i < kLut2Padded / 16; i += kThreads) reinterpret_cast<uint4 *>(s_lut)[i] = __ldg(reinterpret_cast<const uint4 *>(args.lut) + i);
+  ptx::griddep_wait();  // the activation buffer we write may still be read by the previous pass
+  ptx::griddep_launch_dependents();
 
   // Frame elements this thread moves per chunk: kTileF rows × (kChunk/4) float4 = 640 vectors.
   constexpr int kXVecs = kTileF * (kChunk / 4);
@@ -184,8 +187,7 @@ cudaError_t input_layer_configure() {
 cudaError_t launch_input_layer(const InputLayerArgs &a, cudaStream_t stream) {
   if (a.M <= 0) return cudaSuccess;
   dim3 grid((a.H + kTileN - 1) / kTileN, (a.M + kTileF - 1) / kTileF);
-  input_layer_kernel<<<grid, kThreads, kSmemBytes, stream>>>(a);
-  return cudaGetLastError();
+  return launch_pdl(input_layer_kernel, grid, dim3(kThreads), size_t(kSmemBytes), stream, pdl_enabled(), a);
 }
 
 }  // namespace fdnn

@@ -5,9 +5,30 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 
+#include <utility>
+
 #include "device_common.cuh"
 
 namespace fdnn {
+
+// Launch helper shared by the launchers: programmatic dependent launch (PDL) lets the next kernel's
+// launch and prologue overlap the tail of the previous one; every kernel executes
+// griddepcontrol.wait before it touches memory another kernel of the pass may own.
+template <class... KArgs, class... Args>
+cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, bool pdl, Args &&...args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+bool pdl_enabled();  // FDNN_PDL=0 turns it off
 
 // ---- fp32 input layer (input_layer.cu) ---------------------------------------------------------
 struct InputLayerArgs {

@@ -151,6 +151,12 @@ __host__ __device__ constexpr uint32_t idesc_i8_u8s8(uint32_t n) {
   return (2u << 4) | (0u << 7) | (1u << 10) | ((n >> 3) << 17) | ((128u >> 4) << 24);
 }
 
+// Programmatic dependent launch: the next kernel in the stream may be launched while this one is
+// still running (its prologue overlaps our tail); wait() blocks until every prerequisite grid has
+// completed and its memory is visible.  No-ops when the kernel was launched without the attribute.
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t threads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }

@@ -10,6 +10,7 @@
 
 #include "device_common.cuh"
 #include "kernels.h"
+#include "ptx.cuh"
 
 namespace fdnn {
 
@@ -25,6 +26,8 @@ __device__ __forceinline__ int dp4a_u8s8(uint32_t a, uint32_t b, int c) {
 
 template <bool kLogits>
 __global__ void __launch_bounds__(kRowsPerBlock) qlayer_simt_kernel(const QLayerArgs args) {
+  ptx::griddep_wait();
+  ptx::griddep_launch_dependents();
   const int row = int(blockIdx.x) * kRowsPerBlock + int(threadIdx.x);
   const int col = int(blockIdx.y) * 16;
   if (row >= args.M) return;
@@ -61,11 +64,8 @@ __global__ void __launch_bounds__(kRowsPerBlock) qlayer_simt_kernel(const QLayer
 cudaError_t launch_qlayer_simt(const QLayerArgs &a, bool logits, cudaStream_t stream) {
   if (a.M <= 0) return cudaSuccess;
   dim3 grid((a.M + kRowsPerBlock - 1) / kRowsPerBlock, (a.N + 15) / 16);
-  if (logits)
-    qlayer_simt_kernel<true><<<grid, kRowsPerBlock, 0, stream>>>(a);
-  else
-    qlayer_simt_kernel<false><<<grid, kRowsPerBlock, 0, stream>>>(a);
-  return cudaGetLastError();
+  if (logits) return launch_pdl(qlayer_simt_kernel<true>, grid, dim3(kRowsPerBlock), size_t(0), stream, pdl_enabled(), a);
+  return launch_pdl(qlayer_simt_kernel<false>, grid, dim3(kRowsPerBlock), size_t(0), stream, pdl_enabled(), a);
 }
 
 }  // namespace fdnn

@@ -11,14 +11,14 @@
 // 128-row × 128-byte boxes straight into 128B-swizzled shared memory and tcgen05.mma kind::i8
 // (A unsigned, B signed) consumes them through shared-memory descriptors; no transposes.
 //
-// Persistent, warp-specialised (24 warps): warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 =
-// TMEM allocator, warps 4-7 = saturation scan, warps 8-23 = epilogue (four warps per TMEM lane
+// Persistent, warp-specialised (28 warps): warp 0 = TMA producer, warp 1 = MMA issuer, warp 2 =
+// TMEM allocator, warps 4-11 = saturation scan, warps 12-27 = epilogue (four warps per TMEM lane
 // quarter, each a quarter of the tile's columns, 16 columns at a time — the tail is ≈20
 // instructions per element, so it needs the issue slots of many warps).  Two accumulator stages
 // in TMEM let the epilogue of tile i overlap the contraction of tile i+1.
 //
-// pmaddubsw's int16 pair saturation is not reproduced by the tensor core.  The scan warps (one
-// thread per tile row) walk the layer's risk entries K block by K block, read the two activation
+// pmaddubsw's int16 pair saturation is not reproduced by the tensor core.  The scan warps (two
+// sets of one thread per tile row, alternating K blocks) walk the layer's risk entries K block by K block, read the two activation
 // bytes of each entry from the very A tile that TMA staged for the MMA, and record the rare
 // non-zero clamp(v) − v as per-row events in shared memory; the epilogue adds them to the raw sums
 // before dequantisation, which makes the sums bit-identical to the reference's.
@@ -37,12 +37,13 @@ namespace {
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 128;  // bytes of K per pipeline stage = one 128B swizzle atom
 constexpr int kUmmaK = 32;    // K per tcgen05.mma for 8-bit operands
-constexpr int kScanWarps = 4;       // one thread per tile row: evaluates saturation risk entries on the staged A tiles
+constexpr int kScanSets = 2;        // scan warps come in sets of 4 (one thread per tile row); set s takes K blocks ≡ s (mod 2)
+constexpr int kScanWarps = 4 * kScanSets;
 constexpr int kEpilogueWarps = 16;  // four per TMEM lane quarter, each owning a quarter of the tile's columns
 constexpr int kScanThreads = kScanWarps * 32;
 constexpr int kEpilogueThreads = kEpilogueWarps * 32;
-constexpr int kFirstScanWarp = 4, kFirstEpilogueWarp = 8;
-constexpr int kThreads = (kFirstEpilogueWarp + kEpilogueWarps) * 32;  // 768
+constexpr int kFirstScanWarp = 4, kFirstEpilogueWarp = kFirstScanWarp + kScanWarps;
+constexpr int kThreads = (kFirstEpilogueWarp + kEpilogueWarps) * 32;  // 896
 constexpr int kAccStages = 2;
 constexpr int kEntCap = 2048;   // risk entries of the tile staged (packed) in shared memory; the rest is read from global
 constexpr int kPtrSlots = 132;  // ≥ k_blocks + 1 → K ≤ 16768
@@ -113,7 +114,7 @@ qlayer_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_cons
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < Cfg::kStages; ++i) {
       ptx::mbar_init(full_bar + i, 1);
-      ptx::mbar_init(empty_bar + i, 1 + kScanWarps);  // MMA commit + one arrival per scan warp
+      ptx::mbar_init(empty_bar + i, 1 + 4);  // MMA commit + one arrival per warp of the scan set that owns the stage
     }
     for (int i = 0; i < kAccStages; ++i) {
       ptx::mbar_init(tmem_full_bar + i, 1);
@@ -131,6 +132,10 @@ qlayer_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_cons
   __syncthreads();
   ptx::tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
+  // everything above touched only constants and this CTA's own shared/tensor memory; from here on
+  // we read the previous kernel's activations and write buffers it may still be reading
+  ptx::griddep_wait();
+  ptx::griddep_launch_dependents();
   if (threadIdx.x == 0) stamp(args.timeline, 1);
 
   if (warp == 0) {
@@ -195,11 +200,15 @@ qlayer_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_cons
     // ===== saturation scan: thread = tile row, reads its two activation bytes per risk entry =====
     // straight from the 128B-swizzled A tile TMA staged for the tensor core (row r, byte b of the
     // 128-byte K block lives at r·128 + ((b/16 ^ r%8)·16 + b%16)).
-    const int st = int(threadIdx.x) - kFirstScanWarp * 32;
-    const uint32_t swz = uint32_t(st & 7) << 4;
+    const int st = int(threadIdx.x) - kFirstScanWarp * 32;  // 0 .. kScanThreads − 1
+    const int srow = st & (kBlockM - 1);                     // tile row of this thread
+    const int sset = st / kBlockM;                           // which K blocks it takes
+    static_assert(Cfg::kStages % kScanSets == 0, "a pipeline stage must always belong to the same scan set");
+    const uint32_t swz = uint32_t(srow & 7) << 4;
     const int kbn = args.fix.k_blocks;  // == k_blocks; the list variant is the one grouped by BN nodes
-    int stage = 0, acc = 0;
-    uint32_t phase = 0, acc_phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    uint32_t it = 0;  // running K-block count across tiles: stage = it % kStages, phase = (it / kStages) & 1
     for (int t = int(blockIdx.x); t < tiles_total; t += int(gridDim.x)) {
       const int n_blk = t % n_blocks;
       const uint32_t *gp = args.fix.ptr + size_t(n_blk) * kbn;
@@ -219,26 +228,34 @@ qlayer_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_cons
         const uint2 fe = __ldg(gent + e);
         E[e] = (fe.x >> 16) | ((fe.y - uint32_t(n_blk * BN)) << 16) | (((2u * (fe.x & 0xffffu)) & 127u) << 24);
       }
+      uint32_t *row_cnt = s_rowcnt + acc * kBlockM + srow;
+      uint32_t *row_ev = s_rowev + (acc * kBlockM + srow) * kRowEvents;
+      if (sset == 0) *row_cnt = 0;
       ptx::named_bar_sync(2, kScanThreads);
-      uint32_t *my_ev = s_rowev + (acc * kBlockM + st) * kRowEvents;
-      uint32_t cnt = 0;
-      auto record = [&](int v, uint32_t node_local) {
+      auto record = [&](int v, uint32_t node_local) {  // rare: the row's scan threads share one event list
         const int d = max(min(v, 32767), -32768) - v;
-        if (cnt < uint32_t(kRowEvents)) my_ev[cnt] = (node_local << 24) | (uint32_t(d) & 0xffffffu);
-        ++cnt;
+        const uint32_t slot = atomicAdd(row_cnt, 1u);
+        if (slot < uint32_t(kRowEvents)) row_ev[slot] = (node_local << 24) | (uint32_t(d) & 0xffffffu);
       };
-      // Entry words are fetched one K block ahead: they do not depend on the data TMA is bringing,
-      // so after the barrier only activation load → dp4a → range check remains on the critical path.
+      // Entry words are fetched one turn ahead: they do not depend on the data TMA is bringing, so
+      // after the barrier only activation load → dp4a → range check remains on the critical path.
       uint32_t w[8];
       auto fetch = [&](uint32_t r0, uint32_t r_end) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) w[i] = E[min(r0 + uint32_t(i), max(r_end, 1u) - 1u)];
       };
-      uint32_t r0 = P[0], r1 = P[1];
-      fetch(r0, min(r1, staged));
-      for (int kb = 0; kb < k_blocks; ++kb) {
-        ptx::mbar_wait(full_bar + stage, phase);
-        const uint32_t a_row = ptx::smem_u32(tiles + stage * Cfg::kStageBytes) + uint32_t(st) * 128u;
+      int kb = int((uint32_t(sset) + kScanSets - it % kScanSets) % kScanSets);  // first K block of this tile owned by this set
+      uint32_t r0 = 0, r1 = 0;
+      if (kb < k_blocks) {
+        r0 = P[kb];
+        r1 = P[kb + 1];
+        fetch(r0, min(r1, staged));
+      }
+      for (; kb < k_blocks; kb += kScanSets) {
+        const uint32_t g = it + uint32_t(kb);
+        const int stage = int(g % uint32_t(Cfg::kStages));
+        ptx::mbar_wait(full_bar + stage, (g / uint32_t(Cfg::kStages)) & 1u);
+        const uint32_t a_row = ptx::smem_u32(tiles + stage * Cfg::kStageBytes) + uint32_t(srow) * 128u;
         const uint32_t fast_end = min(r1, staged);
         for (uint32_t e = r0; e < fast_end; e += 8) {
           if (e != r0) fetch(e, fast_end);
@@ -263,18 +280,15 @@ qlayer_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_cons
         }
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(empty_bar + stage);
-        if (kb + 1 < k_blocks) {
-          r0 = r1;
-          r1 = P[kb + 2];
+        if (kb + kScanSets < k_blocks) {
+          r0 = P[kb + kScanSets];
+          r1 = P[kb + kScanSets + 1];
           fetch(r0, min(r1, staged));
         }
-        if (++stage == Cfg::kStages) {
-          stage = 0;
-          phase ^= 1;
-        }
       }
-      s_rowcnt[acc * kBlockM + st] = cnt;
+      it += uint32_t(k_blocks);
       ptx::mbar_arrive(scan_done_bar + acc);
+      if (st == 0) stamp(args.timeline, 4);
       if (++acc == kAccStages) {
         acc = 0;
         acc_phase ^= 1;
@@ -282,7 +296,7 @@ qlayer_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_cons
     }
   } else if (warp >= kFirstEpilogueWarp) {
     // ===== epilogue: TMEM → registers → + saturation events → reference tail → global =====
-    // 16 warps: warp % 4 selects the TMEM lane quarter (rows), (warp − 8) / 4 the column quarter.
+    // 16 warps: warp % 4 selects the TMEM lane quarter (rows), (warp − 12) / 4 the column quarter.
     const int et = int(threadIdx.x) - kFirstEpilogueWarp * 32;
     const int quarter = warp & 3;
     const int col_group = (warp - kFirstEpilogueWarp) >> 2;
@@ -300,12 +314,12 @@ qlayer_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_cons
       float *bias_s = s_bias + acc * BN;
       for (int i = et; i < BN; i += kEpilogueThreads) bias_s[i] = (n0 + i < N) ? __ldg(args.bias + n0 + i) : 0.0f;
       ptx::named_bar_sync(1, kEpilogueThreads);
-      if (et == 0) stamp(args.timeline, 4);
 
       ptx::mbar_wait_relaxed(tmem_full_bar + acc, acc_phase);
+      if (et == 0) stamp(args.timeline, 5);
       ptx::mbar_wait(scan_done_bar + acc, acc_phase);
       ptx::tc_fence_after_sync();
-      if (et == 0) stamp(args.timeline, 5);
+      if (et == 0) stamp(args.timeline, 7);
       const uint32_t n_ev = s_rowcnt[acc * kBlockM + row_local];
       const uint32_t *ev = s_rowev + (acc * kBlockM + row_local) * kRowEvents;
       const uint32_t t_addr = tmem_base + uint32_t(acc * BN + col_group * Cfg::kColsPerWarp) + (uint32_t(quarter * 32) << 16);
@@ -354,7 +368,6 @@ qlayer_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_cons
 
   ptx::tc_fence_before_sync();
   __syncthreads();
-  if (threadIdx.x == 0) stamp(args.timeline, 7);
   if (warp == 2) {
     ptx::tc_fence_after_sync();
     ptx::tmem_dealloc<Cfg::kTmemCols>(tmem_base);
@@ -366,8 +379,7 @@ cudaError_t launch_one(const CUtensorMap &ta, const CUtensorMap &tw, const QLaye
   using Cfg = TcConfig<BN>;
   const int tiles = ((a.M + kBlockM - 1) / kBlockM) * ((a.N + BN - 1) / BN);
   const int grid = tiles < num_sms ? tiles : num_sms;
-  qlayer_tc_kernel<BN, kLogits><<<grid, kThreads, Cfg::kSmemBytes, stream>>>(ta, tw, a);
-  return cudaGetLastError();
+  return launch_pdl(qlayer_tc_kernel<BN, kLogits>, dim3(grid), dim3(kThreads), size_t(Cfg::kSmemBytes), stream, pdl_enabled(), ta, tw, a);
 }
 
 template <int BN>

@@ -10,6 +10,7 @@
 #include <cuda_runtime.h>
 
 #include "kernels.h"
+#include "ptx.cuh"
 
 namespace fdnn {
 
@@ -34,6 +35,8 @@ template <bool kCache>
 __global__ void __launch_bounds__(kThreads) softmax_kernel(const SoftmaxArgs a) {
   extern __shared__ __align__(16) float s_e[];
   __shared__ float s_red[kThreads / 32];
+  ptx::griddep_wait();
+  ptx::griddep_launch_dependents();
   const int row = int(blockIdx.x);
   const int tid = int(threadIdx.x), O = a.O;
   const float *x = a.logits + size_t(row) * size_t(a.ld);
@@ -110,11 +113,8 @@ cudaError_t launch_softmax(const SoftmaxArgs &a, cudaStream_t stream) {
   // the uncached variant re-reads its input in the second pass, so it cannot run in place
   const bool cache = a.O <= kMaxSmemFloats;
   if (!cache && a.logits == a.out) return cudaErrorInvalidValue;
-  if (cache)
-    softmax_kernel<true><<<a.rows, kThreads, size_t(a.O) * 4, stream>>>(a);
-  else
-    softmax_kernel<false><<<a.rows, kThreads, 0, stream>>>(a);
-  return cudaGetLastError();
+  if (cache) return launch_pdl(softmax_kernel<true>, dim3(a.rows), dim3(kThreads), size_t(a.O) * 4, stream, pdl_enabled(), a);
+  return launch_pdl(softmax_kernel<false>, dim3(a.rows), dim3(kThreads), size_t(0), stream, pdl_enabled(), a);
 }
 
 }  // namespace fdnn

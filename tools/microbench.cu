@@ -64,6 +64,11 @@ __global__ void __launch_bounds__(256) l2_read_kernel(const uint4 *buf, size_t n
   if (acc == 0x12345678u) out[0] = acc;
 }
 
+__global__ void __launch_bounds__(768, 1) empty_kernel(int *out) {
+  extern __shared__ uint8_t dyn[];
+  if (out != nullptr && threadIdx.x == 0 && blockIdx.x == 0) out[0] = int(dyn[0]);
+}
+
 template <class F> float time_ms(F f, int reps) {
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
   f();
@@ -86,7 +91,18 @@ int main() {
            ctas_per_sm, ms_s, lane_ops / ms_s / 1e6, lane_ops / (ms_s * 1e-3) / sms / 1.965e9, ms_p, lane_ops / ms_p / 1e6,
            lane_ops / (ms_p * 1e-3) / sms / 1.965e9);
   }
-  for (size_t mb : {32, 64, 96, 512}) {
+  {
+    cudaFuncSetAttribute(empty_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    for (int smem_kb : {0, 64, 220}) {
+      for (int threads : {128, 768}) {
+        float ms = time_ms([&] { for (int i = 0; i < 50; ++i) empty_kernel<<<128, threads, smem_kb * 1024>>>(nullptr); }, 3);
+        printf("launch probe: empty kernel, 128 CTAs x %d threads, %d KB dynamic smem: %.2f us per back-to-back launch\n", threads, smem_kb, ms * 1000 / 50);
+      }
+    }
+    float ms = time_ms([&] { for (int i = 0; i < 25; ++i) { empty_kernel<<<128, 768, 220 * 1024>>>(nullptr); empty_kernel<<<128, 512, 64 * 1024>>>(nullptr); } }, 3);
+    printf("launch probe: alternating 220 KB / 64 KB kernels: %.2f us per launch\n", ms * 1000 / 50);
+  }
+  for (size_t mb : {32, 512}) {
     size_t bytes = mb << 20; uint4 *buf; cudaMalloc(&buf, bytes); cudaMemset(buf, 1, bytes);
     uint32_t *o; cudaMalloc(&o, 4);
     float ms = time_ms([&] { l2_read_kernel<<<sms * 8, 256>>>(buf, bytes / 16, o, 4); }, 5);

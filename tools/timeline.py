@@ -28,7 +28,7 @@ ctx.timeline(True)
 ctx.forward_device(d_in.data_ptr(), args.batch, d_out.data_ptr(), s)
 torch.cuda.synchronize()
 tl = ctx.timeline(False).astype(np.int64)
-names = ["setup", "first operands", "mma issue done", "(epi staging done)", "acc ready", "tile done", "exit"]
+names = ["setup", "first operands", "mma issue done", "scan done", "epilogue sees acc", "tile done", "epilogue sees scan"]
 for layer in range(tl.shape[0]):
     t = tl[layer]
     used = t[:, 0] > 0
