@@ -142,6 +142,9 @@ struct fdnn_model {
   std::vector<std::array<CUtensorMap, 3>> wmaps;  // per int8 layer, box rows 64 / 128 / 256
   std::vector<bool> tc_ok;
   bool force_simt = false;
+  // Graph capture must not overlap device-wide synchronising calls (cudaFree, blocking copies) made
+  // by this library from other threads: both sides take this lock.
+  std::mutex cuda_mu;
   // contexts cached for fdnn_calculate
   std::mutex pool_mu;
   std::vector<fdnn_ctx *> pool;
@@ -185,6 +188,7 @@ namespace {
 
 void destroy_ctx(fdnn_ctx *c) {
   if (!c) return;
+  std::lock_guard<std::mutex> lk(c->model->cuda_mu);
   DeviceGuard g(c->model->device);
   cudaFree(c->d_in);
   cudaFree(c->d_act[0]);
@@ -219,6 +223,7 @@ int create_ctx(fdnn_model *m, int n, fdnn_ctx **out) {
     return FDNN_ENOMEM;
   }
   std::unique_ptr<fdnn_ctx, void (*)(fdnn_ctx *)> c(new fdnn_ctx, destroy_ctx);
+  std::unique_lock<std::mutex> lk(m->cuda_mu);
   c->model = m;
   c->cap = n;
   CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
@@ -228,8 +233,8 @@ int create_ctx(fdnn_model *m, int n, fdnn_ctx **out) {
   const size_t act_bytes = size_t(round_up(n, 128)) * H;
   CUDA_TRY(cudaMalloc(&c->d_act[0], act_bytes));
   CUDA_TRY(cudaMalloc(&c->d_act[1], act_bytes));
-  CUDA_TRY(cudaMemset(c->d_act[0], 0, act_bytes));
-  CUDA_TRY(cudaMemset(c->d_act[1], 0, act_bytes));
+  CUDA_TRY(cudaMemsetAsync(c->d_act[0], 0, act_bytes, c->stream));
+  CUDA_TRY(cudaMemsetAsync(c->d_act[1], 0, act_bytes, c->stream));
   CUDA_TRY(cudaMalloc(&c->d_logits, size_t(n) * O * 4));
   CUDA_TRY(cudaMalloc(&c->d_row, size_t(O) * 4));
   if (H % 128 == 0 && !m->force_simt) {
@@ -237,7 +242,8 @@ int create_ctx(fdnn_model *m, int n, fdnn_ctx **out) {
     if (int rc = make_tmap(&c->amap[1], c->d_act[1], n, H, 128)) return rc;
     c->amap_ok = true;
   }
-  CUDA_TRY(cudaDeviceSynchronize());  // the memsets above ran on the legacy stream; ours does not wait for it
+  CUDA_TRY(cudaStreamSynchronize(c->stream));
+  lk.unlock();  // (a failing CUDA_TRY above unwinds lk before c, whose deleter takes the lock again)
   *out = c.release();
   return FDNN_OK;
 }
@@ -347,28 +353,29 @@ int run_pass(fdnn_ctx *c, const float *d_in, int m, float *d_out, bool softmax, 
       c->last_frames = m;
       return FDNN_OK;
     }
-  // capture on the context's own stream (thread-local mode: other threads keep using CUDA freely)
+  // Capture on the context's own stream (thread-local mode: other threads keep using CUDA freely).
+  // If the capture is broken by something outside our control (another library synchronising the
+  // device from a different thread), this call simply runs un-captured.
   const long long before = g_launches.load(std::memory_order_relaxed);
-  CUDA_TRY(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
-  int rc = enqueue_until_logits(c, d_in, m, d_out, c->stream);
-  if (rc == FDNN_OK && softmax) rc = enqueue_softmax(c, d_out, nullptr, m, d_out, c->stream);
-  cudaGraph_t graph = nullptr;
-  cudaError_t e = cudaStreamEndCapture(c->stream, &graph);
-  g_launches.store(before, std::memory_order_relaxed);  // capturing is not launching
-  if (rc != FDNN_OK) {
-    if (graph) cudaGraphDestroy(graph);
-    return rc;
-  }
-  if (e != cudaSuccess) {
-    set_error(std::string("graph capture: ") + cudaGetErrorString(e));
-    return FDNN_ECUDA;
-  }
   cudaGraphExec_t exec = nullptr;
-  e = cudaGraphInstantiate(&exec, graph, 0);
-  cudaGraphDestroy(graph);
-  if (e != cudaSuccess) {
-    set_error(std::string("graph instantiate: ") + cudaGetErrorString(e));
-    return FDNN_ECUDA;
+  {
+    std::lock_guard<std::mutex> lk(c->model->cuda_mu);
+    cudaGraph_t graph = nullptr;
+    int rc = FDNN_ECUDA;
+    if (cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+      rc = enqueue_until_logits(c, d_in, m, d_out, c->stream);
+      if (rc == FDNN_OK && softmax) rc = enqueue_softmax(c, d_out, nullptr, m, d_out, c->stream);
+      if (cudaStreamEndCapture(c->stream, &graph) != cudaSuccess) rc = FDNN_ECUDA;
+    }
+    g_launches.store(before, std::memory_order_relaxed);  // capturing is not launching
+    if (rc == FDNN_OK && graph != nullptr && cudaGraphInstantiate(&exec, graph, 0) != cudaSuccess) exec = nullptr;
+    if (graph) cudaGraphDestroy(graph);
+    if (rc != FDNN_OK) exec = nullptr;
+    cudaGetLastError();
+  }
+  if (exec == nullptr) {
+    if (int rc = enqueue_until_logits(c, d_in, m, d_out, stream)) return rc;
+    return softmax ? enqueue_softmax(c, d_out, nullptr, m, d_out, stream) : FDNN_OK;
   }
   if (c->graphs.size() >= 64) {
     cudaGraphExecDestroy(c->graphs.front().exec);
@@ -530,6 +537,7 @@ int fdnn_model_qlayer(const fdnn_model *m, int i, int *nodes, int *inputs, float
   if (nodes) *nodes = q.nodes;
   if (inputs) *inputs = q.inputs;
   if (multiplier) *multiplier = q.multiplier;
+  std::lock_guard<std::mutex> lk(const_cast<fdnn_model *>(m)->cuda_mu);
   DeviceGuard g(m->device);
   if (weights) CUDA_TRY(cudaMemcpy(weights, m->d_blob + q.off_w, size_t(q.nodes) * size_t(q.inputs), cudaMemcpyDeviceToHost));
   if (bias) CUDA_TRY(cudaMemcpy(bias, m->d_blob + q.off_bias, size_t(q.nodes) * 4, cudaMemcpyDeviceToHost));
@@ -582,6 +590,7 @@ int fdnn_ctx_output_dim(const fdnn_ctx *ctx) { return ctx ? ctx->model->hdr.out_
 // 7 exit.  enable = 1 arms, enable = 0 copies the stamps out and disarms.
 int fdnn_ctx_timeline(fdnn_ctx *ctx, int enable, unsigned long long *out) {
   if (!ctx) return FDNN_EINVAL;
+  std::lock_guard<std::mutex> lk(ctx->model->cuda_mu);
   DeviceGuard g(ctx->model->device);
   const size_t bytes = size_t(ctx->model->hdr.n_qlayers) * 1024 * 8 * sizeof(unsigned long long);
   if (enable) {
@@ -716,6 +725,7 @@ int fdnn_ctx_hidden(fdnn_ctx *ctx, int layer, int n_frames, uint8_t *out) {
     set_error("only the last hidden layer is retained unless trace mode was enabled before the forward pass");
     return FDNN_EINVAL;
   }
+  std::lock_guard<std::mutex> lk(ctx->model->cuda_mu);
   CUDA_TRY(cudaMemcpy(out, src, size_t(n_frames) * size_t(H), cudaMemcpyDeviceToHost));
   return FDNN_OK;
 }
@@ -725,6 +735,7 @@ int fdnn_ctx_logits(fdnn_ctx *ctx, int n_frames, float *out) {
     set_error("no resident logits for that many frames");
     return FDNN_EINVAL;
   }
+  std::lock_guard<std::mutex> lk(ctx->model->cuda_mu);
   DeviceGuard g(ctx->model->device);
   CUDA_TRY(cudaMemcpy(out, ctx->d_logits, size_t(n_frames) * size_t(ctx->model->hdr.out_dim) * 4, cudaMemcpyDeviceToHost));
   return FDNN_OK;

@@ -174,17 +174,20 @@ def test_shared_model_many_threads(loaded):
     errors = []
 
     def work(seed):
-        rng = np.random.default_rng(seed)
-        for _ in range(6):
-            perm = rng.permutation(96)[: int(rng.integers(1, 96))]
-            got = dnn.calculate(frames[perm], 10)
-            if not np.array_equal(got, want[perm]):
-                errors.append(seed)
+        try:
+            rng = np.random.default_rng(seed)
+            for _ in range(6):
+                perm = rng.permutation(96)[: int(rng.integers(1, 96))]
+                got = dnn.calculate(frames[perm], 10)
+                if not np.array_equal(got, want[perm]):
+                    errors.append((seed, "mismatch"))
+        except Exception as e:  # surfaced by the assert below instead of dying silently in the thread
+            errors.append((seed, repr(e)))
 
     threads = [threading.Thread(target=work, args=(s,)) for s in range(8)]
     [t.start() for t in threads]
     [t.join() for t in threads]
-    assert not errors
+    assert not errors, errors
 
 
 def test_headline_network_batch512(loaded):
