@@ -394,6 +394,10 @@ int upload_model(const uint8_t *host_view, const void *src, bool src_on_device, 
   std::memcpy(m->q.data(), host_view + m->hdr.off_qlayers, sizeof(BlobQLayer) * m->q.size());
   m->device = device;
   m->blob_size = size;
+  if (m->hdr.in_dim > input_layer_max_dim()) {
+    set_error("input dimension " + std::to_string(m->hdr.in_dim) + " exceeds the input-layer kernel's limit of " + std::to_string(input_layer_max_dim()));
+    return FDNN_EFORMAT;
+  }
   const char *env = std::getenv("FDNN_FORCE_SIMT");
   m->force_simt = env && env[0] == '1';
   DeviceGuard g(device);

@@ -12,11 +12,15 @@
 // mul.rn.f32x2 + add.rn.f32x2 into a fused FFMA2 even with --fmad=false, which would change
 // results — tools/microbench.cu, DESIGN.md §Measured hardware facts).
 //
-// Tiling: a CTA (16 warps) computes 64 frames × 128 nodes; a warp 16 frames × 32 nodes; a thread
-// 4 frames × 4 nodes, strided (frames fg + 4i, nodes ng + 8j with lane = 8·fg + ng) so that every
-// 128-bit shared-memory read is either a broadcast or conflict-free with the 44-float row pitch —
-// 8 wavefronts per 128 math instructions.  K is streamed in 40-float chunks, double
-// buffered: weights by cp.async, frames through registers so shift/scale is applied on the way in.
+// Tiling: a CTA (16 warps) computes 64 frames × 128 nodes; a warp 16 frames × 32 nodes.  Shared
+// memory bandwidth, not arithmetic, is what a naive register tile runs out of here (a 128-bit load
+// costs four wavefronts however much of it is broadcast), so the four SSE lanes are split across
+// four adjacent threads: thread (group g, lane r) owns SSE lane r of an 8 × 8 block — 64
+// accumulators, and per 4-wide K step 16 one-wavefront 32-bit loads for 128 math instructions.
+// The lanes are recombined as (l0 + l1) + (l2 + l3) with two shuffles at the end.  K is streamed
+// in 40-float chunks through a 3-stage cp.async ring (frames and weight rows alike, issued two
+// chunks ahead); the frame rows of a stage are shifted and scaled in place one iteration before
+// they are used, so the loop has one barrier per chunk and no exposed global-memory latency.
 
 #include <cuda_runtime.h>
 
@@ -33,140 +37,145 @@ constexpr int kTileN = 128;   // nodes per CTA
 constexpr int kChunk = 40;    // floats of K per stage
 constexpr int kPitch = 44;    // smem row pitch in floats (≡ 12 mod 32 → conflict-free LDS.128 over consecutive rows)
 constexpr int kThreads = 512;
-constexpr int kTF = 4, kTN = 4;
+constexpr int kTF = 8, kTN = 8;  // per-thread block of one SSE lane
+constexpr int kStages = 3;
 constexpr int kStageFloats = (kTileF + kTileN) * kPitch;
-constexpr int kSmemBytes = 2 * kStageFloats * 4 + kLut2Padded;
-static_assert(kTileF * kTileN <= 2 * kStageFloats * 4, "u8 output tile must fit in the pipeline buffers");
+constexpr int kMaxI = 1024;   // shift/scale are kept in shared memory
+constexpr int kSmemBytes = kStages * kStageFloats * 4 + kLut2Padded + 2 * kMaxI * 4;
+static_assert(kTileF * kTileN <= kStages * kStageFloats * 4, "u8 output tile must fit in the pipeline buffers");
 
 __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(uint32_t(__cvta_generic_to_shared(smem_dst))), "l"(gmem_src) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+template <int kPending>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(kPending) : "memory");
+}
 
 __global__ void __launch_bounds__(kThreads, 1) input_layer_kernel(const InputLayerArgs args) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   float *stage_buf = reinterpret_cast<float *>(smem_raw);
-  uint8_t *s_lut = smem_raw + 2 * kStageFloats * 4;
+  uint8_t *s_lut = smem_raw + kStages * kStageFloats * 4;
+  float *s_shift = reinterpret_cast<float *>(s_lut + kLut2Padded);
+  float *s_scale = s_shift + kMaxI;
 
   const int tid = int(threadIdx.x);
   const int warp = tid / 32, lane = tid % 32;
-  const int fg = lane / 8, ng = lane % 8;
+  const int r = lane & 3;                // SSE lane this thread accumulates
+  const int fg = (lane >> 2) & 1;        // frames fg + 2i   (i < 8) of the warp tile
+  const int ng = lane >> 3;              // nodes  ng + 4j   (j < 8)
   const int wf = (warp / 4) * 16, wn = (warp % 4) * 32;  // warp tile origin inside the CTA tile
   const int f0 = int(blockIdx.y) * kTileF, n0 = int(blockIdx.x) * kTileN;
   const int M = args.M, I = args.I, H = args.H;
   const int n_chunks = (I + kChunk - 1) / kChunk;
 
   for (int i = tid; i < kLut2Padded / 16; i += kThreads) reinterpret_cast<uint4 *>(s_lut)[i] = __ldg(reinterpret_cast<const uint4 *>(args.lut) + i);
+  for (int i = tid; i < I; i += kThreads) {
+    s_shift[i] = __ldg(args.shift + i);
+    s_scale[i] = __ldg(args.scale + i);
+  }
   ptx::griddep_wait();  // the activation buffer we write may still be read by the previous pass
   ptx::griddep_launch_dependents();
 
-  // Frame elements this thread moves per chunk: kTileF rows × (kChunk/4) float4 = 640 vectors.
-  constexpr int kXVecs = kTileF * (kChunk / 4);
-  constexpr int kXPerThread = (kXVecs + kThreads - 1) / kThreads;
-  float4 xr[kXPerThread];
-
-  auto load_x_regs = [&](int c) {
-    const int k0 = c * kChunk, kc = min(kChunk, I - k0);
-#pragma unroll
-    for (int j = 0; j < kXPerThread; ++j) {
-      const int v = tid + j * kThreads;
-      const int r = v / (kChunk / 4), q = v % (kChunk / 4);
-      float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (v < kXVecs && 4 * q < kc && f0 + r < M) {
-        const float4 raw = __ldg(reinterpret_cast<const float4 *>(args.in + size_t(f0 + r) * size_t(I) + k0) + q);
-        const float4 sh = __ldg(reinterpret_cast<const float4 *>(args.shift + k0) + q);
-        const float4 sc = __ldg(reinterpret_cast<const float4 *>(args.scale + k0) + q);
-        val.x = __fmul_rn(__fadd_rn(raw.x, sh.x), sc.x);
-        val.y = __fmul_rn(__fadd_rn(raw.y, sh.y), sc.y);
-        val.z = __fmul_rn(__fadd_rn(raw.z, sh.z), sc.z);
-        val.w = __fmul_rn(__fadd_rn(raw.w, sh.w), sc.w);
-      }
-      xr[j] = val;
-    }
-  };
-  auto store_x_regs = [&](int buf) {
-    float *xs = stage_buf + buf * kStageFloats;
-#pragma unroll
-    for (int j = 0; j < kXPerThread; ++j) {
-      const int v = tid + j * kThreads;
-      if (v < kXVecs) {
+  // Stage c of the ring holds, for K chunk c: rows [0, 64) = frames (raw on arrival, shifted and
+  // scaled in place one iteration before use), rows [64, 192) = weight rows.  Both arrive by cp.async.
+  auto issue = [&](int c) {
+    if (c < n_chunks) {
+      const int k0 = c * kChunk, kc = min(kChunk, I - k0);
+      float *st = stage_buf + (c % kStages) * kStageFloats;
+      for (int v = tid; v < (kTileF + kTileN) * (kChunk / 4); v += kThreads) {
         const int r = v / (kChunk / 4), q = v % (kChunk / 4);
-        *reinterpret_cast<float4 *>(xs + r * kPitch + 4 * q) = xr[j];
+        float *dst = st + r * kPitch + 4 * q;
+        const bool is_x = r < kTileF;
+        const int src_row = is_x ? f0 + r : n0 + r - kTileF;
+        const bool ok = 4 * q < kc && (is_x ? src_row < M : src_row < H);
+        if (ok)
+          cp_async16(dst, (is_x ? args.in : args.w0) + size_t(src_row) * size_t(I) + k0 + 4 * q);
+        else
+          *reinterpret_cast<float4 *>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+    cp_async_commit();  // (possibly empty) group: keeps the wait_group arithmetic uniform
+  };
+  // ApplyShiftAndScale (dnn.cc:175-192) on the frame rows of chunk c, in place: add, then multiply
+  auto transform = [&](int c) {
+    if (c >= n_chunks) return;
+    const int k0 = c * kChunk, kc = min(kChunk, I - k0);
+    float *st = stage_buf + (c % kStages) * kStageFloats;
+    for (int v = tid; v < kTileF * (kChunk / 4); v += kThreads) {
+      const int r = v / (kChunk / 4), q = v % (kChunk / 4);
+      if (4 * q < kc) {
+        float4 x = *reinterpret_cast<float4 *>(st + r * kPitch + 4 * q);
+        const float4 sh = *reinterpret_cast<const float4 *>(s_shift + k0 + 4 * q);
+        const float4 sc = *reinterpret_cast<const float4 *>(s_scale + k0 + 4 * q);
+        x.x = __fmul_rn(__fadd_rn(x.x, sh.x), sc.x);
+        x.y = __fmul_rn(__fadd_rn(x.y, sh.y), sc.y);
+        x.z = __fmul_rn(__fadd_rn(x.z, sh.z), sc.z);
+        x.w = __fmul_rn(__fadd_rn(x.w, sh.w), sc.w);
+        *reinterpret_cast<float4 *>(st + r * kPitch + 4 * q) = x;
       }
     }
   };
-  auto issue_w = [&](int c, int buf) {
-    const int k0 = c * kChunk, kc = min(kChunk, I - k0);
-    float *ws = stage_buf + buf * kStageFloats + kTileF * kPitch;
-    for (int v = tid; v < kTileN * (kChunk / 4); v += kThreads) {
-      const int r = v / (kChunk / 4), q = v % (kChunk / 4);
-      float *dst = ws + r * kPitch + 4 * q;
-      if (4 * q < kc && n0 + r < H)
-        cp_async16(dst, args.w0 + size_t(n0 + r) * size_t(I) + k0 + 4 * q);
-      else
-        *reinterpret_cast<float4 *>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-    cp_async_commit();
-  };
 
-  // acc[i][j] = the four SSE lanes of frame fg+4i, node ng+8j
-  float4 acc[kTF][kTN];
+  // acc[i][j] = SSE lane r of frame fg+2i, node ng+4j
+  float acc[kTF][kTN];
 #pragma unroll
   for (int i = 0; i < kTF; ++i)
 #pragma unroll
-    for (int j = 0; j < kTN; ++j) acc[i][j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int j = 0; j < kTN; ++j) acc[i][j] = 0.f;
 
-  load_x_regs(0);
-  issue_w(0, 0);
-  store_x_regs(0);
-  cp_async_wait_all();
-  __syncthreads();
+  issue(0);
+  issue(1);
+  cp_async_wait<1>();  // chunk 0 landed (this thread's part)
+  __syncthreads();     // … everyone's part, and s_shift/s_scale
+  transform(0);
 
   for (int c = 0; c < n_chunks; ++c) {
-    const int buf = c & 1;
-    const bool more = c + 1 < n_chunks;
-    if (more) {
-      issue_w(c + 1, buf ^ 1);
-      load_x_regs(c + 1);
-    }
-    const float *xs = stage_buf + buf * kStageFloats + (wf + fg) * kPitch;
-    const float *ws = stage_buf + buf * kStageFloats + (kTileF + wn + ng) * kPitch;
+    // chunk c+1 has landed, chunk c has been transformed by the previous iteration, chunk c−1 is done with
+    cp_async_wait<0>();
+    __syncthreads();
+    issue(c + 2);      // into the stage chunk c−1 occupied
+    transform(c + 1);  // nobody reads it before the next barrier
+    const float *xs = stage_buf + (c % kStages) * kStageFloats + (wf + fg) * kPitch + r;
+    const float *ws = stage_buf + (c % kStages) * kStageFloats + (kTileF + wn + ng) * kPitch + r;
     const int kc4 = (min(kChunk, I - c * kChunk)) / 4;
 #pragma unroll 2
     for (int q = 0; q < kc4; ++q) {
-      float4 xv[kTF], wv[kTN];
+      float xv[kTF], wv[kTN];
 #pragma unroll
-      for (int i = 0; i < kTF; ++i) xv[i] = *reinterpret_cast<const float4 *>(xs + (4 * i) * kPitch + 4 * q);
+      for (int i = 0; i < kTF; ++i) xv[i] = xs[(2 * i) * kPitch + 4 * q];
 #pragma unroll
-      for (int j = 0; j < kTN; ++j) wv[j] = *reinterpret_cast<const float4 *>(ws + (8 * j) * kPitch + 4 * q);
+      for (int j = 0; j < kTN; ++j) wv[j] = ws[(4 * j) * kPitch + 4 * q];
 #pragma unroll
       for (int i = 0; i < kTF; ++i)
 #pragma unroll
-        for (int j = 0; j < kTN; ++j) {
-          acc[i][j].x = __fadd_rn(acc[i][j].x, __fmul_rn(xv[i].x, wv[j].x));
-          acc[i][j].y = __fadd_rn(acc[i][j].y, __fmul_rn(xv[i].y, wv[j].y));
-          acc[i][j].z = __fadd_rn(acc[i][j].z, __fmul_rn(xv[i].z, wv[j].z));
-          acc[i][j].w = __fadd_rn(acc[i][j].w, __fmul_rn(xv[i].w, wv[j].w));
-        }
+        for (int j = 0; j < kTN; ++j) acc[i][j] = __fadd_rn(acc[i][j], __fmul_rn(xv[i], wv[j]));
     }
-    if (more) store_x_regs(buf ^ 1);
-    cp_async_wait_all();
-    __syncthreads();
   }
+  cp_async_wait<0>();
+  __syncthreads();
 
   // ---- epilogue: lanes → h, + bias, LUT; stage the u8 tile in shared memory ------------------------
   uint8_t *s_out = smem_raw;  // [kTileF][kTileN], pipeline buffers are free after the last barrier
-  float bias[kTN];
-#pragma unroll
-  for (int j = 0; j < kTN; ++j) bias[j] = (n0 + wn + ng + 8 * j < H) ? __ldg(args.bias0 + n0 + wn + ng + 8 * j) : 0.0f;
+  // horizontalSum (dnn.cc:168-172): (l0 + l1) + (l2 + l3); fp32 addition is commutative, so every
+  // lane of the quad ends up with the same bits.  Lane r then finishes the outputs with j ≡ r (mod 4).
 #pragma unroll
   for (int i = 0; i < kTF; ++i)
 #pragma unroll
     for (int j = 0; j < kTN; ++j) {
-      const float h = __fadd_rn(__fadd_rn(acc[i][j].x, acc[i][j].y), __fadd_rn(acc[i][j].z, acc[i][j].w));
-      s_out[(wf + fg + 4 * i) * kTileN + wn + ng + 8 * j] = s_lut[qsig_slot(__fadd_rn(h, bias[j]))];
+      const float pair = __fadd_rn(acc[i][j], __shfl_xor_sync(0xffffffffu, acc[i][j], 1));
+      acc[i][j] = __fadd_rn(pair, __shfl_xor_sync(0xffffffffu, pair, 2));
     }
+#pragma unroll
+  for (int j = 0; j < kTN; ++j) {
+    if ((j & 3) == r) {
+      const int node = wn + ng + 4 * j;
+      const float bias = (n0 + node < H) ? __ldg(args.bias0 + n0 + node) : 0.0f;
+#pragma unroll
+      for (int i = 0; i < kTF; ++i) s_out[(wf + fg + 2 * i) * kTileN + node] = s_lut[qsig_slot(__fadd_rn(acc[i][j], bias))];
+    }
+  }
   __syncthreads();
 
   const int cols = min(kTileN, H - n0);  // multiple of 16
@@ -184,8 +193,11 @@ cudaError_t input_layer_configure() {
   return cudaFuncSetAttribute(input_layer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
 }
 
+int input_layer_max_dim() { return kMaxI; }
+
 cudaError_t launch_input_layer(const InputLayerArgs &a, cudaStream_t stream) {
   if (a.M <= 0) return cudaSuccess;
+  if (a.I > kMaxI || a.I % 4 != 0) return cudaErrorInvalidValue;
   dim3 grid((a.H + kTileN - 1) / kTileN, (a.M + kTileF - 1) / kTileF);
   return launch_pdl(input_layer_kernel, grid, dim3(kThreads), size_t(kSmemBytes), stream, pdl_enabled(), a);
 }

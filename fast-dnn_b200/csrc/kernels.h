@@ -42,6 +42,7 @@ struct InputLayerArgs {
   int M, I, H;
 };
 cudaError_t input_layer_configure();
+int input_layer_max_dim();  // widest (padded) input the kernel takes
 cudaError_t launch_input_layer(const InputLayerArgs &a, cudaStream_t stream);
 
 // ---- int8 layers -------------------------------------------------------------------------------

@@ -256,19 +256,27 @@ qlayer_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_cons
         const int stage = int(g % uint32_t(Cfg::kStages));
         ptx::mbar_wait(full_bar + stage, (g / uint32_t(Cfg::kStages)) & 1u);
         const uint32_t a_row = ptx::smem_u32(tiles + stage * Cfg::kStageBytes) + uint32_t(srow) * 128u;
+        // rows are 128-byte aligned, so "row base + (offset with its 16-byte chunk index XORed by row%8)"
+        // is a single XOR of the entry's byte offset into a pre-swizzled base
+        const uint32_t a_swz = a_row ^ swz;
         const uint32_t fast_end = min(r1, staged);
         for (uint32_t e = r0; e < fast_end; e += 8) {
           if (e != r0) fetch(e, fast_end);
           uint32_t a01[8];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const uint32_t b = w[i] >> 24;
-            a01[i] = ptx::lds_u16(a_row + (((b & 0x70u) ^ swz) | (b & 15u)));
-          }
+          for (int i = 0; i < 8; ++i) a01[i] = ptx::lds_u16(a_swz ^ (w[i] >> 24));
+          // branch-free common case: collect "pair sum left the int16 range" bits, look closer only if any is set
+          int v[8];
+          uint32_t fired = 0;
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            const int v = dp4a_u8s8(a01[i], w[i], 0);
-            if (uint32_t(v + 32768) > 65535u && e + uint32_t(i) < fast_end) record(v, (w[i] >> 16) & 0xffu);
+            v[i] = dp4a_u8s8(a01[i], w[i], 0);
+            fired |= (uint32_t(v[i] + 32768) >> 16) << i;  // non-zero ⇔ v ∉ [−32768, 32767]; |v| < 2¹⁷ so at most 2 bits
+          }
+          if (fired != 0) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              if (uint32_t(v[i] + 32768) > 65535u && e + uint32_t(i) < fast_end) record(v[i], (w[i] >> 16) & 0xffu);
           }
         }
         for (uint32_t e = max(r0, staged); e < r1; ++e) {  // beyond the staging capacity (dense risk lists)
