@@ -164,7 +164,7 @@ struct fdnn_ctx {
   int8_t *d_masks = nullptr;  // [cap][O], allocated on first lazy use
   float *d_row = nullptr;     // [O] scratch for single-row lazy output
   float *d_lazy = nullptr;    // [cap][O] masked softmax rows, allocated on first batched lazy use
-  CUtensorMap amap[2];
+  CUtensorMap amap[2][3];  // per activation buffer: TMA box of 128 / 64 / 32 rows (cluster 1 / 2 / 4 sharing the tile)
   bool amap_ok = false;
   cudaStream_t stream = nullptr;
   bool trace = false;
@@ -238,8 +238,9 @@ int create_ctx(fdnn_model *m, int n, fdnn_ctx **out) {
   CUDA_TRY(cudaMalloc(&c->d_logits, size_t(n) * O * 4));
   CUDA_TRY(cudaMalloc(&c->d_row, size_t(O) * 4));
   if (H % 128 == 0 && !m->force_simt) {
-    if (int rc = make_tmap(&c->amap[0], c->d_act[0], n, H, 128)) return rc;
-    if (int rc = make_tmap(&c->amap[1], c->d_act[1], n, H, 128)) return rc;
+    for (int b = 0; b < 2; ++b)
+      for (int v = 0; v < 3; ++v)
+        if (int rc = make_tmap(&c->amap[b][v], c->d_act[b], n, H, 128 >> v)) return rc;
     c->amap_ok = true;
   }
   CUDA_TRY(cudaStreamSynchronize(c->stream));
@@ -304,10 +305,13 @@ int enqueue_until_logits(fdnn_ctx *c, const float *d_in, int m, float *d_logits,
       a.out_u8 = c->d_act[(j + 1) & 1];
     }
     if (mod->tc_ok[size_t(j)] && c->amap_ok) {
-      const int bn = qlayer_tc_block_n(m, ql.nodes, mod->num_sms);
-      const int which = bn == 64 ? 0 : (bn == 128 ? 1 : 2);
-      a.fix = fix_of(j, which);
-      CUDA_TRY(launch_qlayer_tc(c->amap[j & 1], mod->wmaps[size_t(j)][size_t(which)], a, logits, bn, mod->num_sms, stream));
+      const TcPlan plan = qlayer_tc_plan(m, ql.nodes, mod->num_sms);
+      const int which = plan.block_n == 64 ? 0 : (plan.block_n == 128 ? 1 : 2);
+      a.fix = fix_of(j, which);  // the risk list grouped by the tile width
+      const int act_box = plan.share_a ? (plan.cluster == 4 ? 2 : (plan.cluster == 2 ? 1 : 0)) : 0;
+      const int w_rows = plan.share_a ? plan.block_n : plan.block_n / plan.cluster;
+      const int w_box = w_rows == 64 ? 0 : (w_rows == 128 ? 1 : 2);
+      CUDA_TRY(launch_qlayer_tc(c->amap[j & 1][act_box], mod->wmaps[size_t(j)][size_t(w_box)], a, logits, plan, mod->num_sms, stream));
     } else {
       CUDA_TRY(launch_qlayer_simt(a, logits, stream));
     }

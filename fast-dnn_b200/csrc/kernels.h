@@ -49,9 +49,17 @@ cudaError_t launch_input_layer(const InputLayerArgs &a, cudaStream_t stream);
 // tcgen05 path (qlayer_tc.cu): needs K a multiple of 128 and, for hidden layers, N a multiple of 32.
 cudaError_t qlayer_tc_configure();
 bool qlayer_tc_supported(int N, int K, bool logits);
-int qlayer_tc_block_n(int M, int N, int num_sms);
-cudaError_t launch_qlayer_tc(const CUtensorMap &tmap_act, const CUtensorMap &tmap_w, const QLayerArgs &a, bool logits, int block_n,
-                             int num_sms, cudaStream_t stream);
+// Launch shape: N-tile width (64/128/256), cluster size (1/2/4) and which operand the cluster shares.
+// The activation map must have a box of 128/cluster rows when share_a (else 128); the weight map a
+// box of block_n rows when share_a (else block_n/cluster).
+struct TcPlan {
+  int block_n;
+  int cluster;
+  bool share_a;
+};
+TcPlan qlayer_tc_plan(int M, int N, int num_sms);
+cudaError_t launch_qlayer_tc(const CUtensorMap &tmap_act, const CUtensorMap &tmap_w, const QLayerArgs &a, bool logits, TcPlan plan, int num_sms,
+                             cudaStream_t stream);
 // dp4a path (qlayer_simt.cu): any legal network (K a multiple of 16); used for narrow layers.
 cudaError_t launch_qlayer_simt(const QLayerArgs &a, bool logits, cudaStream_t stream);
 

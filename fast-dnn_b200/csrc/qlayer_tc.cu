@@ -17,6 +17,14 @@
 // instructions per element, so it needs the issue slots of many warps).  Two accumulator stages
 // in TMEM let the epilogue of tile i overlap the contraction of tile i+1.
 //
+// Thread-block clusters: at every batch size the operand tiles come out of L2, and L2→SM
+// bandwidth, not the tensor pipe, is what the contraction waits for.  CTAs that need the same
+// operand tile therefore form a cluster and fetch it once: each CTA loads 1/C of the shared tile
+// and TMA-multicasts it into all C shared memories (kShareA: C neighbouring N tiles share the
+// activation tile — small batches; otherwise C neighbouring M tiles share the weight tile —
+// streams).  A pipeline stage is then only free when every CTA of the cluster has released it,
+// so the MMA commit and the scan warps arrive on the empty barrier of all C CTAs.
+//
 // pmaddubsw's int16 pair saturation is not reproduced by the tensor core.  The scan warps (two
 // sets of one thread per tile row, alternating K blocks) walk the layer's risk entries K block by K block, read the two activation
 // bytes of each entry from the very A tile that TMA staged for the MMA, and record the rare
@@ -25,6 +33,8 @@
 
 #include <cuda.h>
 #include <cuda_runtime.h>
+
+#include <cstdlib>
 
 #include "device_common.cuh"
 #include "kernels.h"
@@ -77,10 +87,39 @@ struct TcConfig {
   static_assert(kSmemBytes <= 232448, "shared memory budget");
 };
 
-template <int BN, bool kLogits>
+// Which tile of the layer a CTA works on in round `ct` of its cluster.  Tiles past the edge of the
+// matrix ("dummy" tiles of a partially filled cluster) run the whole protocol on zero-filled
+// operands and store nothing.
+template <int BN, int C, bool kShareA>
+struct TileMap {
+  int m_blocks, n_blocks, groups, total;
+  __device__ TileMap(int M, int N) {
+    m_blocks = (M + kBlockM - 1) / kBlockM;
+    n_blocks = (N + BN - 1) / BN;
+    groups = kShareA ? (n_blocks + C - 1) / C : (m_blocks + C - 1) / C;
+    total = C == 1 ? m_blocks * n_blocks : (kShareA ? m_blocks * groups : groups * n_blocks);
+  }
+  __device__ void decode(int ct, int rank, int &m_blk, int &n_blk) const {
+    if (C == 1) {
+      m_blk = ct / n_blocks;
+      n_blk = ct % n_blocks;
+    } else if (kShareA) {
+      m_blk = ct / groups;
+      n_blk = (ct % groups) * C + rank;
+    } else {
+      m_blk = (ct / n_blocks) * C + rank;
+      n_blk = ct % n_blocks;
+    }
+  }
+};
+
+template <int BN, bool kLogits, int C, bool kShareA>
 __global__ void __launch_bounds__(kThreads, 1)
 qlayer_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_constant__ CUtensorMap tmap_w, const QLayerArgs args) {
   using Cfg = TcConfig<BN>;
+  static_assert(C == 1 || C == 2 || C == 4, "cluster size");
+  static_assert(kBlockM % C == 0 && BN % C == 0, "operand slices");
+  constexpr uint16_t kClusterMask = uint16_t((1u << C) - 1u);
   // 128B-swizzled tiles need 1024-byte alignment.  Dynamic shared memory starts at the base of the
   // CTA's window (this kernel has no static shared memory); keeping the pointers derived from the
   // array itself (no integer round-trip) lets the compiler emit LDS/STS instead of generic accesses.
@@ -103,9 +142,12 @@ qlayer_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_cons
   const int warp = int(threadIdx.x) / 32, lane = int(threadIdx.x) % 32;
   if (threadIdx.x == 0) stamp(args.timeline, 0);
   const int M = args.M, N = args.N, K = args.K;
-  const int m_blocks = (M + kBlockM - 1) / kBlockM, n_blocks = (N + BN - 1) / BN;
-  const int tiles_total = m_blocks * n_blocks;
+  const TileMap<BN, C, kShareA> tmap(M, N);
+  const int n_blocks = tmap.n_blocks;
+  const int tiles_total = tmap.total;
   const int k_blocks = (K + kBlockK - 1) / kBlockK;
+  const int rank = C == 1 ? 0 : int(ptx::cluster_ctarank());
+  const int first_ct = int(blockIdx.x) / C, ct_step = int(gridDim.x) / C;
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&tmap_act);
@@ -114,7 +156,7 @@ qlayer_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_cons
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < Cfg::kStages; ++i) {
       ptx::mbar_init(full_bar + i, 1);
-      ptx::mbar_init(empty_bar + i, 1 + 4);  // MMA commit + one arrival per warp of the scan set that owns the stage
+      ptx::mbar_init(empty_bar + i, C * (1 + 4));  // per CTA of the cluster: MMA commit + the 4 warps of the scan set that owns the stage
     }
     for (int i = 0; i < kAccStages; ++i) {
       ptx::mbar_init(tmem_full_bar + i, 1);
@@ -130,6 +172,7 @@ qlayer_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_cons
   }
   ptx::tc_fence_before_sync();
   __syncthreads();
+  if (C > 1) ptx::cluster_sync_all();  // peers' barriers must exist before anything is multicast into them
   ptx::tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
   // everything above touched only constants and this CTA's own shared/tensor memory; from here on
@@ -143,14 +186,32 @@ qlayer_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_cons
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int t = int(blockIdx.x); t < tiles_total; t += int(gridDim.x)) {
-        const int m_blk = t / n_blocks, n_blk = t % n_blocks;
+      for (int ct = first_ct; ct < tiles_total; ct += ct_step) {
+        int m_blk, n_blk;
+        tmap.decode(ct, rank, m_blk, n_blk);
         for (int kb = 0; kb < k_blocks; ++kb) {
-          ptx::mbar_wait(empty_bar + stage, phase ^ 1);
+          if (C == 1)
+            ptx::mbar_wait(empty_bar + stage, phase ^ 1);
+          else
+            ptx::mbar_wait_cluster(empty_bar + stage, phase ^ 1);
           uint8_t *sa = tiles + stage * Cfg::kStageBytes;
+          uint8_t *sb = sa + Cfg::kABytes;
           ptx::mbar_arrive_expect_tx(full_bar + stage, Cfg::kStageBytes);
-          ptx::tma_load_2d(&tmap_act, full_bar + stage, sa, kb * kBlockK, m_blk * kBlockM);
-          ptx::tma_load_2d(&tmap_w, full_bar + stage, sa + Cfg::kABytes, kb * kBlockK, n_blk * BN);
+          if (C == 1) {
+            ptx::tma_load_2d(&tmap_act, full_bar + stage, sa, kb * kBlockK, m_blk * kBlockM);
+            ptx::tma_load_2d(&tmap_w, full_bar + stage, sb, kb * kBlockK, n_blk * BN);
+          } else if (kShareA) {
+            // my quarter (half) of the activation tile, to everybody; my own weight tile
+            constexpr int kRows = kBlockM / C;
+            ptx::tma_load_2d_multicast(&tmap_act, full_bar + stage, sa + rank * kRows * kBlockK, kb * kBlockK, m_blk * kBlockM + rank * kRows,
+                                       kClusterMask);
+            ptx::tma_load_2d(&tmap_w, full_bar + stage, sb, kb * kBlockK, n_blk * BN);
+          } else {
+            constexpr int kRows = BN / C;
+            ptx::tma_load_2d(&tmap_act, full_bar + stage, sa, kb * kBlockK, m_blk * kBlockM);
+            ptx::tma_load_2d_multicast(&tmap_w, full_bar + stage, sb + rank * kRows * kBlockK, kb * kBlockK, n_blk * BN + rank * kRows,
+                                       kClusterMask);
+          }
           if (++stage == Cfg::kStages) {
             stage = 0;
             phase ^= 1;
@@ -163,7 +224,7 @@ qlayer_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_cons
     constexpr uint32_t idesc = ptx::idesc_i8_u8s8(BN);
     int stage = 0, acc = 0;
     uint32_t phase = 0, acc_phase = 0;
-    for (int t = int(blockIdx.x); t < tiles_total; t += int(gridDim.x)) {
+    for (int ct = first_ct; ct < tiles_total; ct += ct_step) {
       ptx::mbar_wait(tmem_empty_bar + acc, acc_phase ^ 1);
       ptx::tc_fence_after_sync();
       const uint32_t d_tmem = tmem_base + uint32_t(acc * BN);
@@ -179,7 +240,10 @@ qlayer_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_cons
             // advancing K inside the swizzle atom = advancing the start address (16-byte units)
             ptx::mma_i8_ss(d_tmem, da + uint64_t(k * (kUmmaK / 16)), db + uint64_t(k * (kUmmaK / 16)), idesc, uint32_t((kb | k) != 0));
           }
-          ptx::mma_commit(empty_bar + stage);
+          if (C == 1)
+            ptx::mma_commit(empty_bar + stage);
+          else
+            ptx::mma_commit_multicast(empty_bar + stage, kClusterMask);
           if (kb == k_blocks - 1) {
             ptx::mma_commit(tmem_full_bar + acc);
             stamp(args.timeline, 3);
@@ -209,16 +273,18 @@ qlayer_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_cons
     int acc = 0;
     uint32_t acc_phase = 0;
     uint32_t it = 0;  // running K-block count across tiles: stage = it % kStages, phase = (it / kStages) & 1
-    for (int t = int(blockIdx.x); t < tiles_total; t += int(gridDim.x)) {
-      const int n_blk = t % n_blocks;
-      const uint32_t *gp = args.fix.ptr + size_t(n_blk) * kbn;
+    for (int ct = first_ct; ct < tiles_total; ct += ct_step) {
+      int m_blk_unused, n_blk;
+      tmap.decode(ct, rank, m_blk_unused, n_blk);
+      const bool real = n_blk < n_blocks;  // a dummy tile has no risk entries
+      const uint32_t *gp = args.fix.ptr + size_t(real ? n_blk : 0) * kbn;
       uint32_t *P = s_ptr + acc * kPtrSlots;  // K-block offsets of this tile's entries, relative to its first one
       uint32_t *E = s_ent + acc * kEntCap;
       // the event slots of this accumulator stage are free once its previous tile has been drained
       ptx::mbar_wait(tmem_empty_bar + acc, acc_phase ^ 1);
       const uint32_t ent_begin = __ldg(gp);
-      for (int i = st; i <= kbn; i += kScanThreads) P[i] = __ldg(gp + i) - ent_begin;
-      const uint32_t n_ent = __ldg(gp + kbn) - ent_begin;
+      for (int i = st; i <= kbn; i += kScanThreads) P[i] = real ? __ldg(gp + i) - ent_begin : 0u;
+      const uint32_t n_ent = real ? __ldg(gp + kbn) - ent_begin : 0u;
       const uint32_t staged = min(n_ent, uint32_t(kEntCap));
       // staged form, one word per entry: w0 | w1 << 8 | (node − n0) << 16 | (byte offset of the pair
       // inside its 128-byte K block) << 24 — dp4a of that word with the zero-extended activation
@@ -287,7 +353,14 @@ qlayer_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_cons
           if (uint32_t(v + 32768) > 65535u) record(v, fe.y - uint32_t(n_blk * BN));
         }
         __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(empty_bar + stage);
+        if (lane == 0) {
+          if (C == 1) {
+            ptx::mbar_arrive(empty_bar + stage);
+          } else {
+#pragma unroll
+            for (int p = 0; p < C; ++p) ptx::mbar_arrive_cluster(empty_bar + stage, uint32_t(p));
+          }
+        }
         if (kb + kScanSets < k_blocks) {
           r0 = P[kb + kScanSets];
           r1 = P[kb + kScanSets + 1];
@@ -311,8 +384,9 @@ qlayer_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_cons
     const int row_local = quarter * 32 + lane;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int t = int(blockIdx.x); t < tiles_total; t += int(gridDim.x)) {
-      const int m_blk = t / n_blocks, n_blk = t % n_blocks;
+    for (int ct = first_ct; ct < tiles_total; ct += ct_step) {
+      int m_blk, n_blk;
+      tmap.decode(ct, rank, m_blk, n_blk);
       const int n0 = n_blk * BN;
       const int row = m_blk * kBlockM + row_local;
       const bool row_ok = row < M;
@@ -376,34 +450,67 @@ qlayer_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_cons
 
   ptx::tc_fence_before_sync();
   __syncthreads();
+  if (C > 1) ptx::cluster_sync_all();  // nobody leaves while a peer may still multicast into it or arrive on its barriers
   if (warp == 2) {
     ptx::tc_fence_after_sync();
     ptx::tmem_dealloc<Cfg::kTmemCols>(tmem_base);
   }
 }
 
-template <int BN, bool kLogits>
+template <int BN, bool kLogits, int C, bool kShareA>
 cudaError_t launch_one(const CUtensorMap &ta, const CUtensorMap &tw, const QLayerArgs &a, int num_sms, cudaStream_t stream) {
   using Cfg = TcConfig<BN>;
-  const int tiles = ((a.M + kBlockM - 1) / kBlockM) * ((a.N + BN - 1) / BN);
-  const int grid = tiles < num_sms ? tiles : num_sms;
-  return launch_pdl(qlayer_tc_kernel<BN, kLogits>, dim3(grid), dim3(kThreads), size_t(Cfg::kSmemBytes), stream, pdl_enabled(), ta, tw, a);
+  const int m_blocks = (a.M + kBlockM - 1) / kBlockM, n_blocks = (a.N + BN - 1) / BN;
+  const int cluster_tiles = C == 1 ? m_blocks * n_blocks : (kShareA ? m_blocks * ((n_blocks + C - 1) / C) : ((m_blocks + C - 1) / C) * n_blocks);
+  // clusters of 4 cannot use every SM of a GPC; stay below what can be co-resident so the grid is one wave
+  const int max_clusters = C == 1 ? num_sms : (C == 2 ? num_sms / 2 : (num_sms * 7 / 8) / 4);
+  const int clusters = cluster_tiles < max_clusters ? cluster_tiles : max_clusters;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(unsigned(clusters * C));
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = size_t(Cfg::kSmemBytes);
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  int n_attr = 0;
+  if (pdl_enabled()) {
+    attr[n_attr].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n_attr].val.programmaticStreamSerializationAllowed = 1;
+    ++n_attr;
+  }
+  if (C > 1) {
+    attr[n_attr].id = cudaLaunchAttributeClusterDimension;
+    attr[n_attr].val.clusterDim.x = C;
+    attr[n_attr].val.clusterDim.y = 1;
+    attr[n_attr].val.clusterDim.z = 1;
+    ++n_attr;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = unsigned(n_attr);
+  return cudaLaunchKernelEx(&cfg, qlayer_tc_kernel<BN, kLogits, C, kShareA>, ta, tw, a);
 }
 
-template <int BN>
+template <int BN, int C, bool kShareA>
 cudaError_t configure_one() {
-  cudaError_t e = cudaFuncSetAttribute(qlayer_tc_kernel<BN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcConfig<BN>::kSmemBytes);
+  cudaError_t e = cudaFuncSetAttribute(qlayer_tc_kernel<BN, false, C, kShareA>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcConfig<BN>::kSmemBytes);
   if (e != cudaSuccess) return e;
-  return cudaFuncSetAttribute(qlayer_tc_kernel<BN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcConfig<BN>::kSmemBytes);
+  return cudaFuncSetAttribute(qlayer_tc_kernel<BN, true, C, kShareA>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcConfig<BN>::kSmemBytes);
+}
+
+template <int BN, int C, bool kShareA>
+cudaError_t launch_mode(const CUtensorMap &ta, const CUtensorMap &tw, const QLayerArgs &a, bool logits, int num_sms, cudaStream_t stream) {
+  return logits ? launch_one<BN, true, C, kShareA>(ta, tw, a, num_sms, stream) : launch_one<BN, false, C, kShareA>(ta, tw, a, num_sms, stream);
 }
 
 }  // namespace
 
 // Opt in to the large dynamic shared memory carve-out on the current device (once per device).
 cudaError_t qlayer_tc_configure() {
-  cudaError_t e = configure_one<64>();
-  if (e == cudaSuccess) e = configure_one<128>();
-  if (e == cudaSuccess) e = configure_one<256>();
+  cudaError_t e = configure_one<64, 1, true>();
+  if (e == cudaSuccess) e = configure_one<128, 1, true>();
+  if (e == cudaSuccess) e = configure_one<256, 1, true>();
+  if (e == cudaSuccess) e = configure_one<64, 4, true>();
+  if (e == cudaSuccess) e = configure_one<128, 4, true>();
+  if (e == cudaSuccess) e = configure_one<256, 2, false>();
   return e;
 }
 
@@ -414,27 +521,48 @@ bool qlayer_tc_supported(int N, int K, bool logits) {
   return true;
 }
 
-int qlayer_tc_block_n(int M, int N, int num_sms) {
-  // Largest tile that still gives every SM work; small batches trade tile size for parallelism.
+// Tile width and cluster shape for a launch.  Small batches: narrow tiles so that every SM has one,
+// four neighbouring N tiles share the activation tile.  Streams: 128×256 tiles, two neighbouring
+// M tiles share the weight tile.  FDNN_CLUSTER=0 keeps every CTA on its own (for A/B comparisons).
+TcPlan qlayer_tc_plan(int M, int N, int num_sms) {
+  static const bool clusters = [] {
+    const char *e = std::getenv("FDNN_CLUSTER");
+    return !(e && e[0] == '0');
+  }();
   const int m_blocks = (M + kBlockM - 1) / kBlockM;
-  if (m_blocks * ((N + 255) / 256) >= 2 * num_sms) return 256;
-  if (m_blocks * ((N + 127) / 128) >= num_sms) return 128;
-  return 64;
+  TcPlan p{64, 1, true};
+  if (m_blocks * ((N + 255) / 256) >= 2 * num_sms) {
+    p.block_n = 256;
+    if (clusters && m_blocks % 2 == 0) {
+      p.cluster = 2;
+      p.share_a = false;
+    }
+    return p;
+  }
+  p.block_n = m_blocks * ((N + 127) / 128) >= num_sms ? 128 : 64;
+  if (clusters && (N + p.block_n - 1) / p.block_n >= 4) {
+    p.cluster = 4;
+    p.share_a = true;
+  }
+  return p;
 }
 
-cudaError_t launch_qlayer_tc(const CUtensorMap &tmap_act, const CUtensorMap &tmap_w, const QLayerArgs &a, bool logits, int block_n,
-                             int num_sms, cudaStream_t stream) {
+cudaError_t launch_qlayer_tc(const CUtensorMap &tmap_act, const CUtensorMap &tmap_w, const QLayerArgs &a, bool logits, TcPlan plan, int num_sms,
+                             cudaStream_t stream) {
   if (a.M <= 0) return cudaSuccess;
-  switch (block_n) {
-    case 64:
-      return logits ? launch_one<64, true>(tmap_act, tmap_w, a, num_sms, stream) : launch_one<64, false>(tmap_act, tmap_w, a, num_sms, stream);
-    case 128:
-      return logits ? launch_one<128, true>(tmap_act, tmap_w, a, num_sms, stream) : launch_one<128, false>(tmap_act, tmap_w, a, num_sms, stream);
-    case 256:
-      return logits ? launch_one<256, true>(tmap_act, tmap_w, a, num_sms, stream) : launch_one<256, false>(tmap_act, tmap_w, a, num_sms, stream);
-    default:
-      return cudaErrorInvalidValue;
+  if (plan.cluster == 1) {
+    switch (plan.block_n) {
+      case 64: return launch_mode<64, 1, true>(tmap_act, tmap_w, a, logits, num_sms, stream);
+      case 128: return launch_mode<128, 1, true>(tmap_act, tmap_w, a, logits, num_sms, stream);
+      case 256: return launch_mode<256, 1, true>(tmap_act, tmap_w, a, logits, num_sms, stream);
+    }
+  } else if (plan.cluster == 4 && plan.share_a) {
+    if (plan.block_n == 64) return launch_mode<64, 4, true>(tmap_act, tmap_w, a, logits, num_sms, stream);
+    if (plan.block_n == 128) return launch_mode<128, 4, true>(tmap_act, tmap_w, a, logits, num_sms, stream);
+  } else if (plan.cluster == 2 && !plan.share_a && plan.block_n == 256) {
+    return launch_mode<256, 2, false>(tmap_act, tmap_w, a, logits, num_sms, stream);
   }
+  return cudaErrorInvalidValue;
 }
 
 }  // namespace fdnn
