@@ -31,6 +31,7 @@ struct QLayerArgs {
   int out_ld;
   // optional per-CTA phase timestamps (SM clock), 8 slots per CTA; nullptr in normal operation
   unsigned long long *timeline;
+  int debug_flags;  // profiling experiments only (FDNN_DEBUG): 1 = scan warps skip their entries (results wrong)
 };
 
 __device__ __forceinline__ void stamp(unsigned long long *timeline, int slot) {

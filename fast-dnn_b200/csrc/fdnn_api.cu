@@ -297,6 +297,13 @@ int enqueue_until_logits(fdnn_ctx *c, const float *d_in, int m, float *d_logits,
     a.N = ql.nodes;
     a.K = ql.inputs;
     a.fix = fix_of(j, 0);
+    {
+      static const int dbg = [] {
+        const char *e = std::getenv("FDNN_DEBUG");
+        return e ? std::atoi(e) : 0;
+      }();
+      a.debug_flags = dbg;
+    }
     a.timeline = c->d_timeline ? c->d_timeline + size_t(j) * 1024 * 8 : nullptr;
     if (logits) {
       a.out_f32 = d_logits;

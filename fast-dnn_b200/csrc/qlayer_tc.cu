@@ -23,7 +23,12 @@
 // and TMA-multicasts it into all C shared memories (kShareA: C neighbouring N tiles share the
 // activation tile — small batches; otherwise C neighbouring M tiles share the weight tile —
 // streams).  A pipeline stage is then only free when every CTA of the cluster has released it,
-// so the MMA commit and the scan warps arrive on the empty barrier of all C CTAs.
+// so the MMA commit and the scan warps arrive on the empty barrier of all C CTAs.  Measured on B200
+// (profiles/r1_cluster_multicast.md): correct, but slower than independent CTAs at C ≤ 4 — the
+// cluster-wide stage hand-off costs more than the multicast saves — so it is opt-in (FDNN_CLUSTER=1).
+//
+// K rotation: CTAs that share an operand tile start their K loop at different K blocks (integer
+// accumulation is order-independent), so they do not all ask L2 for the same lines at the same time.
 //
 // pmaddubsw's int16 pair saturation is not reproduced by the tensor core.  The scan warps (two
 // sets of one thread per tile row, alternating K blocks) walk the layer's risk entries K block by K block, read the two activation
@@ -113,6 +118,14 @@ struct TileMap {
   }
 };
 
+// First K block of a tile's (rotated) K loop: spreads the CTAs that share an activation tile (same
+// m_blk) and those that share a weight tile (same n_blk) over different K blocks.  In a cluster the
+// shared operand is multicast K block by K block, so its members must agree: no rotation there.
+template <int C>
+__device__ __forceinline__ int first_k_block(int m_blk, int n_blk, int k_blocks) {
+  return C == 1 ? (n_blk + 5 * m_blk) % k_blocks : 0;
+}
+
 template <int BN, bool kLogits, int C, bool kShareA>
 __global__ void __launch_bounds__(kThreads, 1)
 qlayer_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_constant__ CUtensorMap tmap_w, const QLayerArgs args) {
@@ -189,7 +202,8 @@ qlayer_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_cons
       for (int ct = first_ct; ct < tiles_total; ct += ct_step) {
         int m_blk, n_blk;
         tmap.decode(ct, rank, m_blk, n_blk);
-        for (int kb = 0; kb < k_blocks; ++kb) {
+        int kb = first_k_block<C>(m_blk, n_blk, k_blocks);
+        for (int i = 0; i < k_blocks; ++i, kb = (kb + 1 == k_blocks ? 0 : kb + 1)) {
           if (C == 1)
             ptx::mbar_wait(empty_bar + stage, phase ^ 1);
           else
@@ -228,7 +242,7 @@ qlayer_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_cons
       ptx::mbar_wait(tmem_empty_bar + acc, acc_phase ^ 1);
       ptx::tc_fence_after_sync();
       const uint32_t d_tmem = tmem_base + uint32_t(acc * BN);
-      for (int kb = 0; kb < k_blocks; ++kb) {
+      for (int kb = 0; kb < k_blocks; ++kb) {  // kb counts pipeline turns here; which K block a turn carries does not matter to the MMA
         ptx::mbar_wait(full_bar + stage, phase);
         ptx::tc_fence_after_sync();
         if (lane == 0) {
@@ -274,8 +288,10 @@ qlayer_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_cons
     uint32_t acc_phase = 0;
     uint32_t it = 0;  // running K-block count across tiles: stage = it % kStages, phase = (it / kStages) & 1
     for (int ct = first_ct; ct < tiles_total; ct += ct_step) {
-      int m_blk_unused, n_blk;
-      tmap.decode(ct, rank, m_blk_unused, n_blk);
+      int m_blk, n_blk;
+      tmap.decode(ct, rank, m_blk, n_blk);
+      const int kb0 = first_k_block<C>(m_blk, n_blk, k_blocks);
+      auto k_block_of = [&](int turn) { return (kb0 + turn) % k_blocks; };  // which K block pipeline turn `turn` carries
       const bool real = n_blk < n_blocks;  // a dummy tile has no risk entries
       const uint32_t *gp = args.fix.ptr + size_t(real ? n_blk : 0) * kbn;
       uint32_t *P = s_ptr + acc * kPtrSlots;  // K-block offsets of this tile's entries, relative to its first one
@@ -283,8 +299,8 @@ qlayer_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_cons
       // the event slots of this accumulator stage are free once its previous tile has been drained
       ptx::mbar_wait(tmem_empty_bar + acc, acc_phase ^ 1);
       const uint32_t ent_begin = __ldg(gp);
-      for (int i = st; i <= kbn; i += kScanThreads) P[i] = real ? __ldg(gp + i) - ent_begin : 0u;
-      const uint32_t n_ent = real ? __ldg(gp + kbn) - ent_begin : 0u;
+      for (int i = st; i <= kbn; i += kScanThreads) P[i] = (real && !(args.debug_flags & 1)) ? __ldg(gp + i) - ent_begin : 0u;
+      const uint32_t n_ent = (real && !(args.debug_flags & 1)) ? __ldg(gp + kbn) - ent_begin : 0u;
       const uint32_t staged = min(n_ent, uint32_t(kEntCap));
       // staged form, one word per entry: w0 | w1 << 8 | (node − n0) << 16 | (byte offset of the pair
       // inside its 128-byte K block) << 24 — dp4a of that word with the zero-extended activation
@@ -310,11 +326,11 @@ qlayer_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_cons
 #pragma unroll
         for (int i = 0; i < 8; ++i) w[i] = E[min(r0 + uint32_t(i), max(r_end, 1u) - 1u)];
       };
-      int kb = int((uint32_t(sset) + kScanSets - it % kScanSets) % kScanSets);  // first K block of this tile owned by this set
+      int kb = int((uint32_t(sset) + kScanSets - it % kScanSets) % kScanSets);  // first pipeline turn of this tile owned by this set
       uint32_t r0 = 0, r1 = 0;
       if (kb < k_blocks) {
-        r0 = P[kb];
-        r1 = P[kb + 1];
+        r0 = P[k_block_of(kb)];
+        r1 = P[k_block_of(kb) + 1];
         fetch(r0, min(r1, staged));
       }
       for (; kb < k_blocks; kb += kScanSets) {
@@ -362,8 +378,8 @@ qlayer_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_cons
           }
         }
         if (kb + kScanSets < k_blocks) {
-          r0 = P[kb + kScanSets];
-          r1 = P[kb + kScanSets + 1];
+          r0 = P[k_block_of(kb + kScanSets)];
+          r1 = P[k_block_of(kb + kScanSets) + 1];
           fetch(r0, min(r1, staged));
         }
       }
@@ -522,15 +538,22 @@ bool qlayer_tc_supported(int N, int K, bool logits) {
 }
 
 // Tile width and cluster shape for a launch.  Small batches: narrow tiles so that every SM has one,
-// four neighbouring N tiles share the activation tile.  Streams: 128×256 tiles, two neighbouring
-// M tiles share the weight tile.  FDNN_CLUSTER=0 keeps every CTA on its own (for A/B comparisons).
+// optionally (FDNN_CLUSTER=1) four neighbouring N tiles share the activation tile.  Streams: 128×256
+// tiles, optionally two neighbouring M tiles share the weight tile.
 TcPlan qlayer_tc_plan(int M, int N, int num_sms) {
   static const bool clusters = [] {
     const char *e = std::getenv("FDNN_CLUSTER");
-    return !(e && e[0] == '0');
+    return e && e[0] == '1';
   }();
   const int m_blocks = (M + kBlockM - 1) / kBlockM;
   TcPlan p{64, 1, true};
+  if (const char *e = std::getenv("FDNN_FORCE_BN")) {  // tuning experiments
+    const int bn = std::atoi(e);
+    if ((bn == 64 || bn == 128 || bn == 256) && N >= 4096) {
+      p.block_n = bn;
+      return p;
+    }
+  }
   if (m_blocks * ((N + 255) / 256) >= 2 * num_sms) {
     p.block_n = 256;
     if (clusters && m_blocks % 2 == 0) {
@@ -539,8 +562,11 @@ TcPlan qlayer_tc_plan(int M, int N, int num_sms) {
     }
     return p;
   }
-  p.block_n = m_blocks * ((N + 127) / 128) >= num_sms ? 128 : 64;
-  if (clusters && (N + p.block_n - 1) / p.block_n >= 4) {
+  // widest tile that still gives (nearly) every SM one: measured on B200, 128 tiles of 128×256 beat
+  // 252 tiles of 128×128 (two rounds) on the 8000-wide output layer at batch 512
+  const int enough = num_sms * 85 / 100;
+  p.block_n = m_blocks * ((N + 255) / 256) >= enough ? 256 : (m_blocks * ((N + 127) / 128) >= enough ? 128 : 64);
+  if (clusters && p.block_n <= 128 && (N + p.block_n - 1) / p.block_n >= 4) {
     p.cluster = 4;
     p.share_a = true;
   }
