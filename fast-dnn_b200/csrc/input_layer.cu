@@ -80,40 +80,59 @@ __global__ void __launch_bounds__(kThreads, 1) input_layer_kernel(const InputLay
 
   // Stage c of the ring holds, for K chunk c: rows [0, 64) = frames (raw on arrival, shifted and
   // scaled in place one iteration before use), rows [64, 192) = weight rows.  Both arrive by cp.async.
+  // The (row, 16-byte column) slots a thread moves are the same for every chunk: resolve them once.
+  constexpr int kVecsPerRow = kChunk / 4;
+  constexpr int kSlots = ((kTileF + kTileN) * kVecsPerRow + kThreads - 1) / kThreads;  // 4
+  constexpr int kXSlots = (kTileF * kVecsPerRow + kThreads - 1) / kThreads;             // 2
+  const float *slot_src[kSlots];  // global address of the slot in chunk 0, nullptr if the row does not exist
+  int slot_dst[kSlots];           // float offset inside a stage
+  int slot_col[kSlots];           // first K index of the slot inside the chunk
+#pragma unroll
+  for (int j = 0; j < kSlots; ++j) {
+    const int v = tid + j * kThreads;
+    const int row = v / kVecsPerRow, q = v % kVecsPerRow;
+    const bool in_range = v < (kTileF + kTileN) * kVecsPerRow;
+    const bool is_x = row < kTileF;
+    const int src_row = is_x ? f0 + row : n0 + row - kTileF;
+    const bool ok = in_range && (is_x ? src_row < M : src_row < H);
+    slot_src[j] = ok ? (is_x ? args.in : args.w0) + size_t(src_row) * size_t(I) + 4 * q : nullptr;
+    slot_dst[j] = in_range ? row * kPitch + 4 * q : -1;
+    slot_col[j] = 4 * q;
+  }
   auto issue = [&](int c) {
     if (c < n_chunks) {
       const int k0 = c * kChunk, kc = min(kChunk, I - k0);
       float *st = stage_buf + (c % kStages) * kStageFloats;
-      for (int v = tid; v < (kTileF + kTileN) * (kChunk / 4); v += kThreads) {
-        const int r = v / (kChunk / 4), q = v % (kChunk / 4);
-        float *dst = st + r * kPitch + 4 * q;
-        const bool is_x = r < kTileF;
-        const int src_row = is_x ? f0 + r : n0 + r - kTileF;
-        const bool ok = 4 * q < kc && (is_x ? src_row < M : src_row < H);
-        if (ok)
-          cp_async16(dst, (is_x ? args.in : args.w0) + size_t(src_row) * size_t(I) + k0 + 4 * q);
-        else
-          *reinterpret_cast<float4 *>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int j = 0; j < kSlots; ++j) {
+        if (slot_dst[j] >= 0) {
+          if (slot_src[j] != nullptr && slot_col[j] < kc)
+            cp_async16(st + slot_dst[j], slot_src[j] + k0);
+          else
+            *reinterpret_cast<float4 *>(st + slot_dst[j]) = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
       }
     }
     cp_async_commit();  // (possibly empty) group: keeps the wait_group arithmetic uniform
   };
-  // ApplyShiftAndScale (dnn.cc:175-192) on the frame rows of chunk c, in place: add, then multiply
+  // ApplyShiftAndScale (dnn.cc:175-192) on the frame rows of chunk c, in place: add, then multiply.
+  // Frame rows are the first kTileF·kVecsPerRow slots, so a thread transforms slots it loaded itself
+  // or a neighbour did — either way after the barrier that made them visible.
   auto transform = [&](int c) {
     if (c >= n_chunks) return;
     const int k0 = c * kChunk, kc = min(kChunk, I - k0);
     float *st = stage_buf + (c % kStages) * kStageFloats;
-    for (int v = tid; v < kTileF * (kChunk / 4); v += kThreads) {
-      const int r = v / (kChunk / 4), q = v % (kChunk / 4);
-      if (4 * q < kc) {
-        float4 x = *reinterpret_cast<float4 *>(st + r * kPitch + 4 * q);
-        const float4 sh = *reinterpret_cast<const float4 *>(s_shift + k0 + 4 * q);
-        const float4 sc = *reinterpret_cast<const float4 *>(s_scale + k0 + 4 * q);
+#pragma unroll
+    for (int j = 0; j < kXSlots; ++j) {
+      if (tid + j * kThreads < kTileF * kVecsPerRow && slot_col[j] < kc) {
+        float4 x = *reinterpret_cast<float4 *>(st + slot_dst[j]);
+        const float4 sh = *reinterpret_cast<const float4 *>(s_shift + k0 + slot_col[j]);
+        const float4 sc = *reinterpret_cast<const float4 *>(s_scale + k0 + slot_col[j]);
         x.x = __fmul_rn(__fadd_rn(x.x, sh.x), sc.x);
         x.y = __fmul_rn(__fadd_rn(x.y, sh.y), sc.y);
         x.z = __fmul_rn(__fadd_rn(x.z, sh.z), sc.z);
         x.w = __fmul_rn(__fadd_rn(x.w, sh.w), sc.w);
-        *reinterpret_cast<float4 *>(st + r * kPitch + 4 * q) = x;
+        *reinterpret_cast<float4 *>(st + slot_dst[j]) = x;
       }
     }
   };

@@ -284,7 +284,27 @@ int pack_model(const char *path, float cutoff, std::vector<uint8_t> &blob) {
       std::vector<uint32_t> cursor(ptr.begin(), ptr.end() - 1);
       std::vector<FixEntry> &ent = fix[size_t(q)][size_t(v)];
       ent.resize(all.size());
-      for (const FixEntry &e : all) ent[cursor[bucket_of(e)]++] = e;  // stable: keeps (node, pair) order inside a bucket
+      for (const FixEntry &e : all) ent[cursor[bucket_of(e)]++] = e;
+      // Inside a bucket the order is free.  The scan warps read the activation pairs of four
+      // consecutive entries (positions 4i … 4i+3 of the bucket) with one shared-memory instruction,
+      // which is conflict-free when the four pairs sit at different word offsets of their 16-byte
+      // chunk, i.e. differ in (pair >> 1) & 3 — so deal the entries out round-robin by that class.
+      std::vector<FixEntry> cls[4], mixed;
+      for (size_t b = 0; b < buckets; ++b) {
+        const uint32_t lo = ptr[b], hi = ptr[b + 1];
+        if (hi - lo < 2) continue;
+        for (auto &c : cls) c.clear();
+        for (uint32_t e = lo; e < hi; ++e) cls[((ent[e].pair_w & 0xffffu) >> 1) & 3u].push_back(ent[e]);
+        mixed.clear();
+        size_t taken[4] = {0, 0, 0, 0};
+        while (mixed.size() < size_t(hi - lo)) {
+          int order[4] = {0, 1, 2, 3};  // fullest class first, so the short ones run out last
+          std::sort(order, order + 4, [&](int a, int c) { return cls[a].size() - taken[a] > cls[c].size() - taken[c]; });
+          for (int k : order)
+            if (taken[k] < cls[k].size()) mixed.push_back(cls[k][taken[k]++]);
+        }
+        std::copy(mixed.begin(), mixed.end(), ent.begin() + lo);
+      }
     }
   }
 

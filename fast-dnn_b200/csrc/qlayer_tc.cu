@@ -278,11 +278,16 @@ qlayer_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_cons
     // ===== saturation scan: thread = tile row, reads its two activation bytes per risk entry =====
     // straight from the 128B-swizzled A tile TMA staged for the tensor core (row r, byte b of the
     // 128-byte K block lives at r·128 + ((b/16 ^ r%8)·16 + b%16)).
+    // Work split inside a scan warp: 8 rows × 4 entries per shared-memory instruction (lane = 8·entry
+    // + row%8).  The 128B swizzle puts the same byte offset of 8 consecutive rows into 8 different
+    // 16-byte chunks, and the packer orders entries so that 4 consecutive ones differ in their word
+    // offset within the chunk: 32 lanes, 32 banks.
     const int st = int(threadIdx.x) - kFirstScanWarp * 32;  // 0 .. kScanThreads − 1
-    const int srow = st & (kBlockM - 1);                     // tile row of this thread
-    const int sset = st / kBlockM;                           // which K blocks it takes
+    const int sset = st / kBlockM;                           // which K blocks this thread's set takes
+    const int row_sub = lane & 7, ent_sub = lane >> 3;
+    const int row_base = ((st % kBlockM) / 32) * 32 + row_sub;  // rows row_base + 8j, j < 4
     static_assert(Cfg::kStages % kScanSets == 0, "a pipeline stage must always belong to the same scan set");
-    const uint32_t swz = uint32_t(srow & 7) << 4;
+    const uint32_t swz = uint32_t(row_sub) << 4;
     const int kbn = args.fix.k_blocks;  // == k_blocks; the list variant is the one grouped by BN nodes
     int acc = 0;
     uint32_t acc_phase = 0;
@@ -310,21 +315,22 @@ qlayer_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_cons
         const uint2 fe = __ldg(gent + e);
         E[e] = (fe.x >> 16) | ((fe.y - uint32_t(n_blk * BN)) << 16) | (((2u * (fe.x & 0xffffu)) & 127u) << 24);
       }
-      uint32_t *row_cnt = s_rowcnt + acc * kBlockM + srow;
-      uint32_t *row_ev = s_rowev + (acc * kBlockM + srow) * kRowEvents;
-      if (sset == 0) *row_cnt = 0;
+      uint32_t *cnt_s = s_rowcnt + acc * kBlockM;
+      uint32_t *ev_s = s_rowev + acc * kBlockM * kRowEvents;
+      if (st < kBlockM) cnt_s[st] = 0;
       ptx::named_bar_sync(2, kScanThreads);
-      auto record = [&](int v, uint32_t node_local) {  // rare: the row's scan threads share one event list
+      auto record = [&](int row, int v, uint32_t node_local) {  // rare: a row's events come from several threads
         const int d = max(min(v, 32767), -32768) - v;
-        const uint32_t slot = atomicAdd(row_cnt, 1u);
-        if (slot < uint32_t(kRowEvents)) row_ev[slot] = (node_local << 24) | (uint32_t(d) & 0xffffffu);
+        const uint32_t slot = atomicAdd(cnt_s + row, 1u);
+        if (slot < uint32_t(kRowEvents)) ev_s[row * kRowEvents + slot] = (node_local << 24) | (uint32_t(d) & 0xffffffu);
       };
       // Entry words are fetched one turn ahead: they do not depend on the data TMA is bringing, so
       // after the barrier only activation load → dp4a → range check remains on the critical path.
-      uint32_t w[8];
+      uint32_t w0 = 0, w1 = 0;
       auto fetch = [&](uint32_t r0, uint32_t r_end) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) w[i] = E[min(r0 + uint32_t(i), max(r_end, 1u) - 1u)];
+        const uint32_t last = max(r_end, 1u) - 1u;
+        w0 = E[min(r0 + uint32_t(ent_sub), last)];
+        w1 = E[min(r0 + 4u + uint32_t(ent_sub), last)];
       };
       int kb = int((uint32_t(sset) + kScanSets - it % kScanSets) % kScanSets);  // first pipeline turn of this tile owned by this set
       uint32_t r0 = 0, r1 = 0;
@@ -337,36 +343,45 @@ qlayer_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_cons
         const uint32_t g = it + uint32_t(kb);
         const int stage = int(g % uint32_t(Cfg::kStages));
         ptx::mbar_wait(full_bar + stage, (g / uint32_t(Cfg::kStages)) & 1u);
-        const uint32_t a_row = ptx::smem_u32(tiles + stage * Cfg::kStageBytes) + uint32_t(srow) * 128u;
         // rows are 128-byte aligned, so "row base + (offset with its 16-byte chunk index XORed by row%8)"
         // is a single XOR of the entry's byte offset into a pre-swizzled base
-        const uint32_t a_swz = a_row ^ swz;
+        const uint32_t a_swz = (ptx::smem_u32(tiles + stage * Cfg::kStageBytes) + uint32_t(row_base) * 128u) ^ swz;
         const uint32_t fast_end = min(r1, staged);
         for (uint32_t e = r0; e < fast_end; e += 8) {
           if (e != r0) fetch(e, fast_end);
-          uint32_t a01[8];
+          uint32_t a0[4], a1[4];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) a01[i] = ptx::lds_u16(a_swz ^ (w[i] >> 24));
+          for (int j = 0; j < 4; ++j) {
+            a0[j] = ptx::lds_u16((a_swz + uint32_t(j) * 1024u) ^ (w0 >> 24));
+            a1[j] = ptx::lds_u16((a_swz + uint32_t(j) * 1024u) ^ (w1 >> 24));
+          }
           // branch-free common case: collect "pair sum left the int16 range" bits, look closer only if any is set
-          int v[8];
+          int v0[4], v1[4];
           uint32_t fired = 0;
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            v[i] = dp4a_u8s8(a01[i], w[i], 0);
-            fired |= (uint32_t(v[i] + 32768) >> 16) << i;  // non-zero ⇔ v ∉ [−32768, 32767]; |v| < 2¹⁷ so at most 2 bits
+          for (int j = 0; j < 4; ++j) {
+            v0[j] = dp4a_u8s8(a0[j], w0, 0);
+            v1[j] = dp4a_u8s8(a1[j], w1, 0);
+            fired |= (uint32_t(v0[j] + 32768) | uint32_t(v1[j] + 32768)) >> 16;  // non-zero ⇔ some v ∉ [−32768, 32767]
           }
           if (fired != 0) {
+            const bool ok0 = e + uint32_t(ent_sub) < fast_end, ok1 = e + 4u + uint32_t(ent_sub) < fast_end;
 #pragma unroll
-            for (int i = 0; i < 8; ++i)
-              if (uint32_t(v[i] + 32768) > 65535u && e + uint32_t(i) < fast_end) record(v[i], (w[i] >> 16) & 0xffu);
+            for (int j = 0; j < 4; ++j) {
+              if (ok0 && uint32_t(v0[j] + 32768) > 65535u) record(row_base + 8 * j, v0[j], (w0 >> 16) & 0xffu);
+              if (ok1 && uint32_t(v1[j] + 32768) > 65535u) record(row_base + 8 * j, v1[j], (w1 >> 16) & 0xffu);
+            }
           }
         }
-        for (uint32_t e = max(r0, staged); e < r1; ++e) {  // beyond the staging capacity (dense risk lists)
+        // beyond the staging capacity (dense risk lists): one entry per pass, 32 rows per warp
+        for (uint32_t e = max(r0, staged); e < r1; ++e) {
           const uint2 fe = __ldg(gent + e);
           const uint32_t b = (2u * (fe.x & 0xffffu)) & 127u;
-          const uint32_t a01s = ptx::lds_u16(a_row + (((b & 0x70u) ^ swz) | (b & 15u)));
+          const int row = (st % kBlockM);
+          const uint32_t a_addr = ptx::smem_u32(tiles + stage * Cfg::kStageBytes) + uint32_t(row) * 128u;
+          const uint32_t a01s = ptx::lds_u16(a_addr + (((b & 0x70u) ^ (uint32_t(row & 7) << 4)) | (b & 15u)));
           const int v = dp4a_u8s8(a01s, fe.x >> 16, 0);
-          if (uint32_t(v + 32768) > 65535u) record(v, fe.y - uint32_t(n_blk * BN));
+          if (uint32_t(v + 32768) > 65535u) record(row, v, fe.y - uint32_t(n_blk * BN));
         }
         __syncwarp();
         if (lane == 0) {

@@ -2,10 +2,13 @@
 //   SoftMax::apply           src/cpp/dnn.cc:534-544   e = exp(x); total = Σ e; e / total — no max subtraction
 //   LazyOutputActivations    src/cpp/dnn.cc:355-392   masked-out nodes enter as logit 0 (e = 1) and
 //                                                     come back as 1/total, not 0
-// The reference adds the exponentials sequentially in fp32 and uses glibc's expf; here the sum is a
-// fixed-shape tree (deterministic) and expf is CUDA's (≤ 2 ulp), which is where the stated float
-// tolerance of the softmax scores comes from (tests/test_gpu_parity.py).  One CTA per row; the
-// exponentials are kept in shared memory between the two passes.
+// The reference adds the exponentials sequentially in fp32, uses glibc's expf and divides; here the
+// sum is a fixed-shape tree (deterministic), the exponential is 2^(x·log2e) on the SFU with the
+// rounding error of the product folded back in (≈ 3e-7 relative), and the division is a multiply by
+// the row's IEEE reciprocal (≤ 1 ulp) — which is where the stated float tolerance of the softmax
+// scores comes from (tests/conftest.py: 1e-9 + 2e-5·|ref|; the logits themselves are bit-exact).
+// The kernel is instruction-bound otherwise (ncu: 35 instructions per element with expf and
+// __fdiv_rn).  One CTA per row; the exponentials stay in shared memory between the two passes.
 
 #include <cuda_runtime.h>
 
@@ -18,6 +21,17 @@ namespace {
 
 constexpr int kThreads = 256;
 constexpr int kMaxSmemFloats = 56 * 1024;  // 224 KB of exponentials; wider rows recompute instead
+
+// e^x.  t = RN(x·log2e_hi) goes to ex2.approx; r = (x·log2e − t) is recovered exactly with one fma
+// plus the low part of log2e, and 2^r ≈ 1 + r·ln2 (|r| < 2^-17).  Overflows to +inf above 88.72 like
+// the reference's expf does (there is no max subtraction, dnn.cc:534-544); NaN stays NaN.
+__device__ __forceinline__ float exp_fast(float x) {
+  const float t = __fmul_rn(x, 1.4426950216293335f);
+  const float r = fmaf(x, 1.9259629911e-8f, fmaf(x, 1.4426950216293335f, -t));
+  float p;
+  asm("ex2.approx.f32 %0, %1;" : "=f"(p) : "f"(t));
+  return fmaf(p, r * 0.6931471805599453f, p);
+}
 
 __device__ __forceinline__ float block_sum(float v, float *s_red) {
 #pragma unroll
@@ -55,7 +69,7 @@ __global__ void __launch_bounds__(kThreads) softmax_kernel(const SoftmaxArgs a) 
         v.z = k.z ? v.z : 0.0f;
         v.w = k.w ? v.w : 0.0f;
       }
-      float4 e = make_float4(expf(v.x), expf(v.y), expf(v.z), expf(v.w));
+      float4 e = make_float4(exp_fast(v.x), exp_fast(v.y), exp_fast(v.z), exp_fast(v.w));
       if (kCache) reinterpret_cast<float4 *>(s_e)[i] = e;
       part = __fadd_rn(part, __fadd_rn(__fadd_rn(e.x, e.y), __fadd_rn(e.z, e.w)));
     }
@@ -63,12 +77,13 @@ __global__ void __launch_bounds__(kThreads) softmax_kernel(const SoftmaxArgs a) 
     for (int i = tid; i < O; i += kThreads) {
       float v = x[i];
       if (m && m[i] == 0) v = 0.0f;
-      const float e = expf(v);
+      const float e = exp_fast(v);
       if (kCache) s_e[i] = e;
       part = __fadd_rn(part, e);
     }
   }
   const float total = block_sum(part, s_red);  // contains the barrier that orders s_e writes/reads
+  const float inv = __fdiv_rn(1.0f, total);
   if (vec) {
     for (int i = tid; i < O / 4; i += kThreads) {
       float4 e;
@@ -83,9 +98,9 @@ __global__ void __launch_bounds__(kThreads) softmax_kernel(const SoftmaxArgs a) 
           v.z = k.z ? v.z : 0.0f;
           v.w = k.w ? v.w : 0.0f;
         }
-        e = make_float4(expf(v.x), expf(v.y), expf(v.z), expf(v.w));
+        e = make_float4(exp_fast(v.x), exp_fast(v.y), exp_fast(v.z), exp_fast(v.w));
       }
-      reinterpret_cast<float4 *>(y)[i] = make_float4(__fdiv_rn(e.x, total), __fdiv_rn(e.y, total), __fdiv_rn(e.z, total), __fdiv_rn(e.w, total));
+      reinterpret_cast<float4 *>(y)[i] = make_float4(e.x * inv, e.y * inv, e.z * inv, e.w * inv);
     }
   } else {
     for (int i = tid; i < O; i += kThreads) {
@@ -95,9 +110,9 @@ __global__ void __launch_bounds__(kThreads) softmax_kernel(const SoftmaxArgs a) 
       } else {
         float v = x[i];
         if (m && m[i] == 0) v = 0.0f;
-        e = expf(v);
+        e = exp_fast(v);
       }
-      y[i] = __fdiv_rn(e, total);
+      y[i] = e * inv;
     }
   }
 }
