@@ -312,7 +312,7 @@ int enqueue_until_logits(fdnn_ctx *c, const float *d_in, int m, float *d_logits,
       a.out_u8 = c->d_act[(j + 1) & 1];
     }
     if (mod->tc_ok[size_t(j)] && c->amap_ok) {
-      const TcPlan plan = qlayer_tc_plan(m, ql.nodes, mod->num_sms);
+      const TcPlan plan = qlayer_tc_plan(m, ql.nodes, logits, mod->num_sms);
       const int which = plan.block_n == 64 ? 0 : (plan.block_n == 128 ? 1 : 2);
       a.fix = fix_of(j, which);  // the risk list grouped by the tile width
       const int act_box = plan.share_a ? (plan.cluster == 4 ? 2 : (plan.cluster == 2 ? 1 : 0)) : 0;
@@ -483,6 +483,30 @@ int fdnn_pack(const char *path, float cutoff, void **blob, size_t *size) {
 }
 
 void fdnn_blob_free(void *blob) { std::free(blob); }
+
+int fdnn_align_dnn_bin(const char *in_path, const char *out_path, int input_alignment, int hidden_alignment) {
+  return align_dnn_bin(in_path, out_path, input_alignment, hidden_alignment);
+}
+
+int fdnn_feature_bin_read(const char *path, int *frames, int *dim, float **data) {
+  if (!path || !frames || !dim || !data) {
+    set_error("null argument");
+    return FDNN_EINVAL;
+  }
+  std::vector<float> v;
+  if (int rc = read_feature_bin(path, frames, dim, v)) return rc;
+  float *p = static_cast<float *>(std::malloc(std::max<size_t>(v.size(), 1) * sizeof(float)));
+  if (!p) {
+    set_error("out of host memory");
+    return FDNN_ENOMEM;
+  }
+  if (!v.empty()) std::memcpy(p, v.data(), v.size() * sizeof(float));
+  *data = p;
+  return FDNN_OK;
+}
+
+int fdnn_feature_bin_write(const char *path, const float *data, int frames, int dim) { return write_feature_bin(path, data, frames, dim); }
+int fdnn_output_dump_write(const char *path, const float *data, int frames, int dim) { return write_output_dump(path, data, frames, dim); }
 
 int fdnn_load_blob(const void *blob, size_t size, int device, fdnn_model **out) {
   if (!blob || !out) {

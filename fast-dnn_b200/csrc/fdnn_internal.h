@@ -84,6 +84,11 @@ const char *get_error();
 int pack_model(const char *path, float cutoff, std::vector<uint8_t> &blob);
 // Structural validation of a blob (bounds, magic, constraints).
 int validate_blob(const uint8_t *blob, size_t size);
+// Offline tooling: network aligner/writer and feature-file IO.
+int align_dnn_bin(const char *in_path, const char *out_path, int input_alignment, int hidden_alignment);
+int read_feature_bin(const char *path, int *frames, int *dim, std::vector<float> &data);
+int write_feature_bin(const char *path, const float *data, int frames, int dim);
+int write_output_dump(const char *path, const float *data, int frames, int dim);
 // Reference LUT (1280 entries, dnn.cc:100-115).
 void build_reference_lut(uint8_t out[1280]);
 

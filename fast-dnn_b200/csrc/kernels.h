@@ -57,7 +57,7 @@ struct TcPlan {
   int cluster;
   bool share_a;
 };
-TcPlan qlayer_tc_plan(int M, int N, int num_sms);
+TcPlan qlayer_tc_plan(int M, int N, bool logits, int num_sms);
 cudaError_t launch_qlayer_tc(const CUtensorMap &tmap_act, const CUtensorMap &tmap_w, const QLayerArgs &a, bool logits, TcPlan plan, int num_sms,
                              cudaStream_t stream);
 // dp4a path (qlayer_simt.cu): any legal network (K a multiple of 16); used for narrow layers.

@@ -442,4 +442,141 @@ int validate_blob(const uint8_t *blob, size_t size) {
   return FDNN_OK;
 }
 
+// ---- offline tooling either side of the hot path -----------------------
+
+namespace {
+
+void put_be32(std::vector<uint8_t> &out, uint32_t v) {
+  out.push_back(uint8_t(v >> 24));
+  out.push_back(uint8_t(v >> 16));
+  out.push_back(uint8_t(v >> 8));
+  out.push_back(uint8_t(v));
+}
+void put_be_float(std::vector<uint8_t> &out, float f) {
+  uint32_t u;
+  std::memcpy(&u, &f, 4);
+  put_be32(out, u);
+}
+int write_file(const char *path, const std::vector<uint8_t> &bytes) {
+  FILE *f = std::fopen(path, "wb");
+  if (!f) {
+    set_error(std::string("cannot create ") + path);
+    return FDNN_EIO;
+  }
+  const size_t put = bytes.empty() ? 0 : std::fwrite(bytes.data(), 1, bytes.size(), f);
+  const bool ok = std::fclose(f) == 0 && put == bytes.size();
+  if (!ok) {
+    set_error(std::string("short write on ") + path);
+    return FDNN_EIO;
+  }
+  return FDNN_OK;
+}
+
+}  // namespace
+
+// FeedForwardNetwork.align(inputAlignment, hiddenAlignment) + saveBinary
+// (src/java/suskun/nn/FeedForwardNetwork.java:50-58, 226-235, 264-281, 331-340): pad the input
+// width (and shift/scale) to a multiple of `input_alignment`, every hidden width to a multiple of
+// `hidden_alignment`, with zero weights and zero bias; the output layer keeps its width.  The
+// reference's README lists doing this on the C++ side as a TODO (README.md:76).
+int align_dnn_bin(const char *in_path, const char *out_path, int input_alignment, int hidden_alignment) {
+  if (!in_path || !out_path || input_alignment <= 0 || hidden_alignment <= 0) {
+    set_error("bad argument to fdnn_align_dnn_bin");
+    return FDNN_EINVAL;
+  }
+  FileBytes fb;
+  if (int rc = read_file(in_path, fb.data)) return rc;
+  const int layer_count = int(fb.word());
+  if (fb.short_read || layer_count < 1 || layer_count > 4096) {
+    set_error("not a dnn.bin file");
+    return FDNN_EFORMAT;
+  }
+  std::vector<FloatLayer> layers(size_t(layer_count), FloatLayer{});
+  for (int j = 0; j < layer_count; ++j) {
+    FloatLayer &l = layers[size_t(j)];
+    l.in = int(fb.word());
+    l.out = int(fb.word());
+    if (fb.short_read || l.in <= 0 || l.out <= 0 || size_t(l.in) * size_t(l.out) > (fb.data.size() - fb.pos) / 4) {
+      set_error("dnn.bin truncated or corrupt at layer " + std::to_string(j));
+      return fb.short_read ? FDNN_EIO : FDNN_EFORMAT;
+    }
+    if (j > 0 && l.in != layers[size_t(j - 1)].out) {
+      set_error("layer " + std::to_string(j) + " input width does not match previous layer");
+      return FDNN_EFORMAT;
+    }
+    l.w.resize(size_t(l.in) * size_t(l.out));
+    l.bias.resize(size_t(l.out));
+    if (!fb.floats(l.w.data(), l.w.size()) || !fb.floats(l.bias.data(), l.bias.size())) {
+      set_error("dnn.bin truncated inside layer " + std::to_string(j));
+      return FDNN_EIO;
+    }
+  }
+  const int in0 = layers[0].in;
+  std::vector<float> shift(size_t(in0), 0.0f), scale(size_t(in0), 0.0f);
+  if (!fb.floats(shift.data(), shift.size()) || !fb.floats(scale.data(), scale.size())) {
+    set_error("dnn.bin truncated in shift/scale");
+    return FDNN_EIO;
+  }
+  std::vector<uint8_t> out;
+  put_be32(out, uint32_t(layer_count));
+  for (int j = 0; j < layer_count; ++j) {
+    const FloatLayer &l = layers[size_t(j)];
+    const int in_pad = round_up(l.in, j == 0 ? input_alignment : hidden_alignment);
+    const int out_pad = j == layer_count - 1 ? l.out : round_up(l.out, hidden_alignment);
+    put_be32(out, uint32_t(in_pad));
+    put_be32(out, uint32_t(out_pad));
+    for (int o = 0; o < out_pad; ++o)
+      for (int i = 0; i < in_pad; ++i) put_be_float(out, (o < l.out && i < l.in) ? l.w[size_t(o) * size_t(l.in) + size_t(i)] : 0.0f);
+    for (int o = 0; o < out_pad; ++o) put_be_float(out, o < l.out ? l.bias[size_t(o)] : 0.0f);
+  }
+  const int in_pad0 = round_up(in0, input_alignment);
+  for (int i = 0; i < in_pad0; ++i) put_be_float(out, i < in0 ? shift[size_t(i)] : 0.0f);
+  for (int i = 0; i < in_pad0; ++i) put_be_float(out, i < in0 ? scale[size_t(i)] : 0.0f);
+  return write_file(out_path, out);
+}
+
+// Feature matrix: big-endian int32 frames, int32 dimension, fp32 rows (BatchData.java:80-91, 107-139;
+// float_dnn.cc:85-105).  Only the `frames` rows the header announces are read (the shipped
+// data/16khz.bin carries one extra row).
+int read_feature_bin(const char *path, int *frames, int *dim, std::vector<float> &data) {
+  FileBytes fb;
+  if (int rc = read_file(path, fb.data)) return rc;
+  const int n = int(fb.word()), d = int(fb.word());
+  if (fb.short_read || n < 0 || d <= 0 || size_t(n) * size_t(d) > (fb.data.size() - fb.pos) / 4) {
+    set_error(std::string("not a usable feature file: ") + path);
+    return fb.short_read ? FDNN_EIO : FDNN_EFORMAT;
+  }
+  data.resize(size_t(n) * size_t(d));
+  fb.floats(data.data(), data.size());
+  *frames = n;
+  *dim = d;
+  return FDNN_OK;
+}
+
+int write_feature_bin(const char *path, const float *data, int frames, int dim) {
+  if (!path || (!data && frames > 0) || frames < 0 || dim <= 0) {
+    set_error("bad argument to fdnn_feature_bin_write");
+    return FDNN_EINVAL;
+  }
+  std::vector<uint8_t> out;
+  out.reserve(8 + size_t(frames) * size_t(dim) * 4);
+  put_be32(out, uint32_t(frames));
+  put_be32(out, uint32_t(dim));
+  for (size_t i = 0; i < size_t(frames) * size_t(dim); ++i) put_be_float(out, data[i]);
+  return write_file(path, out);
+}
+
+// BatchData::dumpToFile(…, binary = true) (float_dnn.cc:128-164): NATIVE-endian uint32 n, uint32 d, fp32 rows.
+int write_output_dump(const char *path, const float *data, int frames, int dim) {
+  if (!path || (!data && frames > 0) || frames < 0 || dim <= 0) {
+    set_error("bad argument to fdnn_output_dump_write");
+    return FDNN_EINVAL;
+  }
+  std::vector<uint8_t> out(8 + size_t(frames) * size_t(dim) * 4);
+  const uint32_t hdr[2] = {uint32_t(frames), uint32_t(dim)};
+  std::memcpy(out.data(), hdr, 8);
+  if (frames > 0) std::memcpy(out.data() + 8, data, size_t(frames) * size_t(dim) * 4);
+  return write_file(path, out);
+}
+
 }  // namespace fdnn

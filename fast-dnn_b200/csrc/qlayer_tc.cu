@@ -179,10 +179,6 @@ qlayer_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_cons
     ptx::fence_barrier_init();
   }
   if (warp == 2) ptx::tmem_alloc<Cfg::kTmemCols>(tmem_slot);
-  if (warp >= kFirstEpilogueWarp && !kLogits) {
-    for (int i = int(threadIdx.x) - kFirstEpilogueWarp * 32; i < kLut2Padded / 16; i += kEpilogueThreads)
-      reinterpret_cast<uint4 *>(s_lut)[i] = __ldg(reinterpret_cast<const uint4 *>(args.lut) + i);
-  }
   ptx::tc_fence_before_sync();
   __syncthreads();
   if (C > 1) ptx::cluster_sync_all();  // peers' barriers must exist before anything is multicast into them
@@ -413,6 +409,11 @@ qlayer_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_cons
     const int quarter = warp & 3;
     const int col_group = (warp - kFirstEpilogueWarp) >> 2;
     const int row_local = quarter * 32 + lane;
+    // the sigmoid table is only needed here, so fetching it overlaps the first tile's contraction
+    // (the per-tile named barrier below orders it before its first use)
+    if (!kLogits) {
+      for (int i = et; i < kLut2Padded / 16; i += kEpilogueThreads) reinterpret_cast<uint4 *>(s_lut)[i] = __ldg(reinterpret_cast<const uint4 *>(args.lut) + i);
+    }
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int ct = first_ct; ct < tiles_total; ct += ct_step) {
@@ -555,7 +556,7 @@ bool qlayer_tc_supported(int N, int K, bool logits) {
 // Tile width and cluster shape for a launch.  Small batches: narrow tiles so that every SM has one,
 // optionally (FDNN_CLUSTER=1) four neighbouring N tiles share the activation tile.  Streams: 128×256
 // tiles, optionally two neighbouring M tiles share the weight tile.
-TcPlan qlayer_tc_plan(int M, int N, int num_sms) {
+TcPlan qlayer_tc_plan(int M, int N, bool logits, int num_sms) {
   static const bool clusters = [] {
     const char *e = std::getenv("FDNN_CLUSTER");
     return e && e[0] == '1';
@@ -577,10 +578,18 @@ TcPlan qlayer_tc_plan(int M, int N, int num_sms) {
     }
     return p;
   }
-  // widest tile that still gives (nearly) every SM one: measured on B200, 128 tiles of 128×256 beat
-  // 252 tiles of 128×128 (two rounds) on the 8000-wide output layer at batch 512
-  const int enough = num_sms * 85 / 100;
-  p.block_n = m_blocks * ((N + 255) / 256) >= enough ? 256 : (m_blocks * ((N + 127) / 128) >= enough ? 128 : 64);
+  // Below that, measured on B200 (tools/stage_times.py): per-tile time grows faster than the tile
+  // (fewer pipeline stages fit), so take the narrowest tile that still finishes in one round; if even
+  // 128-wide tiles need a second round, the 8000-wide output layer is better off with one round of
+  // 128×256 tiles (batch 512: 30.9 us vs 34.7 us), the 2048-wide hidden layers with two rounds of
+  // 128×128 (batch 2048: 27 us vs 37 us).
+  auto tiles = [&](int bn) { return m_blocks * ((N + bn - 1) / bn); };
+  if (tiles(64) <= num_sms)
+    p.block_n = 64;
+  else if (tiles(128) <= num_sms)
+    p.block_n = 128;
+  else
+    p.block_n = (logits && tiles(256) <= num_sms) ? 256 : 128;
   if (clusters && p.block_n <= 128 && (N + p.block_n - 1) / p.block_n >= 4) {
     p.cluster = 4;
     p.share_a = true;

@@ -96,3 +96,25 @@ def write_output_dump(path, rows) -> None:
     with open(path, "wb") as f:
         f.write(np.array(rows.shape, dtype="<u4").tobytes())
         rows.tofile(f)
+
+
+def align_network(layers, shift, scale, input_alignment: int = 4, hidden_alignment: int = 16):
+    """numpy mirror of FeedForwardNetwork.align (FeedForwardNetwork.java:50-58, Layer.align :264-281):
+    zero-pad the input width, every hidden width and the matching input widths; output width kept."""
+    out = []
+    for j, (w, b) in enumerate(layers):
+        w = np.asarray(w, dtype=np.float32)
+        b = np.asarray(b, dtype=np.float32)
+        in_pad = pad_to(w.shape[1], input_alignment if j == 0 else hidden_alignment)
+        out_pad = w.shape[0] if j == len(layers) - 1 else pad_to(w.shape[0], hidden_alignment)
+        w2 = np.zeros((out_pad, in_pad), dtype=np.float32)
+        w2[:w.shape[0], :w.shape[1]] = w
+        b2 = np.zeros(out_pad, dtype=np.float32)
+        b2[:b.shape[0]] = b
+        out.append((w2, b2))
+    in0 = pad_to(len(shift), input_alignment)
+    sh = np.zeros(in0, dtype=np.float32)
+    sc = np.zeros(in0, dtype=np.float32)
+    sh[:len(shift)] = shift
+    sc[:len(scale)] = scale
+    return out, sh, sc

@@ -42,6 +42,10 @@ SIGNATURES = {
     "fdnn_pack": (_I, [C.c_char_p, _F, C.POINTER(_P), C.POINTER(_SZ)]),
     "fdnn_blob_free": (None, [_P]),
     "fdnn_load_blob": (_I, [_P, _SZ, _I, C.POINTER(_P)]),
+    "fdnn_align_dnn_bin": (_I, [C.c_char_p, C.c_char_p, _I, _I]),
+    "fdnn_feature_bin_read": (_I, [C.c_char_p, C.POINTER(_I), C.POINTER(_I), C.POINTER(_P)]),
+    "fdnn_feature_bin_write": (_I, [C.c_char_p, _P, _I, _I]),
+    "fdnn_output_dump_write": (_I, [C.c_char_p, _P, _I, _I]),
     "fdnn_free": (_I, [_P]),
     "fdnn_input_dim": (_I, [_P]),
     "fdnn_output_dim": (_I, [_P]),
@@ -124,6 +128,30 @@ def pack(path: str, cutoff: float = 3.0) -> np.ndarray:
         return np.ctypeslib.as_array(C.cast(blob, C.POINTER(C.c_uint8)), shape=(size.value,)).copy()
     finally:
         lib().fdnn_blob_free(blob)
+
+
+def align_dnn_bin(in_path, out_path, input_alignment: int = 4, hidden_alignment: int = 16) -> None:
+    """FeedForwardNetwork.align(4, 16) + saveBinary on the C++ side (host only)."""
+    _check(lib().fdnn_align_dnn_bin(os.fsencode(in_path), os.fsencode(out_path), input_alignment, hidden_alignment))
+
+
+def read_feature_bin(path) -> np.ndarray:
+    n, d, data = C.c_int(), C.c_int(), C.c_void_p()
+    _check(lib().fdnn_feature_bin_read(os.fsencode(path), C.byref(n), C.byref(d), C.byref(data)))
+    try:
+        return np.ctypeslib.as_array(C.cast(data, C.POINTER(C.c_float)), shape=(n.value * d.value,)).reshape(n.value, d.value).copy()
+    finally:
+        lib().fdnn_blob_free(data)
+
+
+def write_feature_bin(path, frames) -> None:
+    x = np.ascontiguousarray(frames, dtype=np.float32)
+    _check(lib().fdnn_feature_bin_write(os.fsencode(path), _ptr(x), x.shape[0], x.shape[1]))
+
+
+def write_output_dump(path, rows) -> None:
+    x = np.ascontiguousarray(rows, dtype=np.float32)
+    _check(lib().fdnn_output_dump_write(os.fsencode(path), _ptr(x), x.shape[0], x.shape[1]))
 
 
 class PinnedArray:

@@ -57,6 +57,19 @@ void fdnn_blob_free(void *blob);
 /* `blob` may be a host pointer or a device pointer on `device` (e.g. an NCCL receive buffer). */
 int fdnn_load_blob(const void *blob, size_t size, int device, fdnn_model **out);
 
+/* ---- offline tooling either side of the path (host only, no GPU needed) -------------------------
+ * FeedForwardNetwork.align + saveBinary (src/java/suskun/nn/FeedForwardNetwork.java:50-58,226-235,
+ * 264-281,331-340): read a dnn.bin of any shape, zero-pad the input width to a multiple of
+ * input_alignment (4) and every hidden width to a multiple of hidden_alignment (16), write a dnn.bin
+ * that fdnn_load accepts.  The reference does this in Java only (README.md:76 lists C++ as a TODO). */
+int fdnn_align_dnn_bin(const char *in_path, const char *out_path, int input_alignment, int hidden_alignment);
+/* Feature matrices: big-endian int32 frames, int32 dim, fp32 rows (BatchData.java:80-91,107-139;
+ * float_dnn.cc:85-105).  *data is malloc'ed (release with fdnn_blob_free). */
+int fdnn_feature_bin_read(const char *path, int *frames, int *dim, float **data);
+int fdnn_feature_bin_write(const char *path, const float *data, int frames, int dim);
+/* BatchData::dumpToFile(..., binary) (float_dnn.cc:128-164): native-endian uint32 n, uint32 d, fp32 rows */
+int fdnn_output_dump_write(const char *path, const float *data, int frames, int dim);
+
 /* Java_suskun_nn_QuantizedDnn_delete (jni_dnn.cc:128-133) */
 int fdnn_free(fdnn_model *model);
 

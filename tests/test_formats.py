@@ -1,0 +1,91 @@
+"""Formats and offline tooling either side of the hot path: the C++
+aligner/writer against the numpy mirror of FeedForwardNetwork.align, feature-file IO against the
+shipped fixtures' layout, the output dump, and the quantization-quality criterion of FuncTest.diff."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import REFERENCE_ROOT
+from fast_dnn_b200 import formats, synth
+from fast_dnn_b200 import quantized_dnn as qd
+import oracle_py
+
+
+def test_cpp_aligner_equals_java_semantics(tmp_path):
+    layers, shift, scale = synth.make_network((10, 40, 3, 7), seed=5)  # input 10 → 12, hidden 40 → 48, output stays 7
+    raw, aligned_cpp, aligned_np = (str(tmp_path / n) for n in ("raw.bin", "cpp.bin", "np.bin"))
+    formats.write_dnn_bin(raw, layers, shift, scale)
+    with pytest.raises(qd.FdnnError):
+        qd.pack(raw)  # hidden width 40 is not a multiple of 16: the loader refuses it, like the reference would misbehave
+    qd.align_dnn_bin(raw, aligned_cpp, 4, 16)
+    formats.write_dnn_bin(aligned_np, *formats.align_network(layers, shift, scale, 4, 16))
+    assert open(aligned_cpp, "rb").read() == open(aligned_np, "rb").read()
+    got, sh, sc = formats.read_dnn_bin(aligned_cpp)
+    assert [w.shape for w, _ in got] == [(48, 12), (48, 48), (48, 48), (7, 48)]
+    assert np.all(got[0][0][40:] == 0) and np.all(got[1][0][:, 40:] == 0) and np.all(got[0][1][40:] == 0) and sh.shape == (12,)
+    # padding does not change any real output: the oracle on the aligned file vs a float64 forward of the unaligned net
+    port = oracle_py.Port(aligned_cpp)
+    frames = synth.make_frames(16, 12, seed=3)
+    frames[:, 10:] = 0
+    q = port.calculate(frames)
+    assert q.shape == (16, 7) and np.allclose(q.sum(axis=1), 1.0, atol=1e-5)
+    qd.pack(aligned_cpp)  # and our loader now takes it
+    assert qd.lib().fdnn_align_dnn_bin(b"/nonexistent/x", aligned_cpp.encode(), 4, 16) == qd.FDNN_EIO
+
+
+def test_feature_bin_round_trip_and_dump(tmp_path):
+    x = synth.make_frames(37, 24, seed=1)
+    a, b = str(tmp_path / "a.bin"), str(tmp_path / "b.bin")
+    qd.write_feature_bin(a, x)
+    formats.write_feature_bin(b, x)
+    assert open(a, "rb").read() == open(b, "rb").read()
+    assert np.array_equal(qd.read_feature_bin(a), x) and np.array_equal(formats.read_feature_bin(a), x)
+    dump = str(tmp_path / "out.bin")
+    qd.write_output_dump(dump, x)
+    assert np.array_equal(formats.read_output_dump(dump), x)  # native-endian, unlike the inputs (float_dnn.cc:128-164)
+    raw = np.fromfile(dump, dtype="<u4", count=2)
+    assert tuple(raw) == (37, 24)
+
+
+@pytest.mark.skipif(not os.path.isdir(REFERENCE_ROOT), reason="shipped fixtures live in /root/reference")
+def test_reads_shipped_feature_files():
+    x = qd.read_feature_bin(os.path.join(REFERENCE_ROOT, "data", "8khz.aligned.bin"))
+    assert x.shape == (389, 432) and np.all(x[:, 429:] == 0)
+    y = qd.read_feature_bin(os.path.join(REFERENCE_ROOT, "data", "16khz.bin"))
+    assert y.shape == (100, 432)  # header says 100; the 101st row in the file is ignored (float_dnn.cc:88-102)
+    assert np.array_equal(x, formats.read_feature_bin(os.path.join(REFERENCE_ROOT, "data", "8khz.aligned.bin")))
+
+
+def naive_forward(layers, shift, scale, frames):
+    """FeedForwardNetwork.calculate (FeedForwardNetwork.java:133-148, 360-414) in float64"""
+    a = (frames.astype(np.float64) + shift) * scale
+    for i, (w, b) in enumerate(layers):
+        z = a @ w.astype(np.float64).T + b
+        if i < len(layers) - 1:
+            a = 1.0 / (1.0 + np.exp(-z))
+        else:
+            e = np.exp(z)
+            a = e / e.sum(axis=1, keepdims=True)
+    return a
+
+
+@pytest.mark.parametrize("shape", ["S", "P"])
+def test_quantization_quality_criterion(shape):
+    """FuncTest.diff (FuncTest.java:59-74): per output node, Σ over frames |quantized − naive| ≤ 0.1"""
+    layers, shift, scale = synth.make_network(shape)
+    frames = synth.make_frames(100, layers[0][0].shape[1], seed=7)
+    q = oracle_py.Port(synth.network_file(shape)).calculate(frames)
+    f = naive_forward(layers, shift, scale, frames)
+    assert np.abs(q - f).sum(axis=0).max() < 0.1
+    assert np.array_equal(q.argmax(axis=1), f.argmax(axis=1))
+
+
+@pytest.mark.gpu
+def test_gpu_path_meets_the_quality_criterion_too():
+    layers, shift, scale = synth.make_network("S")
+    frames = synth.make_frames(100, 440, seed=7)
+    dnn = qd.QuantizedDnn.load_from_file(synth.network_file("S"))
+    q = dnn.calculate(frames)
+    dnn.delete()
+    assert np.abs(q - naive_forward(layers, shift, scale, frames)).sum(axis=0).max() < 0.1
