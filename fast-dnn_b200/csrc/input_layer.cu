@@ -35,7 +35,7 @@ namespace {
 constexpr int kTileF = 64;    // frames per CTA
 constexpr int kTileN = 128;   // nodes per CTA
 constexpr int kChunk = 40;    // floats of K per stage
-constexpr int kPitch = 44;    // smem row pitch in floats (≡ 12 mod 32 → conflict-free LDS.128 over consecutive rows)
+constexpr int kPitch = 44;    // smem row pitch in floats (≡ 12 mod 32: consecutive rows land in different bank quads)
 constexpr int kThreads = 512;
 constexpr int kTF = 8, kTN = 8;  // per-thread block of one SSE lane
 constexpr int kStages = 3;
