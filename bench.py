@@ -250,6 +250,30 @@ def run_gpu_arm(args):
               "softmax_ms": float(stage_ms[n_layers]), "sum_ms": total_stage,
               "output_plus_softmax_hbm_gbs": (BATCH * O_DIM * 4 * 3 + O_DIM * H_DIM) / ((stage_ms[n_layers - 1] + stage_ms[n_layers]) * 1e-3) / 1e9}
 
+    # ---- the same kernels on a long stream (BASELINE configs[4] regime: 16384-frame chunks) ----------
+    stream_info = None
+    if rank == 0 and not args.no_stream:
+        m_big = 16384
+        big_in = torch.from_numpy(synth.make_frames(m_big, I_DIM, seed=99)).to(dev)
+        big_out = torch.empty(m_big, O_DIM, dtype=torch.float32, device=dev)
+        big_ctx = dnn.get_new_lazy_context(m_big)
+        big_ms = big_ctx.profile_stages(big_in.data_ptr(), m_big, big_out.data_ptr(), iters=5)
+        for _ in range(3):
+            big_ctx.forward_device(big_in.data_ptr(), m_big, big_out.data_ptr(), stream.cuda_stream)
+        b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        b0.record(stream)
+        for _ in range(5):
+            big_ctx.forward_device(big_in.data_ptr(), m_big, big_out.data_ptr(), stream.cuda_stream)
+        b1.record(stream)
+        torch.cuda.synchronize()
+        big_hidden = float(np.mean(big_ms[1:n_layers - 1]))
+        big_tops = 2.0 * m_big * H_DIM * H_DIM / (big_hidden * 1e-3) / 1e12
+        stream_info = {"frames_per_pass": m_big, "frames_per_s": m_big * 5 / (b0.elapsed_time(b1) * 1e-3),
+                       "hidden_kernel_ms": big_hidden, "hidden_kernel_tops": big_tops, "hidden_kernel_frac_of_peak": big_tops / int8_peak,
+                       "input_ms": float(big_ms[0]), "output_ms": float(big_ms[n_layers - 1]), "softmax_ms": float(big_ms[n_layers])}
+        big_ctx.delete()
+        del big_in, big_out
+
     # ---- end to end through the public call (fdnn_calculate): pinned HOST buffers, H2D + D2H inside
     e2e_threads = 3
     e2e_pool = 2
@@ -324,7 +348,7 @@ def run_gpu_arm(args):
                              "the 45 MB of weights stay L2-resident as in steady-state serving",
                        "parallelism": f"frames sharded over {world} GPU(s), one NCCL broadcast of the weight blob at load, no per-frame collective"},
             "e2e": e2e, "gpu_launches": int(launches), "clocks": sampler.summary(), "roofline": roofline, "stages": stages,
-            "cpu_baseline": cpu_baseline,
+            "cpu_baseline": cpu_baseline, "stream_regime": stream_info,
         }, default=plain))
     ctx.delete()
     dnn.delete()
@@ -339,6 +363,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-stream", action="store_true", help="skip the extra long-stream measurement")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

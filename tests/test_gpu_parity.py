@@ -216,3 +216,25 @@ def test_headline_network_batch512(loaded):
     # a frame's result does not depend on its neighbours or its position in the batch
     again = dnn.calculate(frames[::-1].copy())
     assert np.array_equal(again[::-1], got)
+
+
+def test_cluster_multicast_path_is_bit_exact(net_file):
+    """FDNN_CLUSTER=1 (TMA multicast across thread-block clusters, opt-in): same bytes as the default path"""
+    import subprocess
+    import sys
+    code = (
+        "import sys, numpy as np; sys.path.insert(0, %r); import fast_dnn_b200\n"
+        "from fast_dnn_b200 import quantized_dnn as qd, synth\n"
+        "dnn = qd.QuantizedDnn.load_from_file(%r)\n"
+        "x = synth.make_frames(300, 440, seed=4)\n"
+        "ctx = dnn.get_new_lazy_context(300); ctx.calculate_until_output(x)\n"
+        "np.save(sys.argv[1], ctx.hidden()); np.save(sys.argv[2], ctx.logits())\n"
+    ) % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), net_file("S"))
+    outs = {}
+    for flag in ("0", "1"):
+        paths = [f"/tmp/fdnn_cluster_{flag}_{k}.npy" for k in ("h", "l")]
+        env = dict(os.environ, FDNN_CLUSTER=flag)
+        subprocess.run([sys.executable, "-c", code] + paths, check=True, env=env, timeout=240)
+        outs[flag] = [np.load(p) for p in paths]
+    assert np.array_equal(outs["0"][0], outs["1"][0])
+    assert np.array_equal(outs["0"][1].view(np.uint32), outs["1"][1].view(np.uint32))
