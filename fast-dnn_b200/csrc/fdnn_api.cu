@@ -139,7 +139,7 @@ struct fdnn_model {
   size_t blob_size = 0;
   BlobHeader hdr{};
   std::vector<BlobQLayer> q;
-  std::vector<std::array<CUtensorMap, 3>> wmaps;  // per int8 layer, box rows 64 / 128 / 256
+  std::vector<std::array<CUtensorMap, 4>> wmaps;  // per int8 layer, box rows 64 / 128 / 256 / 32
   std::vector<bool> tc_ok;
   bool force_simt = false;
   // Graph capture must not overlap device-wide synchronising calls (cudaFree, blocking copies) made
@@ -317,8 +317,11 @@ int enqueue_until_logits(fdnn_ctx *c, const float *d_in, int m, float *d_logits,
       a.fix = fix_of(j, which);  // the risk list grouped by the tile width
       const int act_box = plan.share_a ? (plan.cluster == 4 ? 2 : (plan.cluster == 2 ? 1 : 0)) : 0;
       const int w_rows = plan.share_a ? plan.block_n : plan.block_n / plan.cluster;
-      const int w_box = w_rows == 64 ? 0 : (w_rows == 128 ? 1 : 2);
-      CUDA_TRY(launch_qlayer_tc(c->amap[j & 1][act_box], mod->wmaps[size_t(j)][size_t(w_box)], a, logits, plan, mod->num_sms, stream));
+      const int w_box = w_rows == 64 ? 0 : (w_rows == 128 ? 1 : (w_rows == 256 ? 2 : 3));
+      if (plan.pair)
+        CUDA_TRY(launch_qlayer_pair(c->amap[j & 1][0], mod->wmaps[size_t(j)][size_t(w_box)], a, logits, plan.block_n, mod->num_sms, stream));
+      else
+        CUDA_TRY(launch_qlayer_tc(c->amap[j & 1][act_box], mod->wmaps[size_t(j)][size_t(w_box)], a, logits, plan, mod->num_sms, stream));
     } else {
       CUDA_TRY(launch_qlayer_simt(a, logits, stream));
     }
@@ -436,6 +439,10 @@ int upload_model(const uint8_t *host_view, const void *src, bool src_on_device, 
     set_error(std::string("qlayer_tc_configure: ") + cudaGetErrorString(ce));
     return fail(FDNN_ECUDA);
   }
+  if (cudaError_t ce = qlayer_pair_configure(); ce != cudaSuccess) {
+    set_error(std::string("qlayer_pair_configure: ") + cudaGetErrorString(ce));
+    return fail(FDNN_ECUDA);
+  }
   if (cudaError_t ce = softmax_configure(); ce != cudaSuccess) {
     set_error(std::string("softmax_configure: ") + cudaGetErrorString(ce));
     return fail(FDNN_ECUDA);
@@ -446,8 +453,8 @@ int upload_model(const uint8_t *host_view, const void *src, bool src_on_device, 
     const BlobQLayer &ql = m->q[j];
     const bool logits = j + 1 == m->q.size();
     if (m->force_simt || !qlayer_tc_supported(ql.nodes, ql.inputs, logits)) continue;
-    const int boxes[3] = {64, 128, 256};
-    for (int b = 0; b < 3; ++b)
+    const int boxes[4] = {64, 128, 256, 32};
+    for (int b = 0; b < 4; ++b)
       if (int rc = make_tmap(&m->wmaps[j][size_t(b)], m->d_blob + ql.off_w, ql.nodes, ql.inputs, boxes[b])) return fail(rc);
     m->tc_ok[j] = true;
   }

@@ -56,10 +56,15 @@ struct TcPlan {
   int block_n;
   int cluster;
   bool share_a;
+  bool pair;  // CTA pairs (tcgen05 cta_group::2, qlayer_pair.cu): activation box 128 rows, weight box block_n/2 rows
 };
 TcPlan qlayer_tc_plan(int M, int N, bool logits, int num_sms);
 cudaError_t launch_qlayer_tc(const CUtensorMap &tmap_act, const CUtensorMap &tmap_w, const QLayerArgs &a, bool logits, TcPlan plan, int num_sms,
                              cudaStream_t stream);
+// CTA-pair path (qlayer_pair.cu): two CTAs per 256×block_n tile sharing the weight tile.
+cudaError_t qlayer_pair_configure();
+cudaError_t launch_qlayer_pair(const CUtensorMap &tmap_act, const CUtensorMap &tmap_w, const QLayerArgs &a, bool logits, int block_n, int num_sms,
+                               cudaStream_t stream);
 // dp4a path (qlayer_simt.cu): any legal network (K a multiple of 16); used for narrow layers.
 cudaError_t launch_qlayer_simt(const QLayerArgs &a, bool logits, cudaStream_t stream);
 

@@ -174,6 +174,86 @@ __host__ __device__ constexpr uint32_t idesc_i8_u8s8(uint32_t n) {
   return (2u << 4) | (0u << 7) | (1u << 10) | ((n >> 3) << 17) | ((128u >> 4) << 24);
 }
 
+// ---- CTA pairs (cta_group::2): two CTAs of a cluster on the SMs of one TPC run one MMA together ----
+// Shared-memory address of `local_addr` in CTA `rank` of this cluster.
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t local_addr, uint32_t rank) {
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local_addr), "r"(rank));
+  return remote;
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// Waits with a suspend-time hint: the hardware parks the thread until the phase completes or the
+// hint (ns) runs out, so a long wait costs a handful of polls instead of a spin loop that competes
+// with the working warps for issue slots.  Still bounded: a protocol bug traps.
+__device__ __forceinline__ void mbar_wait_parked(uint64_t *bar, uint32_t parity) {
+  uint32_t polls = 0, ok = 0;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred P;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2, %3;\n\t"
+        "selp.b32 %0, 1, 0, P;\n\t}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(5000u)
+        : "memory");
+    if (!ok && ++polls > (1u << 20)) __trap();
+  } while (!ok);
+}
+// … that also orders against arrivals made by the peer CTA
+__device__ __forceinline__ void mbar_wait_parked_cluster(uint64_t *bar, uint32_t parity) {
+  uint32_t polls = 0, ok = 0;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred P;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P, [%1], %2, %3;\n\t"
+        "selp.b32 %0, 1, 0, P;\n\t}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(5000u)
+        : "memory");
+    if (!ok && ++polls > (1u << 20)) __trap();
+  } while (!ok);
+}
+// 2D tile into this CTA's shared memory; the bytes are counted on a barrier that may live in the
+// peer CTA (`bar_cluster_addr` is a shared::cluster address — the pair's leader owns the "full" barriers).
+__device__ __forceinline__ void tma_load_2d_pair(const CUtensorMap *map, uint32_t bar_cluster_addr, void *smem_dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
+      : "memory");
+}
+// Executed by the same warp of BOTH CTAs of the pair; allocates the same columns in both tensor memories.
+template <uint32_t kCols>
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t *smem_result) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)), "n"(kCols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+template <uint32_t kCols>
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(kCols) : "memory");
+}
+// D[tmem of both CTAs] (+)= A[256 rows: 128 from each CTA's smem] · B[N rows: N/2 from each CTA's smem].
+// Issued by one thread of the leader CTA; descriptors are leader-relative, the peer uses the same offsets.
+__device__ __forceinline__ void mma_i8_ss_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n\t}\n"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// All previously issued pair MMAs arrive on the barrier at this offset in both CTAs when complete.
+__device__ __forceinline__ void mma_commit_pair(uint64_t *bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+               "h"(uint16_t(3))
+               : "memory");
+}
+// Instruction descriptor, kind::i8, for the pair: M = 256 (128 rows per CTA).
+__host__ __device__ constexpr uint32_t idesc_i8_u8s8_pair(uint32_t n) {
+  return (2u << 4) | (0u << 7) | (1u << 10) | ((n >> 3) << 17) | ((256u >> 4) << 24);
+}
+
 // Programmatic dependent launch: the next kernel in the stream may be launched while this one is
 // still running (its prologue overlaps our tail); wait() blocks until every prerequisite grid has
 // completed and its memory is visible.  No-ops when the kernel was launched without the attribute.

@@ -562,7 +562,18 @@ TcPlan qlayer_tc_plan(int M, int N, bool logits, int num_sms) {
     return e && e[0] == '1';
   }();
   const int m_blocks = (M + kBlockM - 1) / kBlockM;
-  TcPlan p{64, 1, true};
+  TcPlan p{64, 1, true, false};
+  // FDNN_PAIR=<bn>: every tensor-core layer on CTA pairs with that tile width (tuning experiments)
+  if (const char *e = std::getenv("FDNN_PAIR")) {
+    const int bn = std::atoi(e);
+    if ((bn == 64 || bn == 128 || bn == 256) && num_sms >= 2) {
+      p.block_n = bn;
+      p.cluster = 2;
+      p.share_a = false;
+      p.pair = true;
+      return p;
+    }
+  }
   if (const char *e = std::getenv("FDNN_FORCE_BN")) {  // tuning experiments
     const int bn = std::atoi(e);
     if ((bn == 64 || bn == 128 || bn == 256) && N >= 4096) {

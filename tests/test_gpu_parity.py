@@ -238,3 +238,28 @@ def test_cluster_multicast_path_is_bit_exact(net_file):
         outs[flag] = [np.load(p) for p in paths]
     assert np.array_equal(outs["0"][0], outs["1"][0])
     assert np.array_equal(outs["0"][1].view(np.uint32), outs["1"][1].view(np.uint32))
+
+
+@pytest.mark.parametrize("stress", [False, True])
+def test_cta_pair_path_is_bit_exact(net_file, stress):
+    """FDNN_PAIR=<tile width>: every int8 layer on CTA pairs (tcgen05 cta_group::2, qlayer_pair.cu) — same
+    bytes as the single-CTA path (itself checked against the oracle above), ragged row count, dense saturation"""
+    import subprocess
+    import sys
+    code = (
+        "import sys, numpy as np; sys.path.insert(0, %r); import fast_dnn_b200\n"
+        "from fast_dnn_b200 import quantized_dnn as qd, synth\n"
+        "dnn = qd.QuantizedDnn.load_from_file(%r)\n"
+        "x = synth.make_frames(300, 440, seed=4)\n"
+        "ctx = dnn.get_new_lazy_context(300); ctx.calculate_until_output(x)\n"
+        "np.save(sys.argv[1], ctx.hidden()); np.save(sys.argv[2], ctx.logits())\n"
+    ) % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), net_file("S", stress=stress))
+    outs = {}
+    for flag in ("", "64", "128", "256"):
+        paths = [f"/tmp/fdnn_pair_{int(stress)}_{flag}_{k}.npy" for k in ("h", "l")]
+        env = dict(os.environ, FDNN_PAIR=flag)
+        subprocess.run([sys.executable, "-c", code] + paths, check=True, env=env, timeout=240)
+        outs[flag] = [np.load(p) for p in paths]
+    for flag in ("64", "128", "256"):
+        assert np.array_equal(outs[""][0], outs[flag][0]), f"pair tile {flag}: last-hidden bytes differ"
+        assert np.array_equal(outs[""][1].view(np.uint32), outs[flag][1].view(np.uint32)), f"pair tile {flag}: logits differ"
