@@ -14,6 +14,7 @@
 #include <algorithm>
 #include <array>
 #include <atomic>
+#include <cmath>
 #include <cstdlib>
 #include <cstring>
 #include <functional>
@@ -141,6 +142,7 @@ struct fdnn_model {
   std::vector<BlobQLayer> q;
   std::vector<std::array<CUtensorMap, 4>> wmaps;  // per int8 layer, box rows 64 / 128 / 256 / 32
   std::vector<bool> tc_ok;
+  std::vector<int> fast_tail;  // per int8 layer: the packed-f32x2 epilogue is provably bit-identical (device_common.cuh)
   bool force_simt = false;
   // Graph capture must not overlap device-wide synchronising calls (cudaFree, blocking copies) made
   // by this library from other threads: both sides take this lock.
@@ -293,6 +295,9 @@ int enqueue_until_logits(fdnn_ctx *c, const float *d_in, int m, float *d_logits,
     a.coeff = ql.coeff;
     a.rcp = ql.rcp_coeff;
     a.fast_div = int(ql.fast_div);
+    a.fast_tail = mod->fast_tail[size_t(j)];
+    a.one = 1.0f;
+    a.neg_zero = -0.0f;
     a.M = m;
     a.N = ql.nodes;
     a.K = ql.inputs;
@@ -449,6 +454,22 @@ int upload_model(const uint8_t *host_view, const void *src, bool src_on_device, 
   }
   m->wmaps.resize(m->q.size());
   m->tc_ok.assign(m->q.size(), false);
+  // The fast epilogue drops the reference's NaN / ≥ 2³¹ handling (x86 cvttss2si "integer indefinite"), so it
+  // is only enabled where neither can occur: |sum| ≤ 255·128·K, so |lin| ≤ 255·128·K / coeff (+ 1 ulp slack).
+  m->fast_tail.assign(m->q.size(), 0);
+  static const bool allow_fast_tail = env_flag("FDNN_FAST_TAIL", true);
+  for (size_t j = 0; j < m->q.size(); ++j) {
+    const BlobQLayer &ql = m->q[j];
+    const float *bias = reinterpret_cast<const float *>(host_view + ql.off_bias);
+    double max_bias = 0.0;
+    bool finite = std::isfinite(ql.coeff) && ql.coeff > 0.0f && std::isfinite(ql.rcp_coeff);
+    for (int i = 0; i < ql.nodes && finite; ++i) {
+      finite = std::isfinite(bias[i]);
+      max_bias = std::max(max_bias, std::fabs(double(bias[i])));
+    }
+    const double max_lin = 255.0 * 128.0 * double(ql.inputs) / double(ql.coeff) * 1.001;
+    m->fast_tail[j] = (allow_fast_tail && finite && ql.fast_div && (max_lin + max_bias) * 200.0 < 2.0e9) ? 1 : 0;
+  }
   for (size_t j = 0; j < m->q.size(); ++j) {
     const BlobQLayer &ql = m->q[j];
     const bool logits = j + 1 == m->q.size();

@@ -57,6 +57,13 @@ __device__ __forceinline__ uint32_t lds_u16(uint32_t smem_addr) {
   return v;
 }
 
+template <int kOffset>
+__device__ __forceinline__ uint32_t lds_u16_off(uint32_t smem_addr) {
+  uint16_t v;
+  asm volatile("ld.shared.u16 %0, [%1+%2];" : "=h"(v) : "r"(smem_addr), "n"(kOffset));
+  return v;
+}
+
 // ---- thread-block clusters ----------------------------------------------------------------------
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;

@@ -16,10 +16,19 @@
 // allocator (cta_group::2, both CTAs), warps 4-11 saturation scan of this CTA's 128 rows, warps 12-27
 // epilogue of this CTA's 128 rows × BN columns out of its own tensor memory.
 //
-// The scan reads a stage AFTER the MMA has consumed it (it waits for the commit, not for TMA): the
-// peer has no barrier of its own that tells it "my tile landed", the commit is visible in both CTAs,
-// and the scan's result is only needed at the end of the tile anyway.  A stage returns to the producer
-// when the four scan warps that own it have arrived.
+// Instruction issue, not the tensor pipe or shared memory, was what the single-CTA kernel ran out of on
+// long streams (ncu: ≈ 80 k warp instructions per 128×256 tile against the 32 k issue slots its 8192
+// tensor-pipe cycles offer).  Hence, here: (1) saturation events go into per-(16-column chunk, row)
+// cells, so that the epilogue applies at most two 16-way selects per chunk instead of walking the
+// row's whole event list for every chunk; (2) the per-element tail runs on packed FFMA2
+// (finish_chunk_fast); (3) one epilogue warp polls the tile barriers, the other fifteen sleep in a
+// hardware barrier; (4) the scan folds the range check into dp4a's accumulator and ORs the results.
+//
+// The scan reads a stage AFTER the MMA has consumed it (it waits for the commit, not for TMA): only the
+// leader's full barrier sees the TMA bytes, the commit is visible in both CTAs, and the scan's result is
+// only needed at the end of the tile anyway.  A stage returns to the producer when the four scan warps
+// that own it have arrived.  (Measured alternative, B200: scan concurrent with the MMA, the leader
+// relaying "stage landed" to the peer — 102 us instead of 94 us per 16384-frame hidden layer.)
 
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -47,7 +56,9 @@ constexpr int kThreads = (kFirstEpilogueWarp + kEpilogueWarps) * 32;  // 896
 constexpr int kAccStages = 2;
 constexpr int kEntCap = 1024;   // risk entries of the tile staged (packed) in shared memory; the rest is read from global
 constexpr int kPtrSlots = 132;  // ≥ k_blocks + 1 → K ≤ 16768
-constexpr int kRowEvents = 8;
+constexpr int kRowEvents = 4;    // overflow events kept per tile row (third and later event of one 16-column chunk)
+constexpr int kCellSlots = 2;    // events a (chunk, row) cell holds
+constexpr int kListCap = 128;    // events a scan warp collects per tile before it files them into the cells
 
 static_assert(kBlockK == kFixKBlock, "risk-list order is tied to the tiling");
 
@@ -62,7 +73,11 @@ struct PairConfig {
   static constexpr int kABytes = kBlockM * kBlockK;     // this CTA's 128 activation rows
   static constexpr int kBBytes = (BN / 2) * kBlockK;    // this CTA's half of the weight rows
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = BN == 256 ? 6 : 8;
+  static constexpr int kStages = BN == 256 ? 5 : (BN == 128 ? 7 : 8);
+  static constexpr int kAllChunks = BN / 16;
+  static constexpr int kCellWords = kCellSlots * kAllChunks * kBlockM;  // per accumulator stage
+  static constexpr int kCellBytes = kAccStages * kCellWords * 4;
+  static constexpr int kListBytes = kScanWarps * kListCap * 4;  // only the scan warps use it, one tile at a time
   static constexpr int kTmemCols = kAccStages * BN;
   static constexpr int kColsPerWarp = BN / 4;
   static constexpr int kChunks = kColsPerWarp / 16;
@@ -72,7 +87,8 @@ struct PairConfig {
   static constexpr int kEvBytes = kAccStages * kBlockM * kRowEvents * 4;
   static constexpr int kCntBytes = kAccStages * kBlockM * 4;
   static constexpr int kBarBytes = (3 * kStages + 4 * kAccStages) * 8 + 16;
-  static constexpr int kSmemBytes = kStages * kStageBytes + kBiasBytes + kLut2Padded + kEntBytes + kPtrBytes + kEvBytes + kCntBytes + kBarBytes;
+  static constexpr int kSmemBytes =
+      kStages * kStageBytes + kBiasBytes + kLut2Padded + kEntBytes + kPtrBytes + kEvBytes + kCntBytes + kCellBytes + kListBytes + kBarBytes;
   static_assert(kStageBytes % 1024 == 0, "stages must keep the 1024-byte alignment of swizzled tiles");
   static_assert(kSmemBytes <= 232448, "shared memory budget");
 };
@@ -90,7 +106,9 @@ qlayer_pair_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_co
   uint32_t *s_ptr = reinterpret_cast<uint32_t *>(reinterpret_cast<uint8_t *>(s_ent) + Cfg::kEntBytes);
   uint32_t *s_rowev = reinterpret_cast<uint32_t *>(reinterpret_cast<uint8_t *>(s_ptr) + Cfg::kPtrBytes);
   uint32_t *s_rowcnt = reinterpret_cast<uint32_t *>(reinterpret_cast<uint8_t *>(s_rowev) + Cfg::kEvBytes);
-  uint64_t *full_bar = reinterpret_cast<uint64_t *>(reinterpret_cast<uint8_t *>(s_rowcnt) + Cfg::kCntBytes);  // leader's copy is the live one
+  uint32_t *s_cell = reinterpret_cast<uint32_t *>(reinterpret_cast<uint8_t *>(s_rowcnt) + Cfg::kCntBytes);  // [acc][slot][chunk][row]
+  uint32_t *s_list = reinterpret_cast<uint32_t *>(reinterpret_cast<uint8_t *>(s_cell) + Cfg::kCellBytes);  // [scan warp][kListCap]
+  uint64_t *full_bar = reinterpret_cast<uint64_t *>(reinterpret_cast<uint8_t *>(s_list) + Cfg::kListBytes);  // leader's copy is the live one
   uint64_t *done_bar = full_bar + Cfg::kStages;    // MMA has consumed the stage (commit, both CTAs)
   uint64_t *empty_bar = done_bar + Cfg::kStages;   // this CTA's scan has released the stage
   uint64_t *tmem_full_bar = empty_bar + Cfg::kStages;
@@ -100,7 +118,8 @@ qlayer_pair_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_co
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(scan_done_bar + kAccStages);
 
   const int warp = int(threadIdx.x) / 32, lane = int(threadIdx.x) % 32;
-  if (threadIdx.x == 0) stamp(args.timeline, 0);
+  auto tstamp = [&](int slot) { stamp(args.timeline, slot); };
+  if (threadIdx.x == 0) tstamp(0);
   const int M = args.M, N = args.N, K = args.K;
   const int m_pairs = (M + 2 * kBlockM - 1) / (2 * kBlockM);
   const int n_blocks = (N + BN - 1) / BN;
@@ -144,7 +163,7 @@ qlayer_pair_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_co
   const uint32_t tmem_base = *tmem_slot;
   ptx::griddep_wait();
   ptx::griddep_launch_dependents();
-  if (threadIdx.x == 0) stamp(args.timeline, 1);
+  if (threadIdx.x == 0) tstamp(1);
 
   if (warp == 0) {
     // ===== TMA producer (both CTAs): my 128 activation rows + my half of the weight rows =====
@@ -177,14 +196,14 @@ qlayer_pair_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_co
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
       for (int ct = first_ct; ct < tiles_total; ct += ct_step) {
-        ptx::mbar_wait_parked_cluster(acc_free_bar + acc, acc_phase ^ 1);
+        ptx::mbar_wait_cluster(acc_free_bar + acc, acc_phase ^ 1);
         ptx::tc_fence_after_sync();
         const uint32_t d_tmem = tmem_base + uint32_t(acc * BN);
         for (int kb = 0; kb < k_blocks; ++kb) {
-          ptx::mbar_wait_parked(full_bar + stage, phase);
+          ptx::mbar_wait(full_bar + stage, phase);
           ptx::tc_fence_after_sync();
           if (lane == 0) {
-            if (kb == 0) stamp(args.timeline, 2);
+            if (kb == 0) tstamp(2);
             const uint32_t a_addr = ptx::smem_u32(tiles + stage * Cfg::kStageBytes);
             const uint64_t da = ptx::smem_desc_k_sw128(a_addr), db = ptx::smem_desc_k_sw128(a_addr + Cfg::kABytes);
 #pragma unroll
@@ -194,7 +213,7 @@ qlayer_pair_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_co
             ptx::mma_commit_pair(done_bar + stage);
             if (kb == k_blocks - 1) {
               ptx::mma_commit_pair(tmem_full_bar + acc);
-              stamp(args.timeline, 3);
+              tstamp(3);
             }
           }
           __syncwarp();
@@ -210,7 +229,12 @@ qlayer_pair_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_co
       }
     }
   } else if (warp >= kFirstScanWarp && warp < kFirstEpilogueWarp) {
-    // ===== saturation scan of this CTA's rows (see qlayer_tc.cu for the lane layout) =====
+    // ===== saturation scan of this CTA's rows =====
+    // Thread ↔ tile rows, straight from the 128B-swizzled A tile TMA staged for the tensor core (row r,
+    // byte b of the 128-byte K block lives at r·128 + ((b/16 ^ r%8)·16 + b%16)).  One shared-memory
+    // instruction covers 8 rows × 4 entries (lane = 8·entry + row%8): the swizzle puts the same byte
+    // offset of 8 consecutive rows into 8 different 16-byte chunks, and the packer orders entries so that
+    // 4 consecutive ones differ in their word offset within the chunk — 32 lanes, 32 banks.
     const int st = int(threadIdx.x) - kFirstScanWarp * 32;
     const int sset = st / kBlockM;
     const int row_sub = lane & 7, ent_sub = lane >> 3;
@@ -229,7 +253,10 @@ qlayer_pair_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_co
       const uint32_t *gp = args.fix.ptr + size_t(n_blk) * kbn;
       uint32_t *P = s_ptr + acc * kPtrSlots;
       uint32_t *E = s_ent + acc * kEntCap;
-      // the event slots of this accumulator stage are free once its previous tile has been drained
+      uint32_t *cell = s_cell + acc * Cfg::kCellWords;
+      uint32_t *flag_s = s_rowcnt + acc * kBlockM;  // per row: overflow count << 16 | chunks that overflowed
+      uint32_t *ev_s = s_rowev + acc * kBlockM * kRowEvents;
+      // the event cells of this accumulator stage are free once its previous tile has been drained
       ptx::mbar_wait_parked(tmem_empty_bar + acc, acc_phase ^ 1);
       const uint32_t ent_begin = __ldg(gp);
       for (int i = st; i <= kbn; i += kScanThreads) P[i] = scan_on ? __ldg(gp + i) - ent_begin : 0u;
@@ -243,15 +270,44 @@ qlayer_pair_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_co
         const uint2 fe = __ldg(gent + e);
         E[e] = (fe.x >> 16) | ((fe.y - uint32_t(n_blk * BN)) << 16) | (((2u * (fe.x & 0xffffu)) & 127u) << 24);
       }
-      uint32_t *cnt_s = s_rowcnt + acc * kBlockM;
-      uint32_t *ev_s = s_rowev + acc * kBlockM * kRowEvents;
-      if (st < kBlockM) cnt_s[st] = 0;
+      for (int i = st; i < Cfg::kCellWords / 4; i += kScanThreads) reinterpret_cast<uint4 *>(cell)[i] = make_uint4(0u, 0u, 0u, 0u);
+      if (st < kBlockM) flag_s[st] = 0;
       ptx::named_bar_sync(2, kScanThreads);
-      auto record = [&](int row, int v, uint32_t node_local) {  // rare: a row's events come from several threads
-        const int d = max(min(v, 32767), -32768) - v;
-        const uint32_t slot = atomicAdd(cnt_s + row, 1u);
-        if (slot < uint32_t(kRowEvents)) ev_s[row * kRowEvents + slot] = (node_local << 24) | (uint32_t(d) & 0xffffffu);
+      // Events (pair sum left the int16 range; ≈ 1 per 150 evaluations on the synthetic network, i.e. in
+      // almost every pass of the loop below) are first appended to this warp's list — a ballot and a plain
+      // store, nothing the K pipeline has to wait for — and filed at the end of the tile: event
+      // clamp(v) − v (20 bits) | column within the chunk << 20 goes into the first free slot of its
+      // (16-column chunk, row) cell, a third event of one cell to the row's overflow list.
+      auto file = [&](int row, int d, uint32_t node_local) {
+        const uint32_t word = (uint32_t(d) & 0xfffffu) | ((node_local & 15u) << 20);
+        uint32_t *c0 = cell + (node_local >> 4) * kBlockM + row;
+        if (atomicCAS(c0, 0u, word) != 0u && atomicCAS(c0 + Cfg::kAllChunks * kBlockM, 0u, word) != 0u) {
+          const uint32_t slot = atomicAdd(flag_s + row, 0x10000u) >> 16;
+          if (slot >= 0x8000u) atomicSub(flag_s + row, 0x10000u);  // dense risk lists: the count must not wrap (such a row recomputes anyway)
+          atomicOr(flag_s + row, 1u << (node_local >> 4));
+          if (slot < uint32_t(kRowEvents)) ev_s[row * kRowEvents + slot] = (node_local << 24) | (uint32_t(d) & 0xffffffu);
+        }
       };
+      uint32_t *list = s_list + (warp - kFirstScanWarp) * kListCap;
+      uint32_t n_list = 0;  // warp-uniform
+      const uint32_t lanes_below = (1u << lane) - 1u;
+      // warp-collective: lanes with `f` append (v32 = pair sum + 32768)
+      auto push = [&](bool f, int row, int v32, uint32_t node_local) {
+        const uint32_t m = __ballot_sync(0xffffffffu, f);
+        if (m != 0u) {
+          if (f) {
+            const int v = v32 - 32768;
+            const int d = max(min(v, 32767), -32768) - v;
+            const uint32_t pos = n_list + uint32_t(__popc(m & lanes_below));
+            if (pos < uint32_t(kListCap))
+              list[pos] = (uint32_t(d) & 0x1ffffu) | (node_local << 17) | (uint32_t(row) << 25);
+            else
+              file(row, d, node_local);  // dense risk lists
+          }
+          n_list += uint32_t(__popc(m));
+        }
+      };
+      // Entry words are fetched one turn ahead: they do not depend on the data of the stage.
       uint32_t w0 = 0, w1 = 0;
       auto fetch = [&](uint32_t r0, uint32_t r_end) {
         const uint32_t last = max(r_end, 1u) - 1u;
@@ -269,31 +325,29 @@ qlayer_pair_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_co
         const uint32_t g = it + uint32_t(kb);
         const int stage = int(g % uint32_t(Cfg::kStages));
         ptx::mbar_wait_parked(done_bar + stage, (g / uint32_t(Cfg::kStages)) & 1u);
-        const uint32_t a_swz = (ptx::smem_u32(tiles + stage * Cfg::kStageBytes) + uint32_t(row_base) * 128u) ^ swz;
+        // rows are 128-byte aligned: address = row base | (entry's byte offset with its 16-byte chunk index XORed by row%8)
+        const uint32_t a_rows = ptx::smem_u32(tiles + stage * Cfg::kStageBytes) + uint32_t(row_base) * 128u;
         const uint32_t fast_end = min(r1, staged);
         for (uint32_t e = r0; e < fast_end; e += 8) {
           if (e != r0) fetch(e, fast_end);
-          uint32_t a0[4], a1[4];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            a0[j] = ptx::lds_u16((a_swz + uint32_t(j) * 1024u) ^ (w0 >> 24));
-            a1[j] = ptx::lds_u16((a_swz + uint32_t(j) * 1024u) ^ (w1 >> 24));
-          }
-          int v0[4], v1[4];
-          uint32_t fired = 0;
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            v0[j] = dp4a_u8s8(a0[j], w0, 0);
-            v1[j] = dp4a_u8s8(a1[j], w1, 0);
-            fired |= (uint32_t(v0[j] + 32768) | uint32_t(v1[j] + 32768)) >> 16;  // non-zero ⇔ some v ∉ [−32768, 32767]
-          }
-          if (fired != 0) {
+          const uint32_t x0 = a_rows | ((w0 >> 24) ^ swz), x1 = a_rows | ((w1 >> 24) ^ swz);
+          const uint32_t a00 = ptx::lds_u16_off<0>(x0), a01 = ptx::lds_u16_off<1024>(x0), a02 = ptx::lds_u16_off<2048>(x0), a03 = ptx::lds_u16_off<3072>(x0);
+          const uint32_t a10 = ptx::lds_u16_off<0>(x1), a11 = ptx::lds_u16_off<1024>(x1), a12 = ptx::lds_u16_off<2048>(x1), a13 = ptx::lds_u16_off<3072>(x1);
+          // pair sum + 32768 ∈ [0, 65535] unless pmaddubsw would have saturated: OR them all, look closer only if a high bit is set
+          const int v00 = dp4a_u8s8(a00, w0, 32768), v01 = dp4a_u8s8(a01, w0, 32768), v02 = dp4a_u8s8(a02, w0, 32768), v03 = dp4a_u8s8(a03, w0, 32768);
+          const int v10 = dp4a_u8s8(a10, w1, 32768), v11 = dp4a_u8s8(a11, w1, 32768), v12 = dp4a_u8s8(a12, w1, 32768), v13 = dp4a_u8s8(a13, w1, 32768);
+          const uint32_t fired = uint32_t(v00 | v01 | v02 | v03 | v10 | v11 | v12 | v13) >> 16;
+          if (__any_sync(0xffffffffu, fired != 0u)) {
             const bool ok0 = e + uint32_t(ent_sub) < fast_end, ok1 = e + 4u + uint32_t(ent_sub) < fast_end;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              if (ok0 && uint32_t(v0[j] + 32768) > 65535u) record(row_base + 8 * j, v0[j], (w0 >> 16) & 0xffu);
-              if (ok1 && uint32_t(v1[j] + 32768) > 65535u) record(row_base + 8 * j, v1[j], (w1 >> 16) & 0xffu);
-            }
+            const uint32_t n0l = (w0 >> 16) & 0xffu, n1l = (w1 >> 16) & 0xffu;
+            push(ok0 && uint32_t(v00) > 65535u, row_base, v00, n0l);
+            push(ok0 && uint32_t(v01) > 65535u, row_base + 8, v01, n0l);
+            push(ok0 && uint32_t(v02) > 65535u, row_base + 16, v02, n0l);
+            push(ok0 && uint32_t(v03) > 65535u, row_base + 24, v03, n0l);
+            push(ok1 && uint32_t(v10) > 65535u, row_base, v10, n1l);
+            push(ok1 && uint32_t(v11) > 65535u, row_base + 8, v11, n1l);
+            push(ok1 && uint32_t(v12) > 65535u, row_base + 16, v12, n1l);
+            push(ok1 && uint32_t(v13) > 65535u, row_base + 24, v13, n1l);
           }
         }
         // beyond the staging capacity (dense risk lists): one entry per pass, 32 rows per warp
@@ -303,8 +357,8 @@ qlayer_pair_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_co
           const int row = (st % kBlockM);
           const uint32_t a_addr = ptx::smem_u32(tiles + stage * Cfg::kStageBytes) + uint32_t(row) * 128u;
           const uint32_t a01s = ptx::lds_u16(a_addr + (((b & 0x70u) ^ (uint32_t(row & 7) << 4)) | (b & 15u)));
-          const int v = dp4a_u8s8(a01s, fe.x >> 16, 0);
-          if (uint32_t(v + 32768) > 65535u) record(row, v, fe.y - uint32_t(n_blk * BN));
+          const int v32 = dp4a_u8s8(a01s, fe.x >> 16, 32768);
+          push(uint32_t(v32) > 65535u, row, v32, fe.y - uint32_t(n_blk * BN));
         }
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(empty_bar + stage);
@@ -315,9 +369,15 @@ qlayer_pair_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_co
         }
       }
       it += uint32_t(k_blocks);
+      // file this warp's events, one per lane at a time
+      __syncwarp();
+      for (uint32_t i = uint32_t(lane); i < min(n_list, uint32_t(kListCap)); i += 32u) {
+        const uint32_t w = list[i];
+        file(int(w >> 25), int(w << 15) >> 15, (w >> 17) & 0xffu);
+      }
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(scan_done_bar + acc);
-      if (st == 0) stamp(args.timeline, 4);
+      if (st == 0) tstamp(4);
       if (++acc == kAccStages) {
         acc = 0;
         acc_phase ^= 1;
@@ -325,6 +385,7 @@ qlayer_pair_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_co
     }
   } else if (warp >= kFirstEpilogueWarp) {
     // ===== epilogue: this CTA's TMEM → registers → + saturation events → reference tail → global =====
+    // 16 warps: warp % 4 selects the TMEM lane quarter (rows), (warp − 12) / 4 the column quarter.
     const int et = int(threadIdx.x) - kFirstEpilogueWarp * 32;
     const int quarter = warp & 3;
     const int col_group = (warp - kFirstEpilogueWarp) >> 2;
@@ -346,17 +407,24 @@ qlayer_pair_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_co
 
       float *bias_s = s_bias + acc * BN;
       for (int i = et; i < BN; i += kEpilogueThreads) bias_s[i] = (n0 + i < N) ? __ldg(args.bias + n0 + i) : 0.0f;
+      // one warp polls the tile's barriers; the others wait for it in the hardware barrier below, which
+      // costs no issue slots (and also publishes the bias tile)
+      if (warp == kFirstEpilogueWarp) {
+        ptx::mbar_wait_parked(tmem_full_bar + acc, acc_phase);
+        if (et == 0) tstamp(5);
+        ptx::mbar_wait_parked(scan_done_bar + acc, acc_phase);
+        if (et == 0) tstamp(7);
+        ptx::tc_fence_after_sync();
+        ptx::tc_fence_before_sync();
+      }
       ptx::named_bar_sync(1, kEpilogueThreads);
-
-      ptx::mbar_wait_parked(tmem_full_bar + acc, acc_phase);
-      if (et == 0) stamp(args.timeline, 5);
-      ptx::mbar_wait_parked(scan_done_bar + acc, acc_phase);
       ptx::tc_fence_after_sync();
-      if (et == 0) stamp(args.timeline, 7);
-      const uint32_t n_ev = s_rowcnt[acc * kBlockM + row_local];
+      const uint32_t flags = s_rowcnt[acc * kBlockM + row_local];
+      const bool many = (flags >> 16) > uint32_t(kRowEvents);  // more overflow events than slots: this row recomputes from global memory
       const uint32_t *ev = s_rowev + (acc * kBlockM + row_local) * kRowEvents;
+      const uint32_t *cell = s_cell + acc * Cfg::kCellWords + row_local;
       const uint32_t t_addr = tmem_base + uint32_t(acc * BN + col_group * Cfg::kColsPerWarp) + (uint32_t(quarter * 32) << 16);
-      auto release_acc = [&]() {  // accumulator stage and its event slots fully read by this warp
+      auto release_acc = [&]() {  // accumulator stage and its event cells fully read by this warp
         ptx::tc_fence_before_sync();
         __syncwarp();
         if (lane == 0) {
@@ -368,6 +436,8 @@ qlayer_pair_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_co
 #pragma unroll
       for (int j = 0; j < Cfg::kChunks; ++j) {
         if (j < n_valid) {
+          const int chunk = col_group * Cfg::kChunks + j;
+          uint32_t e0 = cell[chunk * kBlockM], e1 = cell[(Cfg::kAllChunks + chunk) * kBlockM];
           uint32_t raw[16];
           ptx::tmem_ld_32x16(t_addr + uint32_t(j * 16), raw);
           ptx::tmem_ld_wait();
@@ -375,8 +445,20 @@ qlayer_pair_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_co
 #pragma unroll
           for (int i = 0; i < 16; ++i) s[i] = int32_t(raw[i]);
           const int col = col0 + j * 16;
-          if (n_ev != 0 && row_ok) {
-            if (n_ev <= uint32_t(kRowEvents)) {
+          if (many || !row_ok) e0 = e1 = 0u;
+          // an empty cell is the zero word: it adds 0 to column 0
+          auto apply = [&](uint32_t e) {
+            const uint32_t rel = (e >> 20) & 15u;
+            const int d = int(e << 12) >> 12;
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              if (rel == uint32_t(i)) s[i] += d;
+          };
+          if (__any_sync(0xffffffffu, e0 != 0u)) apply(e0);
+          if (__any_sync(0xffffffffu, e1 != 0u)) apply(e1);
+          if (row_ok && ((flags >> chunk) & 1u) != 0u) {
+            if (!many) {
+              const uint32_t n_ev = flags >> 16;
               for (uint32_t k = 0; k < n_ev; ++k) {
                 const uint32_t e = ev[k];
                 const uint32_t rel = (e >> 24) - uint32_t(col - n0);
@@ -384,15 +466,19 @@ qlayer_pair_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_co
 #pragma unroll
                 for (int i = 0; i < 16; ++i) s[i] += (rel == uint32_t(i)) ? d : 0;
               }
-            } else {
-              brute_force_corrections(s, row, col, args);  // more events than slots in this row: recompute them
             }
           }
+          if (many && row_ok) brute_force_corrections(s, row, col, args);
           if (j == n_valid - 1) release_acc();  // before the math: the MMA of tile i+2 can start
-          if (row_ok) finish_chunk<kLogits>(s, row, col, args, bias_s + (col - n0), s_lut);
+          if (row_ok) {
+            if (args.fast_tail)
+              finish_chunk_fast<kLogits>(s, row, col, args, bias_s + (col - n0), s_lut);
+            else
+              finish_chunk<kLogits>(s, row, col, args, bias_s + (col - n0), s_lut);
+          }
         }
       }
-      if (et == 0) stamp(args.timeline, 6);
+      if (et == 0) tstamp(6);
       if (++acc == kAccStages) {
         acc = 0;
         acc_phase ^= 1;
