@@ -10,19 +10,22 @@
 // and only HALF of the weight rows, and the tensor cores read the peer's half over the pair link —
 // 32 KB per SM per 512 cycles, and one third fewer shared-memory wavefronts for the same math.
 //
-// Roles per CTA (28 warps, as in qlayer_tc.cu): warp 0 TMA producer (both CTAs; all bytes are counted
-// on the LEADER's full barrier via cp.async.bulk.tensor.cta_group::2), warp 1 MMA issuer (leader
-// only; tcgen05.commit multicasts "stage consumed" / "accumulator ready" to both CTAs), warp 2 TMEM
-// allocator (cta_group::2, both CTAs), warps 4-11 saturation scan of this CTA's 128 rows, warps 12-27
-// epilogue of this CTA's 128 rows × BN columns out of its own tensor memory.
+// Roles per CTA (28 warps): warp 0 TMA producer (both CTAs; all bytes are counted on the LEADER's full
+// barrier via cp.async.bulk.tensor.cta_group::2), warp 1 MMA issuer (leader only; tcgen05.commit
+// multicasts "stage consumed" / "accumulator ready" to both CTAs), warp 2 TMEM allocator
+// (cta_group::2, both CTAs), warps 4-19 saturation scan of this CTA's 128 rows (four sets of four
+// warps, a set per pipeline turn), warps 20-27 epilogue of this CTA's 128 rows × BN columns out of its
+// own tensor memory.
 //
 // Instruction issue, not the tensor pipe or shared memory, was what the single-CTA kernel ran out of on
 // long streams (ncu: ≈ 80 k warp instructions per 128×256 tile against the 32 k issue slots its 8192
 // tensor-pipe cycles offer).  Hence, here: (1) saturation events go into per-(16-column chunk, row)
 // cells, so that the epilogue applies at most two 16-way selects per chunk instead of walking the
 // row's whole event list for every chunk; (2) the per-element tail runs on packed FFMA2
-// (finish_chunk_fast); (3) one epilogue warp polls the tile barriers, the other fifteen sleep in a
-// hardware barrier; (4) the scan folds the range check into dp4a's accumulator and ORs the results.
+// (finish_chunk_fast); (3) one epilogue warp polls the tile barriers, the others sleep in a hardware
+// barrier; (4) the scan folds the range check into dp4a's accumulator and ORs the results; (5) the scan
+// is latency-bound (dependent shared-memory loads), so it gets 16 warps and nothing else to do — the
+// epilogue warps, idle most of a tile, stage its entry lists, zero its cells and file its events.
 //
 // The scan reads a stage AFTER the MMA has consumed it (it waits for the commit, not for TMA): only the
 // leader's full barrier sees the TMA bytes, the commit is visible in both CTAs, and the scan's result is
@@ -46,10 +49,9 @@ namespace {
 constexpr int kBlockM = 128;  // rows per CTA; the pair's MMA is 256 rows
 constexpr int kBlockK = 128;  // bytes of K per pipeline stage = one 128B swizzle atom
 constexpr int kUmmaK = 32;
-constexpr int kScanSets = 2;
+constexpr int kScanSets = 4;         // scan warps come in sets of 4 (one lane group per tile row); set s takes pipeline turns ≡ s (mod 4)
 constexpr int kScanWarps = 4 * kScanSets;
-constexpr int kEpilogueWarps = 16;
-constexpr int kScanThreads = kScanWarps * 32;
+constexpr int kEpilogueWarps = 8;    // four TMEM lane quarters × two column halves
 constexpr int kEpilogueThreads = kEpilogueWarps * 32;
 constexpr int kFirstScanWarp = 4, kFirstEpilogueWarp = kFirstScanWarp + kScanWarps;
 constexpr int kThreads = (kFirstEpilogueWarp + kEpilogueWarps) * 32;  // 896
@@ -58,7 +60,7 @@ constexpr int kEntCap = 1024;   // risk entries of the tile staged (packed) in s
 constexpr int kPtrSlots = 132;  // ≥ k_blocks + 1 → K ≤ 16768
 constexpr int kRowEvents = 4;    // overflow events kept per tile row (third and later event of one 16-column chunk)
 constexpr int kCellSlots = 2;    // events a (chunk, row) cell holds
-constexpr int kListCap = 128;    // events a scan warp collects per tile before it files them into the cells
+constexpr int kListCap = 64;     // events a scan warp collects per tile; the epilogue warps file them into the cells
 
 static_assert(kBlockK == kFixKBlock, "risk-list order is tied to the tiling");
 
@@ -66,6 +68,22 @@ __device__ __forceinline__ int dp4a_u8s8(uint32_t a, uint32_t b, int c) {
   int d;
   asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
   return d;
+}
+
+// File one saturation event of tile row `row`, column `node_local` (clamp(v) − v = d) for the epilogue:
+// d (20 bits) | column within its 16-column chunk << 20 goes into the first free slot of the (chunk, row)
+// cell; a third event of one cell goes to the row's overflow list (count << 16 | chunk mask in flag_s).
+template <int BN>
+__device__ __forceinline__ void file_event(uint32_t *cell, uint32_t *flag_s, uint32_t *ev_s, int row, int d, uint32_t node_local) {
+  constexpr int kAllChunks = BN / 16;
+  const uint32_t word = (uint32_t(d) & 0xfffffu) | ((node_local & 15u) << 20);
+  uint32_t *c0 = cell + (node_local >> 4) * kBlockM + row;
+  if (atomicCAS(c0, 0u, word) != 0u && atomicCAS(c0 + kAllChunks * kBlockM, 0u, word) != 0u) {
+    const uint32_t slot = atomicAdd(flag_s + row, 0x10000u) >> 16;
+    if (slot >= 0x8000u) atomicSub(flag_s + row, 0x10000u);  // dense risk lists: the count must not wrap (such a row recomputes anyway)
+    atomicOr(flag_s + row, 1u << (node_local >> 4));
+    if (slot < uint32_t(kRowEvents)) ev_s[row * kRowEvents + slot] = (node_local << 24) | (uint32_t(d) & 0xffffffu);
+  }
 }
 
 template <int BN>
@@ -77,9 +95,9 @@ struct PairConfig {
   static constexpr int kAllChunks = BN / 16;
   static constexpr int kCellWords = kCellSlots * kAllChunks * kBlockM;  // per accumulator stage
   static constexpr int kCellBytes = kAccStages * kCellWords * 4;
-  static constexpr int kListBytes = kScanWarps * kListCap * 4;  // only the scan warps use it, one tile at a time
+  static constexpr int kListBytes = kAccStages * (kScanWarps * kListCap + kScanWarps) * 4;  // lists + their lengths
   static constexpr int kTmemCols = kAccStages * BN;
-  static constexpr int kColsPerWarp = BN / 4;
+  static constexpr int kColsPerWarp = BN / (kEpilogueWarps / 4);
   static constexpr int kChunks = kColsPerWarp / 16;
   static constexpr int kBiasBytes = kAccStages * BN * 4;
   static constexpr int kEntBytes = kAccStages * kEntCap * 4;
@@ -107,13 +125,14 @@ qlayer_pair_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_co
   uint32_t *s_rowev = reinterpret_cast<uint32_t *>(reinterpret_cast<uint8_t *>(s_ptr) + Cfg::kPtrBytes);
   uint32_t *s_rowcnt = reinterpret_cast<uint32_t *>(reinterpret_cast<uint8_t *>(s_rowev) + Cfg::kEvBytes);
   uint32_t *s_cell = reinterpret_cast<uint32_t *>(reinterpret_cast<uint8_t *>(s_rowcnt) + Cfg::kCntBytes);  // [acc][slot][chunk][row]
-  uint32_t *s_list = reinterpret_cast<uint32_t *>(reinterpret_cast<uint8_t *>(s_cell) + Cfg::kCellBytes);  // [scan warp][kListCap]
+  uint32_t *s_list = reinterpret_cast<uint32_t *>(reinterpret_cast<uint8_t *>(s_cell) + Cfg::kCellBytes);  // [acc][scan warp][kListCap], then [acc][scan warp] lengths
+  uint32_t *s_listn = s_list + kAccStages * kScanWarps * kListCap;
   uint64_t *full_bar = reinterpret_cast<uint64_t *>(reinterpret_cast<uint8_t *>(s_list) + Cfg::kListBytes);  // leader's copy is the live one
   uint64_t *done_bar = full_bar + Cfg::kStages;    // MMA has consumed the stage (commit, both CTAs)
   uint64_t *empty_bar = done_bar + Cfg::kStages;   // this CTA's scan has released the stage
   uint64_t *tmem_full_bar = empty_bar + Cfg::kStages;
-  uint64_t *tmem_empty_bar = tmem_full_bar + kAccStages;  // this CTA's epilogue has drained the stage (for the scan)
-  uint64_t *acc_free_bar = tmem_empty_bar + kAccStages;   // both CTAs' epilogues have (leader's copy, for the MMA)
+  uint64_t *prep_bar = tmem_full_bar + kAccStages;        // this CTA's epilogue has set up the stage's scan state for its next tile
+  uint64_t *acc_free_bar = prep_bar + kAccStages;         // both CTAs' epilogues have drained the stage (leader's copy, for the MMA)
   uint64_t *scan_done_bar = acc_free_bar + kAccStages;
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(scan_done_bar + kAccStages);
 
@@ -149,7 +168,7 @@ qlayer_pair_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_co
     }
     for (int i = 0; i < kAccStages; ++i) {
       ptx::mbar_init(tmem_full_bar + i, 1);
-      ptx::mbar_init(tmem_empty_bar + i, kEpilogueWarps);
+      ptx::mbar_init(prep_bar + i, kEpilogueWarps);
       ptx::mbar_init(acc_free_bar + i, 2 * kEpilogueWarps);
       ptx::mbar_init(scan_done_bar + i, kScanWarps);
     }
@@ -235,12 +254,16 @@ qlayer_pair_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_co
     // instruction covers 8 rows × 4 entries (lane = 8·entry + row%8): the swizzle puts the same byte
     // offset of 8 consecutive rows into 8 different 16-byte chunks, and the packer orders entries so that
     // 4 consecutive ones differ in their word offset within the chunk — 32 lanes, 32 banks.
+    // The scan warps do nothing but this loop: the per-tile set-up (entry staging, zeroed event cells) and
+    // the filing of the events they find are the epilogue warps' job, so no stage waits for either.
     const int st = int(threadIdx.x) - kFirstScanWarp * 32;
+    const int sw = warp - kFirstScanWarp;
     const int sset = st / kBlockM;
     const int row_sub = lane & 7, ent_sub = lane >> 3;
     const int row_base = ((st % kBlockM) / 32) * 32 + row_sub;  // rows row_base + 8j, j < 4
     const uint32_t swz = uint32_t(row_sub) << 4;
     const int kbn = args.fix.k_blocks;
+    const uint32_t lanes_below = (1u << lane) - 1u;
     int acc = 0;
     uint32_t acc_phase = 0;
     uint32_t it = 0;  // running K-block count across tiles: stage = it % kStages, phase = (it / kStages) & 1
@@ -249,48 +272,17 @@ qlayer_pair_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_co
       decode(ct, m_blk, n_blk);
       const int kb0 = first_k_block(ct);
       auto k_block_of = [&](int turn) { return (kb0 + turn) % k_blocks; };
-      const bool scan_on = !(args.debug_flags & 1);
-      const uint32_t *gp = args.fix.ptr + size_t(n_blk) * kbn;
-      uint32_t *P = s_ptr + acc * kPtrSlots;
-      uint32_t *E = s_ent + acc * kEntCap;
+      const uint32_t *P = s_ptr + acc * kPtrSlots;  // K-block offsets of this tile's entries, relative to its first one
+      const uint32_t *E = s_ent + acc * kEntCap;    // one word per entry: w0 | w1 << 8 | (node − n0) << 16 | byte offset of the pair in its K block << 24
       uint32_t *cell = s_cell + acc * Cfg::kCellWords;
-      uint32_t *flag_s = s_rowcnt + acc * kBlockM;  // per row: overflow count << 16 | chunks that overflowed
+      uint32_t *flag_s = s_rowcnt + acc * kBlockM;
       uint32_t *ev_s = s_rowev + acc * kBlockM * kRowEvents;
-      // the event cells of this accumulator stage are free once its previous tile has been drained
-      ptx::mbar_wait_parked(tmem_empty_bar + acc, acc_phase ^ 1);
-      const uint32_t ent_begin = __ldg(gp);
-      for (int i = st; i <= kbn; i += kScanThreads) P[i] = scan_on ? __ldg(gp + i) - ent_begin : 0u;
-      const uint32_t n_ent = scan_on ? __ldg(gp + kbn) - ent_begin : 0u;
-      const uint32_t staged = min(n_ent, uint32_t(kEntCap));
-      // staged form, one word per entry: w0 | w1 << 8 | (node − n0) << 16 | (byte offset of the pair
-      // inside its 128-byte K block) << 24 — dp4a of that word with the zero-extended activation
-      // pair is exactly a0·w0 + a1·w1
-      const uint2 *gent = reinterpret_cast<const uint2 *>(args.fix.ent) + ent_begin;
-      for (uint32_t e = uint32_t(st); e < staged; e += kScanThreads) {
-        const uint2 fe = __ldg(gent + e);
-        E[e] = (fe.x >> 16) | ((fe.y - uint32_t(n_blk * BN)) << 16) | (((2u * (fe.x & 0xffffu)) & 127u) << 24);
-      }
-      for (int i = st; i < Cfg::kCellWords / 4; i += kScanThreads) reinterpret_cast<uint4 *>(cell)[i] = make_uint4(0u, 0u, 0u, 0u);
-      if (st < kBlockM) flag_s[st] = 0;
-      ptx::named_bar_sync(2, kScanThreads);
-      // Events (pair sum left the int16 range; ≈ 1 per 150 evaluations on the synthetic network, i.e. in
-      // almost every pass of the loop below) are first appended to this warp's list — a ballot and a plain
-      // store, nothing the K pipeline has to wait for — and filed at the end of the tile: event
-      // clamp(v) − v (20 bits) | column within the chunk << 20 goes into the first free slot of its
-      // (16-column chunk, row) cell, a third event of one cell to the row's overflow list.
-      auto file = [&](int row, int d, uint32_t node_local) {
-        const uint32_t word = (uint32_t(d) & 0xfffffu) | ((node_local & 15u) << 20);
-        uint32_t *c0 = cell + (node_local >> 4) * kBlockM + row;
-        if (atomicCAS(c0, 0u, word) != 0u && atomicCAS(c0 + Cfg::kAllChunks * kBlockM, 0u, word) != 0u) {
-          const uint32_t slot = atomicAdd(flag_s + row, 0x10000u) >> 16;
-          if (slot >= 0x8000u) atomicSub(flag_s + row, 0x10000u);  // dense risk lists: the count must not wrap (such a row recomputes anyway)
-          atomicOr(flag_s + row, 1u << (node_local >> 4));
-          if (slot < uint32_t(kRowEvents)) ev_s[row * kRowEvents + slot] = (node_local << 24) | (uint32_t(d) & 0xffffffu);
-        }
-      };
-      uint32_t *list = s_list + (warp - kFirstScanWarp) * kListCap;
+      uint32_t *list = s_list + (acc * kScanWarps + sw) * kListCap;
+      ptx::mbar_wait_parked(prep_bar + acc, acc_phase);  // the epilogue warps have staged P and E and zeroed the cells
+      const uint32_t staged = min(P[kbn], uint32_t(kEntCap));
       uint32_t n_list = 0;  // warp-uniform
-      const uint32_t lanes_below = (1u << lane) - 1u;
+      // Events (pair sum left the int16 range; ≈ 1 per 150 evaluations on the synthetic network, i.e. in every
+      // other pass of the loop below) are appended to this warp's list with a ballot and a plain store.
       // warp-collective: lanes with `f` append (v32 = pair sum + 32768)
       auto push = [&](bool f, int row, int v32, uint32_t node_local) {
         const uint32_t m = __ballot_sync(0xffffffffu, f);
@@ -302,7 +294,7 @@ qlayer_pair_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_co
             if (pos < uint32_t(kListCap))
               list[pos] = (uint32_t(d) & 0x1ffffu) | (node_local << 17) | (uint32_t(row) << 25);
             else
-              file(row, d, node_local);  // dense risk lists
+              file_event<BN>(cell, flag_s, ev_s, row, d, node_local);  // dense risk lists
           }
           n_list += uint32_t(__popc(m));
         }
@@ -351,14 +343,17 @@ qlayer_pair_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_co
           }
         }
         // beyond the staging capacity (dense risk lists): one entry per pass, 32 rows per warp
-        for (uint32_t e = max(r0, staged); e < r1; ++e) {
-          const uint2 fe = __ldg(gent + e);
-          const uint32_t b = (2u * (fe.x & 0xffffu)) & 127u;
-          const int row = (st % kBlockM);
-          const uint32_t a_addr = ptx::smem_u32(tiles + stage * Cfg::kStageBytes) + uint32_t(row) * 128u;
-          const uint32_t a01s = ptx::lds_u16(a_addr + (((b & 0x70u) ^ (uint32_t(row & 7) << 4)) | (b & 15u)));
-          const int v32 = dp4a_u8s8(a01s, fe.x >> 16, 32768);
-          push(uint32_t(v32) > 65535u, row, v32, fe.y - uint32_t(n_blk * BN));
+        if (r1 > staged) {
+          const uint2 *gent = reinterpret_cast<const uint2 *>(args.fix.ent) + __ldg(args.fix.ptr + size_t(n_blk) * kbn);
+          for (uint32_t e = max(r0, staged); e < r1; ++e) {
+            const uint2 fe = __ldg(gent + e);
+            const uint32_t b = (2u * (fe.x & 0xffffu)) & 127u;
+            const int row = (st % kBlockM);
+            const uint32_t a_addr = ptx::smem_u32(tiles + stage * Cfg::kStageBytes) + uint32_t(row) * 128u;
+            const uint32_t a01s = ptx::lds_u16(a_addr + (((b & 0x70u) ^ (uint32_t(row & 7) << 4)) | (b & 15u)));
+            const int v32 = dp4a_u8s8(a01s, fe.x >> 16, 32768);
+            push(uint32_t(v32) > 65535u, row, v32, fe.y - uint32_t(n_blk * BN));
+          }
         }
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(empty_bar + stage);
@@ -369,14 +364,11 @@ qlayer_pair_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_co
         }
       }
       it += uint32_t(k_blocks);
-      // file this warp's events, one per lane at a time
       __syncwarp();
-      for (uint32_t i = uint32_t(lane); i < min(n_list, uint32_t(kListCap)); i += 32u) {
-        const uint32_t w = list[i];
-        file(int(w >> 25), int(w << 15) >> 15, (w >> 17) & 0xffu);
+      if (lane == 0) {
+        s_listn[acc * kScanWarps + sw] = min(n_list, uint32_t(kListCap));
+        ptx::mbar_arrive(scan_done_bar + acc);
       }
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(scan_done_bar + acc);
       if (st == 0) tstamp(4);
       if (++acc == kAccStages) {
         acc = 0;
@@ -385,15 +377,44 @@ qlayer_pair_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_co
     }
   } else if (warp >= kFirstEpilogueWarp) {
     // ===== epilogue: this CTA's TMEM → registers → + saturation events → reference tail → global =====
-    // 16 warps: warp % 4 selects the TMEM lane quarter (rows), (warp − 12) / 4 the column quarter.
+    // 8 warps: warp % 4 selects the TMEM lane quarter (rows), (warp − first) / 4 the column half.  Around the
+    // tile's drain they also do the scan warps' housekeeping: file the events the scan found into the
+    // (16-column chunk, row) cells, and set up the accumulator stage's scan state for the tile after next.
     const int et = int(threadIdx.x) - kFirstEpilogueWarp * 32;
     const int quarter = warp & 3;
     const int col_group = (warp - kFirstEpilogueWarp) >> 2;
     const int row_local = quarter * 32 + lane;
+    const int kbn = args.fix.k_blocks;
     if (!kLogits) {
       for (int i = et; i < kLut2Padded / 16; i += kEpilogueThreads) reinterpret_cast<uint4 *>(s_lut)[i] = __ldg(reinterpret_cast<const uint4 *>(args.lut) + i);
     }
     const uint32_t leader_acc_free = ptx::mapa_u32(ptx::smem_u32(acc_free_bar), 0);
+    // scan state of accumulator stage `a` for tile `ct2`: entry offsets per K block, packed entry words, zeroed cells and flags
+    auto prepare = [&](int a, int ct2) {
+      if (ct2 < tiles_total) {
+        const int n_blk2 = ct2 % n_blocks;
+        const bool scan_on = !(args.debug_flags & 1);
+        const uint32_t *gp = args.fix.ptr + size_t(n_blk2) * kbn;
+        const uint32_t ent_begin = __ldg(gp);
+        uint32_t *P = s_ptr + a * kPtrSlots;
+        uint32_t *E = s_ent + a * kEntCap;
+        for (int i = et; i <= kbn; i += kEpilogueThreads) P[i] = scan_on ? __ldg(gp + i) - ent_begin : 0u;
+        const uint32_t n_ent = scan_on ? __ldg(gp + kbn) - ent_begin : 0u;
+        const uint32_t staged = min(n_ent, uint32_t(kEntCap));
+        const uint2 *gent = reinterpret_cast<const uint2 *>(args.fix.ent) + ent_begin;
+        for (uint32_t e = uint32_t(et); e < staged; e += kEpilogueThreads) {
+          const uint2 fe = __ldg(gent + e);
+          E[e] = (fe.x >> 16) | ((fe.y - uint32_t(n_blk2 * BN)) << 16) | (((2u * (fe.x & 0xffffu)) & 127u) << 24);
+        }
+        uint4 *cz = reinterpret_cast<uint4 *>(s_cell + a * Cfg::kCellWords);
+        for (int i = et; i < Cfg::kCellWords / 4; i += kEpilogueThreads) cz[i] = make_uint4(0u, 0u, 0u, 0u);
+        if (et < kBlockM) s_rowcnt[a * kBlockM + et] = 0;
+      }
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(prep_bar + a);
+    };
+    prepare(0, first_ct);
+    prepare(1, first_ct + ct_step);
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int ct = first_ct; ct < tiles_total; ct += ct_step) {
@@ -419,18 +440,30 @@ qlayer_pair_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_co
       }
       ptx::named_bar_sync(1, kEpilogueThreads);
       ptx::tc_fence_after_sync();
-      const uint32_t flags = s_rowcnt[acc * kBlockM + row_local];
+      // file the scan warps' events: 16 threads per list
+      uint32_t *cell_all = s_cell + acc * Cfg::kCellWords;
+      uint32_t *flag_s = s_rowcnt + acc * kBlockM;
+      uint32_t *ev_s = s_rowev + acc * kBlockM * kRowEvents;
+      {
+        constexpr int kPerList = kEpilogueThreads / kScanWarps;
+        const int lw = et / kPerList;
+        const uint32_t n_l = s_listn[acc * kScanWarps + lw];
+        const uint32_t *list = s_list + (acc * kScanWarps + lw) * kListCap;
+        for (uint32_t i = uint32_t(et % kPerList); i < n_l; i += uint32_t(kPerList)) {
+          const uint32_t w = list[i];
+          file_event<BN>(cell_all, flag_s, ev_s, int(w >> 25), int(w << 15) >> 15, (w >> 17) & 0xffu);
+        }
+      }
+      ptx::named_bar_sync(1, kEpilogueThreads);
+      const uint32_t flags = flag_s[row_local];
       const bool many = (flags >> 16) > uint32_t(kRowEvents);  // more overflow events than slots: this row recomputes from global memory
-      const uint32_t *ev = s_rowev + (acc * kBlockM + row_local) * kRowEvents;
-      const uint32_t *cell = s_cell + acc * Cfg::kCellWords + row_local;
+      const uint32_t *ev = ev_s + row_local * kRowEvents;
+      const uint32_t *cell = cell_all + row_local;
       const uint32_t t_addr = tmem_base + uint32_t(acc * BN + col_group * Cfg::kColsPerWarp) + (uint32_t(quarter * 32) << 16);
-      auto release_acc = [&]() {  // accumulator stage and its event cells fully read by this warp
+      auto release_acc = [&]() {  // accumulator stage fully read by this warp
         ptx::tc_fence_before_sync();
         __syncwarp();
-        if (lane == 0) {
-          ptx::mbar_arrive(tmem_empty_bar + acc);
-          ptx::mbar_arrive_remote(leader_acc_free + uint32_t(acc) * 8u);
-        }
+        if (lane == 0) ptx::mbar_arrive_remote(leader_acc_free + uint32_t(acc) * 8u);
       };
       if (n_valid == 0) release_acc();
 #pragma unroll
@@ -479,6 +512,9 @@ qlayer_pair_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_co
         }
       }
       if (et == 0) tstamp(6);
+      // everybody is done with this stage's cells, flags, lists and entry words: set it up for the tile after next
+      ptx::named_bar_sync(1, kEpilogueThreads);
+      prepare(acc, ct + 2 * ct_step);
       if (++acc == kAccStages) {
         acc = 0;
         acc_phase ^= 1;

@@ -563,16 +563,17 @@ TcPlan qlayer_tc_plan(int M, int N, bool logits, int num_sms) {
   }();
   const int m_blocks = (M + kBlockM - 1) / kBlockM;
   TcPlan p{64, 1, true, false};
-  // FDNN_PAIR=<bn>: every tensor-core layer on CTA pairs with that tile width (tuning experiments)
-  if (const char *e = std::getenv("FDNN_PAIR")) {
-    const int bn = std::atoi(e);
-    if ((bn == 64 || bn == 128 || bn == 256) && num_sms >= 2) {
-      p.block_n = bn;
-      p.cluster = 2;
-      p.share_a = false;
-      p.pair = true;
-      return p;
-    }
+  // CTA pairs (qlayer_pair.cu) once there is at least a full wave of 256×256 pair tiles: measured on B200
+  // (profiles/r1_experiments.md) they beat single-CTA tiles from there on (16384 frames: hidden layer 87 vs
+  // 116 us, output layer 389 vs 509 us) and are level or behind below.  FDNN_PAIR=<bn> forces pairs with
+  // that tile width for every layer, FDNN_PAIR=0 turns them off (tuning experiments, parity tests).
+  {
+    const char *e = std::getenv("FDNN_PAIR");
+    const int forced = (e && e[0]) ? std::atoi(e) : -1;
+    const bool can_pair = num_sms >= 2;
+    if (can_pair && (forced == 64 || forced == 128 || forced == 256)) return TcPlan{forced, 2, false, true};
+    const int pair_tiles = ((M + 255) / 256) * ((N + 255) / 256);
+    if (can_pair && forced != 0 && pair_tiles >= num_sms / 2) return TcPlan{256, 2, false, true};
   }
   if (const char *e = std::getenv("FDNN_FORCE_BN")) {  // tuning experiments
     const int bn = std::atoi(e);

@@ -255,11 +255,35 @@ def test_cta_pair_path_is_bit_exact(net_file, stress):
         "np.save(sys.argv[1], ctx.hidden()); np.save(sys.argv[2], ctx.logits())\n"
     ) % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), net_file("S", stress=stress))
     outs = {}
-    for flag in ("", "64", "128", "256"):
+    for flag in ("0", "64", "128", "256"):
         paths = [f"/tmp/fdnn_pair_{int(stress)}_{flag}_{k}.npy" for k in ("h", "l")]
         env = dict(os.environ, FDNN_PAIR=flag)
         subprocess.run([sys.executable, "-c", code] + paths, check=True, env=env, timeout=240)
         outs[flag] = [np.load(p) for p in paths]
     for flag in ("64", "128", "256"):
-        assert np.array_equal(outs[""][0], outs[flag][0]), f"pair tile {flag}: last-hidden bytes differ"
-        assert np.array_equal(outs[""][1].view(np.uint32), outs[flag][1].view(np.uint32)), f"pair tile {flag}: logits differ"
+        assert np.array_equal(outs["0"][0], outs[flag][0]), f"pair tile {flag}: last-hidden bytes differ"
+        assert np.array_equal(outs["0"][1].view(np.uint32), outs[flag][1].view(np.uint32)), f"pair tile {flag}: logits differ"
+
+
+def test_headline_network_stream_chunk_uses_pairs(loaded):
+    """BASELINE configs[4] regime: a 3100-frame chunk (ragged against the 256-row pair tiles) of the 7×2048/8000
+    network — every int8 layer takes the CTA-pair kernel by default here; last-hidden bytes and logits bit-exact
+    against the oracle, scores within tolerance."""
+    dnn, port = loaded("L")
+    n = 3100
+    frames = synth.make_frames(n, 440, seed=21)
+    ctx = dnn.get_new_lazy_context(n)
+    try:
+        ctx.calculate_until_output(frames)
+        hidden = ctx.hidden()
+        want_hidden = port.until_output(frames, threads=os.cpu_count() or 8)
+        assert np.array_equal(hidden, want_hidden)
+        rows = np.r_[0:8, 250:262, 3090:3100]
+        lin = port.output_linear(want_hidden[rows])
+        _, bias, _ = port.qlayer(port.qlayer_count - 1)
+        assert np.array_equal(ctx.logits()[rows].view(np.uint32), (lin + bias).astype(np.float32).view(np.uint32))
+    finally:
+        ctx.delete()
+    got = dnn.calculate(frames[:700])
+    for r in (0, 255, 256, 699):
+        softmax_close(got[r], port.calculate(frames[r:r + 1])[0])
