@@ -76,8 +76,14 @@ int make_tmap(CUtensorMap *map, const void *base, int rows, int K, int box_rows)
   cuuint64_t strides[1] = {cuuint64_t(K)};
   cuuint32_t box[2] = {128u, cuuint32_t(box_rows)};
   cuuint32_t estr[2] = {1u, 1u};
+  static const int promo = [] {  // tuning experiments: FDNN_L2PROMO = 0 (none) / 1 (64 B) / 2 (128 B) / 3 (256 B, default)
+    const char *e = std::getenv("FDNN_L2PROMO");
+    return (e && e[0] >= '0' && e[0] <= '3') ? e[0] - '0' : 3;
+  }();
+  const CUtensorMapL2promotion promos[4] = {CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                            CU_TENSOR_MAP_L2_PROMOTION_L2_256B};
   CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                  CU_TENSOR_MAP_SWIZZLE_128B, promos[promo], CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed with CUresult " + std::to_string(int(r)));
     return FDNN_ECUDA;

@@ -191,6 +191,12 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t local_addr, uint32_t rank)
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
+// Without release semantics: no GPU-scope memory barrier in front of the arrive (a release.cluster arrive
+// waits for every earlier global store of the thread).  Enough where the arrive only hands back tensor memory
+// that tcgen05.wait::ld + tcgen05.fence::before_thread_sync have already finished reading.
+__device__ __forceinline__ void mbar_arrive_remote_relaxed(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
 // Waits with a suspend-time hint: the hardware parks the thread until the phase completes or the
 // hint (ns) runs out, so a long wait costs a handful of polls instead of a spin loop that competes
 // with the working warps for issue slots.  Still bounded: a protocol bug traps.

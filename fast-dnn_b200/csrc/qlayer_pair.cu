@@ -316,7 +316,10 @@ qlayer_pair_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_co
       for (; kb < k_blocks; kb += kScanSets) {
         const uint32_t g = it + uint32_t(kb);
         const int stage = int(g % uint32_t(Cfg::kStages));
-        ptx::mbar_wait_parked(done_bar + stage, (g / uint32_t(Cfg::kStages)) & 1u);
+        // one warp of the set polls the stage's barrier, the other three wait for it in a hardware barrier: a
+        // set idles three turns out of four, and sixteen polling warps would take a third of the issue slots
+        if ((sw & 3) == 0) ptx::mbar_wait_parked(done_bar + stage, (g / uint32_t(Cfg::kStages)) & 1u);
+        ptx::named_bar_sync(2 + uint32_t(sset), 128);
         // rows are 128-byte aligned: address = row base | (entry's byte offset with its 16-byte chunk index XORed by row%8)
         const uint32_t a_rows = ptx::smem_u32(tiles + stage * Cfg::kStageBytes) + uint32_t(row_base) * 128u;
         const uint32_t fast_end = min(r1, staged);
@@ -392,7 +395,8 @@ qlayer_pair_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_co
     // scan state of accumulator stage `a` for tile `ct2`: entry offsets per K block, packed entry words, zeroed cells and flags
     auto prepare = [&](int a, int ct2) {
       if (ct2 < tiles_total) {
-        const int n_blk2 = ct2 % n_blocks;
+        int m_blk2, n_blk2;
+        decode(ct2, m_blk2, n_blk2);
         const bool scan_on = !(args.debug_flags & 1);
         const uint32_t *gp = args.fix.ptr + size_t(n_blk2) * kbn;
         const uint32_t ent_begin = __ldg(gp);
@@ -463,7 +467,7 @@ qlayer_pair_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_co
       auto release_acc = [&]() {  // accumulator stage fully read by this warp
         ptx::tc_fence_before_sync();
         __syncwarp();
-        if (lane == 0) ptx::mbar_arrive_remote(leader_acc_free + uint32_t(acc) * 8u);
+        if (lane == 0) ptx::mbar_arrive_remote_relaxed(leader_acc_free + uint32_t(acc) * 8u);
       };
       if (n_valid == 0) release_acc();
 #pragma unroll

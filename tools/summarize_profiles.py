@@ -25,6 +25,8 @@ KEYS = [
     "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed",
     "l1tex__data_pipe_tc_wavefronts_mem_shared.sum", "l1tex__data_pipe_tc_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed",
     "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "sm__cycles_elapsed.max",
+    "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active",
+    "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio", "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
 ]
 
 
@@ -36,7 +38,7 @@ def raw(rep):
 
 
 kernels = []
-for name in ("hidden", "input", "hidden_stream"):
+for name in ("hidden", "input", "hidden_stream", "output_stream"):
     rep = os.path.join(OUT, f"{tag}_{name}.ncu-rep")
     if not os.path.exists(rep):
         continue
@@ -54,7 +56,7 @@ with open(os.path.join(PROF, f"{tag}_kernels.csv"), "w", newline="") as f:
     for d in kernels:
         w.writerow(d)
 
-for suffix in ("launches.csv", "launches_warm.csv", "bench.json", "bench_reference.json"):
+for suffix in ("launches.csv", "launches_warm.csv", "bench.json", "bench_reference.json", "stage_times.log"):
     src = os.path.join(OUT, f"{tag}_{suffix}")
     if os.path.exists(src):
         shutil.copy(src, os.path.join(PROF, f"{tag}_{suffix}"))
