@@ -522,6 +522,10 @@ int fdnn_align_dnn_bin(const char *in_path, const char *out_path, int input_alig
   return align_dnn_bin(in_path, out_path, input_alignment, hidden_alignment);
 }
 
+int fdnn_import_kaldi_nnet1(const char *nnet_txt_path, const char *transform_txt_path, const char *out_dnn_bin_path) {
+  return import_kaldi_nnet1(nnet_txt_path, transform_txt_path, out_dnn_bin_path);
+}
+
 int fdnn_feature_bin_read(const char *path, int *frames, int *dim, float **data) {
   if (!path || !frames || !dim || !data) {
     set_error("null argument");

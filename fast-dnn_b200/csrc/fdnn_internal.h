@@ -86,6 +86,7 @@ int pack_model(const char *path, float cutoff, std::vector<uint8_t> &blob);
 int validate_blob(const uint8_t *blob, size_t size);
 // Offline tooling: network aligner/writer and feature-file IO.
 int align_dnn_bin(const char *in_path, const char *out_path, int input_alignment, int hidden_alignment);
+int import_kaldi_nnet1(const char *nnet_path, const char *transform_path, const char *out_path);
 int read_feature_bin(const char *path, int *frames, int *dim, std::vector<float> &data);
 int write_feature_bin(const char *path, const float *data, int frames, int dim);
 int write_output_dump(const char *path, const float *data, int frames, int dim);

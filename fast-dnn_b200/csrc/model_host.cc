@@ -16,6 +16,7 @@
 #include <climits>
 #include <cmath>
 #include <cstdio>
+#include <cctype>
 #include <cstring>
 #include <memory>
 
@@ -532,6 +533,146 @@ int align_dnn_bin(const char *in_path, const char *out_path, int input_alignment
   const int in_pad0 = round_up(in0, input_alignment);
   for (int i = 0; i < in_pad0; ++i) put_be_float(out, i < in0 ? shift[size_t(i)] : 0.0f);
   for (int i = 0; i < in_pad0; ++i) put_be_float(out, i < in0 ? scale[size_t(i)] : 0.0f);
+  return write_file(out_path, out);
+}
+
+// Kaldi nnet1 text model + feature-transform text → dnn.bin (unaligned; run align_dnn_bin afterwards).
+// Follows FeedForwardNetwork.loadFromTextFile / loadLayersFromTextFile (FeedForwardNetwork.java:86-119,
+// 159-207): an "<AffineTransform> out in" line announces a layer; lines that start with '<' or consist of a
+// single bracket are skipped; the next `out` lines are the weight rows (brackets stripped), one more line is
+// the bias.  The transform file is searched for "[ … ]" blocks: three blocks = <Splice> (dropped), shift,
+// scale; two blocks = shift, scale; both must be as wide as the first layer's input.
+namespace {
+
+std::string trim(const std::string &s) {
+  size_t a = 0, b = s.size();
+  while (a < b && std::isspace(static_cast<unsigned char>(s[a]))) ++a;
+  while (b > a && std::isspace(static_cast<unsigned char>(s[b - 1]))) --b;
+  return s.substr(a, b - a);
+}
+
+// floats of a line with '[' and ']' removed; false on a token that is not a number
+bool parse_floats(const std::string &line, std::vector<float> &out) {
+  out.clear();
+  std::string clean;
+  clean.reserve(line.size());
+  for (char c : line) clean.push_back((c == '[' || c == ']') ? ' ' : c);
+  const char *p = clean.c_str();
+  for (;;) {
+    while (*p && std::isspace(static_cast<unsigned char>(*p))) ++p;
+    if (!*p) return true;
+    char *end = nullptr;
+    const float v = std::strtof(p, &end);
+    if (end == p) return false;
+    out.push_back(v);
+    p = end;
+  }
+}
+
+bool next_line(const std::vector<uint8_t> &text, size_t &pos, std::string &line) {
+  if (pos >= text.size()) return false;
+  size_t e = pos;
+  while (e < text.size() && text[e] != '\n') ++e;
+  line.assign(reinterpret_cast<const char *>(text.data()) + pos, e - pos);
+  if (!line.empty() && line.back() == '\r') line.pop_back();
+  pos = e + 1;
+  return true;
+}
+
+}  // namespace
+
+int import_kaldi_nnet1(const char *nnet_path, const char *transform_path, const char *out_path) {
+  if (!nnet_path || !transform_path || !out_path) {
+    set_error("bad argument to fdnn_import_kaldi_nnet1");
+    return FDNN_EINVAL;
+  }
+  std::vector<uint8_t> text;
+  if (int rc = read_file(nnet_path, text)) return rc;
+  std::vector<FloatLayer> layers;
+  size_t pos = 0;
+  std::string line;
+  int nodes = -1, inputs = -1;
+  std::vector<float> row;
+  while (next_line(text, pos, line)) {
+    line = trim(line);
+    if (line.empty()) continue;
+    if (line.compare(0, 17, "<AffineTransform>") == 0) {
+      std::vector<float> dims;
+      if (!parse_floats(line.substr(17), dims) || dims.size() < 2 || dims[0] < 1 || dims[1] < 1 || dims[0] > 1e7f || dims[1] > 1e7f) {
+        set_error("malformed <AffineTransform> line in " + std::string(nnet_path));
+        return FDNN_EFORMAT;
+      }
+      nodes = int(dims[0]);
+      inputs = int(dims[1]);
+    }
+    if (nodes == -1 || line[0] == '<' || line == "[" || line == "]") continue;
+    FloatLayer l;
+    l.in = inputs;
+    l.out = nodes;
+    l.w.resize(size_t(nodes) * size_t(inputs));
+    l.bias.resize(size_t(nodes));
+    for (int i = 0; i <= nodes; ++i) {
+      if (i > 0 && !next_line(text, pos, line)) {
+        set_error("nnet1 text ends inside layer " + std::to_string(layers.size()));
+        return FDNN_EFORMAT;
+      }
+      const size_t want = size_t(i < nodes ? inputs : nodes);
+      if (!parse_floats(line, row) || row.size() < want) {
+        set_error("layer " + std::to_string(layers.size()) + ", row " + std::to_string(i) + ": expected " + std::to_string(want) + " numbers");
+        return FDNN_EFORMAT;
+      }
+      std::memcpy(i < nodes ? l.w.data() + size_t(i) * size_t(inputs) : l.bias.data(), row.data(), want * sizeof(float));
+    }
+    if (!layers.empty() && layers.back().out != l.in) {
+      set_error("layer " + std::to_string(layers.size()) + " input width does not match previous layer");
+      return FDNN_EFORMAT;
+    }
+    layers.push_back(std::move(l));
+  }
+  if (layers.empty()) {
+    set_error("no <AffineTransform> layers in " + std::string(nnet_path));
+    return FDNN_EFORMAT;
+  }
+  // feature transform: every "[ … ]" block of the whole file
+  if (int rc = read_file(transform_path, text)) return rc;
+  std::vector<std::vector<float>> blocks;
+  for (size_t i = 0; i < text.size(); ++i) {
+    if (text[i] != '[') continue;
+    size_t e = i + 1;
+    while (e < text.size() && text[e] != ']') ++e;
+    if (e == text.size()) break;
+    std::vector<float> v;
+    std::string body(reinterpret_cast<const char *>(text.data()) + i + 1, e - i - 1);
+    for (char &c : body)
+      if (c == '\n' || c == '\r') c = ' ';
+    if (!parse_floats(body, v)) {
+      set_error("non-numeric token in a [ ] block of " + std::string(transform_path));
+      return FDNN_EFORMAT;
+    }
+    blocks.push_back(std::move(v));
+    i = e;
+  }
+  if (blocks.size() == 3) blocks.erase(blocks.begin());  // <Splice>
+  if (blocks.size() != 2) {
+    set_error("unexpected feature transformation vector count: " + std::to_string(blocks.size()));
+    return FDNN_EFORMAT;
+  }
+  const size_t in0 = size_t(layers[0].in);
+  if (blocks[0].size() != in0 || blocks[1].size() != in0) {
+    set_error("shift/scale vectors (" + std::to_string(blocks[0].size()) + ", " + std::to_string(blocks[1].size()) + ") do not match the input dimension " +
+              std::to_string(in0));
+    return FDNN_EFORMAT;
+  }
+  std::vector<uint8_t> out;
+  put_be32(out, uint32_t(layers.size()));
+  for (const FloatLayer &l : layers) {
+    put_be32(out, uint32_t(l.in));
+    put_be32(out, uint32_t(l.out));
+    for (float f : l.w) put_be_float(out, f);
+    for (float f : l.bias) put_be_float(out, f);
+  }
+  for (float f : blocks[0]) put_be_float(out, f);
+  for (float f : blocks[1]) put_be_float(out, f);
   return write_file(out_path, out);
 }
 

@@ -43,6 +43,7 @@ SIGNATURES = {
     "fdnn_blob_free": (None, [_P]),
     "fdnn_load_blob": (_I, [_P, _SZ, _I, C.POINTER(_P)]),
     "fdnn_align_dnn_bin": (_I, [C.c_char_p, C.c_char_p, _I, _I]),
+    "fdnn_import_kaldi_nnet1": (_I, [C.c_char_p, C.c_char_p, C.c_char_p]),
     "fdnn_feature_bin_read": (_I, [C.c_char_p, C.POINTER(_I), C.POINTER(_I), C.POINTER(_P)]),
     "fdnn_feature_bin_write": (_I, [C.c_char_p, _P, _I, _I]),
     "fdnn_output_dump_write": (_I, [C.c_char_p, _P, _I, _I]),
@@ -133,6 +134,12 @@ def pack(path: str, cutoff: float = 3.0) -> np.ndarray:
 def align_dnn_bin(in_path, out_path, input_alignment: int = 4, hidden_alignment: int = 16) -> None:
     """FeedForwardNetwork.align(4, 16) + saveBinary on the C++ side (host only)."""
     _check(lib().fdnn_align_dnn_bin(os.fsencode(in_path), os.fsencode(out_path), input_alignment, hidden_alignment))
+
+
+def import_kaldi_nnet1(nnet_txt_path, transform_txt_path, out_path) -> None:
+    """FeedForwardNetwork.loadFromTextFile + saveBinary on the C++ side (host only): Kaldi nnet1 text model and
+    feature-transform text → unaligned dnn.bin (follow with align_dnn_bin)."""
+    _check(lib().fdnn_import_kaldi_nnet1(os.fsencode(nnet_txt_path), os.fsencode(transform_txt_path), os.fsencode(out_path)))
 
 
 def read_feature_bin(path) -> np.ndarray:

@@ -63,6 +63,10 @@ int fdnn_load_blob(const void *blob, size_t size, int device, fdnn_model **out);
  * input_alignment (4) and every hidden width to a multiple of hidden_alignment (16), write a dnn.bin
  * that fdnn_load accepts.  The reference does this in Java only (README.md:76 lists C++ as a TODO). */
 int fdnn_align_dnn_bin(const char *in_path, const char *out_path, int input_alignment, int hidden_alignment);
+/* FeedForwardNetwork.loadFromTextFile + saveBinary (FeedForwardNetwork.java:86-119,159-207,226-235): Kaldi nnet1
+ * text model ("<AffineTransform> out in" blocks) plus the feature-transform text (optional <Splice> block,
+ * shift, scale) → an unaligned dnn.bin; follow with fdnn_align_dnn_bin.  Java-only in the reference. */
+int fdnn_import_kaldi_nnet1(const char *nnet_txt_path, const char *transform_txt_path, const char *out_dnn_bin_path);
 /* Feature matrices: big-endian int32 frames, int32 dim, fp32 rows (BatchData.java:80-91,107-139;
  * float_dnn.cc:85-105).  *data is malloc'ed (release with fdnn_blob_free). */
 int fdnn_feature_bin_read(const char *path, int *frames, int *dim, float **data);

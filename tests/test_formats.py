@@ -89,3 +89,50 @@ def test_gpu_path_meets_the_quality_criterion_too():
     q = dnn.calculate(frames)
     dnn.delete()
     assert np.abs(q - naive_forward(layers, shift, scale, frames)).sum(axis=0).max() < 0.1
+
+
+def _kaldi_text(layers, with_splice=True):
+    """nnet1 text the way Kaldi's nnet-copy --binary=false prints it, and the matching feature-transform text"""
+    out = ["<Nnet> "]
+    for j, (w, b) in enumerate(layers):
+        out.append(f"<AffineTransform> {w.shape[0]} {w.shape[1]} ")
+        out.append("<LearnRateCoef> 1 <BiasLearnRateCoef> 1 <MaxNorm> 0  [")
+        for r, row in enumerate(w):
+            out.append("  " + " ".join(repr(float(v)) for v in row) + (" ]" if r == w.shape[0] - 1 else " "))
+        out.append(" [ " + " ".join(repr(float(v)) for v in b) + " ]")
+        out.append(f"<Sigmoid> {w.shape[0]} {w.shape[0]} " if j + 1 < len(layers) else f"<Softmax> {w.shape[0]} {w.shape[0]} ")
+    out.append("</Nnet> ")
+    return "\n".join(out) + "\n"
+
+
+def _transform_text(shift, scale, with_splice):
+    out = ["<Nnet> "]
+    if with_splice:
+        out += [f"<Splice> {len(shift)} {len(shift) // 11} ", "[ -5 -4 -3 -2 -1 0 1 2 3 4 5 ]"]
+    out += [f"<AddShift> {len(shift)} {len(shift)} ", "<LearnRateCoef> 0  [ " + " ".join(repr(float(v)) for v in shift) + " ]"]
+    out += [f"<Rescale> {len(scale)} {len(scale)} ", "<LearnRateCoef> 0  [ " + " ".join(repr(float(v)) for v in scale[: len(scale) // 2])]
+    out += ["  " + " ".join(repr(float(v)) for v in scale[len(scale) // 2:]) + " ]", "</Nnet> "]
+    return "\n".join(out) + "\n"
+
+
+@pytest.mark.parametrize("with_splice", [True, False])
+def test_kaldi_nnet1_text_importer(tmp_path, with_splice):
+    """SURVEY.md §8f row 3 (FeedForwardNetwork.loadFromTextFile, FeedForwardNetwork.java:86-119,159-207): text model +
+    feature transform → the same dnn.bin bytes as the binary writer produces from the same numbers"""
+    layers, shift, scale = synth.make_network((22, 40, 3, 7), seed=9)
+    nnet, trans, got, want = (str(tmp_path / n) for n in ("final.nnet.txt", "final.feature_transform", "imported.bin", "direct.bin"))
+    open(nnet, "w").write(_kaldi_text(layers))
+    open(trans, "w").write(_transform_text(shift, scale, with_splice))
+    qd.import_kaldi_nnet1(nnet, trans, got)
+    formats.write_dnn_bin(want, layers, shift, scale)
+    assert open(got, "rb").read() == open(want, "rb").read()
+    # the imported network goes through the aligner and the packer like any other
+    aligned = str(tmp_path / "aligned.bin")
+    qd.align_dnn_bin(got, aligned, 4, 16)
+    assert qd.pack(aligned).size > 0
+    # error behaviour: wrong transform width (IllegalStateException in the reference), missing file, no layers
+    open(trans, "w").write(_transform_text(shift[:-1], scale[:-1], with_splice))
+    assert qd.lib().fdnn_import_kaldi_nnet1(nnet.encode(), trans.encode(), got.encode()) == qd.FDNN_EFORMAT
+    assert qd.lib().fdnn_import_kaldi_nnet1(b"/nonexistent/x", trans.encode(), got.encode()) == qd.FDNN_EIO
+    open(nnet, "w").write("<Nnet>\n</Nnet>\n")
+    assert qd.lib().fdnn_import_kaldi_nnet1(nnet.encode(), trans.encode(), got.encode()) == qd.FDNN_EFORMAT
