@@ -186,9 +186,36 @@ def run_gpu_arm(args):
     ctx = dnn.get_new_lazy_context(BATCH)
     stream = torch.cuda.current_stream()
     sampler = ClockSampler(local)
+    # Steps are independent batches, so — like the reference's own multi-caller pattern (several callers share one
+    # immutable model, each with its own context: MultiThreadedStressTest.java:48-61, and the e2e leg below) — INFLIGHT
+    # contexts take the steps round-robin on their own streams; kernels of neighbouring steps fill each other's tails and
+    # the SMs a 128-CTA kernel leaves idle (measured on B200: 144 → 124 → 115 → 112 us per step for 1 → 2 → 3 → 4).
+    # Several callers in flight is what the library's "throughput" tile policy is for (include/fdnn.h): same results,
+    # wider tiles, less SM time per frame.  The single-stream figure reported beside it uses the default "latency" policy.
+    INFLIGHT = 4
+    dnn.set_tile_policy("throughput")
+    flight = [dnn.get_new_lazy_context(BATCH) for _ in range(INFLIGHT)]
+    dnn.set_tile_policy("latency")
+    streams = [stream] + [torch.cuda.Stream(device=dev) for _ in range(INFLIGHT - 1)]
 
-    def step(i):
-        ctx.forward_device(d_in[i % pool].data_ptr(), BATCH, d_out[i % pool].data_ptr(), stream.cuda_stream)
+    def step(i, lanes=INFLIGHT):
+        k = i % lanes
+        c = ctx if lanes == 1 else flight[k]
+        c.forward_device(d_in[i % pool].data_ptr(), BATCH, d_out[i % pool].data_ptr(), streams[k].cuda_stream)
+
+    def timed(steps, lanes):
+        """device time of `steps` steps over `lanes` streams: from one start event every stream waits on to the last stream's end"""
+        ev0 = torch.cuda.Event(enable_timing=True)
+        ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(lanes)]
+        ev0.record(stream)
+        for s in streams[1:lanes]:
+            s.wait_event(ev0)
+        for i in range(steps):
+            step(i, lanes)
+        for s, e in zip(streams[:lanes], ev1):
+            e.record(s)
+        torch.cuda.synchronize()
+        return max(ev0.elapsed_time(e) for e in ev1)
 
     def barrier():
         torch.cuda.synchronize()
@@ -196,19 +223,20 @@ def run_gpu_arm(args):
             dist.barrier()
             torch.cuda.synchronize()
 
-    for i in range(max(args.warmup, 3)):
+    dnn.set_tile_policy("throughput")  # (a context caches its launch sequence per shape on first use)
+    for i in range(max(args.warmup, 3) * INFLIGHT):  # every context captures its graphs before the clock starts
         step(i)
+    barrier()
+    dnn.set_tile_policy("latency")
+    for i in range(max(args.warmup, 3)):
+        step(i, 1)
+    barrier()
+    ms_single = timed(args.steps, 1)  # one context, one stream: reported beside the headline value
     barrier()
     sampler.start()
     launches0 = qd.launch_count()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record(stream)
-    for i in range(args.steps):
-        step(i)
-    ev1.record(stream)
-    torch.cuda.synchronize()
+    ms_total = timed(args.steps, INFLIGHT)
     launches = qd.launch_count() - launches0
-    ms_total = ev0.elapsed_time(ev1)
     if world > 1:
         t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -346,11 +374,15 @@ def run_gpu_arm(args):
             "config": {"workload": f"BASELINE configs[2]: 440-7x2048-8000 synthetic network, batch {BATCH} synthetic frames per step and GPU",
                        "l2": f"inputs and outputs rotate over a {pool}-deep pool ({pool * BATCH * (I_DIM + O_DIM) * 4 / 1e6:.0f} MB > 126 MB L2); "
                              "the 45 MB of weights stay L2-resident as in steady-state serving",
+                       "inflight": f"{INFLIGHT} contexts on {INFLIGHT} streams take the steps round-robin (independent batches; one shared model; "
+                                   "tile policy 'throughput'); single_stream = one context, one stream, tile policy 'latency'",
                        "parallelism": f"frames sharded over {world} GPU(s), one NCCL broadcast of the weight blob at load, no per-frame collective"},
+            "single_stream": {"value": world * BATCH * args.steps / (ms_single * 1e-3), "ms_per_step": ms_single / args.steps},
             "e2e": e2e, "gpu_launches": int(launches), "clocks": sampler.summary(), "roofline": roofline, "stages": stages,
             "cpu_baseline": cpu_baseline, "stream_regime": stream_info,
         }, default=plain))
-    ctx.delete()
+    for c in flight + [ctx]:
+        c.delete()
     dnn.delete()
     if world > 1:
         dist.destroy_process_group()

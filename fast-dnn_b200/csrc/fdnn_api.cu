@@ -150,6 +150,7 @@ struct fdnn_model {
   std::vector<bool> tc_ok;
   std::vector<int> fast_tail;  // per int8 layer: the packed-f32x2 epilogue is provably bit-identical (device_common.cuh)
   bool force_simt = false;
+  std::atomic<int> tile_policy{FDNN_POLICY_LATENCY};
   // Graph capture must not overlap device-wide synchronising calls (cudaFree, blocking copies) made
   // by this library from other threads: both sides take this lock.
   std::mutex cuda_mu;
@@ -323,7 +324,7 @@ int enqueue_until_logits(fdnn_ctx *c, const float *d_in, int m, float *d_logits,
       a.out_u8 = c->d_act[(j + 1) & 1];
     }
     if (mod->tc_ok[size_t(j)] && c->amap_ok) {
-      const TcPlan plan = qlayer_tc_plan(m, ql.nodes, logits, mod->num_sms);
+      const TcPlan plan = qlayer_tc_plan(m, ql.nodes, logits, mod->num_sms, mod->tile_policy.load(std::memory_order_relaxed));
       const int which = plan.block_n == 64 ? 0 : (plan.block_n == 128 ? 1 : 2);
       a.fix = fix_of(j, which);  // the risk list grouped by the tile width
       const int act_box = plan.share_a ? (plan.cluster == 4 ? 2 : (plan.cluster == 2 ? 1 : 0)) : 0;
@@ -594,6 +595,14 @@ int fdnn_input_dim(const fdnn_model *m) { return m ? m->hdr.in_dim : FDNN_EINVAL
 int fdnn_output_dim(const fdnn_model *m) { return m ? m->hdr.out_dim : FDNN_EINVAL; }
 int fdnn_hidden_dim(const fdnn_model *m) { return m ? m->hdr.hidden : FDNN_EINVAL; }
 int fdnn_device(const fdnn_model *m) { return m ? m->device : FDNN_EINVAL; }
+int fdnn_set_tile_policy(fdnn_model *m, int policy) {
+  if (!m || (policy != FDNN_POLICY_LATENCY && policy != FDNN_POLICY_THROUGHPUT)) {
+    set_error("bad argument to fdnn_set_tile_policy");
+    return FDNN_EINVAL;
+  }
+  m->tile_policy.store(policy, std::memory_order_relaxed);
+  return FDNN_OK;
+}
 int fdnn_layer_count(const fdnn_model *m) { return m ? m->hdr.n_qlayers + 1 : FDNN_EINVAL; }
 
 int fdnn_layer_dim(const fdnn_model *m, int i) {

@@ -58,7 +58,7 @@ struct TcPlan {
   bool share_a;
   bool pair;  // CTA pairs (tcgen05 cta_group::2, qlayer_pair.cu): activation box 128 rows, weight box block_n/2 rows
 };
-TcPlan qlayer_tc_plan(int M, int N, bool logits, int num_sms);
+TcPlan qlayer_tc_plan(int M, int N, bool logits, int num_sms, int policy = 0);  // policy: FDNN_POLICY_* (include/fdnn.h)
 cudaError_t launch_qlayer_tc(const CUtensorMap &tmap_act, const CUtensorMap &tmap_w, const QLayerArgs &a, bool logits, TcPlan plan, int num_sms,
                              cudaStream_t stream);
 // CTA-pair path (qlayer_pair.cu): two CTAs per 256×block_n tile sharing the weight tile.

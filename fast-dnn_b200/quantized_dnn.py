@@ -51,6 +51,7 @@ SIGNATURES = {
     "fdnn_input_dim": (_I, [_P]),
     "fdnn_output_dim": (_I, [_P]),
     "fdnn_layer_count": (_I, [_P]),
+    "fdnn_set_tile_policy": (_I, [_P, _I]),
     "fdnn_layer_dim": (_I, [_P, _I]),
     "fdnn_hidden_dim": (_I, [_P]),
     "fdnn_device": (_I, [_P]),
@@ -234,6 +235,11 @@ class QuantizedDnn:
 
     def device(self) -> int:
         return lib().fdnn_device(self._h)
+
+    def set_tile_policy(self, policy: str) -> None:
+        """'latency' (default: shortest pass for one caller) or 'throughput' (least SM time per frame, for several contexts in
+        flight on this model); results are identical.  Applies to contexts created afterwards."""
+        _check(lib().fdnn_set_tile_policy(self._h, {"latency": 0, "throughput": 1}[policy]))
 
     inputDimension, outputDimension, layerCount, layerDimension = input_dimension, output_dimension, layer_count, layer_dimension
 

@@ -88,6 +88,15 @@ int fdnn_layer_count(const fdnn_model *model);
 int fdnn_layer_dim(const fdnn_model *model, int i);
 int fdnn_hidden_dim(const fdnn_model *model);
 int fdnn_device(const fdnn_model *model);
+/* Tile policy of the tensor-core layers for SHORT batches (no counterpart in the reference, whose batchSize only blocks for
+ * the CPU cache).  FDNN_POLICY_LATENCY (default): the narrowest tiles that fill the GPU in one wave — shortest time for
+ * one caller.  FDNN_POLICY_THROUGHPUT: one step wider tiles, half as many CTAs that each move fewer operand bytes per
+ * result — less SM time per frame, for callers that keep several contexts in flight on one model (the pattern of
+ * MultiThreadedStressTest.java:48-61).  Results are identical.  Set it before the contexts that should use it exist
+ * (a context caches the launch sequence of the first pass of each shape). */
+#define FDNN_POLICY_LATENCY 0
+#define FDNN_POLICY_THROUGHPUT 1
+int fdnn_set_tile_policy(fdnn_model *model, int policy);
 
 /* ---- full forward ---------------------------------------------------------------------------
  * Java_suskun_nn_QuantizedDnn_calculate (jni_dnn.cc:35-62) = CalculationContext::Calculate

@@ -287,3 +287,23 @@ def test_headline_network_stream_chunk_uses_pairs(loaded):
     got = dnn.calculate(frames[:700])
     for r in (0, 255, 256, 699):
         softmax_close(got[r], port.calculate(frames[r:r + 1])[0])
+
+
+def test_throughput_tile_policy_gives_identical_results(net_file):
+    """fdnn_set_tile_policy: wider tiles for callers that keep several contexts in flight — same bytes as the default policy"""
+    dnn = qd.QuantizedDnn.load_from_file(net_file("L"))
+    try:
+        frames = synth.make_frames(512, 440, seed=33)
+        outs = []
+        for policy in ("latency", "throughput"):
+            dnn.set_tile_policy(policy)
+            ctx = dnn.get_new_lazy_context(512)
+            ctx.calculate_until_output(frames)
+            outs.append((ctx.hidden().copy(), ctx.logits().copy()))
+            ctx.delete()
+        assert np.array_equal(outs[0][0], outs[1][0])
+        assert np.array_equal(outs[0][1].view(np.uint32), outs[1][1].view(np.uint32))
+        with pytest.raises(qd.FdnnError):
+            qd._check(qd.lib().fdnn_set_tile_policy(dnn._h, 7))
+    finally:
+        dnn.delete()
