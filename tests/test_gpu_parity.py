@@ -243,16 +243,20 @@ def test_cluster_multicast_path_is_bit_exact(net_file):
 @pytest.mark.parametrize("stress", [False, True])
 def test_cta_pair_path_is_bit_exact(net_file, stress):
     """FDNN_PAIR=<tile width>: every int8 layer on CTA pairs (tcgen05 cta_group::2, qlayer_pair.cu) — same
-    bytes as the single-CTA path (itself checked against the oracle above), ragged row count, dense saturation"""
+    bytes as the single-CTA path (itself checked against the oracle above): one frame, ragged row counts around
+    the 128-row CTA and 256-row pair boundaries, several tiles per pair, dense saturation (stress network)"""
     import subprocess
     import sys
     code = (
         "import sys, numpy as np; sys.path.insert(0, %r); import fast_dnn_b200\n"
         "from fast_dnn_b200 import quantized_dnn as qd, synth\n"
         "dnn = qd.QuantizedDnn.load_from_file(%r)\n"
-        "x = synth.make_frames(300, 440, seed=4)\n"
-        "ctx = dnn.get_new_lazy_context(300); ctx.calculate_until_output(x)\n"
-        "np.save(sys.argv[1], ctx.hidden()); np.save(sys.argv[2], ctx.logits())\n"
+        "hs, ls = [], []\n"
+        "for n in (1, 129, 300, 1000):\n"
+        "    x = synth.make_frames(n, 440, seed=4 + n)\n"
+        "    ctx = dnn.get_new_lazy_context(n); ctx.calculate_until_output(x)\n"
+        "    hs.append(ctx.hidden().copy()); ls.append(ctx.logits().copy()); ctx.delete()\n"
+        "np.save(sys.argv[1], np.concatenate(hs)); np.save(sys.argv[2], np.concatenate(ls))\n"
     ) % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), net_file("S", stress=stress))
     outs = {}
     for flag in ("0", "64", "128", "256"):
