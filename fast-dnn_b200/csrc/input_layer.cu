@@ -18,7 +18,8 @@
 // four adjacent threads: thread (group g, lane r) owns SSE lane r of an 8 × 8 block — 64
 // accumulators, and per 4-wide K step 16 one-wavefront 32-bit loads for 128 math instructions.
 // The lanes are recombined as (l0 + l1) + (l2 + l3) with two shuffles at the end.  K is streamed
-// in 40-float chunks through a 3-stage cp.async ring (frames and weight rows alike, issued two
+// in 88-float chunks (5 per 440-wide input: fewer barriers than with 40-float ones, 58.7 → 56.9 µs per 512 frames)
+// through a 3-stage cp.async ring (frames and weight rows alike, issued two
 // chunks ahead); the frame rows of a stage are shifted and scaled in place one iteration before
 // they are used, so the loop has one barrier per chunk and no exposed global-memory latency.
 
@@ -34,8 +35,8 @@ namespace {
 
 constexpr int kTileF = 64;    // frames per CTA
 constexpr int kTileN = 128;   // nodes per CTA
-constexpr int kChunk = 40;    // floats of K per stage
-constexpr int kPitch = 44;    // smem row pitch in floats (≡ 12 mod 32: consecutive rows land in different bank quads)
+constexpr int kChunk = 88;    // floats of K per stage
+constexpr int kPitch = 92;    // smem row pitch in floats (≡ 28 mod 32: consecutive rows land in different bank quads)
 constexpr int kThreads = 512;
 constexpr int kTF = 8, kTN = 8;  // per-thread block of one SSE lane
 constexpr int kStages = 3;
@@ -159,7 +160,7 @@ __global__ void __launch_bounds__(kThreads, 1) input_layer_kernel(const InputLay
     const float *xs = stage_buf + (c % kStages) * kStageFloats + (wf + fg) * kPitch + r;
     const float *ws = stage_buf + (c % kStages) * kStageFloats + (kTileF + wn + ng) * kPitch + r;
     const int kc4 = (min(kChunk, I - c * kChunk)) / 4;
-#pragma unroll 2
+#pragma unroll 1
     for (int q = 0; q < kc4; ++q) {
       float xv[kTF], wv[kTN];
 #pragma unroll
