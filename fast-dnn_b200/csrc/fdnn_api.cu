@@ -149,6 +149,12 @@ struct fdnn_model {
   std::vector<std::array<CUtensorMap, 4>> wmaps;  // per int8 layer, box rows 64 / 128 / 256 / 32
   std::vector<bool> tc_ok;
   std::vector<int> fast_tail;  // per int8 layer: the packed-f32x2 epilogue is provably bit-identical (device_common.cuh)
+  // certified tensor-core input layer (input_tc.cu): fixed-point limb planes and per-node statistics of layer 0
+  bool input_tc = false;
+  uint8_t *d_w0_limbs = nullptr;        // 3 planes of [w_plane_rows][kInputTcPitch]
+  InputNodeStats *d_node_stats = nullptr;
+  int w_plane_rows = 0;
+  CUtensorMap w0map;
   bool force_simt = false;
   std::atomic<int> tile_policy{FDNN_POLICY_LATENCY};
   // Graph capture must not overlap device-wide synchronising calls (cudaFree, blocking copies) made
@@ -173,6 +179,16 @@ struct fdnn_ctx {
   int8_t *d_masks = nullptr;  // [cap][O], allocated on first lazy use
   float *d_row = nullptr;     // [O] scratch for single-row lazy output
   float *d_lazy = nullptr;    // [cap][O] masked softmax rows, allocated on first batched lazy use
+  // certified tensor-core input layer: transformed frames, their limb planes, row statistics, undecided elements
+  float *d_xq = nullptr;
+  uint8_t *d_xlimbs = nullptr;
+  int x_plane_rows = 0;
+  InputRowStats *d_rowstats = nullptr;
+  uint2 *d_unc_list = nullptr;
+  uint32_t *d_unc_count = nullptr;
+  uint32_t unc_cap = 0;
+  CUtensorMap xmap;
+  bool input_tc = false;
   CUtensorMap amap[2][3];  // per activation buffer: TMA box of 128 / 64 / 32 rows (cluster 1 / 2 / 4 sharing the tile)
   bool amap_ok = false;
   cudaStream_t stream = nullptr;
@@ -208,6 +224,11 @@ void destroy_ctx(fdnn_ctx *c) {
   cudaFree(c->d_lazy);
   cudaFree(c->d_trace);
   cudaFree(c->d_timeline);
+  cudaFree(c->d_xq);
+  cudaFree(c->d_xlimbs);
+  cudaFree(c->d_rowstats);
+  cudaFree(c->d_unc_list);
+  cudaFree(c->d_unc_count);
   for (auto &g : c->graphs) cudaGraphExecDestroy(g.exec);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
@@ -252,6 +273,20 @@ int create_ctx(fdnn_model *m, int n, fdnn_ctx **out) {
         if (int rc = make_tmap(&c->amap[b][v], c->d_act[b], n, H, 128 >> v)) return rc;
     c->amap_ok = true;
   }
+  if (m->input_tc) {
+    c->x_plane_rows = round_up(n, 128);
+    const size_t plane = size_t(c->x_plane_rows) * kInputTcPitch;
+    CUDA_TRY(cudaMalloc(&c->d_xq, size_t(n) * I * 4));
+    CUDA_TRY(cudaMalloc(&c->d_xlimbs, 3 * plane));
+    CUDA_TRY(cudaMemsetAsync(c->d_xlimbs, 0, 3 * plane, c->stream));  // K padding and the rows past n stay zero
+    CUDA_TRY(cudaMalloc(&c->d_rowstats, size_t(n) * sizeof(InputRowStats)));
+    const size_t cap = std::max<size_t>(4096, size_t(n) * size_t(H) / 6);  // the certificate leaves ≈ 3 % undecided on the synthetic network
+    c->unc_cap = uint32_t(std::min<size_t>(cap, 0x7fffffffu));
+    CUDA_TRY(cudaMalloc(&c->d_unc_list, size_t(c->unc_cap) * sizeof(uint2)));
+    CUDA_TRY(cudaMalloc(&c->d_unc_count, sizeof(uint32_t)));
+    if (int rc = make_tmap(&c->xmap, c->d_xlimbs, 3 * c->x_plane_rows, kInputTcPitch, 128)) return rc;
+    c->input_tc = true;
+  }
   CUDA_TRY(cudaStreamSynchronize(c->stream));
   lk.unlock();  // (a failing CUDA_TRY above unwinds lk before c, whose deleter takes the lock again)
   *out = c.release();
@@ -285,8 +320,35 @@ int enqueue_until_logits(fdnn_ctx *c, const float *d_in, int m, float *d_logits,
   ia.M = m;
   ia.I = h.in_dim;
   ia.H = h.hidden;
-  CUDA_TRY(launch_input_layer(ia, stream));
-  g_launches.fetch_add(1, std::memory_order_relaxed);
+  if (c->input_tc) {
+    InputTcArgs ta{};
+    ta.in = d_in;
+    ta.shift = ia.shift;
+    ta.scale = ia.scale;
+    ta.w0 = ia.w0;
+    ta.bias0 = ia.bias0;
+    ta.lut = ia.lut;
+    ta.node_stats = mod->d_node_stats;
+    ta.xq = c->d_xq;
+    ta.x_limbs = c->d_xlimbs;
+    ta.x_plane = size_t(c->x_plane_rows) * kInputTcPitch;
+    ta.x_plane_rows = c->x_plane_rows;
+    ta.w_plane_rows = mod->w_plane_rows;
+    ta.row_stats = c->d_rowstats;
+    ta.unc_list = c->d_unc_list;
+    ta.unc_count = c->d_unc_count;
+    ta.unc_cap = c->unc_cap;
+    ta.out_u8 = c->d_act[0];
+    ta.M = m;
+    ta.I = h.in_dim;
+    ta.H = h.hidden;
+    ta.fixup_ctas = mod->num_sms * 8;
+    CUDA_TRY(launch_input_tc(c->xmap, mod->w0map, ta, stream));
+    g_launches.fetch_add(3, std::memory_order_relaxed);
+  } else {
+    CUDA_TRY(launch_input_layer(ia, stream));
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+  }
   if (after_stage) after_stage(0);
   const size_t act_bytes = size_t(m) * size_t(h.hidden);
   if (c->trace) CUDA_TRY(cudaMemcpyAsync(c->d_trace, c->d_act[0], act_bytes, cudaMemcpyDeviceToDevice, stream));
@@ -367,7 +429,7 @@ int enqueue_softmax(fdnn_ctx *c, const float *d_logits, const int8_t *d_masks, i
 // cached CUDA graph when possible.
 int run_pass(fdnn_ctx *c, const float *d_in, int m, float *d_out, bool softmax, cudaStream_t stream) {
   static const bool use_graphs = env_flag("FDNN_GRAPHS", true);
-  const int kernels = c->model->hdr.n_qlayers + 1 + (softmax ? 1 : 0);
+  const int kernels = c->model->hdr.n_qlayers + (c->input_tc ? 3 : 1) + (softmax ? 1 : 0);
   if (!use_graphs || c->trace || c->d_timeline != nullptr || m <= 0) {
     if (int rc = enqueue_until_logits(c, d_in, m, d_out, stream)) return rc;
     return softmax ? enqueue_softmax(c, d_out, nullptr, m, d_out, stream) : FDNN_OK;
@@ -441,6 +503,8 @@ int upload_model(const uint8_t *host_view, const void *src, bool src_on_device, 
   }
   auto fail = [&](int rc) {
     cudaFree(m->d_blob);
+    cudaFree(m->d_w0_limbs);
+    cudaFree(m->d_node_stats);
     return rc;
   };
   if (cudaError_t ce = input_layer_configure(); ce != cudaSuccess) {
@@ -458,6 +522,64 @@ int upload_model(const uint8_t *host_view, const void *src, bool src_on_device, 
   if (cudaError_t ce = softmax_configure(); ce != cudaSuccess) {
     set_error(std::string("softmax_configure: ") + cudaGetErrorString(ce));
     return fail(FDNN_ECUDA);
+  }
+  // Layer 0 for the certified tensor-core path (input_tc.cu): every weight row as a block-fixed-point integer vector
+  // (|W_k| ≤ 2²², three 8-bit limbs, K padded with zeros to the plane pitch) plus scale, ‖w‖₂ and Σ|W_k| per node.
+  static const bool allow_input_tc = env_flag("FDNN_INPUT_TC", true);
+  if (allow_input_tc && !m->force_simt && input_tc_supported(m->hdr.in_dim, m->hdr.hidden)) {
+    const int I0 = m->hdr.in_dim, H0 = m->hdr.hidden;
+    m->w_plane_rows = round_up(H0, 64);
+    const size_t plane = size_t(m->w_plane_rows) * kInputTcPitch;
+    std::vector<uint8_t> limbs(3 * plane, 0);
+    std::vector<InputNodeStats> stats((size_t(H0)));
+    const float *w0 = reinterpret_cast<const float *>(host_view + m->hdr.off_w0);
+    const float *b0 = reinterpret_cast<const float *>(host_view + m->hdr.off_bias0);
+    for (int n = 0; n < H0; ++n) {
+      const float *w = w0 + size_t(n) * size_t(I0);
+      float mx = 0.0f;
+      bool bad = !std::isfinite(b0[n]);
+      double n2 = 0.0, n2c = 0.0;
+      for (int k = 0; k < I0; ++k) {
+        bad = bad || !std::isfinite(w[k]);
+        mx = std::max(mx, std::fabs(w[k]));
+        n2 += double(w[k]) * double(w[k]);
+        n2c += input_round_count(k, I0) * double(w[k]) * double(w[k]);
+      }
+      int e = mx > 0.0f ? std::ilogb(mx) + 1 : 0;
+      if (e < -40 || e > 40) bad = true;
+      if (bad) e = 0;
+      double sum_abs = 0.0;
+      for (int k = 0; k < I0 && !bad; ++k) {
+        const int W = int(std::lrint(std::ldexp(double(w[k]), 22 - e)));  // exact scaling, round to nearest
+        sum_abs += std::abs(W);
+        const size_t o = size_t(n) * kInputTcPitch + size_t(k);
+        limbs[o] = uint8_t(W & 255);
+        limbs[plane + o] = uint8_t((W >> 8) & 255);
+        limbs[2 * plane + o] = uint8_t((W >> 16) & 255);
+      }
+      // certificate constants, every bound rounded up (derivation in input_tc.cu)
+      const double u = 5.9604644775390625e-8, up = 1.0 + 1e-6;
+      auto ru = [](double v) { return std::nextafter(float(v), INFINITY); };
+      const double sc = std::ldexp(1.0, e - 22), nw = std::sqrt(n2) * (1.0 + 1e-9);
+      InputNodeStats &s = stats[size_t(n)];
+      s.c = bad ? -1.0f : float(sc);
+      s.bc = bad ? 0.0f : b0[n] * 100.0f;
+      s.q = ru(std::sqrt(n2c) * (1.0 + 1e-9) * up);
+      s.qp = ru((nw + sc * 131072.0 * std::sqrt(double(I0))) * up);
+      s.e = ru(sc * (0.5 * sum_abs + 0.25 * double(I0)) * up);
+      s.f = ru((u * std::fabs(double(s.bc)) + 2.1 * u + 1e-9) * up);
+      s.pad[0] = s.pad[1] = 0.0f;
+    }
+    CUDA_TRY(cudaMalloc(&m->d_w0_limbs, limbs.size()));
+    CUDA_TRY(cudaMemcpy(m->d_w0_limbs, limbs.data(), limbs.size(), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMalloc(&m->d_node_stats, stats.size() * sizeof(InputNodeStats)));
+    CUDA_TRY(cudaMemcpy(m->d_node_stats, stats.data(), stats.size() * sizeof(InputNodeStats), cudaMemcpyHostToDevice));
+    if (int rc = make_tmap(&m->w0map, m->d_w0_limbs, 3 * m->w_plane_rows, kInputTcPitch, 64)) return fail(rc);
+    if (cudaError_t ce = input_tc_configure(); ce != cudaSuccess) {
+      set_error(std::string("input_tc_configure: ") + cudaGetErrorString(ce));
+      return fail(FDNN_ECUDA);
+    }
+    m->input_tc = true;
   }
   m->wmaps.resize(m->q.size());
   m->tc_ok.assign(m->q.size(), false);
@@ -587,6 +709,8 @@ int fdnn_free(fdnn_model *model) {
   for (fdnn_ctx *c : model->pool) destroy_ctx(c);
   DeviceGuard g(model->device);
   cudaFree(model->d_blob);
+  cudaFree(model->d_w0_limbs);
+  cudaFree(model->d_node_stats);
   delete model;
   return FDNN_OK;
 }
@@ -831,6 +955,19 @@ int fdnn_ctx_logits(fdnn_ctx *ctx, int n_frames, float *out) {
 // the kernels.  ms[0] = input layer, ms[1 .. nq−1] = hidden int8 layers, ms[nq] = output int8
 // layer, ms[nq+1] = softmax (averages, milliseconds).  Event pairs between back-to-back kernels
 // include the inter-kernel launch gap.
+int fdnn_ctx_input_undecided(fdnn_ctx *ctx, unsigned *undecided) {
+  if (!ctx || !undecided) {
+    set_error("bad argument to fdnn_ctx_input_undecided");
+    return FDNN_EINVAL;
+  }
+  *undecided = 0xffffffffu;
+  if (!ctx->input_tc) return FDNN_OK;
+  DeviceGuard g(ctx->model->device);
+  CUDA_TRY(cudaDeviceSynchronize());
+  CUDA_TRY(cudaMemcpy(undecided, ctx->d_unc_count, sizeof(unsigned), cudaMemcpyDeviceToHost));
+  return FDNN_OK;
+}
+
 int fdnn_ctx_profile_stages(fdnn_ctx *ctx, const float *d_in, int n_frames, float *d_out, int iters, float *ms) {
   if (!ctx || !d_in || !d_out || !ms || iters <= 0 || n_frames <= 0 || n_frames > ctx->cap) {
     set_error("bad argument to fdnn_ctx_profile_stages");

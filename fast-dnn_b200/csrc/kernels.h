@@ -45,6 +45,57 @@ cudaError_t input_layer_configure();
 int input_layer_max_dim();  // widest (padded) input the kernel takes
 cudaError_t launch_input_layer(const InputLayerArgs &a, cudaStream_t stream);
 
+// ---- fp32 input layer, certified on the tensor cores (input_tc.cu) ------------------------------
+constexpr int kInputTcMaxI = 512;   // widest (padded) input the fixed-point path takes
+constexpr int kInputTcPitch = 512;  // bytes per row of a limb plane (K padded with zeros)
+// How many fp32 roundings term k of a frame·weight-row dot product goes through in the reference (dnn.cc:219-247,
+// 168-172): its product, the adds of its SSE lane (k mod 4) that come after it, the two adds that combine the lanes;
+// + 1 for safety.  I = padded input width (multiple of 4).
+__host__ __device__ inline double input_round_count(int k, int I) {
+  const int n = I / 4, q = k / 4;
+  return double((q == 0 ? n - 1 : n - q) + 3 + 1);
+}
+// Certificate constants (all fp32, every bound rounded UP; derivation in input_tc.cu).
+struct InputRowStats {   // per frame, written by the prepare kernel
+  float a[5];            // 100 · 2^(e−22) · 256^s: weight of shift class s in z (exact); a[0] < 0 = certify nothing in this row
+  float p;               // 100 · u · ‖√c · x'‖₂                     (the reference's own rounding, c = input_round_count)
+  float pp;              // 100 · 7u · (‖x'‖₂ + 2^(e−22)·2¹⁷·√I)      (fp32 evaluation of z from the class sums)
+  float r1;              // 100 · 2^(e−22) · ½ Σ|X_k|                 (quantisation of the weights)
+  float ar;              // 100 · 2^(e−22)                            (… of the frame, with InputNodeStats::e)
+  float pad[3];
+};
+struct InputNodeStats {  // per node of layer 0, built when the model is uploaded
+  float c;               // 2^(e_w−22) (exact); < 0 = certify nothing for this node
+  float bc;              // fl(bias · 100)
+  float q;               // ‖√c · w‖₂
+  float qp;              // ‖w‖₂ + 2^(e_w−22)·2¹⁷·√I
+  float e;               // 2^(e_w−22) · (½ Σ|W_k| + ¼ I)
+  float f;               // u·|bc| + 2.1u + 1e-9: rounding of bias·100, of the reference's "+ bias" and "· 100" at |z| = 0
+  float pad[2];
+};
+struct InputTcArgs {
+  const float *in;      // [M][I] raw frames
+  const float *shift, *scale;
+  const float *w0;      // [H][I] fp32 (exact path)
+  const float *bias0;   // [H]
+  const uint8_t *lut;   // doubled sigmoid LUT
+  const InputNodeStats *node_stats;  // [H]
+  float *xq;            // [M][I] transformed frames (scratch, read by the exact path)
+  uint8_t *x_limbs;     // 3 planes of [x_plane_rows][kInputTcPitch] bytes
+  size_t x_plane;       // bytes per plane
+  int x_plane_rows, w_plane_rows;
+  InputRowStats *row_stats;  // [M]
+  uint2 *unc_list;      // (row, node) of the elements the certificate could not decide
+  uint32_t *unc_count;
+  uint32_t unc_cap;
+  uint8_t *out_u8;      // [M][H]
+  int M, I, H;
+  int fixup_ctas;
+};
+cudaError_t input_tc_configure();
+bool input_tc_supported(int I, int H);
+cudaError_t launch_input_tc(const CUtensorMap &tmap_x, const CUtensorMap &tmap_w, const InputTcArgs &a, cudaStream_t stream);
+
 // ---- int8 layers -------------------------------------------------------------------------------
 // tcgen05 path (qlayer_tc.cu): needs K a multiple of 128 and, for hidden layers, N a multiple of 32.
 cudaError_t qlayer_tc_configure();

@@ -68,6 +68,7 @@ SIGNATURES = {
     "fdnn_ctx_lazy_batch_device": (_I, [_P, _P, _I, _P, _P]),
     "fdnn_ctx_profile_stages": (_I, [_P, _P, _I, _P, _I, _P]),
     "fdnn_ctx_timeline": (_I, [_P, _I, _P]),
+    "fdnn_ctx_input_undecided": (_I, [_P, C.POINTER(C.c_uint)]),
     "fdnn_ctx_set_trace": (_I, [_P, _I]),
     "fdnn_ctx_hidden": (_I, [_P, _I, _I, _P]),
     "fdnn_ctx_logits": (_I, [_P, _I, _P]),
@@ -354,6 +355,12 @@ class LazyContext:
 
     def lazy_batch_device(self, d_masks: int, n_frames: int, d_out: int, stream: int = 0) -> None:
         _check(lib().fdnn_ctx_lazy_batch_device(self._h, C.c_void_p(d_masks), n_frames, C.c_void_p(d_out), C.c_void_p(stream)))
+
+    def input_undecided(self):
+        """elements of the last pass the certified tensor-core input layer handed to the exact path (None: plain exact kernel)"""
+        n = C.c_uint()
+        _check(lib().fdnn_ctx_input_undecided(self._h, C.byref(n)))
+        return None if n.value == 0xFFFFFFFF else int(n.value)
 
     def timeline(self, enable: bool):
         """arm (True) / read back (False) per-CTA phase stamps of the tensor-core layer kernels"""

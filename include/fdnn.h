@@ -158,6 +158,10 @@ int fdnn_sigmoid_lut(uint8_t out[1280]);
  * averages in milliseconds, synchronised on return. */
 int fdnn_ctx_profile_stages(fdnn_ctx *ctx, const float *d_in, int n_frames, float *d_out, int iters, float *ms);
 
+/* Diagnostics of the certified tensor-core input layer (csrc/input_tc.cu): how many (frame, node) elements of the last pass
+ * the error-bound certificate left to the exact CUDA-core path; *undecided = 0xffffffff when the context uses the plain
+ * exact kernel.  Synchronises the context's stream. */
+int fdnn_ctx_input_undecided(fdnn_ctx *ctx, unsigned *undecided);
 /* Profiling aid: per-CTA phase timestamps of the tensor-core layer kernels.  enable=1 arms the
  * next forward pass; enable=0 copies [layers-1][1024][8] uint64 SM-clock stamps to `out` and disarms. */
 int fdnn_ctx_timeline(fdnn_ctx *ctx, int enable, unsigned long long *out);
