@@ -184,9 +184,8 @@ struct fdnn_ctx {
   uint8_t *d_xlimbs = nullptr;
   int x_plane_rows = 0;
   InputRowStats *d_rowstats = nullptr;
-  uint2 *d_unc_list = nullptr;
+  uint32_t *d_unc_bits = nullptr;
   uint32_t *d_unc_count = nullptr;
-  uint32_t unc_cap = 0;
   CUtensorMap xmap;
   bool input_tc = false;
   CUtensorMap amap[2][3];  // per activation buffer: TMA box of 128 / 64 / 32 rows (cluster 1 / 2 / 4 sharing the tile)
@@ -227,7 +226,7 @@ void destroy_ctx(fdnn_ctx *c) {
   cudaFree(c->d_xq);
   cudaFree(c->d_xlimbs);
   cudaFree(c->d_rowstats);
-  cudaFree(c->d_unc_list);
+  cudaFree(c->d_unc_bits);
   cudaFree(c->d_unc_count);
   for (auto &g : c->graphs) cudaGraphExecDestroy(g.exec);
   if (c->stream) cudaStreamDestroy(c->stream);
@@ -280,9 +279,7 @@ int create_ctx(fdnn_model *m, int n, fdnn_ctx **out) {
     CUDA_TRY(cudaMalloc(&c->d_xlimbs, 3 * plane));
     CUDA_TRY(cudaMemsetAsync(c->d_xlimbs, 0, 3 * plane, c->stream));  // K padding and the rows past n stay zero
     CUDA_TRY(cudaMalloc(&c->d_rowstats, size_t(n) * sizeof(InputRowStats)));
-    const size_t cap = std::max<size_t>(4096, size_t(n) * size_t(H) / 6);  // the certificate leaves ≈ 3 % undecided on the synthetic network
-    c->unc_cap = uint32_t(std::min<size_t>(cap, 0x7fffffffu));
-    CUDA_TRY(cudaMalloc(&c->d_unc_list, size_t(c->unc_cap) * sizeof(uint2)));
+    CUDA_TRY(cudaMalloc(&c->d_unc_bits, size_t(n) * size_t((H + 31) / 32) * sizeof(uint32_t)));
     CUDA_TRY(cudaMalloc(&c->d_unc_count, sizeof(uint32_t)));
     if (int rc = make_tmap(&c->xmap, c->d_xlimbs, 3 * c->x_plane_rows, kInputTcPitch, 128)) return rc;
     c->input_tc = true;
@@ -335,9 +332,9 @@ int enqueue_until_logits(fdnn_ctx *c, const float *d_in, int m, float *d_logits,
     ta.x_plane_rows = c->x_plane_rows;
     ta.w_plane_rows = mod->w_plane_rows;
     ta.row_stats = c->d_rowstats;
-    ta.unc_list = c->d_unc_list;
+    ta.unc_bits = c->d_unc_bits;
+    ta.unc_words = (h.hidden + 31) / 32;
     ta.unc_count = c->d_unc_count;
-    ta.unc_cap = c->unc_cap;
     ta.out_u8 = c->d_act[0];
     ta.M = m;
     ta.I = h.in_dim;

@@ -26,12 +26,12 @@
 //                           bias·100 here and of "+ bias", "· 100" in the reference.  Every constant is rounded up.
 //                           If no half-integer lies within D of z, every value the reference can have produced
 //                           rounds to the same k: the byte is certain.  Otherwise (≈ 4 % of the elements on the
-//                           synthetic network) the element goes on a list.
-//   3. input_fixup_kernel   the listed elements, with the reference's exact arithmetic (same code path as
-//                           input_layer.cu: four lane sums, FMUL + FADD, never FMA).
+//                           synthetic network) the element's bit is set in a [frame][node] bitmap.
+//   3. input_fixup_kernel   the flagged elements, with the reference's exact arithmetic (as input_layer.cu: four
+//                           lane sums, FMUL + FADD, never FMA), a warp per frame.
 //
-// Rows with non-finite or extreme values, nodes with non-finite bias, and a list that overflows all fall back
-// to step 3 for everything they touch, so the result is bit-identical to input_layer.cu for any input.
+// Rows with non-finite or extreme values and nodes with non-finite weights or bias are left to step 3 entirely,
+// so the result is bit-identical to input_layer.cu for any input.
 
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -270,25 +270,12 @@ input_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
       if (row_ok && col_base + g * 8 < a.H)  // hidden widths are multiples of 16: an 8-column group is whole or absent
         *reinterpret_cast<uint2 *>(a.out_u8 + size_t(row) * size_t(a.H) + col_base + g * 8) = make_uint2(bytes[0], bytes[1]);
     }
-    // uncertain elements → global list (one atomic per warp)
-    const uint32_t mine = uint32_t(__popc(unc_mask));
-    uint32_t incl = mine;
+    // undecided elements → one bitmap word per (frame, 32 nodes); every word of the bitmap has exactly one writer
+    if (row_ok && col_base < a.H) a.unc_bits[size_t(row) * size_t(a.unc_words) + size_t(col_base / 32)] = unc_mask;
+    uint32_t n_unc = uint32_t(__popc(unc_mask));
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
-      if (lane >= o) incl += v;
-    }
-    const uint32_t warp_total = __shfl_sync(0xffffffffu, incl, 31);
-    uint32_t base = 0;
-    if (lane == 31 && warp_total != 0) base = atomicAdd(a.unc_count, warp_total);
-    base = __shfl_sync(0xffffffffu, base, 31);
-    uint32_t pos = base + incl - mine;
-    while (unc_mask != 0u) {
-      const int c = __ffs(unc_mask) - 1;
-      unc_mask &= unc_mask - 1u;
-      if (pos < a.unc_cap) a.unc_list[pos] = make_uint2(uint32_t(row), uint32_t(col_base + c));
-      ++pos;
-    }
+    for (int o = 16; o > 0; o >>= 1) n_unc += __shfl_xor_sync(0xffffffffu, n_unc, o);
+    if (lane == 0 && n_unc != 0u) atomicAdd(a.unc_count, n_unc);
   }
 
   ptx::tc_fence_before_sync();
@@ -299,50 +286,64 @@ input_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
   }
 }
 
-// ---- 3. exact arithmetic for the listed elements (or for all of them if the list overflowed) ---------------------
-__global__ void __launch_bounds__(128) input_fixup_kernel(const InputTcArgs a) {
-  const uint32_t count = *a.unc_count;
-  const bool all = count > a.unc_cap;
-  const unsigned long long total = all ? (unsigned long long)a.M * (unsigned long long)a.H : count;
-  const int r = int(threadIdx.x) & 3;  // SSE lane of this thread
-  const unsigned long long stride = (unsigned long long)gridDim.x * (blockDim.x / 4);
-  for (unsigned long long e = (unsigned long long)blockIdx.x * (blockDim.x / 4) + threadIdx.x / 4;; e += stride) {
-    // the four threads of an element stay together, so the loop condition is uniform per quad; full-warp shuffles below
-    // need every lane alive: run the loop on a per-warp condition and mask the work
-    const unsigned long long e_warp0 = e - (threadIdx.x % 32) / 4;
-    if (e_warp0 >= total) break;
-    const bool live = e < total;
-    int row = 0, col = 0;
-    if (live) {
-      if (all) {
-        row = int(e / (unsigned long long)a.H);
-        col = int(e % (unsigned long long)a.H);
-      } else {
-        const uint2 rc = a.unc_list[e];
-        row = int(rc.x);
-        col = int(rc.y);
-      }
-    }
-    const float *__restrict__ x = a.xq + size_t(row) * size_t(a.I);
-    const float *__restrict__ w = a.w0 + size_t(col) * size_t(a.I);
-    float acc = 0.0f;
-    if (live) {
-      int k = r;
-      for (; k + 28 < a.I; k += 32) {  // eight steps of this lane at a time: loads first, then the dependent adds
-        float xv[8], wv[8];
+// ---- 3. exact arithmetic for the undecided elements -------------------------------------------------------------
+// One warp per frame: the transformed frame sits in shared memory, the frame's undecided nodes are compacted from
+// its bitmap words into a list, and the eight quads of the warp take eight nodes at a time, exactly as the reference
+// computes them (dnn.cc:219-247), weights straight from L2.
+constexpr int kFixWarps = 8;
+// `warps_per_row` (1, 2, 4 or 8, a launch parameter) warps share a frame when there are too few frames to fill the GPU with
+// one warp each; they build the same node list and take its 8-node rounds in turn.
+__global__ void __launch_bounds__(kFixWarps * 32) input_fixup_kernel(const InputTcArgs a, const int warps_per_row) {
+  __shared__ __align__(16) float s_x[kFixWarps][kInputTcMaxI];
+  __shared__ uint16_t s_cols[kFixWarps][1024];
+  const int warp = int(threadIdx.x) / 32, lane = int(threadIdx.x) % 32;
+  const int quad = lane >> 2, r = lane & 3;
+  const int I = a.I;
+  const int rows_per_cta = kFixWarps / warps_per_row;
+  const int sub = warp % warps_per_row;  // which share of the frame's rounds this warp takes
+  for (int row = int(blockIdx.x) * rows_per_cta + warp / warps_per_row; row < a.M; row += int(gridDim.x) * rows_per_cta) {
+    __syncwarp();
+    for (int k = lane; k < I; k += 32) s_x[warp][k] = a.xq[size_t(row) * size_t(I) + k];
+    for (int w0 = 0; w0 < a.unc_words; w0 += 32) {  // 32 bitmap words = up to 1024 nodes per pass
+      const uint32_t bits = (w0 + lane < a.unc_words) ? a.unc_bits[size_t(row) * size_t(a.unc_words) + size_t(w0 + lane)] : 0u;
+      const uint32_t mine = uint32_t(__popc(bits));
+      uint32_t incl = mine;
 #pragma unroll
-        for (int t = 0; t < 8; ++t) {
-          xv[t] = __ldg(x + k + 4 * t);
-          wv[t] = __ldg(w + k + 4 * t);
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+      }
+      const uint32_t n = __shfl_sync(0xffffffffu, incl, 31);
+      __syncwarp();
+      uint32_t pos = incl - mine, b = bits;
+      while (b != 0u) {
+        s_cols[warp][pos++] = uint16_t(32 * (w0 + lane) + __ffs(b) - 1);
+        b &= b - 1u;
+      }
+      __syncwarp();
+      // a round = 8 nodes, one per quad: thread (quad, r) accumulates SSE lane r of its node.  (Measured on B200, 16384
+      // frames: two nodes per quad 349 us, a node per thread with 16-byte loads 372 us, this 318 us — the kernel is
+      // bound by the latency of scattered weight-row reads from L2, ≈ 4 TB/s, whatever the mapping.)
+      for (uint32_t e0 = 8u * uint32_t(sub); e0 < n; e0 += 8u * uint32_t(warps_per_row)) {
+        const bool live = e0 + uint32_t(quad) < n;
+        const int col = live ? int(s_cols[warp][e0 + quad]) : int(s_cols[warp][e0]);
+        const float *__restrict__ w = a.w0 + size_t(col) * size_t(I);
+        const float *x = s_x[warp];
+        float acc = 0.0f;
+        int k = r;
+        for (; k + 28 < I; k += 32) {  // eight steps of this lane at a time: loads first, then the dependent adds
+          float wv[8];
+#pragma unroll
+          for (int t = 0; t < 8; ++t) wv[t] = __ldg(w + k + 4 * t);
+#pragma unroll
+          for (int t = 0; t < 8; ++t) acc = __fadd_rn(acc, __fmul_rn(x[k + 4 * t], wv[t]));  // dnn.cc:219-247, lane r
         }
-#pragma unroll
-        for (int t = 0; t < 8; ++t) acc = __fadd_rn(acc, __fmul_rn(xv[t], wv[t]));  // dnn.cc:219-247, lane r
+        for (; k < I; k += 4) acc = __fadd_rn(acc, __fmul_rn(x[k], __ldg(w + k)));
+        const float pair = __fadd_rn(acc, __shfl_xor_sync(0xffffffffu, acc, 1));
+        const float h = __fadd_rn(pair, __shfl_xor_sync(0xffffffffu, pair, 2));  // (l0 + l1) + (l2 + l3), dnn.cc:168-172
+        if (live && r == 0) a.out_u8[size_t(row) * size_t(a.H) + col] = a.lut[qsig_slot(__fadd_rn(h, a.bias0[col]))];
       }
-      for (; k < a.I; k += 4) acc = __fadd_rn(acc, __fmul_rn(__ldg(x + k), __ldg(w + k)));
     }
-    const float pair = __fadd_rn(acc, __shfl_xor_sync(0xffffffffu, acc, 1));
-    const float h = __fadd_rn(pair, __shfl_xor_sync(0xffffffffu, pair, 2));  // (l0 + l1) + (l2 + l3), dnn.cc:168-172
-    if (live && r == 0) a.out_u8[size_t(row) * size_t(a.H) + col] = a.lut[qsig_slot(__fadd_rn(h, a.bias0[col]))];
   }
 }
 
@@ -350,7 +351,7 @@ __global__ void __launch_bounds__(128) input_fixup_kernel(const InputTcArgs a) {
 
 cudaError_t input_tc_configure() { return cudaFuncSetAttribute(input_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmem); }
 
-bool input_tc_supported(int I, int H) { return I > 0 && I <= kInputTcMaxI && I % 4 == 0 && H % 16 == 0; }
+bool input_tc_supported(int I, int H) { return I > 0 && I <= kInputTcMaxI && I % 4 == 0 && H % 16 == 0 && H <= 65536; }
 
 // Enqueues the three kernels.  tmap_x: [3 · x_plane_rows][512] u8, box 128 rows × 128 B, 128B swizzle;
 // tmap_w: [3 · w_plane_rows][512], box 64 rows × 128 B.
@@ -363,7 +364,11 @@ cudaError_t launch_input_tc(const CUtensorMap &tmap_x, const CUtensorMap &tmap_w
   input_tc_kernel<<<grid, dim3(kTcThreads), kTcSmem, stream>>>(tmap_x, tmap_w, a);
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
-  input_fixup_kernel<<<dim3(a.fixup_ctas), dim3(128), 0, stream>>>(a);
+  // enough warps to keep every SM busy: several warps per frame when the batch is short
+  int warps_per_row = 1;
+  while (warps_per_row < kFixWarps && a.M * warps_per_row < a.fixup_ctas * 2) warps_per_row *= 2;
+  const int fix_ctas = (a.M * warps_per_row + kFixWarps - 1) / kFixWarps;
+  input_fixup_kernel<<<dim3(fix_ctas < a.fixup_ctas ? fix_ctas : a.fixup_ctas), dim3(kFixWarps * 32), 0, stream>>>(a, warps_per_row);
   return cudaGetLastError();
 }
 

@@ -85,9 +85,9 @@ struct InputTcArgs {
   size_t x_plane;       // bytes per plane
   int x_plane_rows, w_plane_rows;
   InputRowStats *row_stats;  // [M]
-  uint2 *unc_list;      // (row, node) of the elements the certificate could not decide
-  uint32_t *unc_count;
-  uint32_t unc_cap;
+  uint32_t *unc_bits;   // [M][unc_words]: bit n%32 of word n/32 = node n of this frame is left to the exact path
+  int unc_words;        // ceil(H / 32)
+  uint32_t *unc_count;  // how many bits are set (diagnostics)
   uint8_t *out_u8;      // [M][H]
   int M, I, H;
   int fixup_ctas;
