@@ -340,6 +340,7 @@ int enqueue_until_logits(fdnn_ctx *c, const float *d_in, int m, float *d_logits,
     ta.I = h.in_dim;
     ta.H = h.hidden;
     ta.fixup_ctas = mod->num_sms * 8;
+    ta.num_sms = mod->num_sms;
     CUDA_TRY(launch_input_tc(c->xmap, mod->w0map, ta, stream));
     g_launches.fetch_add(3, std::memory_order_relaxed);
   } else {

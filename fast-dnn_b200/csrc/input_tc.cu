@@ -144,12 +144,16 @@ input_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
   uint8_t *tiles = smem;
   uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + kStages * kStageBytes);
   uint64_t *empty_bar = full_bar + kStages;
-  uint64_t *acc_bar = empty_bar + kStages;
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_bar + 1);
+  uint64_t *acc_bar = empty_bar + kStages;   // the tile's accumulators are complete
+  uint64_t *acc_free = acc_bar + 1;          // the epilogue warps have read them
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_free + 1);
   uint8_t *s_lut = smem + kStages * kStageBytes + kBarRegion;
 
   const int warp = int(threadIdx.x) / 32, lane = int(threadIdx.x) % 32;
-  const int n_blk = int(blockIdx.x), m_blk = int(blockIdx.y);
+  // persistent: CTA b takes tiles b, b + grid, …; the TMA ring runs on across tile boundaries, so the next tile's operands
+  // arrive while this tile's epilogue drains the (single) set of accumulators
+  const int n_blocks = (a.H + kTileN - 1) / kTileN, m_blocks = (a.M + kTileM - 1) / kTileM;
+  const int tiles_total = n_blocks * m_blocks;
   const int k_blocks = (a.I + kBlockK - 1) / kBlockK;
 
   if (warp == 0 && lane == 0) {
@@ -162,6 +166,7 @@ input_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
       ptx::mbar_init(empty_bar + i, 1);
     }
     ptx::mbar_init(acc_bar, 1);
+    ptx::mbar_init(acc_free, kEpiWarps);
     ptx::fence_barrier_init();
   }
   if (warp == 2) ptx::tmem_alloc<kTmemCols>(tmem_slot);
@@ -172,22 +177,32 @@ input_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
 
   if (warp == 0) {
     if (lane == 0) {
-      for (int kb = 0; kb < k_blocks; ++kb) {
-        const int stage = kb % kStages;
-        if (kb >= kStages) ptx::mbar_wait(empty_bar + stage, ((kb / kStages) - 1) & 1);
-        uint8_t *st = tiles + stage * kStageBytes;
-        ptx::mbar_arrive_expect_tx(full_bar + stage, kStageBytes);
+      uint32_t it = 0;  // K blocks issued so far: stage = it % kStages, use number = it / kStages
+      for (int tile = int(blockIdx.x); tile < tiles_total; tile += int(gridDim.x)) {
+        const int m_blk = tile / n_blocks, n_blk = tile % n_blocks;
+        for (int kb = 0; kb < k_blocks; ++kb, ++it) {
+          const int stage = int(it % kStages);
+          if (it >= uint32_t(kStages)) ptx::mbar_wait(empty_bar + stage, ((it / kStages) - 1u) & 1u);
+          uint8_t *st = tiles + stage * kStageBytes;
+          ptx::mbar_arrive_expect_tx(full_bar + stage, kStageBytes);
 #pragma unroll
-        for (int l = 0; l < kLimbs; ++l) {
-          ptx::tma_load_2d(&tmap_x, full_bar + stage, st + l * kXBytes, kb * kBlockK, l * a.x_plane_rows + m_blk * kTileM);
-          ptx::tma_load_2d(&tmap_w, full_bar + stage, st + kLimbs * kXBytes + l * kWBytes, kb * kBlockK, l * a.w_plane_rows + n_blk * kTileN);
+          for (int l = 0; l < kLimbs; ++l) {
+            ptx::tma_load_2d(&tmap_x, full_bar + stage, st + l * kXBytes, kb * kBlockK, l * a.x_plane_rows + m_blk * kTileM);
+            ptx::tma_load_2d(&tmap_w, full_bar + stage, st + kLimbs * kXBytes + l * kWBytes, kb * kBlockK, l * a.w_plane_rows + n_blk * kTileN);
+          }
         }
       }
     }
   } else if (warp == 1) {
-    for (int kb = 0; kb < k_blocks; ++kb) {
-      const int stage = kb % kStages;
-      ptx::mbar_wait(full_bar + stage, (kb / kStages) & 1);
+    uint32_t it = 0, tile_no = 0;
+    for (int tile = int(blockIdx.x); tile < tiles_total; tile += int(gridDim.x), ++tile_no) {
+    if (tile_no != 0) {
+      ptx::mbar_wait(acc_free, (tile_no - 1u) & 1u);  // the previous tile's accumulators have been read
+      ptx::tc_fence_after_sync();
+    }
+    for (int kb = 0; kb < k_blocks; ++kb, ++it) {
+      const int stage = int(it % kStages);
+      ptx::mbar_wait(full_bar + stage, (it / kStages) & 1u);
       ptx::tc_fence_after_sync();
       if (lane == 0) {
         const uint32_t base = ptx::smem_u32(tiles + stage * kStageBytes);
@@ -213,25 +228,30 @@ input_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
       }
       __syncwarp();
     }
+    }
   } else if (warp >= 4) {
     const int et = int(threadIdx.x) - 128;
     for (int i = et; i < kLut2Padded / 16; i += kEpiWarps * 32) reinterpret_cast<uint4 *>(s_lut)[i] = __ldg(reinterpret_cast<const uint4 *>(a.lut) + i);
     ptx::named_bar_sync(1, kEpiWarps * 32);
     const int quarter = warp & 3, half = (warp - 4) >> 2;
+    InputNodeStats *s_node = reinterpret_cast<InputNodeStats *>(s_lut + kLut2Padded);
+    uint32_t tile_no = 0;
+    for (int tile = int(blockIdx.x); tile < tiles_total; tile += int(gridDim.x), ++tile_no) {
+    const int m_blk = tile / n_blocks, n_blk = tile % n_blocks;
     const int row = m_blk * kTileM + quarter * 32 + lane;
     const bool row_ok = row < a.M;
     InputRowStats rs;
     rs.a[0] = -1.0f;
     if (row_ok) rs = a.row_stats[row];
-    // this tile's node constants: shared memory, read as broadcasts
-    InputNodeStats *s_node = reinterpret_cast<InputNodeStats *>(s_lut + kLut2Padded);
+    // this tile's node constants: shared memory, read as broadcasts (everybody is done with the previous tile's first)
+    ptx::named_bar_sync(1, kEpiWarps * 32);
     for (int i = et; i < kTileN; i += kEpiWarps * 32) {
       InputNodeStats ns{};
       ns.c = -1.0f;
       if (n_blk * kTileN + i < a.H) ns = a.node_stats[n_blk * kTileN + i];
       s_node[i] = ns;
     }
-    if (warp == 4) ptx::mbar_wait_parked(acc_bar, 0);
+    if (warp == 4) ptx::mbar_wait_parked(acc_bar, tile_no & 1u);
     ptx::named_bar_sync(1, kEpiWarps * 32);
     ptx::tc_fence_after_sync();
     uint32_t unc_mask = 0;  // bit c: column (half·32 + c) of this row is uncertain
@@ -244,6 +264,11 @@ input_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
       for (int s = 0; s < kClasses; ++s)
         tmem_ld_32x8(tmem_base + uint32_t(s * kTileN + half * 32 + g * 8) + (uint32_t(quarter * 32) << 16), acc[s]);
       ptx::tmem_ld_wait();
+      if (g == 3) {  // accumulators fully read by this warp: the next tile's MMAs may overwrite them
+        ptx::tc_fence_before_sync();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(acc_free);
+      }
       uint32_t bytes[2] = {0u, 0u};
 #pragma unroll
       for (int c = 0; c < 8; ++c) {
@@ -276,6 +301,7 @@ input_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) n_unc += __shfl_xor_sync(0xffffffffu, n_unc, o);
     if (lane == 0 && n_unc != 0u) atomicAdd(a.unc_count, n_unc);
+    }
   }
 
   ptx::tc_fence_before_sync();
@@ -360,8 +386,8 @@ cudaError_t launch_input_tc(const CUtensorMap &tmap_x, const CUtensorMap &tmap_w
   input_prep_kernel<<<dim3((a.M + 7) / 8), dim3(256), 0, stream>>>(a);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
-  const dim3 grid((a.H + kTileN - 1) / kTileN, (a.M + kTileM - 1) / kTileM);
-  input_tc_kernel<<<grid, dim3(kTcThreads), kTcSmem, stream>>>(tmap_x, tmap_w, a);
+  const int tiles = ((a.H + kTileN - 1) / kTileN) * ((a.M + kTileM - 1) / kTileM);
+  input_tc_kernel<<<dim3(tiles < a.num_sms ? tiles : a.num_sms), dim3(kTcThreads), kTcSmem, stream>>>(tmap_x, tmap_w, a);
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   // enough warps to keep every SM busy: several warps per frame when the batch is short

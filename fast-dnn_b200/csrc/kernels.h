@@ -90,7 +90,8 @@ struct InputTcArgs {
   uint32_t *unc_count;  // how many bits are set (diagnostics)
   uint8_t *out_u8;      // [M][H]
   int M, I, H;
-  int fixup_ctas;
+  int fixup_ctas;       // upper limit for the exact kernel's grid
+  int num_sms;
 };
 cudaError_t input_tc_configure();
 bool input_tc_supported(int I, int H);
