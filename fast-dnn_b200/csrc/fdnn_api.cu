@@ -546,10 +546,11 @@ int upload_model(const uint8_t *host_view, const void *src, bool src_on_device, 
       int e = mx > 0.0f ? std::ilogb(mx) + 1 : 0;
       if (e < -40 || e > 40) bad = true;
       if (bad) e = 0;
-      double sum_abs = 0.0;
+      double sum_abs = 0.0, sum_low = 0.0;
       for (int k = 0; k < I0 && !bad; ++k) {
         const int W = int(std::lrint(std::ldexp(double(w[k]), 22 - e)));  // exact scaling, round to nearest
         sum_abs += std::abs(W);
+        sum_low += double(W & 255);
         const size_t o = size_t(n) * kInputTcPitch + size_t(k);
         limbs[o] = uint8_t(W & 255);
         limbs[plane + o] = uint8_t((W >> 8) & 255);
@@ -564,7 +565,7 @@ int upload_model(const uint8_t *host_view, const void *src, bool src_on_device, 
       s.bc = bad ? 0.0f : b0[n] * 100.0f;
       s.q = ru(std::sqrt(n2c) * (1.0 + 1e-9) * up);
       s.qp = ru((nw + sc * 131072.0 * std::sqrt(double(I0))) * up);
-      s.e = ru(sc * (0.5 * sum_abs + 0.25 * double(I0)) * up);
+      s.e = ru(sc * (0.5 * sum_abs + 0.25 * double(I0) + 255.0 * sum_low) * up);  // + the low-limb products the kernel skips
       s.f = ru((u * std::fabs(double(s.bc)) + 2.1 * u + 1e-9) * up);
       s.pad[0] = s.pad[1] = 0.0f;
     }

@@ -11,8 +11,10 @@
 //   1. input_prep_kernel    x' = fl(fl(x + shift)·scale) exactly as the reference; each row is written as a
 //                           block-fixed-point integer vector X (|X_k| ≤ 2²², three 8-bit limbs) together with
 //                           its scale, Σ|X_k| and ‖x'‖₂.  W0 gets the same treatment once, at model upload.
-//   2. input_tc_kernel      Σ_k X_k·W_k EXACTLY: nine limb-pair products on tcgen05.mma kind::i8 (u8/s8 mixes,
-//                           s32 accumulators in tensor memory, one accumulator per shift class s = i + j).
+//   2. input_tc_kernel      Σ_k X_k·W_k EXACTLY up to the product of the two lowest limbs (bounded by 255·ΣW₀ and
+//                           put into ε_q): eight limb-pair products on tcgen05.mma kind::i8 (u8/s8 mixes, s32
+//                           accumulators in tensor memory, one per shift class s = i + j = 1 … 4, two sets so
+//                           that a tile's epilogue overlaps the next tile's MMAs).
 //                           z = (h_fix + bias)·100 is then evaluated in fp32 from the five class sums and
 //                             D = 100·(u·‖√c·x'‖₂·‖√c·w‖₂ + ε_q) + 100·7u·‖x'‖₂'·‖w‖₂' + 3.1u·|z| + u·|bias·100| + 2.1u
 //                           where u = 2⁻²⁴ and c_k counts the roundings term k goes through in the reference (its
@@ -48,13 +50,14 @@ namespace {
 
 constexpr int kTileM = 128, kTileN = 64, kBlockK = 128, kUmmaK = 32;
 constexpr int kLimbs = 3;
-constexpr int kClasses = 2 * kLimbs - 1;  // shift classes i + j
+constexpr int kClasses = 2 * kLimbs - 2;  // shift classes i + j = 1 … 4; class 0 (low limb × low limb) is bounded, not computed
+constexpr int kAccSets = 2;               // two sets of accumulators: the next tile's MMAs run under this tile's epilogue
 constexpr int kStages = 3;
 constexpr int kXBytes = kTileM * kBlockK, kWBytes = kTileN * kBlockK;
 constexpr int kStageBytes = kLimbs * (kXBytes + kWBytes);  // 72 KB
 constexpr int kEpiWarps = 8;
 constexpr int kTcThreads = (4 + kEpiWarps) * 32;
-constexpr int kTmemCols = 512;  // 5 accumulators × 64 columns, rounded up to a power of two
+constexpr int kTmemCols = kAccSets * kClasses * kTileN;  // 2 × 4 × 64 = 512
 constexpr int kBarRegion = 128;  // 2·kStages + 1 barriers, the TMEM address
 constexpr int kTcSmem = kStages * kStageBytes + kBarRegion + kLut2Padded + kTileN * int(sizeof(InputNodeStats));
 
@@ -144,9 +147,9 @@ input_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
   uint8_t *tiles = smem;
   uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + kStages * kStageBytes);
   uint64_t *empty_bar = full_bar + kStages;
-  uint64_t *acc_bar = empty_bar + kStages;   // the tile's accumulators are complete
-  uint64_t *acc_free = acc_bar + 1;          // the epilogue warps have read them
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_free + 1);
+  uint64_t *acc_bar = empty_bar + kStages;   // [set] the tile's accumulators are complete
+  uint64_t *acc_free = acc_bar + kAccSets;   // [set] the epilogue warps have read them
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_free + kAccSets);
   uint8_t *s_lut = smem + kStages * kStageBytes + kBarRegion;
 
   const int warp = int(threadIdx.x) / 32, lane = int(threadIdx.x) % 32;
@@ -165,8 +168,10 @@ input_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
       ptx::mbar_init(full_bar + i, 1);
       ptx::mbar_init(empty_bar + i, 1);
     }
-    ptx::mbar_init(acc_bar, 1);
-    ptx::mbar_init(acc_free, kEpiWarps);
+    for (int i = 0; i < kAccSets; ++i) {
+      ptx::mbar_init(acc_bar + i, 1);
+      ptx::mbar_init(acc_free + i, kEpiWarps);
+    }
     ptx::fence_barrier_init();
   }
   if (warp == 2) ptx::tmem_alloc<kTmemCols>(tmem_slot);
@@ -196,8 +201,9 @@ input_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
   } else if (warp == 1) {
     uint32_t it = 0, tile_no = 0;
     for (int tile = int(blockIdx.x); tile < tiles_total; tile += int(gridDim.x), ++tile_no) {
-    if (tile_no != 0) {
-      ptx::mbar_wait(acc_free, (tile_no - 1u) & 1u);  // the previous tile's accumulators have been read
+    const uint32_t set = tile_no % kAccSets, use = tile_no / kAccSets;
+    if (use != 0) {
+      ptx::mbar_wait(acc_free + set, (use - 1u) & 1u);  // this set's previous tile has been read
       ptx::tc_fence_after_sync();
     }
     for (int kb = 0; kb < k_blocks; ++kb, ++it) {
@@ -217,14 +223,15 @@ input_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
             // come first in this loop order for their class only when (i == 0 || j == 0) … simpler: class s is first
             // touched by the pair with the smallest i, which is (max(0, s − 2), s − max(0, s − 2))
             const int s = i + j;
+            if (s == 0) continue;  // |Σ X₀·W₀| ≤ 255·ΣW₀ goes into the certificate's error bound instead (InputNodeStats::e)
             const bool first_of_class = (i == (s > kLimbs - 1 ? s - (kLimbs - 1) : 0));
 #pragma unroll
             for (int k = 0; k < kBlockK / kUmmaK; ++k)
-              ptx::mma_i8_ss(tmem_base + uint32_t(s * kTileN), da + uint64_t(k * (kUmmaK / 16)), db + uint64_t(k * (kUmmaK / 16)), idesc,
+              ptx::mma_i8_ss(tmem_base + uint32_t(int(set) * kClasses * kTileN + (s - 1) * kTileN), da + uint64_t(k * (kUmmaK / 16)), db + uint64_t(k * (kUmmaK / 16)), idesc,
                              uint32_t(!(kb == 0 && k == 0 && first_of_class)));
           }
         ptx::mma_commit(empty_bar + stage);
-        if (kb == k_blocks - 1) ptx::mma_commit(acc_bar);
+        if (kb == k_blocks - 1) ptx::mma_commit(acc_bar + set);
       }
       __syncwarp();
     }
@@ -251,7 +258,8 @@ input_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
       if (n_blk * kTileN + i < a.H) ns = a.node_stats[n_blk * kTileN + i];
       s_node[i] = ns;
     }
-    if (warp == 4) ptx::mbar_wait_parked(acc_bar, tile_no & 1u);
+    const uint32_t set = tile_no % kAccSets, use = tile_no / kAccSets;
+    if (warp == 4) ptx::mbar_wait_parked(acc_bar + set, use & 1u);
     ptx::named_bar_sync(1, kEpiWarps * 32);
     ptx::tc_fence_after_sync();
     uint32_t unc_mask = 0;  // bit c: column (half·32 + c) of this row is uncertain
@@ -262,21 +270,21 @@ input_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
       uint32_t acc[kClasses][8];
 #pragma unroll
       for (int s = 0; s < kClasses; ++s)
-        tmem_ld_32x8(tmem_base + uint32_t(s * kTileN + half * 32 + g * 8) + (uint32_t(quarter * 32) << 16), acc[s]);
+        tmem_ld_32x8(tmem_base + uint32_t(int(set) * kClasses * kTileN + s * kTileN + half * 32 + g * 8) + (uint32_t(quarter * 32) << 16), acc[s]);
       ptx::tmem_ld_wait();
       if (g == 3) {  // accumulators fully read by this warp: the next tile's MMAs may overwrite them
         ptx::tc_fence_before_sync();
         __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(acc_free);
+        if (lane == 0) ptx::mbar_arrive(acc_free + set);
       }
       uint32_t bytes[2] = {0u, 0u};
 #pragma unroll
       for (int c = 0; c < 8; ++c) {
         const InputNodeStats ns = s_node[half * 32 + g * 8 + c];
         // z in fp32 from the class sums; its evaluation error is part of D (InputRowStats::pp · InputNodeStats::qp)
-        float v = __int2float_rn(int32_t(acc[0][c])) * rs.a[0];
+        float v = __int2float_rn(int32_t(acc[0][c])) * rs.a[1];  // acc[s] holds shift class s + 1
 #pragma unroll
-        for (int s = 1; s < kClasses; ++s) v = fmaf(__int2float_rn(int32_t(acc[s][c])), rs.a[s], v);
+        for (int s = 1; s < kClasses; ++s) v = fmaf(__int2float_rn(int32_t(acc[s][c])), rs.a[s + 1], v);
         const float z = fmaf(v, ns.c, ns.bc);
         const float az = fabsf(z);
         float D = fmaf(rs.p, ns.q, fmaf(rs.pp, ns.qp, fmaf(rs.r1, ns.c, fmaf(rs.ar, ns.e, fmaf(1.85e-7f, az, ns.f)))));  // 3.1u = 1.85e-7

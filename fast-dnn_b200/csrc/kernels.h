@@ -69,7 +69,7 @@ struct InputNodeStats {  // per node of layer 0, built when the model is uploade
   float bc;              // fl(bias · 100)
   float q;               // ‖√c · w‖₂
   float qp;              // ‖w‖₂ + 2^(e_w−22)·2¹⁷·√I
-  float e;               // 2^(e_w−22) · (½ Σ|W_k| + ¼ I)
+  float e;               // 2^(e_w−22) · (½ Σ|W_k| + ¼ I + 255 · Σ (W_k mod 256))
   float f;               // u·|bc| + 2.1u + 1e-9: rounding of bias·100, of the reference's "+ bias" and "· 100" at |z| = 0
   float pad[2];
 };
