@@ -67,24 +67,34 @@ __global__ void __launch_bounds__(256) input_prep_kernel(const InputTcArgs a) {
   const int row = int(blockIdx.x) * 8 + warp;
   if (blockIdx.x == 0 && threadIdx.x == 0) *a.unc_count = 0u;
   if (row >= a.M) return;
-  const int I = a.I;
-  float xv[kInputTcMaxI / 32];
+  const int I = a.I, I4 = I / 4;
+  constexpr int kVec = kInputTcMaxI / 128;  // float4 per lane
+  float4 xv[kVec];
   float mx = 0.0f;
   bool bad = false;
   double n2 = 0.0, n2c = 0.0;
+  const float4 *in4 = reinterpret_cast<const float4 *>(a.in + size_t(row) * size_t(I));
+  float4 *xq4 = reinterpret_cast<float4 *>(a.xq + size_t(row) * size_t(I));
 #pragma unroll
-  for (int t = 0; t < kInputTcMaxI / 32; ++t) {
-    const int k = lane + 32 * t;
-    float v = 0.0f;
-    if (k < I) {
-      v = __fmul_rn(__fadd_rn(a.in[size_t(row) * size_t(I) + k], a.shift[k]), a.scale[k]);  // dnn.cc:175-192
-      a.xq[size_t(row) * size_t(I) + k] = v;
+  for (int t = 0; t < kVec; ++t) {
+    const int q = lane + 32 * t;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (q < I4) {
+      const float4 x = in4[q], sh = reinterpret_cast<const float4 *>(a.shift)[q], sc = reinterpret_cast<const float4 *>(a.scale)[q];
+      v.x = __fmul_rn(__fadd_rn(x.x, sh.x), sc.x);  // dnn.cc:175-192: add, then multiply, each rounded
+      v.y = __fmul_rn(__fadd_rn(x.y, sh.y), sc.y);
+      v.z = __fmul_rn(__fadd_rn(x.z, sh.z), sc.z);
+      v.w = __fmul_rn(__fadd_rn(x.w, sh.w), sc.w);
+      xq4[q] = v;
+      const double c = input_round_count(4 * q, I);  // the four SSE lanes of a K step go through the same number of adds
+      const double sq = double(v.x) * double(v.x) + double(v.y) * double(v.y) + double(v.z) * double(v.z) + double(v.w) * double(v.w);
+      n2 += sq;
+      n2c += c * sq;
     }
     xv[t] = v;
-    bad |= !(fabsf(v) <= 3.0e38f);  // NaN or inf
-    mx = fmaxf(mx, fabsf(v));
-    n2 += double(v) * double(v);
-    n2c += input_round_count(k, I) * double(v) * double(v);
+    const float m4 = fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w)));
+    bad |= !(m4 <= 3.0e38f);  // NaN or inf
+    mx = fmaxf(mx, m4);
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -96,18 +106,28 @@ __global__ void __launch_bounds__(256) input_prep_kernel(const InputTcArgs a) {
   int e = (mx > 0.0f) ? ilogbf(mx) + 1 : 0;  // mx < 2^e
   if (e < -40 || e > 40) bad = true;
   if (bad) e = 0;
-  const float q = ldexpf(1.0f, 22 - e);  // exact power of two
+  const float qs = ldexpf(1.0f, 22 - e);  // exact power of two
   long long sx = 0;
+  uint32_t *p0 = reinterpret_cast<uint32_t *>(a.x_limbs + size_t(row) * kInputTcPitch);
+  uint32_t *p1 = reinterpret_cast<uint32_t *>(a.x_limbs + a.x_plane + size_t(row) * kInputTcPitch);
+  uint32_t *p2 = reinterpret_cast<uint32_t *>(a.x_limbs + 2 * a.x_plane + size_t(row) * kInputTcPitch);
 #pragma unroll
-  for (int t = 0; t < kInputTcMaxI / 32; ++t) {
-    const int k = lane + 32 * t;
-    if (k < I) {
-      const int X = bad ? 0 : __float2int_rn(xv[t] * q);  // |X| ≤ 2²², exact scaling
-      sx += X < 0 ? -X : X;
-      const size_t o = size_t(row) * kInputTcPitch + size_t(k);
-      a.x_limbs[o] = uint8_t(X & 255);
-      a.x_limbs[a.x_plane + o] = uint8_t((X >> 8) & 255);
-      a.x_limbs[2 * a.x_plane + o] = uint8_t((X >> 16) & 255);  // signed top limb
+  for (int t = 0; t < kVec; ++t) {
+    const int q = lane + 32 * t;
+    if (q < I4) {
+      const float f[4] = {xv[t].x, xv[t].y, xv[t].z, xv[t].w};
+      uint32_t w0 = 0, w1 = 0, w2 = 0;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int X = bad ? 0 : __float2int_rn(f[j] * qs);  // |X| ≤ 2²², exact scaling
+        sx += X < 0 ? -X : X;
+        w0 |= uint32_t(X & 255) << (8 * j);
+        w1 |= uint32_t((X >> 8) & 255) << (8 * j);
+        w2 |= uint32_t((X >> 16) & 255) << (8 * j);  // signed top limb
+      }
+      p0[q] = w0;
+      p1[q] = w1;
+      p2[q] = w2;
     }
   }
 #pragma unroll
