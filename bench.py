@@ -274,7 +274,11 @@ def run_gpu_arm(args):
         "traffic": traffic, "peak_source": f"2 x bf16_tflops {peak_src}; the file has no int8 entry, nominal dense int8 is 4500",
         "avg_launch_ms": hid_avg, "share_of_step": float(np.sum(hidden_ms)) / total_stage,
     }
-    stages = {"input_fp32_ms": float(stage_ms[0]), "hidden_int8_ms": hidden_ms, "output_int8_ms": float(stage_ms[n_layers - 1]),
+    und = ctx.input_undecided()
+    stages = {"input_layer": ("input_tc.cu: fixed-point dot products on tcgen05 int8 + rounding-error certificate, exact CUDA-core arithmetic for the "
+                              f"{100.0 * und / (BATCH * H_DIM):.2f} % of the elements it leaves undecided (3 kernels)") if und is not None
+              else "input_layer.cu: exact CUDA-core arithmetic for every element (1 kernel)",
+              "input_fp32_ms": float(stage_ms[0]), "hidden_int8_ms": hidden_ms, "output_int8_ms": float(stage_ms[n_layers - 1]),
               "softmax_ms": float(stage_ms[n_layers]), "sum_ms": total_stage,
               "output_plus_softmax_hbm_gbs": (BATCH * O_DIM * 4 * 3 + O_DIM * H_DIM) / ((stage_ms[n_layers - 1] + stage_ms[n_layers]) * 1e-3) / 1e9}
 

@@ -311,3 +311,32 @@ def test_throughput_tile_policy_gives_identical_results(net_file):
             qd._check(qd.lib().fdnn_set_tile_policy(dnn._h, 7))
     finally:
         dnn.delete()
+
+
+def test_certified_input_layer_equals_exact_kernel_on_hostile_frames(net_file):
+    """csrc/input_tc.cu (tensor-core certificate + exact fix-up) against csrc/input_layer.cu (FDNN_INPUT_TC=0) on frames
+    with NaN, ±inf, huge, tiny, zero and constant rows: every layer-0 byte and the logits must be identical, and the
+    certificate must have decided most of the ordinary elements itself"""
+    import subprocess
+    import sys
+    code = (
+        "import sys, numpy as np; sys.path.insert(0, %r); import fast_dnn_b200\n"
+        "from fast_dnn_b200 import quantized_dnn as qd, synth\n"
+        "dnn = qd.QuantizedDnn.load_from_file(%r)\n"
+        "x = synth.make_frames(300, 440, seed=12)\n"
+        "x[3, 7] = np.nan; x[5, :] = 0.0; x[9, 100] = np.inf; x[11, 5] = -np.inf; x[13, :] = 1e30; x[17, :] = 1e-30\n"
+        "x[19, :] = 7.25; x[23, 0] = 3e38; x[29, ::2] = -1e-38; x[31, :] *= 1e4; x[37, :] *= 1e-6\n"
+        "ctx = dnn.get_new_lazy_context(300); ctx.set_trace(True); ctx.calculate_until_output(x)\n"
+        "u = ctx.input_undecided()\n"
+        "np.save(sys.argv[1], ctx.hidden(0)); np.save(sys.argv[2], ctx.logits()); np.save(sys.argv[3], np.array([-1 if u is None else u]))\n"
+    ) % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), net_file("S"))
+    outs = {}
+    for flag in ("0", "1"):
+        paths = [f"/tmp/fdnn_itc_{flag}_{k}.npy" for k in ("h0", "l", "u")]
+        env = dict(os.environ, FDNN_INPUT_TC=flag)
+        subprocess.run([sys.executable, "-c", code] + paths, check=True, env=env, timeout=240)
+        outs[flag] = [np.load(p) for p in paths]
+    assert int(outs["0"][2][0]) == -1 and int(outs["1"][2][0]) >= 0, "the two runs did not take the two different paths"
+    assert np.array_equal(outs["0"][0], outs["1"][0]), "layer-0 bytes differ"
+    assert np.array_equal(outs["0"][1].view(np.uint32), outs["1"][1].view(np.uint32)), "logits differ"
+    assert int(outs["1"][2][0]) < 0.1 * 300 * 512, "the certificate left more than 10 % of the elements to the exact path"
