@@ -73,7 +73,7 @@ def launch_table(path):
     return agg
 
 
-lines = [f"# ncu summary `{tag}` (B200, `tools/make_profiles.sh`; all kernels of two passes at batch 512)\n"]
+lines = [f"# ncu summary `{tag}` (B200, `tools/make_profiles.sh`; all kernels of two passes at batch 512; one context, one stream)\n"]
 for suffix, title in (("launches.csv", "cold caches (ncu flushes L2 before every kernel; serialised)"),
                       ("launches_warm.csv", "`--cache-control none` (weights L2-resident, as in the real pass)")):
     p = os.path.join(OUT, f"{tag}_{suffix}")
