@@ -185,6 +185,7 @@ struct fdnn_ctx {
   int x_plane_rows = 0;
   InputRowStats *d_rowstats = nullptr;
   uint32_t *d_unc_bits = nullptr;
+  uint32_t *d_unc_t = nullptr;
   uint32_t *d_unc_count = nullptr;
   CUtensorMap xmap;
   bool input_tc = false;
@@ -227,6 +228,7 @@ void destroy_ctx(fdnn_ctx *c) {
   cudaFree(c->d_xlimbs);
   cudaFree(c->d_rowstats);
   cudaFree(c->d_unc_bits);
+  cudaFree(c->d_unc_t);
   cudaFree(c->d_unc_count);
   for (auto &g : c->graphs) cudaGraphExecDestroy(g.exec);
   if (c->stream) cudaStreamDestroy(c->stream);
@@ -280,6 +282,7 @@ int create_ctx(fdnn_model *m, int n, fdnn_ctx **out) {
     CUDA_TRY(cudaMemsetAsync(c->d_xlimbs, 0, 3 * plane, c->stream));  // K padding and the rows past n stay zero
     CUDA_TRY(cudaMalloc(&c->d_rowstats, size_t(n) * sizeof(InputRowStats)));
     CUDA_TRY(cudaMalloc(&c->d_unc_bits, size_t(n) * size_t((H + 31) / 32) * sizeof(uint32_t)));
+    CUDA_TRY(cudaMalloc(&c->d_unc_t, size_t((n + 31) / 32) * size_t(H) * sizeof(uint32_t)));
     CUDA_TRY(cudaMalloc(&c->d_unc_count, sizeof(uint32_t)));
     if (int rc = make_tmap(&c->xmap, c->d_xlimbs, 3 * c->x_plane_rows, kInputTcPitch, 128)) return rc;
     c->input_tc = true;
@@ -334,6 +337,7 @@ int enqueue_until_logits(fdnn_ctx *c, const float *d_in, int m, float *d_logits,
     ta.row_stats = c->d_rowstats;
     ta.unc_bits = c->d_unc_bits;
     ta.unc_words = (h.hidden + 31) / 32;
+    ta.unc_t = c->d_unc_t;
     ta.unc_count = c->d_unc_count;
     ta.out_u8 = c->d_act[0];
     ta.M = m;

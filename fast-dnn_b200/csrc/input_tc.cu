@@ -39,6 +39,7 @@
 #include <cuda_runtime.h>
 
 #include <cmath>
+#include <cstdlib>
 
 #include "device_common.cuh"
 #include "kernels.h"
@@ -325,6 +326,19 @@ input_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
     }
     // undecided elements → one bitmap word per (frame, 32 nodes); every word of the bitmap has exactly one writer
     if (row_ok && col_base < a.H) a.unc_bits[size_t(row) * size_t(a.unc_words) + size_t(col_base / 32)] = unc_mask;
+    // … and the same 32 frames × 32 nodes transposed (five butterfly steps over the warp): lane c ends up with the word of
+    // node col_base + c, bit f = frame f of this warp's block of 32 frames, for the block fix-up kernel
+    {
+      uint32_t t = unc_mask;
+#pragma unroll
+      for (int j = 16; j > 0; j >>= 1) {
+        const uint32_t m = j == 16 ? 0x0000ffffu : j == 8 ? 0x00ff00ffu : j == 4 ? 0x0f0f0f0fu : j == 2 ? 0x33333333u : 0x55555555u;
+        const uint32_t p = __shfl_xor_sync(0xffffffffu, t, j);
+        t = (lane & j) == 0 ? ((t & m) | ((p & m) << j)) : ((t & ~m) | ((p & ~m) >> j));
+      }
+      const int row0 = m_blk * kTileM + quarter * 32;
+      if (row0 < a.M && col_base + lane < a.H) a.unc_t[size_t(row0 / 32) * size_t(a.H) + size_t(col_base + lane)] = t;
+    }
     uint32_t n_unc = uint32_t(__popc(unc_mask));
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) n_unc += __shfl_xor_sync(0xffffffffu, n_unc, o);
@@ -401,9 +415,217 @@ __global__ void __launch_bounds__(kFixWarps * 32) input_fixup_kernel(const Input
   }
 }
 
+
+// ---- 3b. the same arithmetic, by blocks of 32 frames (the default) -------------------------------------------------
+// The warp-per-frame kernel above lives on scattered 4-byte reads of weight rows through L1 (≈ 4–5 TB/s of L2 reads at
+// best).  Here a CTA owns 32 frames (an unc_t word per node) × a range of nodes: the frames sit in shared memory, one SSE
+// lane after the other, the nodes that are undecided for at least one of the 32 frames are compacted into a list, and a
+// producer warp brings their weight rows in with plain bulk copies (cp.async.bulk, one 4·I-byte row per copy, kFbSlots
+// rows per mbarrier, kFbBufs batches in flight — no L1 miss queue in the way, and a row is fetched once for all of the
+// block's frames that need it).  Eight consumer warps take a batch's (node, frame) elements eight at a time — a quad per
+// element, thread (quad, r) doing SSE lane r exactly as the reference (dnn.cc:219-247, 168-172): FMUL, FADD, never FMA.
+constexpr int kFbFrames = 32;       // = the bits of an unc_t word
+constexpr int kFbConsumers = 12;    // warps doing the arithmetic
+constexpr int kFbBufs = 4;          // batches in flight, and producer warps: each owns a buffer (issuing a bulk copy takes a
+                                    // warp ≈ 33 cycles whatever its size, 16 in a row per batch)
+constexpr int kFbThreads = (kFbConsumers + kFbBufs) * 32;
+constexpr int kFbSlots = 16;        // weight rows per batch
+constexpr int kFbPassNodes = 2048;  // nodes whose words are compacted at a time
+constexpr int kFbPassLoads = (kFbPassNodes + kFbThreads - 1) / kFbThreads;  // unc_t words per thread and pass
+
+struct FbLayout {
+  int seg;      // floats per SSE lane of a frame: I/4 rounded up to an ODD number of float4, so that the four lanes of a
+                // quad read four different 16-byte bank groups
+  int fstride;  // floats per frame
+  int wstride;  // bytes per weight-row slot, an odd number of 16-byte units: any eight consecutive slots are conflict-free
+  int off_lut, off_word, off_node, off_x, off_w, total;
+};
+__host__ __device__ inline FbLayout fb_layout(int I) {
+  FbLayout L;
+  L.seg = (I / 4 + 3) / 4 * 4;
+  if ((L.seg / 4) % 2 == 0) L.seg += 4;
+  L.fstride = 4 * L.seg;
+  L.wstride = 4 * I;
+  if ((L.wstride / 16) % 2 == 0) L.wstride += 16;
+  L.off_lut = 128;  // 2·kFbBufs barriers and the list counter come first
+  L.off_word = L.off_lut + kLut2Padded;
+  L.off_node = L.off_word + 4 * kFbPassNodes;
+  L.off_x = L.off_node + 2 * kFbPassNodes;
+  L.off_w = L.off_x + 4 * kFbFrames * L.fstride;
+  L.total = L.off_w + kFbBufs * kFbSlots * L.wstride;
+  return L;
+}
+
+__global__ void __launch_bounds__(kFbThreads) input_fixup_block_kernel(const InputTcArgs a, const int words_per_cta, const int debug) {
+  extern __shared__ __align__(128) uint8_t fb_smem[];
+  const FbLayout L = fb_layout(a.I);
+  uint64_t *full_bar = reinterpret_cast<uint64_t *>(fb_smem), *empty_bar = full_bar + kFbBufs;
+  uint32_t *s_count = reinterpret_cast<uint32_t *>(fb_smem + 2 * kFbBufs * 8);
+  uint8_t *s_lut = fb_smem + L.off_lut;
+  uint32_t *l_word = reinterpret_cast<uint32_t *>(fb_smem + L.off_word);
+  uint16_t *l_node = reinterpret_cast<uint16_t *>(fb_smem + L.off_node);
+  float *s_x = reinterpret_cast<float *>(fb_smem + L.off_x);
+  uint8_t *ring = fb_smem + L.off_w;
+  const int warp = int(threadIdx.x) / 32, lane = int(threadIdx.x) % 32;
+  const int quad = lane >> 2, r = lane & 3;
+  const int I = a.I, n4 = I / 4;
+  const int fb = int(blockIdx.x), f0 = fb * kFbFrames;
+  const int n_lo = int(blockIdx.y) * words_per_cta * 32;
+  const int n_hi = min(a.H, n_lo + words_per_cta * 32);
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kFbBufs; ++i) {
+      ptx::mbar_init(full_bar + i, 1);
+      ptx::mbar_init(empty_bar + i, kFbConsumers);
+    }
+    ptx::fence_barrier_init();
+  }
+  for (int i = int(threadIdx.x); i < kLut2Padded / 16; i += kFbThreads) reinterpret_cast<uint4 *>(s_lut)[i] = __ldg(reinterpret_cast<const uint4 *>(a.lut) + i);
+  // the first pass's bitmap words, before anything else that waits for memory
+  uint32_t wv[kFbPassLoads];
+#pragma unroll
+  for (int u = 0; u < kFbPassLoads; ++u) {
+    const int i = int(threadIdx.x) + u * kFbThreads;
+    wv[u] = n_lo + i < min(n_hi, n_lo + kFbPassNodes) ? __ldg(a.unc_t + size_t(fb) * size_t(a.H) + size_t(n_lo + i)) : 0u;
+  }
+  // the block's transformed frames: s_x[f][r][t] = x'[f][4t + r]; eight loads in flight per thread (a CTA has the SM to itself)
+  const int rows = min(kFbFrames, a.M - f0);
+  const float4 *xsrc = reinterpret_cast<const float4 *>(a.xq + size_t(f0) * size_t(I));  // rows are contiguous: [rows][n4] float4
+  for (int base = int(threadIdx.x); base < rows * n4; base += 8 * kFbThreads) {
+    float4 v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int idx = base + u * kFbThreads;
+      v[u] = idx < rows * n4 ? __ldg(xsrc + idx) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int idx = base + u * kFbThreads;
+      if (idx < rows * n4) {
+        const int f = idx / n4, t = idx - f * n4;
+        float *d = s_x + f * L.fstride + t;
+        d[0] = v[u].x;
+        d[L.seg] = v[u].y;
+        d[2 * L.seg] = v[u].z;
+        d[3 * L.seg] = v[u].w;
+      }
+    }
+  }
+  uint32_t bn = 0;     // batches so far, over all passes: buffer bn % kFbBufs, use number bn / kFbBufs
+  uint32_t cbase = 0;  // chunks so far: chunk c goes to consumer warp c % kFbConsumers
+  for (int p_lo = n_lo; p_lo < n_hi; p_lo += kFbPassNodes) {
+    __syncthreads();  // barriers initialised, frames stored; nobody reads the previous pass's list any more
+    if (threadIdx.x == 0) *s_count = 0u;
+    __syncthreads();
+#pragma unroll
+    for (int u = 0; u < kFbPassLoads; ++u) {  // nodes with a non-zero word → list (order irrelevant)
+      const int i = int(threadIdx.x) + u * kFbThreads;
+      const uint32_t w = wv[u];
+      const uint32_t nz = __ballot_sync(0xffffffffu, w != 0u);
+      if (nz != 0u) {
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(s_count, uint32_t(__popc(nz)));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (w != 0u) {
+          const uint32_t pos = base + uint32_t(__popc(nz & ((1u << lane) - 1u)));
+          l_word[pos] = w;
+          l_node[pos] = uint16_t(p_lo + i);
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kFbPassLoads; ++u) {  // the next pass's words (wide layers only)
+      const int i = p_lo + kFbPassNodes + int(threadIdx.x) + u * kFbThreads;
+      wv[u] = i < min(n_hi, p_lo + 2 * kFbPassNodes) ? __ldg(a.unc_t + size_t(fb) * size_t(a.H) + size_t(i)) : 0u;
+    }
+    __syncthreads();
+    const uint32_t n_list = *s_count;
+    const uint32_t n_batches = (n_list + kFbSlots - 1) / kFbSlots;
+    if (warp >= kFbConsumers) {
+      // producers: a batch = up to kFbSlots weight rows, one bulk copy each, all landing on the buffer's barrier
+      const uint32_t buf = uint32_t(warp - kFbConsumers);
+      for (uint32_t b = (buf + kFbBufs - bn % kFbBufs) % kFbBufs; b < n_batches; b += kFbBufs) {
+        const uint32_t use = (bn + b) / kFbBufs;
+        if (use != 0u) ptx::mbar_wait(empty_bar + buf, (use - 1u) & 1u);
+        const uint32_t cnt = min(uint32_t(kFbSlots), n_list - b * kFbSlots);
+        const uint32_t row_bytes = (debug & 4) ? 16u : uint32_t(4 * I);
+        if (lane == 0) ptx::mbar_arrive_expect_tx(full_bar + buf, (debug & 2) ? 0u : cnt * row_bytes);
+        __syncwarp();
+        if (uint32_t(lane) < cnt && !(debug & 2))
+          ptx::bulk_load(ring + (buf * kFbSlots + uint32_t(lane)) * uint32_t(L.wstride), a.w0 + size_t(l_node[b * kFbSlots + uint32_t(lane)]) * size_t(I),
+                         row_bytes, full_bar + buf);
+      }
+      bn += n_batches;
+    } else {
+      for (uint32_t b = 0; b < n_batches; ++b, ++bn) {
+        const uint32_t buf = bn % kFbBufs, use = bn / kFbBufs;
+        // both half-warps hold the batch's entries: word, node, inclusive prefix of the element counts
+        const uint32_t entry = b * kFbSlots + uint32_t(lane & (kFbSlots - 1));
+        const bool have = entry < n_list;
+        const uint32_t word = have ? l_word[entry] : 0u;
+        const uint32_t node = have ? uint32_t(l_node[entry]) : 0u;
+        const uint32_t mine = uint32_t(__popc(word));
+        uint32_t incl = mine;
+#pragma unroll
+        for (int o = 1; o < kFbSlots; o <<= 1) {
+          const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o, kFbSlots);
+          if ((lane & (kFbSlots - 1)) >= o) incl += v;
+        }
+        const uint32_t total = __shfl_sync(0xffffffffu, incl, kFbSlots - 1);
+        const uint32_t n_chunks = (total + 7u) / 8u;
+        // every consumer waits for every batch, with or without a chunk of its own in it: its arrival on `empty` must not
+        // run a phase ahead
+        ptx::mbar_wait(full_bar + buf, use & 1u);
+        for (uint32_t j = 0; j < n_chunks; ++j) {
+          if ((cbase + j) % kFbConsumers != uint32_t(warp) || (debug & 1)) continue;
+          const uint32_t e = 8u * j + uint32_t(quad);
+          const bool live = e < total;
+          const uint32_t ee = live ? e : 0u;
+          int idx = 0;  // the entry whose elements include number ee: as many entries end at or before it
+#pragma unroll
+          for (int i = 0; i < kFbSlots - 1; ++i) idx += int(__shfl_sync(0xffffffffu, incl, i) <= ee);
+          const uint32_t ww = __shfl_sync(0xffffffffu, word, idx);
+          const int col = int(__shfl_sync(0xffffffffu, node, idx));
+          uint32_t rank = ee - (__shfl_sync(0xffffffffu, incl, idx) - __shfl_sync(0xffffffffu, mine, idx));
+          uint32_t rest = ww;
+          while (rank != 0u) {  // the rank-th set bit = the frame
+            rest &= rest - 1u;
+            --rank;
+          }
+          const int f = __ffs(int(rest)) - 1;
+          const float bias = __ldg(a.bias0 + col);  // needed at the very end: its latency hides under the dot product
+          const float *wp = reinterpret_cast<const float *>(ring + (buf * kFbSlots + uint32_t(idx)) * uint32_t(L.wstride)) + r;
+          const float *xp = s_x + f * L.fstride + r * L.seg;
+          float acc = 0.0f;
+          int t = 0;
+#pragma unroll 2
+          for (; t + 4 <= n4; t += 4) {  // dnn.cc:219-247, lane r: k = 4t + r
+            const float4 xv = *reinterpret_cast<const float4 *>(xp + t);
+            const float w0 = wp[4 * t], w1 = wp[4 * t + 4], w2 = wp[4 * t + 8], w3 = wp[4 * t + 12];
+            acc = __fadd_rn(acc, __fmul_rn(xv.x, w0));
+            acc = __fadd_rn(acc, __fmul_rn(xv.y, w1));
+            acc = __fadd_rn(acc, __fmul_rn(xv.z, w2));
+            acc = __fadd_rn(acc, __fmul_rn(xv.w, w3));
+          }
+          for (; t < n4; ++t) acc = __fadd_rn(acc, __fmul_rn(xp[t], wp[4 * t]));
+          const float pair = __fadd_rn(acc, __shfl_xor_sync(0xffffffffu, acc, 1));
+          const float h = __fadd_rn(pair, __shfl_xor_sync(0xffffffffu, pair, 2));  // (l0 + l1) + (l2 + l3), dnn.cc:168-172
+          if (live && r == 0) a.out_u8[size_t(f0 + f) * size_t(a.H) + size_t(col)] = s_lut[qsig_slot(__fadd_rn(h, bias))];
+        }
+        cbase += n_chunks;
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(empty_bar + buf);
+      }
+    }
+  }
+}
+
 }  // namespace
 
-cudaError_t input_tc_configure() { return cudaFuncSetAttribute(input_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmem); }
+cudaError_t input_tc_configure() {
+  cudaError_t e = cudaFuncSetAttribute(input_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmem);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(input_fixup_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, fb_layout(kInputTcMaxI).total);
+}
 
 bool input_tc_supported(int I, int H) { return I > 0 && I <= kInputTcMaxI && I % 4 == 0 && H % 16 == 0 && H <= 65536; }
 
@@ -418,11 +640,29 @@ cudaError_t launch_input_tc(const CUtensorMap &tmap_x, const CUtensorMap &tmap_w
   input_tc_kernel<<<dim3(tiles < a.num_sms ? tiles : a.num_sms), dim3(kTcThreads), kTcSmem, stream>>>(tmap_x, tmap_w, a);
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
-  // enough warps to keep every SM busy: several warps per frame when the batch is short
-  int warps_per_row = 1;
-  while (warps_per_row < kFixWarps && a.M * warps_per_row < a.fixup_ctas * 2) warps_per_row *= 2;
-  const int fix_ctas = (a.M * warps_per_row + kFixWarps - 1) / kFixWarps;
-  input_fixup_kernel<<<dim3(fix_ctas < a.fixup_ctas ? fix_ctas : a.fixup_ctas), dim3(kFixWarps * 32), 0, stream>>>(a, warps_per_row);
+  static const bool by_warp = [] {  // FDNN_FIXUP=warp: the warp-per-frame kernel (A/B measurements)
+    const char *v = std::getenv("FDNN_FIXUP");
+    return v != nullptr && v[0] == 'w';
+  }();
+  if (by_warp) {
+    // enough warps to keep every SM busy: several warps per frame when the batch is short
+    int warps_per_row = 1;
+    while (warps_per_row < kFixWarps && a.M * warps_per_row < a.fixup_ctas * 2) warps_per_row *= 2;
+    const int fix_ctas = (a.M * warps_per_row + kFixWarps - 1) / kFixWarps;
+    input_fixup_kernel<<<dim3(fix_ctas < a.fixup_ctas ? fix_ctas : a.fixup_ctas), dim3(kFixWarps * 32), 0, stream>>>(a, warps_per_row);
+    return cudaGetLastError();
+  }
+  // a CTA per block of 32 frames; short batches also split the nodes so that one wave of CTAs covers the GPU
+  const int fblocks = (a.M + kFbFrames - 1) / kFbFrames;
+  int splits = a.num_sms / fblocks;
+  splits = splits < 1 ? 1 : (splits > a.unc_words ? a.unc_words : splits);
+  const int words_per_cta = (a.unc_words + splits - 1) / splits;
+  splits = (a.unc_words + words_per_cta - 1) / words_per_cta;
+  static const int debug = [] {  // FDNN_FB_DEBUG: 1 no arithmetic, 2 no copies, 4 16-byte copies (timing experiments; results wrong)
+    const char *v = std::getenv("FDNN_FB_DEBUG");
+    return v != nullptr ? std::atoi(v) : 0;
+  }();
+  input_fixup_block_kernel<<<dim3(fblocks, splits), dim3(kFbThreads), fb_layout(a.I).total, stream>>>(a, words_per_cta, debug);
   return cudaGetLastError();
 }
 

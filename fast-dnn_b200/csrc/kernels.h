@@ -87,6 +87,7 @@ struct InputTcArgs {
   InputRowStats *row_stats;  // [M]
   uint32_t *unc_bits;   // [M][unc_words]: bit n%32 of word n/32 = node n of this frame is left to the exact path
   int unc_words;        // ceil(H / 32)
+  uint32_t *unc_t;      // [ceil(M / 32)][H]: the same bits by blocks of 32 frames: bit f%32 of word [f/32][n] (block fix-up kernel)
   uint32_t *unc_count;  // how many bits are set (diagnostics)
   uint8_t *out_u8;      // [M][H]
   int M, I, H;

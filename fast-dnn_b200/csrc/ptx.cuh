@@ -107,6 +107,14 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap *map, uint64_t *ba
       : "memory");
 }
 
+// Plain bulk copy global → shared memory (no tensor map): `bytes` a multiple of 16, both addresses 16-byte aligned;
+// completes on `bar` like a TMA tile.
+__device__ __forceinline__ void bulk_load(void *smem_dst, const void *gmem_src, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(gmem_src)), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
 // Same tile, delivered to the same shared-memory offset of every CTA in `cta_mask` (and signalling the
 // barrier at the same offset in each of them).
 __device__ __forceinline__ void tma_load_2d_multicast(const CUtensorMap *map, uint64_t *bar, void *smem_dst, int c0, int c1, uint16_t cta_mask) {

@@ -20,6 +20,7 @@ namespace fdnn {
 namespace {
 
 constexpr int kThreads = 256;
+constexpr int kUnroll = 4;
 constexpr int kMaxSmemFloats = 56 * 1024;  // 224 KB of exponentials; wider rows recompute instead
 
 // e^x.  t = RN(x·log2e_hi) goes to ex2.approx; r = (x·log2e − t) is recovered exactly with one fma
@@ -60,18 +61,27 @@ __global__ void __launch_bounds__(kThreads) softmax_kernel(const SoftmaxArgs a) 
 
   float part = 0.0f;
   if (vec) {
-    for (int i = tid; i < O / 4; i += kThreads) {
-      float4 v = reinterpret_cast<const float4 *>(x)[i];
-      if (m) {
-        const char4 k = reinterpret_cast<const char4 *>(m)[i];
-        v.x = k.x ? v.x : 0.0f;
-        v.y = k.y ? v.y : 0.0f;
-        v.z = k.z ? v.z : 0.0f;
-        v.w = k.w ? v.w : 0.0f;
+    // kUnroll loads in flight per thread before anything waits for them (a row is 8 float4 per thread on the 8000-wide
+    // output layer: the pass was bound by their latency, one after the other, on short batches)
+    for (int i0 = tid; i0 < O / 4; i0 += kThreads * kUnroll) {
+      float4 v[kUnroll];
+      char4 k[kUnroll];
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u) {
+        const int i = i0 + u * kThreads;
+        v[u] = i < O / 4 ? reinterpret_cast<const float4 *>(x)[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+        k[u] = (m && i < O / 4) ? reinterpret_cast<const char4 *>(m)[i] : make_char4(1, 1, 1, 1);
       }
-      float4 e = make_float4(exp_fast(v.x), exp_fast(v.y), exp_fast(v.z), exp_fast(v.w));
-      if (kCache) reinterpret_cast<float4 *>(s_e)[i] = e;
-      part = __fadd_rn(part, __fadd_rn(__fadd_rn(e.x, e.y), __fadd_rn(e.z, e.w)));
+#pragma unroll
+      for (int u = 0; u < kUnroll; ++u) {
+        const int i = i0 + u * kThreads;
+        if (i < O / 4) {
+          const float4 e = make_float4(exp_fast(k[u].x ? v[u].x : 0.0f), exp_fast(k[u].y ? v[u].y : 0.0f), exp_fast(k[u].z ? v[u].z : 0.0f),
+                                       exp_fast(k[u].w ? v[u].w : 0.0f));
+          if (kCache) reinterpret_cast<float4 *>(s_e)[i] = e;
+          part = __fadd_rn(part, __fadd_rn(__fadd_rn(e.x, e.y), __fadd_rn(e.z, e.w)));
+        }
+      }
     }
   } else {
     for (int i = tid; i < O; i += kThreads) {
