@@ -432,13 +432,15 @@ constexpr int kFbThreads = (kFbConsumers + kFbBufs) * 32;
 constexpr int kFbSlots = 16;        // weight rows per batch
 constexpr int kFbPassNodes = 2048;  // nodes whose words are compacted at a time
 constexpr int kFbPassLoads = (kFbPassNodes + kFbThreads - 1) / kFbThreads;  // unc_t words per thread and pass
+constexpr int kFbPassBatches = kFbPassNodes / kFbSlots;                     // 128: each has its own "landed" barrier
+constexpr int kFbMaxChunks = kFbSlots * kFbFrames / 8;                      // 64 chunks of 8 elements in a full batch
 
 struct FbLayout {
   int seg;      // floats per SSE lane of a frame: I/4 rounded up to an ODD number of float4, so that the four lanes of a
                 // quad read four different 16-byte bank groups
   int fstride;  // floats per frame
   int wstride;  // bytes per weight-row slot, an odd number of 16-byte units: any eight consecutive slots are conflict-free
-  int off_lut, off_word, off_node, off_x, off_w, total;
+  int off_lut, off_word, off_node, off_incl, off_cst, off_x, off_w, total;
 };
 __host__ __device__ inline FbLayout fb_layout(int I) {
   FbLayout L;
@@ -447,10 +449,12 @@ __host__ __device__ inline FbLayout fb_layout(int I) {
   L.fstride = 4 * L.seg;
   L.wstride = 4 * I;
   if ((L.wstride / 16) % 2 == 0) L.wstride += 16;
-  L.off_lut = 128;  // 2·kFbBufs barriers and the list counter come first
+  L.off_lut = 8 * (kFbPassBatches + kFbBufs) + 32;  // the barriers and the list counter come first
   L.off_word = L.off_lut + kLut2Padded;
   L.off_node = L.off_word + 4 * kFbPassNodes;
-  L.off_x = L.off_node + 2 * kFbPassNodes;
+  L.off_incl = L.off_node + 2 * kFbPassNodes;
+  L.off_cst = L.off_incl + 2 * kFbPassNodes;
+  L.off_x = L.off_cst + 2 * (kFbPassBatches + 16);
   L.off_w = L.off_x + 4 * kFbFrames * L.fstride;
   L.total = L.off_w + kFbBufs * kFbSlots * L.wstride;
   return L;
@@ -459,8 +463,10 @@ __host__ __device__ inline FbLayout fb_layout(int I) {
 __global__ void __launch_bounds__(kFbThreads) input_fixup_block_kernel(const InputTcArgs a, const int words_per_cta, const int debug) {
   extern __shared__ __align__(128) uint8_t fb_smem[];
   const FbLayout L = fb_layout(a.I);
-  uint64_t *full_bar = reinterpret_cast<uint64_t *>(fb_smem), *empty_bar = full_bar + kFbBufs;
-  uint32_t *s_count = reinterpret_cast<uint32_t *>(fb_smem + 2 * kFbBufs * 8);
+  uint64_t *full_bar = reinterpret_cast<uint64_t *>(fb_smem), *empty_bar = full_bar + kFbPassBatches;
+  uint32_t *s_count = reinterpret_cast<uint32_t *>(fb_smem + 8 * (kFbPassBatches + kFbBufs));
+  uint16_t *l_incl = reinterpret_cast<uint16_t *>(fb_smem + L.off_incl);  // elements up to and including this entry, within its batch
+  uint16_t *s_cst = reinterpret_cast<uint16_t *>(fb_smem + L.off_cst);    // chunks before batch b in this pass; [n_batches] = all
   uint8_t *s_lut = fb_smem + L.off_lut;
   uint32_t *l_word = reinterpret_cast<uint32_t *>(fb_smem + L.off_word);
   uint16_t *l_node = reinterpret_cast<uint16_t *>(fb_smem + L.off_node);
@@ -472,20 +478,19 @@ __global__ void __launch_bounds__(kFbThreads) input_fixup_block_kernel(const Inp
   const int fb = int(blockIdx.x), f0 = fb * kFbFrames;
   const int n_lo = int(blockIdx.y) * words_per_cta * 32;
   const int n_hi = min(a.H, n_lo + words_per_cta * 32);
-  if (threadIdx.x == 0) {
-    for (int i = 0; i < kFbBufs; ++i) {
-      ptx::mbar_init(full_bar + i, 1);
-      ptx::mbar_init(empty_bar + i, kFbConsumers);
-    }
-    ptx::fence_barrier_init();
-  }
+  // a batch's "landed" barrier is used once per pass (any consumer may wait on any batch, in any order, with no phase to
+  // lose track of); a buffer's "free again" barrier takes one arrival per chunk of 8 elements, the producer standing in
+  // for the chunks a batch does not have, and only the buffer's producer waits on it
+  if (threadIdx.x < kFbPassBatches) ptx::mbar_init(full_bar + threadIdx.x, 1);
+  if (threadIdx.x < kFbBufs) ptx::mbar_init(empty_bar + threadIdx.x, kFbMaxChunks);
+  ptx::fence_barrier_init();
   for (int i = int(threadIdx.x); i < kLut2Padded / 16; i += kFbThreads) reinterpret_cast<uint4 *>(s_lut)[i] = __ldg(reinterpret_cast<const uint4 *>(a.lut) + i);
-  // the first pass's bitmap words, before anything else that waits for memory
+  // the CTA's bitmap words (at most kFbPassNodes of them: the launcher splits wider layers), before anything else that waits for memory
   uint32_t wv[kFbPassLoads];
 #pragma unroll
   for (int u = 0; u < kFbPassLoads; ++u) {
-    const int i = int(threadIdx.x) + u * kFbThreads;
-    wv[u] = n_lo + i < min(n_hi, n_lo + kFbPassNodes) ? __ldg(a.unc_t + size_t(fb) * size_t(a.H) + size_t(n_lo + i)) : 0u;
+    const int i = n_lo + int(threadIdx.x) + u * kFbThreads;
+    wv[u] = i < n_hi ? __ldg(a.unc_t + size_t(fb) * size_t(a.H) + size_t(i)) : 0u;
   }
   // the block's transformed frames: s_x[f][r][t] = x'[f][4t + r]; eight loads in flight per thread (a CTA has the SM to itself)
   const int rows = min(kFbFrames, a.M - f0);
@@ -510,12 +515,11 @@ __global__ void __launch_bounds__(kFbThreads) input_fixup_block_kernel(const Inp
       }
     }
   }
-  uint32_t bn = 0;     // batches so far, over all passes: buffer bn % kFbBufs, use number bn / kFbBufs
-  uint32_t cbase = 0;  // chunks so far: chunk c goes to consumer warp c % kFbConsumers
-  for (int p_lo = n_lo; p_lo < n_hi; p_lo += kFbPassNodes) {
-    __syncthreads();  // barriers initialised, frames stored; nobody reads the previous pass's list any more
+  constexpr uint32_t bn = 0;  // (batch b uses buffer b % kFbBufs for the (b / kFbBufs)-th time)
+  const int p_lo = n_lo;
+  {
     if (threadIdx.x == 0) *s_count = 0u;
-    __syncthreads();
+    __syncthreads();  // barriers initialised, frames stored, counter zero
 #pragma unroll
     for (int u = 0; u < kFbPassLoads; ++u) {  // nodes with a non-zero word → list (order irrelevant)
       const int i = int(threadIdx.x) + u * kFbThreads;
@@ -532,51 +536,85 @@ __global__ void __launch_bounds__(kFbThreads) input_fixup_block_kernel(const Inp
         }
       }
     }
-#pragma unroll
-    for (int u = 0; u < kFbPassLoads; ++u) {  // the next pass's words (wide layers only)
-      const int i = p_lo + kFbPassNodes + int(threadIdx.x) + u * kFbThreads;
-      wv[u] = i < min(n_hi, p_lo + 2 * kFbPassNodes) ? __ldg(a.unc_t + size_t(fb) * size_t(a.H) + size_t(i)) : 0u;
-    }
     __syncthreads();
     const uint32_t n_list = *s_count;
     const uint32_t n_batches = (n_list + kFbSlots - 1) / kFbSlots;
+    // per batch, once for everybody: the running element count of its entries and how many chunks of 8 that makes
+    for (uint32_t b = uint32_t(warp); b < n_batches; b += kFbThreads / 32) {
+      const uint32_t entry = b * kFbSlots + uint32_t(lane & (kFbSlots - 1));
+      uint32_t incl = entry < n_list ? uint32_t(__popc(l_word[entry])) : 0u;
+#pragma unroll
+      for (int o = 1; o < kFbSlots; o <<= 1) {
+        const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o, kFbSlots);
+        if ((lane & (kFbSlots - 1)) >= o) incl += v;
+      }
+      if (lane < kFbSlots) l_incl[entry] = uint16_t(incl);
+      if (lane == kFbSlots - 1) s_cst[b + 1] = uint16_t((incl + 7u) / 8u);
+    }
+    __syncthreads();
+    if (warp == 0) {  // chunk counts → running totals (s_cst[b] = chunks before batch b)
+      constexpr int kPer = kFbPassBatches / 32;
+      uint32_t v[kPer], sum = 0;
+#pragma unroll
+      for (int u = 0; u < kPer; ++u) {
+        const uint32_t b = uint32_t(lane * kPer + u);
+        v[u] = b < n_batches ? uint32_t(s_cst[b + 1]) : 0u;
+        sum += v[u];
+      }
+      uint32_t incl = sum;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+      }
+      uint32_t run = incl - sum;
+      __syncwarp();
+      if (lane == 0) s_cst[0] = 0;
+#pragma unroll
+      for (int u = 0; u < kPer; ++u) {
+        const uint32_t b = uint32_t(lane * kPer + u);
+        run += v[u];
+        if (b < n_batches) s_cst[b + 1] = uint16_t(run);
+      }
+    }
+    __syncthreads();
     if (warp >= kFbConsumers) {
-      // producers: a batch = up to kFbSlots weight rows, one bulk copy each, all landing on the buffer's barrier
+      // producers: a batch = up to kFbSlots weight rows, one bulk copy each, all landing on the batch's barrier
       const uint32_t buf = uint32_t(warp - kFbConsumers);
       for (uint32_t b = (buf + kFbBufs - bn % kFbBufs) % kFbBufs; b < n_batches; b += kFbBufs) {
         const uint32_t use = (bn + b) / kFbBufs;
         if (use != 0u) ptx::mbar_wait(empty_bar + buf, (use - 1u) & 1u);
         const uint32_t cnt = min(uint32_t(kFbSlots), n_list - b * kFbSlots);
         const uint32_t row_bytes = (debug & 4) ? 16u : uint32_t(4 * I);
-        if (lane == 0) ptx::mbar_arrive_expect_tx(full_bar + buf, (debug & 2) ? 0u : cnt * row_bytes);
+        if (lane == 0) ptx::mbar_arrive_expect_tx(full_bar + b, (debug & 2) ? 0u : cnt * row_bytes);
         __syncwarp();
         if (uint32_t(lane) < cnt && !(debug & 2))
           ptx::bulk_load(ring + (buf * kFbSlots + uint32_t(lane)) * uint32_t(L.wstride), a.w0 + size_t(l_node[b * kFbSlots + uint32_t(lane)]) * size_t(I),
-                         row_bytes, full_bar + buf);
+                         row_bytes, full_bar + b);
+        const uint32_t absent = uint32_t(kFbMaxChunks) - (uint32_t(s_cst[b + 1]) - uint32_t(s_cst[b]));
+        if (lane == 0 && absent != 0u) ptx::mbar_arrive_n(empty_bar + buf, absent);
       }
-      bn += n_batches;
     } else {
-      for (uint32_t b = 0; b < n_batches; ++b, ++bn) {
-        const uint32_t buf = bn % kFbBufs, use = bn / kFbBufs;
-        // both half-warps hold the batch's entries: word, node, inclusive prefix of the element counts
+      uint32_t c_hi = 0;
+      for (uint32_t b = 0; b < n_batches; ++b) {
+        const uint32_t c_lo = c_hi;
+        c_hi = s_cst[b + 1];
+        // chunk c of the pass belongs to consumer warp c % kFbConsumers; most batches have nothing for this warp
+        uint32_t j = (uint32_t(warp) + uint32_t(kFbConsumers) - c_lo % uint32_t(kFbConsumers)) % uint32_t(kFbConsumers);
+        const uint32_t n_chunks = c_hi - c_lo;
+        if (j >= n_chunks) continue;
+        const uint32_t buf = (bn + b) % kFbBufs;
+        // both half-warps hold the batch's entries: word, node, running element count
         const uint32_t entry = b * kFbSlots + uint32_t(lane & (kFbSlots - 1));
         const bool have = entry < n_list;
         const uint32_t word = have ? l_word[entry] : 0u;
         const uint32_t node = have ? uint32_t(l_node[entry]) : 0u;
+        const uint32_t incl = l_incl[entry];
         const uint32_t mine = uint32_t(__popc(word));
-        uint32_t incl = mine;
-#pragma unroll
-        for (int o = 1; o < kFbSlots; o <<= 1) {
-          const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o, kFbSlots);
-          if ((lane & (kFbSlots - 1)) >= o) incl += v;
-        }
         const uint32_t total = __shfl_sync(0xffffffffu, incl, kFbSlots - 1);
-        const uint32_t n_chunks = (total + 7u) / 8u;
-        // every consumer waits for every batch, with or without a chunk of its own in it: its arrival on `empty` must not
-        // run a phase ahead
-        ptx::mbar_wait(full_bar + buf, use & 1u);
-        for (uint32_t j = 0; j < n_chunks; ++j) {
-          if ((cbase + j) % kFbConsumers != uint32_t(warp) || (debug & 1)) continue;
+        ptx::mbar_wait(full_bar + b, 0u);
+        for (; j < n_chunks; j += kFbConsumers) {
+          if (!(debug & 1)) {
           const uint32_t e = 8u * j + uint32_t(quad);
           const bool live = e < total;
           const uint32_t ee = live ? e : 0u;
@@ -610,10 +648,10 @@ __global__ void __launch_bounds__(kFbThreads) input_fixup_block_kernel(const Inp
           const float pair = __fadd_rn(acc, __shfl_xor_sync(0xffffffffu, acc, 1));
           const float h = __fadd_rn(pair, __shfl_xor_sync(0xffffffffu, pair, 2));  // (l0 + l1) + (l2 + l3), dnn.cc:168-172
           if (live && r == 0) a.out_u8[size_t(f0 + f) * size_t(a.H) + size_t(col)] = s_lut[qsig_slot(__fadd_rn(h, bias))];
+          }
+          __syncwarp();  // every lane has read its operands: the chunk no longer needs the buffer
+          if (lane == 0) ptx::mbar_arrive(empty_bar + buf);
         }
-        cbase += n_chunks;
-        __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(empty_bar + buf);
       }
     }
   }
@@ -655,7 +693,8 @@ cudaError_t launch_input_tc(const CUtensorMap &tmap_x, const CUtensorMap &tmap_w
   // a CTA per block of 32 frames; short batches also split the nodes so that one wave of CTAs covers the GPU
   const int fblocks = (a.M + kFbFrames - 1) / kFbFrames;
   int splits = a.num_sms / fblocks;
-  splits = splits < 1 ? 1 : (splits > a.unc_words ? a.unc_words : splits);
+  const int min_splits = (a.unc_words * 32 + kFbPassNodes - 1) / kFbPassNodes;  // a CTA lists at most kFbPassNodes nodes
+  splits = splits < min_splits ? min_splits : (splits > a.unc_words ? a.unc_words : splits);
   const int words_per_cta = (a.unc_words + splits - 1) / splits;
   splits = (a.unc_words + words_per_cta - 1) / words_per_cta;
   static const int debug = [] {  // FDNN_FB_DEBUG: 1 no arithmetic, 2 no copies, 4 16-byte copies (timing experiments; results wrong)

@@ -340,3 +340,34 @@ def test_certified_input_layer_equals_exact_kernel_on_hostile_frames(net_file):
     assert np.array_equal(outs["0"][0], outs["1"][0]), "layer-0 bytes differ"
     assert np.array_equal(outs["0"][1].view(np.uint32), outs["1"][1].view(np.uint32)), "logits differ"
     assert int(outs["1"][2][0]) < 0.1 * 300 * 512, "the certificate left more than 10 % of the elements to the exact path"
+
+
+def test_block_fixup_wide_layer_long_batch_dense_blocks(net_file):
+    """The block fix-up kernel's corner cases against the exact kernel (FDNN_INPUT_TC=0) and against the warp-per-frame
+    fix-up (FDNN_FIXUP=warp): a hidden layer wider than one compaction pass (2304 > 2048 nodes), a batch long enough for a
+    CTA to own all of them (4800 frames ≥ 32 per SM), a ragged last block, single NaN frames (every node listed with one
+    element: the maximum number of batches) and a whole block of NaN frames (every word all ones: full batches of 64
+    chunks, nothing for the producer to stand in for)."""
+    import subprocess
+    import sys
+    shape = (40, 2304, 2, 64)
+    n = 4800 + 7
+    code = (
+        "import sys, numpy as np; sys.path.insert(0, %r); import fast_dnn_b200\n"
+        "from fast_dnn_b200 import quantized_dnn as qd, synth\n"
+        "dnn = qd.QuantizedDnn.load_from_file(%r)\n"
+        "x = synth.make_frames(%d, 40, seed=21)\n"
+        "x[5, 3] = np.nan; x[40, 0] = np.inf; x[64:96, 1] = np.nan; x[4799, 2] = np.nan; x[4806, :] = 0.0\n"
+        "ctx = dnn.get_new_lazy_context(%d); ctx.set_trace(True); ctx.calculate_until_output(x)\n"
+        "np.save(sys.argv[1], ctx.hidden(0)); np.save(sys.argv[2], ctx.logits())\n"
+    ) % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), net_file(shape), n, n)
+    outs = {}
+    for name, env_add in (("exact", {"FDNN_INPUT_TC": "0"}), ("block", {}), ("warp", {"FDNN_FIXUP": "warp"})):
+        paths = [f"/tmp/fdnn_fb_{name}_{k}.npy" for k in ("h0", "l")]
+        subprocess.run([sys.executable, "-c", code] + paths, check=True, env=dict(os.environ, **env_add), timeout=240)
+        outs[name] = [np.load(p) for p in paths]
+    for name in ("block", "warp"):
+        rows, cols = np.nonzero(outs["exact"][0] != outs[name][0])
+        assert rows.size == 0, (f"layer-0 bytes differ ({name}): {rows.size} elements, rows {np.unique(rows)[:20]} "
+                                f"(blocks {np.unique(rows // 32)[:20]}), cols {np.unique(cols)[:20]} … {np.unique(cols)[-5:]}")
+        assert np.array_equal(outs["exact"][1].view(np.uint32), outs[name][1].view(np.uint32)), f"logits differ ({name})"
