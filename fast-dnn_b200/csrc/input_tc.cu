@@ -425,10 +425,13 @@ __global__ void __launch_bounds__(kFixWarps * 32) input_fixup_kernel(const Input
 // block's frames that need it).  Eight consumer warps take a batch's (node, frame) elements eight at a time — a quad per
 // element, thread (quad, r) doing SSE lane r exactly as the reference (dnn.cc:219-247, 168-172): FMUL, FADD, never FMA.
 constexpr int kFbFrames = 32;       // = the bits of an unc_t word
-constexpr int kFbConsumers = 12;    // warps doing the arithmetic
-constexpr int kFbBufs = 4;          // batches in flight, and producer warps: each owns a buffer (issuing a bulk copy takes a
-                                    // warp ≈ 33 cycles whatever its size, 16 in a row per batch)
+constexpr int kFbConsumers = 12;    // warps doing the arithmetic (measured on B200, 16384 | 512 frames: 12 warps and 4 buffers
+                                    // 224 | 14.5 us, 20 warps and 5 buffers 262 | 15.9 us: warps polling a barrier for a batch
+                                    // that has not landed share the shared-memory pipe with the ones doing the arithmetic)
+constexpr int kFbBufs = 4;          // at most: batches in flight, and producer warps: each owns a buffer (issuing a bulk copy takes
+                                    // a warp ≈ 33 cycles whatever its size, 16 in a row per batch)
 constexpr int kFbThreads = (kFbConsumers + kFbBufs) * 32;
+constexpr int kFbSmemLimit = 227 * 1024 - 1024;  // dynamic shared memory a CTA of this file can ask for
 constexpr int kFbSlots = 16;        // weight rows per batch
 constexpr int kFbPassNodes = 2048;  // nodes whose words are compacted at a time
 constexpr int kFbPassLoads = (kFbPassNodes + kFbThreads - 1) / kFbThreads;  // unc_t words per thread and pass
@@ -440,7 +443,7 @@ struct FbLayout {
                 // quad read four different 16-byte bank groups
   int fstride;  // floats per frame
   int wstride;  // bytes per weight-row slot, an odd number of 16-byte units: any eight consecutive slots are conflict-free
-  int off_lut, off_word, off_node, off_incl, off_cst, off_x, off_w, total;
+  int off_lut, off_word, off_node, off_incl, off_cst, off_x, off_w, n_bufs, total;
 };
 __host__ __device__ inline FbLayout fb_layout(int I) {
   FbLayout L;
@@ -449,14 +452,16 @@ __host__ __device__ inline FbLayout fb_layout(int I) {
   L.fstride = 4 * L.seg;
   L.wstride = 4 * I;
   if ((L.wstride / 16) % 2 == 0) L.wstride += 16;
-  L.off_lut = 8 * (kFbPassBatches + kFbBufs) + 32;  // the barriers and the list counter come first
+  L.off_lut = (8 * (kFbPassBatches + kFbBufs) + 32 + 15) / 16 * 16;  // the barriers and the list counter come first
   L.off_word = L.off_lut + kLut2Padded;
   L.off_node = L.off_word + 4 * kFbPassNodes;
   L.off_incl = L.off_node + 2 * kFbPassNodes;
   L.off_cst = L.off_incl + 2 * kFbPassNodes;
   L.off_x = L.off_cst + 2 * (kFbPassBatches + 16);
   L.off_w = L.off_x + 4 * kFbFrames * L.fstride;
-  L.total = L.off_w + kFbBufs * kFbSlots * L.wstride;
+  L.n_bufs = (kFbSmemLimit - L.off_w) / (kFbSlots * L.wstride);
+  L.n_bufs = L.n_bufs > kFbBufs ? kFbBufs : L.n_bufs;
+  L.total = L.off_w + L.n_bufs * kFbSlots * L.wstride;
   return L;
 }
 
@@ -515,7 +520,7 @@ __global__ void __launch_bounds__(kFbThreads) input_fixup_block_kernel(const Inp
       }
     }
   }
-  constexpr uint32_t bn = 0;  // (batch b uses buffer b % kFbBufs for the (b / kFbBufs)-th time)
+  const uint32_t n_bufs = uint32_t(L.n_bufs);  // batch b uses buffer b % n_bufs for the (b / n_bufs)-th time
   const int p_lo = n_lo;
   {
     if (threadIdx.x == 0) *s_count = 0u;
@@ -581,8 +586,7 @@ __global__ void __launch_bounds__(kFbThreads) input_fixup_block_kernel(const Inp
     if (warp >= kFbConsumers) {
       // producers: a batch = up to kFbSlots weight rows, one bulk copy each, all landing on the batch's barrier
       const uint32_t buf = uint32_t(warp - kFbConsumers);
-      for (uint32_t b = (buf + kFbBufs - bn % kFbBufs) % kFbBufs; b < n_batches; b += kFbBufs) {
-        const uint32_t use = (bn + b) / kFbBufs;
+      for (uint32_t b = buf, use = 0; b < n_batches && buf < n_bufs; b += n_bufs, ++use) {
         if (use != 0u) ptx::mbar_wait(empty_bar + buf, (use - 1u) & 1u);
         const uint32_t cnt = min(uint32_t(kFbSlots), n_list - b * kFbSlots);
         const uint32_t row_bytes = (debug & 4) ? 16u : uint32_t(4 * I);
@@ -603,7 +607,7 @@ __global__ void __launch_bounds__(kFbThreads) input_fixup_block_kernel(const Inp
         uint32_t j = (uint32_t(warp) + uint32_t(kFbConsumers) - c_lo % uint32_t(kFbConsumers)) % uint32_t(kFbConsumers);
         const uint32_t n_chunks = c_hi - c_lo;
         if (j >= n_chunks) continue;
-        const uint32_t buf = (bn + b) % kFbBufs;
+        const uint32_t buf = b % n_bufs;
         // both half-warps hold the batch's entries: word, node, running element count
         const uint32_t entry = b * kFbSlots + uint32_t(lane & (kFbSlots - 1));
         const bool have = entry < n_list;
@@ -662,7 +666,7 @@ __global__ void __launch_bounds__(kFbThreads) input_fixup_block_kernel(const Inp
 cudaError_t input_tc_configure() {
   cudaError_t e = cudaFuncSetAttribute(input_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmem);
   if (e != cudaSuccess) return e;
-  return cudaFuncSetAttribute(input_fixup_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, fb_layout(kInputTcMaxI).total);
+  return cudaFuncSetAttribute(input_fixup_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFbSmemLimit);
 }
 
 bool input_tc_supported(int I, int H) { return I > 0 && I <= kInputTcMaxI && I % 4 == 0 && H % 16 == 0 && H <= 65536; }

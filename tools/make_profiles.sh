@@ -17,6 +17,10 @@ timeout 600 ncu --set full --clock-control none --import-source on -k regex:qlay
     python tools/profile_step.py --steps 1 --warmup 1 > gpurun_out/${TAG}_hidden.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:input_tc_kernel -s 1 -c 1 -o gpurun_out/${TAG}_input -f \
     python tools/profile_step.py --steps 1 --warmup 1 > gpurun_out/${TAG}_input.log 2>&1
+timeout 600 ncu --set full --clock-control none --cache-control none --import-source on -k regex:input_fixup_block -s 1 -c 1 -o gpurun_out/${TAG}_fixup -f \
+    python tools/profile_step.py --steps 1 --warmup 1 > gpurun_out/${TAG}_fixup.log 2>&1
+timeout 600 ncu --set full --clock-control none --cache-control none --import-source on -k regex:input_fixup_block -s 1 -c 1 -o gpurun_out/${TAG}_fixup_stream -f \
+    python tools/profile_step.py --batch 16384 --steps 1 --warmup 1 > gpurun_out/${TAG}_fixup_stream.log 2>&1
 # long-stream regime (16384-frame chunks): every int8 layer runs on CTA pairs (qlayer_pair.cu); first hidden layer and the output layer
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:qlayer_pair -s 7 -c 1 -o gpurun_out/${TAG}_hidden_stream -f \
     python tools/profile_step.py --batch 16384 --steps 1 --warmup 1 > gpurun_out/${TAG}_hidden_stream.log 2>&1

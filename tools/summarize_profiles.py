@@ -38,7 +38,7 @@ def raw(rep):
 
 
 kernels = []
-for name in ("hidden", "input", "hidden_stream", "output_stream"):
+for name in ("hidden", "input", "fixup", "fixup_stream", "hidden_stream", "output_stream"):
     rep = os.path.join(OUT, f"{tag}_{name}.ncu-rep")
     if not os.path.exists(rep):
         continue
