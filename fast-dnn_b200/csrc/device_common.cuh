@@ -105,15 +105,56 @@ __device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
   return d;
 }
 
+// fp32 logits of one row per lane, 16 consecutive columns each, written so that the four lanes of a quad cover 64 contiguous
+// bytes of ONE row per store instruction (4×4 transpose of the 16-byte pieces over the quad, two butterfly steps): a warp-wide
+// store is then 8 rows × two full 32-byte sectors instead of 32 rows × half a sector each.  (Measured on B200 with the
+// kernel's own clock stamps: the logits epilogue of a 128×256 tile took 15 k of the tile's 40 k cycles at batch 512, at
+// ≈ 1.8 cycles per half-sector store request.)  All 32 lanes must call it; the rows of a quad are consecutive.
+__device__ __forceinline__ void store_logits_quad(float4 (&p)[4], float *out, size_t ld, int row, int col, int M) {
+  const int qi = int(threadIdx.x) & 3;
+  {
+    const bool hi = (qi & 1) != 0;  // swap bit 0 of (lane in quad, piece)
+#pragma unroll
+    for (int m = 0; m < 2; ++m) {
+      const float4 send = hi ? p[2 * m] : p[2 * m + 1];
+      float4 recv;
+      recv.x = __shfl_xor_sync(0xffffffffu, send.x, 1);
+      recv.y = __shfl_xor_sync(0xffffffffu, send.y, 1);
+      recv.z = __shfl_xor_sync(0xffffffffu, send.z, 1);
+      recv.w = __shfl_xor_sync(0xffffffffu, send.w, 1);
+      if (hi) p[2 * m] = recv; else p[2 * m + 1] = recv;
+    }
+  }
+  {
+    const bool hi = (qi & 2) != 0;  // … and bit 1
+#pragma unroll
+    for (int m = 0; m < 2; ++m) {
+      const float4 send = hi ? p[m] : p[m + 2];
+      float4 recv;
+      recv.x = __shfl_xor_sync(0xffffffffu, send.x, 2);
+      recv.y = __shfl_xor_sync(0xffffffffu, send.y, 2);
+      recv.z = __shfl_xor_sync(0xffffffffu, send.z, 2);
+      recv.w = __shfl_xor_sync(0xffffffffu, send.w, 2);
+      if (hi) p[m] = recv; else p[m + 2] = recv;
+    }
+  }
+  // p[k] is now piece qi (columns col + 4·qi …) of row (row − qi + k)
+  const int row0 = row - qi;
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+    if (row0 + k < M) *reinterpret_cast<float4 *>(out + size_t(row0 + k) * ld + size_t(col + 4 * qi)) = p[k];
+}
+
 // Same results as finish_chunk below when args.fast_tail is set, in ≈ 8 instead of ≈ 15 issue slots per
 // element: every rounding step of the reference is kept, two elements per FFMA2 —
 //   q = RN(s·rcp) = fma(s, rcp, −0);  e = fma(q, −coeff, s);  lin = fma(e, rcp, q)      (the verified 3-op division)
 //   x = RN(lin + bias) = fma(lin, 1, bias)
 //   hidden: RN(x·200) = 2·RN(x·100) exactly, so trunc(clamp(RN(x·200), ±1282)) is the doubled-LUT slot of
 //   qsig_slot(); fast_tail rules out NaN and |x·200| ≥ 2³¹, the only inputs on which the two differ.
-template <bool kLogits>
+// kQuadStore (logits only): every lane of the warp calls, lane = row, `row_ok` says whether the row exists (row < M)
+template <bool kLogits, bool kQuadStore = false>
 __device__ __forceinline__ void finish_chunk_fast(const int32_t (&s)[16], int row, int col, const QLayerArgs &args, const float *bias16,
-                                                  const uint8_t *lut) {
+                                                  const uint8_t *lut, bool row_ok = true, int M = 0) {
   const uint64_t rcp2 = pack2(args.rcp, args.rcp), ncoeff2 = pack2(-args.coeff, -args.coeff), one2 = pack2(args.one, args.one),
                  nz2 = pack2(args.neg_zero, args.neg_zero);
   uint64_t x[8];
@@ -129,14 +170,21 @@ __device__ __forceinline__ void finish_chunk_fast(const int32_t (&s)[16], int ro
     const int N = args.N;
     float *dst = args.out_f32 + size_t(row) * size_t(args.out_ld) + col;
     if (col + 16 <= N && (args.out_ld & 3) == 0) {
+      float4 v4[4];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         float a, b, c, d;
         unpack2(x[2 * i], a, b);
         unpack2(x[2 * i + 1], c, d);
-        reinterpret_cast<float4 *>(dst)[i] = make_float4(a, b, c, d);
+        v4[i] = make_float4(a, b, c, d);
       }
-    } else {
+      if constexpr (kQuadStore) {
+        store_logits_quad(v4, args.out_f32, size_t(args.out_ld), row, col, M);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) reinterpret_cast<float4 *>(dst)[i] = v4[i];
+      }
+    } else if (row_ok) {
 #pragma unroll
       for (int p = 0; p < 8; ++p) {
         float a, b;
@@ -168,9 +216,9 @@ __device__ __forceinline__ void finish_chunk_fast(const int32_t (&s)[16], int ro
 
 // The reference's per-element tail for one row and one aligned chunk of 16 nodes whose exact
 // (saturation-corrected) sums are in `s`: dequantise → + bias → {LUT → u8 | fp32 logits} → global.
-template <bool kLogits>
+template <bool kLogits, bool kQuadStore = false>
 __device__ __forceinline__ void finish_chunk(const int32_t (&s)[16], int row, int col, const QLayerArgs &args, const float *bias16,
-                                             const uint8_t *lut) {
+                                             const uint8_t *lut, bool row_ok = true, int M = 0) {
   const int N = args.N;
   if constexpr (kLogits) {
     float v[16];
@@ -178,9 +226,16 @@ __device__ __forceinline__ void finish_chunk(const int32_t (&s)[16], int row, in
     for (int i = 0; i < 16; ++i) v[i] = __fadd_rn(dequant(s[i], args.coeff, args.rcp, args.fast_div), bias16[i]);
     float *dst = args.out_f32 + size_t(row) * size_t(args.out_ld) + col;
     if (col + 16 <= N && (args.out_ld & 3) == 0) {
+      float4 v4[4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) reinterpret_cast<float4 *>(dst)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-    } else {
+      for (int i = 0; i < 4; ++i) v4[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+      if constexpr (kQuadStore) {
+        store_logits_quad(v4, args.out_f32, size_t(args.out_ld), row, col, M);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) reinterpret_cast<float4 *>(dst)[i] = v4[i];
+      }
+    } else if (row_ok) {
 #pragma unroll
       for (int i = 0; i < 16; ++i)
         if (col + i < N) dst[i] = v[i];

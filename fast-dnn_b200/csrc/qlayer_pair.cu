@@ -507,11 +507,16 @@ qlayer_pair_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_co
           }
           if (many && row_ok) brute_force_corrections(s, row, col, args);
           if (j == n_valid - 1) release_acc();  // before the math: the MMA of tile i+2 can start
-          if (row_ok) {
+          if constexpr (kLogits) {  // every lane: the quad-transposed store needs the whole warp
             if (args.fast_tail)
-              finish_chunk_fast<kLogits>(s, row, col, args, bias_s + (col - n0), s_lut);
+              finish_chunk_fast<true, true>(s, row, col, args, bias_s + (col - n0), s_lut, row_ok, M);
             else
-              finish_chunk<kLogits>(s, row, col, args, bias_s + (col - n0), s_lut);
+              finish_chunk<true, true>(s, row, col, args, bias_s + (col - n0), s_lut, row_ok, M);
+          } else if (row_ok) {
+            if (args.fast_tail)
+              finish_chunk_fast<false>(s, row, col, args, bias_s + (col - n0), s_lut);
+            else
+              finish_chunk<false>(s, row, col, args, bias_s + (col - n0), s_lut);
           }
         }
       }

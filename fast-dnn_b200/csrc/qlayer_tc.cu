@@ -469,7 +469,11 @@ qlayer_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_cons
             ptx::tc_fence_before_sync();
             ptx::mbar_arrive(tmem_empty_bar + acc);
           }
-          if (row_ok) finish_chunk<kLogits>(s, row, col, args, bias_s + (col - n0), s_lut);
+          if constexpr (kLogits) {  // every lane: the quad-transposed store needs the whole warp
+            finish_chunk<true, true>(s, row, col, args, bias_s + (col - n0), s_lut, row_ok, M);
+          } else {
+            if (row_ok) finish_chunk<false>(s, row, col, args, bias_s + (col - n0), s_lut);
+          }
         }
       }
       if (et == 0) stamp(args.timeline, 6);

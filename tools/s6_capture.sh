@@ -1,4 +1,4 @@
 mkdir -p gpurun_out
-for b in 512 16384; do
-timeout 300 ncu --set full --clock-control none --cache-control none --import-source on -k regex:input_fixup_block -s 1 -c 1 -o gpurun_out/s6_fixup_$b -f python tools/profile_step.py --batch $b --steps 1 --warmup 1 > gpurun_out/s6_fixup_$b.log 2>&1; tail -2 gpurun_out/s6_fixup_$b.log
-done
+timeout 400 python -m pytest tests -m gpu -x -q > gpurun_out/s6_tests.log 2>&1; tail -3 gpurun_out/s6_tests.log
+timeout 200 python tools/stage_times.py > gpurun_out/s6_stage.log 2>&1; cat gpurun_out/s6_stage.log
+timeout 200 python tools/timeline.py 2>&1 | tail -8
