@@ -66,6 +66,8 @@ constexpr int kTcSmem = kStages * kStageBytes + kBarRegion + kLut2Padded + kTile
 __global__ void __launch_bounds__(256) input_prep_kernel(const InputTcArgs a) {
   const int warp = int(threadIdx.x) / 32, lane = int(threadIdx.x) % 32;
   const int row = int(blockIdx.x) * 8 + warp;
+  ptx::griddep_wait();  // launched with programmatic serialization: the previous pass may still be reading what this one writes
+  ptx::griddep_launch_dependents();
   if (blockIdx.x == 0 && threadIdx.x == 0) *a.unc_count = 0u;
   if (row >= a.M) return;
   const int I = a.I, I4 = I / 4;
@@ -200,6 +202,8 @@ input_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
   __syncthreads();
   ptx::tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
+  ptx::griddep_wait();  // barriers, tensor memory and descriptors were set up under the prepare kernel's tail
+  ptx::griddep_launch_dependents();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -369,6 +373,8 @@ __global__ void __launch_bounds__(kFixWarps * 32) input_fixup_kernel(const Input
   const int I = a.I;
   const int rows_per_cta = kFixWarps / warps_per_row;
   const int sub = warp % warps_per_row;  // which share of the frame's rounds this warp takes
+  ptx::griddep_wait();
+  ptx::griddep_launch_dependents();
   for (int row = int(blockIdx.x) * rows_per_cta + warp / warps_per_row; row < a.M; row += int(gridDim.x) * rows_per_cta) {
     __syncwarp();
     for (int k = lane; k < I; k += 32) s_x[warp][k] = a.xq[size_t(row) * size_t(I) + k];
@@ -490,6 +496,8 @@ __global__ void __launch_bounds__(kFbThreads) input_fixup_block_kernel(const Inp
   if (threadIdx.x < kFbBufs) ptx::mbar_init(empty_bar + threadIdx.x, kFbMaxChunks);
   ptx::fence_barrier_init();
   for (int i = int(threadIdx.x); i < kLut2Padded / 16; i += kFbThreads) reinterpret_cast<uint4 *>(s_lut)[i] = __ldg(reinterpret_cast<const uint4 *>(a.lut) + i);
+  ptx::griddep_wait();  // everything above ran under the tensor-core kernel's tail
+  ptx::griddep_launch_dependents();
   // the CTA's bitmap words (at most kFbPassNodes of them: the launcher splits wider layers), before anything else that waits for memory
   uint32_t wv[kFbPassLoads];
 #pragma unroll
@@ -675,12 +683,10 @@ bool input_tc_supported(int I, int H) { return I > 0 && I <= kInputTcMaxI && I %
 // tmap_w: [3 · w_plane_rows][512], box 64 rows × 128 B.
 cudaError_t launch_input_tc(const CUtensorMap &tmap_x, const CUtensorMap &tmap_w, const InputTcArgs &a, cudaStream_t stream) {
   if (a.M <= 0) return cudaSuccess;
-  input_prep_kernel<<<dim3((a.M + 7) / 8), dim3(256), 0, stream>>>(a);
-  cudaError_t e = cudaGetLastError();
+  cudaError_t e = launch_pdl(input_prep_kernel, dim3((a.M + 7) / 8), dim3(256), size_t(0), stream, pdl_enabled(), a);
   if (e != cudaSuccess) return e;
   const int tiles = ((a.H + kTileN - 1) / kTileN) * ((a.M + kTileM - 1) / kTileM);
-  input_tc_kernel<<<dim3(tiles < a.num_sms ? tiles : a.num_sms), dim3(kTcThreads), kTcSmem, stream>>>(tmap_x, tmap_w, a);
-  e = cudaGetLastError();
+  e = launch_pdl(input_tc_kernel, dim3(tiles < a.num_sms ? tiles : a.num_sms), dim3(kTcThreads), size_t(kTcSmem), stream, pdl_enabled(), tmap_x, tmap_w, a);
   if (e != cudaSuccess) return e;
   static const bool by_warp = [] {  // FDNN_FIXUP=warp: the warp-per-frame kernel (A/B measurements)
     const char *v = std::getenv("FDNN_FIXUP");
@@ -691,8 +697,7 @@ cudaError_t launch_input_tc(const CUtensorMap &tmap_x, const CUtensorMap &tmap_w
     int warps_per_row = 1;
     while (warps_per_row < kFixWarps && a.M * warps_per_row < a.fixup_ctas * 2) warps_per_row *= 2;
     const int fix_ctas = (a.M * warps_per_row + kFixWarps - 1) / kFixWarps;
-    input_fixup_kernel<<<dim3(fix_ctas < a.fixup_ctas ? fix_ctas : a.fixup_ctas), dim3(kFixWarps * 32), 0, stream>>>(a, warps_per_row);
-    return cudaGetLastError();
+    return launch_pdl(input_fixup_kernel, dim3(fix_ctas < a.fixup_ctas ? fix_ctas : a.fixup_ctas), dim3(kFixWarps * 32), size_t(0), stream, pdl_enabled(), a, warps_per_row);
   }
   // a CTA per block of 32 frames; short batches also split the nodes so that one wave of CTAs covers the GPU
   const int fblocks = (a.M + kFbFrames - 1) / kFbFrames;
@@ -705,8 +710,7 @@ cudaError_t launch_input_tc(const CUtensorMap &tmap_x, const CUtensorMap &tmap_w
     const char *v = std::getenv("FDNN_FB_DEBUG");
     return v != nullptr ? std::atoi(v) : 0;
   }();
-  input_fixup_block_kernel<<<dim3(fblocks, splits), dim3(kFbThreads), fb_layout(a.I).total, stream>>>(a, words_per_cta, debug);
-  return cudaGetLastError();
+  return launch_pdl(input_fixup_block_kernel, dim3(fblocks, splits), dim3(kFbThreads), size_t(fb_layout(a.I).total), stream, pdl_enabled(), a, words_per_cta, debug);
 }
 
 }  // namespace fdnn
