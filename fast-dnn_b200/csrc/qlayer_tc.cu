@@ -577,7 +577,12 @@ TcPlan qlayer_tc_plan(int M, int N, bool logits, int num_sms, int policy) {
     const bool can_pair = num_sms >= 2;
     if (can_pair && (forced == 64 || forced == 128 || forced == 256)) return TcPlan{forced, 2, false, true};
     const int pair_tiles = ((M + 255) / 256) * ((N + 255) / 256);
-    if (can_pair && forced != 0 && pair_tiles >= num_sms / 2) return TcPlan{256, 2, false, true};
+    static const int logits_min = [] {  // FDNN_PAIR_LOGITS_TILES: from how many pair tiles on the output layer runs on pairs (tuning)
+      const char *v = std::getenv("FDNN_PAIR_LOGITS_TILES");
+      return (v && v[0]) ? std::atoi(v) : 0;
+    }();
+    const int min_tiles = (logits && logits_min > 0) ? logits_min : num_sms / 2;
+    if (can_pair && forced != 0 && pair_tiles >= min_tiles) return TcPlan{256, 2, false, true};
   }
   if (const char *e = std::getenv("FDNN_FORCE_BN")) {  // tuning experiments
     const int bn = std::atoi(e);

@@ -8,6 +8,8 @@ import numpy as np, torch
 from fast_dnn_b200 import quantized_dnn as qd, synth
 B, I, O = 512, 440, 8000
 dnn = qd.QuantizedDnn.load_from_file(synth.network_file("L"), device=0)
+if os.environ.get("POLICY"):
+    dnn.set_tile_policy(os.environ["POLICY"])
 for nctx in [int(x) for x in os.environ.get("SWEEP", "1,2,3,4,6,8").split(",")]:
     pool = 16
     d_in = [torch.from_numpy(synth.make_frames(B, I, seed=100 + i)).cuda() for i in range(pool)]
