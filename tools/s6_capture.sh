@@ -1,5 +1,6 @@
 mkdir -p gpurun_out
-timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 100 --warmup 5 > gpurun_out/s6_b2.json 2> gpurun_out/s6_b2.err; tail -c 300 gpurun_out/s6_b2.err; python -c "
-import json; d=json.loads(open('gpurun_out/s6_b2.json').read().strip().splitlines()[-1]); print(d['n_gpus'], d['value'], d['ms_per_step'], d['e2e']['value'], d['scaling'])"
-timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --impl reference --gpus 2 --steps 2 --warmup 1 2>/dev/null | tail -1 | cut -c1-300
+timeout 400 python -m pytest tests -m gpu -x -q > gpurun_out/s6_tests.log 2>&1; tail -3 gpurun_out/s6_tests.log
+for b in 512 16384; do
+timeout 200 ncu --metrics gpu__time_duration.sum --clock-control none --cache-control none -k regex:input_tc_kernel -c 2 --csv --log-file gpurun_out/s6_tc_$b.csv python tools/profile_step.py --batch $b --steps 2 --warmup 0 > /dev/null 2>&1
+echo "batch $b: $(grep -o 'input_tc_kernel.*' gpurun_out/s6_tc_$b.csv | sed 's/(.*gpu__time_duration.sum//' | tr '\n' ' ')"
+done
