@@ -505,34 +505,22 @@ __global__ void __launch_bounds__(kFbThreads) input_fixup_block_kernel(const Inp
     const int i = n_lo + int(threadIdx.x) + u * kFbThreads;
     wv[u] = i < n_hi ? __ldg(a.unc_t + size_t(fb) * size_t(a.H) + size_t(i)) : 0u;
   }
-  // the block's transformed frames: s_x[f][r][t] = x'[f][4t + r]; eight loads in flight per thread (a CTA has the SM to itself)
+  // the block's transformed frames, eight 16-byte loads per thread, all in flight; they go to shared memory (s_x[f][r][t] =
+  // x'[f][4t + r]) only after the node list has been built, so their latency hides under that work
+  static_assert(kFbFrames * (kInputTcMaxI / 4) <= 8 * kFbThreads, "a block's frames are one round of eight loads per thread");
   const int rows = min(kFbFrames, a.M - f0);
   const float4 *xsrc = reinterpret_cast<const float4 *>(a.xq + size_t(f0) * size_t(I));  // rows are contiguous: [rows][n4] float4
-  for (int base = int(threadIdx.x); base < rows * n4; base += 8 * kFbThreads) {
-    float4 v[8];
+  float4 xv[8];
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      const int idx = base + u * kFbThreads;
-      v[u] = idx < rows * n4 ? __ldg(xsrc + idx) : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-#pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      const int idx = base + u * kFbThreads;
-      if (idx < rows * n4) {
-        const int f = idx / n4, t = idx - f * n4;
-        float *d = s_x + f * L.fstride + t;
-        d[0] = v[u].x;
-        d[L.seg] = v[u].y;
-        d[2 * L.seg] = v[u].z;
-        d[3 * L.seg] = v[u].w;
-      }
-    }
+  for (int u = 0; u < 8; ++u) {
+    const int idx = int(threadIdx.x) + u * kFbThreads;
+    xv[u] = idx < rows * n4 ? __ldg(xsrc + idx) : make_float4(0.f, 0.f, 0.f, 0.f);
   }
   const uint32_t n_bufs = uint32_t(L.n_bufs);  // batch b uses buffer b % n_bufs for the (b / n_bufs)-th time
   const int p_lo = n_lo;
   {
     if (threadIdx.x == 0) *s_count = 0u;
-    __syncthreads();  // barriers initialised, frames stored, counter zero
+    __syncthreads();  // barriers initialised, counter zero
 #pragma unroll
     for (int u = 0; u < kFbPassLoads; ++u) {  // nodes with a non-zero word → list (order irrelevant)
       const int i = int(threadIdx.x) + u * kFbThreads;
@@ -563,6 +551,18 @@ __global__ void __launch_bounds__(kFbThreads) input_fixup_block_kernel(const Inp
       }
       if (lane < kFbSlots) l_incl[entry] = uint16_t(incl);
       if (lane == kFbSlots - 1) s_cst[b + 1] = uint16_t((incl + 7u) / 8u);
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {  // the frames have arrived by now
+      const int idx = int(threadIdx.x) + u * kFbThreads;
+      if (idx < rows * n4) {
+        const int f = idx / n4, t = idx - f * n4;
+        float *d = s_x + f * L.fstride + t;
+        d[0] = xv[u].x;
+        d[L.seg] = xv[u].y;
+        d[2 * L.seg] = xv[u].z;
+        d[3 * L.seg] = xv[u].w;
+      }
     }
     __syncthreads();
     if (warp == 0) {  // chunk counts → running totals (s_cst[b] = chunks before batch b)
