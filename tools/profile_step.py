@@ -17,10 +17,12 @@ ap.add_argument("--shape", default="L")
 ap.add_argument("--batch", type=int, default=512)
 ap.add_argument("--steps", type=int, default=3)
 ap.add_argument("--warmup", type=int, default=2)
+ap.add_argument("--policy", default="latency", help="tile policy: latency (one caller) or throughput (several contexts in flight)")
 args = ap.parse_args()
 
 I, H, nh, O = synth.SHAPES[args.shape]
 dnn = qd.QuantizedDnn.load_from_file(synth.network_file(args.shape), device=0)
+dnn.set_tile_policy(args.policy)
 d_in = torch.from_numpy(synth.make_frames(args.batch, I, seed=7)).cuda()
 d_out = torch.empty(args.batch, O, dtype=torch.float32, device="cuda")
 ctx = dnn.get_new_lazy_context(args.batch)
