@@ -307,7 +307,10 @@ def run_gpu_arm(args):
         del big_in, big_out
 
     # ---- end to end through the public call (fdnn_calculate): pinned HOST buffers, H2D + D2H inside
-    e2e_threads = 3
+    # three callers per GPU overlap copies and compute; with many ranks on one host leave every caller a core of its own
+    # (8 ranks x 3 spinning callers on 16 cores: 2.9 M frames/s at 8 GPUs against 5.0 M at 4)
+    host_cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    e2e_threads = max(1, min(3, host_cores // max(world, 1)))
     e2e_pool = 2
     h_in = [[qd.PinnedArray((BATCH, I_DIM), np.float32) for _ in range(e2e_pool)] for _ in range(e2e_threads)]
     h_out = [[qd.PinnedArray((BATCH, O_DIM), np.float32) for _ in range(e2e_pool)] for _ in range(e2e_threads)]
