@@ -27,10 +27,13 @@
 //                           the two's-complement limbs of negative numbers), and the rest the fp32 roundings of
 //                           bias·100 here and of "+ bias", "· 100" in the reference.  Every constant is rounded up.
 //                           If no half-integer lies within D of z, every value the reference can have produced
-//                           rounds to the same k: the byte is certain.  Otherwise (≈ 4 % of the elements on the
-//                           synthetic network) the element's bit is set in a [frame][node] bitmap.
-//   3. input_fixup_kernel   the flagged elements, with the reference's exact arithmetic (as input_layer.cu: four
-//                           lane sums, FMUL + FADD, never FMA), a warp per frame.
+//                           rounds to the same k: the byte is certain.  Otherwise (≈ 2.6 % of the elements on the
+//                           synthetic network) the element's bit is set in a [frame][node/32] bitmap and in its
+//                           transpose by blocks of 32 frames, [frame/32][node].
+//   3. input_fixup_block_kernel   the flagged elements, with the reference's exact arithmetic (as input_layer.cu: four
+//                           lane sums, FMUL + FADD, never FMA): a CTA per 32 frames × up to 2048 nodes, frames in shared
+//                           memory, the listed nodes' weight rows by bulk copy.  (input_fixup_kernel, a warp per frame
+//                           reading weights through L1, is the earlier version: FDNN_FIXUP=warp.)
 //
 // Rows with non-finite or extreme values and nodes with non-finite weights or bias are left to step 3 entirely,
 // so the result is bit-identical to input_layer.cu for any input.
