@@ -10,6 +10,7 @@
 
 #include <cuda.h>
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 
 #include <algorithm>
 #include <array>
@@ -137,6 +138,17 @@ bool pdl_enabled() {
 }
 }  // namespace fdnn
 
+// Inspection aid (tests/test_gpu_parity.py soak): position-weighted 64-bit checksum of a byte buffer, computed where the
+// bytes are.  Every weight is odd, so a change of any single byte changes the sum; the sum is order-independent (mod 2^64),
+// hence deterministic under atomics.
+__global__ void digest_kernel(const uint8_t *__restrict__ data, size_t n, unsigned long long *out) {
+  unsigned long long acc = 0;
+  for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x)
+    acc += (unsigned long long) (data[i]) * ((i * 0x9E3779B97F4A7C15ull + 0x632BE59BD9B4E019ull) | 1ull);
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) atomicAdd(out, acc);
+}
+
 // ---- handles ----------------------------------------------------------------------------------------
 
 struct fdnn_model {
@@ -157,6 +169,13 @@ struct fdnn_model {
   CUtensorMap w0map;
   bool force_simt = false;
   std::atomic<int> tile_policy{FDNN_POLICY_LATENCY};
+  // Lifetime: the handle holds one reference and every live context one more, so a context may outlive fdnn_free of its
+  // model (the reference's `delete context` never touches the dnn, jni_dnn.cc:119-133); the last release frees the device memory.
+  std::atomic<int> refs{1};
+  // Device group (fdnn_load_devices / FDNN_DEVICES): the primary owns one replica per device, group[0] == the primary
+  // itself; fdnn_calculate shards its frames over them, contexts are handed out round-robin.  Empty for a single device.
+  std::vector<fdnn_model *> group;
+  std::atomic<unsigned> next_ctx{0};
   // Graph capture must not overlap device-wide synchronising calls (cudaFree, blocking copies) made
   // by this library from other threads: both sides take this lock.
   std::mutex cuda_mu;
@@ -179,6 +198,7 @@ struct fdnn_ctx {
   int8_t *d_masks = nullptr;  // [cap][O], allocated on first lazy use
   float *d_row = nullptr;     // [O] scratch for single-row lazy output
   float *d_lazy = nullptr;    // [cap][O] masked softmax rows, allocated on first batched lazy use
+  uint32_t *d_fused = nullptr;  // grid-barrier counters of the fused multi-layer kernel (qlayer_fused.cu)
   // certified tensor-core input layer: transformed frames, their limb planes, row statistics, undecided elements
   float *d_xq = nullptr;
   uint8_t *d_xlimbs = nullptr;
@@ -192,6 +212,14 @@ struct fdnn_ctx {
   CUtensorMap amap[2][3];  // per activation buffer: TMA box of 128 / 64 / 32 rows (cluster 1 / 2 / 4 sharing the tile)
   bool amap_ok = false;
   cudaStream_t stream = nullptr;
+  int policy = FDNN_POLICY_LATENCY;  // tile policy of the model when the context was created (part of every cached launch sequence)
+  // fdnn_calculate on pageable caller memory (the JNI path: jni_dnn.cc:44,54-58 hands us JVM heap copies): page-locked staging
+  // owned by the context, results come down in sub-chunks with one event each so that the copy-out overlaps the transfer
+  float *h_in = nullptr;    // [cap][I]
+  float *h_out = nullptr;   // [cap][O]
+  std::vector<cudaEvent_t> events;  // blocking-sync events: [0] = whole chunk done, [1 + k] = sub-chunk k has landed in h_out
+  int8_t *h_mask = nullptr;  // single-row lazy path: mapped page-locked mask [O] and result row [O]
+  float *h_row = nullptr;
   bool trace = false;
   uint8_t *d_trace = nullptr;  // [n_qlayers][cap][H]
   unsigned long long *d_timeline = nullptr;  // optional [n_qlayers][1024 CTAs][8] phase stamps (profiling aid)
@@ -204,35 +232,59 @@ struct fdnn_ctx {
     float *d_out;
     int m;
     bool softmax;
-    cudaGraphExec_t exec;
+    cudaGraphExec_t exec;  // nullptr: this combination has been seen once and ran un-captured; the next use captures
   };
   std::vector<PassGraph> graphs;
 };
 
 namespace {
 
+void free_model_memory(fdnn_model *m) {
+  DeviceGuard g(m->device);
+  cudaFree(m->d_blob);
+  cudaFree(m->d_w0_limbs);
+  cudaFree(m->d_node_stats);
+  delete m;
+}
+
+void model_release(fdnn_model *m) {
+  if (m && m->refs.fetch_sub(1, std::memory_order_acq_rel) == 1) free_model_memory(m);
+}
+
 void destroy_ctx(fdnn_ctx *c) {
   if (!c) return;
-  std::lock_guard<std::mutex> lk(c->model->cuda_mu);
-  DeviceGuard g(c->model->device);
-  cudaFree(c->d_in);
-  cudaFree(c->d_act[0]);
-  cudaFree(c->d_act[1]);
-  cudaFree(c->d_logits);
-  cudaFree(c->d_masks);
-  cudaFree(c->d_row);
-  cudaFree(c->d_lazy);
-  cudaFree(c->d_trace);
-  cudaFree(c->d_timeline);
-  cudaFree(c->d_xq);
-  cudaFree(c->d_xlimbs);
-  cudaFree(c->d_rowstats);
-  cudaFree(c->d_unc_bits);
-  cudaFree(c->d_unc_t);
-  cudaFree(c->d_unc_count);
-  for (auto &g : c->graphs) cudaGraphExecDestroy(g.exec);
-  if (c->stream) cudaStreamDestroy(c->stream);
-  delete c;
+  fdnn_model *m = c->model;
+  {
+    std::lock_guard<std::mutex> lk(m->cuda_mu);
+    DeviceGuard g(m->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    cudaFree(c->d_in);
+    cudaFree(c->d_act[0]);
+    cudaFree(c->d_act[1]);
+    cudaFree(c->d_logits);
+    cudaFree(c->d_masks);
+    cudaFree(c->d_row);
+    cudaFree(c->d_lazy);
+    cudaFree(c->d_trace);
+    cudaFree(c->d_timeline);
+    cudaFree(c->d_xq);
+    cudaFree(c->d_xlimbs);
+    cudaFree(c->d_rowstats);
+    cudaFree(c->d_unc_bits);
+    cudaFree(c->d_unc_t);
+    cudaFree(c->d_unc_count);
+    cudaFree(c->d_fused);
+    if (c->h_in) cudaFreeHost(c->h_in);
+    if (c->h_out) cudaFreeHost(c->h_out);
+    if (c->h_mask) cudaFreeHost(c->h_mask);
+    if (c->h_row) cudaFreeHost(c->h_row);
+    for (cudaEvent_t e : c->events) cudaEventDestroy(e);
+    for (auto &g2 : c->graphs)
+      if (g2.exec) cudaGraphExecDestroy(g2.exec);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+  }
+  model_release(m);
 }
 
 int create_ctx(fdnn_model *m, int n, fdnn_ctx **out) {
@@ -256,7 +308,9 @@ int create_ctx(fdnn_model *m, int n, fdnn_ctx **out) {
   std::unique_ptr<fdnn_ctx, void (*)(fdnn_ctx *)> c(new fdnn_ctx, destroy_ctx);
   std::unique_lock<std::mutex> lk(m->cuda_mu);
   c->model = m;
+  m->refs.fetch_add(1, std::memory_order_relaxed);
   c->cap = n;
+  c->policy = m->tile_policy.load(std::memory_order_relaxed);
   CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   CUDA_TRY(cudaMalloc(&c->d_in, size_t(n) * I * 4));
   // activations are read by TMA in 128-row boxes; rows past `n` are never stored, but keep the
@@ -388,7 +442,7 @@ int enqueue_until_logits(fdnn_ctx *c, const float *d_in, int m, float *d_logits,
       a.out_u8 = c->d_act[(j + 1) & 1];
     }
     if (mod->tc_ok[size_t(j)] && c->amap_ok) {
-      const TcPlan plan = qlayer_tc_plan(m, ql.nodes, logits, mod->num_sms, mod->tile_policy.load(std::memory_order_relaxed));
+      const TcPlan plan = qlayer_tc_plan(m, ql.nodes, logits, mod->num_sms, c->policy);
       const int which = plan.block_n == 64 ? 0 : (plan.block_n == 128 ? 1 : 2);
       a.fix = fix_of(j, which);  // the risk list grouped by the tile width
       const int act_box = plan.share_a ? (plan.cluster == 4 ? 2 : (plan.cluster == 2 ? 1 : 0)) : 0;
@@ -436,13 +490,40 @@ int run_pass(fdnn_ctx *c, const float *d_in, int m, float *d_out, bool softmax, 
     if (int rc = enqueue_until_logits(c, d_in, m, d_out, stream)) return rc;
     return softmax ? enqueue_softmax(c, d_out, nullptr, m, d_out, stream) : FDNN_OK;
   }
-  for (auto &g : c->graphs)
+  // A launch sequence is captured the SECOND time a (input, output, frames, softmax) combination shows up: callers with
+  // variable-length utterances (every fdnn_calculate with a new frame count) then pay direct launches once instead of a
+  // capture + instantiate per call; steady-state callers replay from their second call on.  LRU over 64 entries.
+  size_t hit = c->graphs.size();
+  for (size_t i = 0; i < c->graphs.size(); ++i) {
+    const auto &g = c->graphs[i];
     if (g.d_in == d_in && g.d_out == d_out && g.m == m && g.softmax == softmax) {
-      CUDA_TRY(cudaGraphLaunch(g.exec, stream));
-      g_launches.fetch_add(kernels, std::memory_order_relaxed);
-      c->last_frames = m;
-      return FDNN_OK;
+      hit = i;
+      break;
     }
+  }
+  auto run_direct = [&]() -> int {
+    if (int rc = enqueue_until_logits(c, d_in, m, d_out, stream)) return rc;
+    return softmax ? enqueue_softmax(c, d_out, nullptr, m, d_out, stream) : FDNN_OK;
+  };
+  if (hit < c->graphs.size() && c->graphs[hit].exec != nullptr) {
+    const fdnn_ctx::PassGraph g = c->graphs[hit];
+    if (hit + 1 != c->graphs.size()) {  // most recently used last
+      c->graphs.erase(c->graphs.begin() + long(hit));
+      c->graphs.push_back(g);
+    }
+    CUDA_TRY(cudaGraphLaunch(g.exec, stream));
+    g_launches.fetch_add(kernels, std::memory_order_relaxed);
+    c->last_frames = m;
+    return FDNN_OK;
+  }
+  if (hit == c->graphs.size()) {  // first sighting: remember it, run un-captured
+    if (c->graphs.size() >= 64) {
+      if (c->graphs.front().exec) cudaGraphExecDestroy(c->graphs.front().exec);
+      c->graphs.erase(c->graphs.begin());
+    }
+    c->graphs.push_back({d_in, d_out, m, softmax, nullptr});
+    return run_direct();
+  }
   // Capture on the context's own stream (thread-local mode: other threads keep using CUDA freely).
   // If the capture is broken by something outside our control (another library synchronising the
   // device from a different thread), this call simply runs un-captured.
@@ -463,17 +544,11 @@ int run_pass(fdnn_ctx *c, const float *d_in, int m, float *d_out, bool softmax, 
     if (rc != FDNN_OK) exec = nullptr;
     cudaGetLastError();
   }
-  if (exec == nullptr) {
-    if (int rc = enqueue_until_logits(c, d_in, m, d_out, stream)) return rc;
-    return softmax ? enqueue_softmax(c, d_out, nullptr, m, d_out, stream) : FDNN_OK;
-  }
-  if (c->graphs.size() >= 64) {
-    cudaGraphExecDestroy(c->graphs.front().exec);
-    c->graphs.erase(c->graphs.begin());
-  }
-  c->graphs.push_back({d_in, d_out, m, softmax, exec});
+  if (exec == nullptr) return run_direct();
+  c->graphs[hit].exec = exec;
   CUDA_TRY(cudaGraphLaunch(exec, stream));
   g_launches.fetch_add(kernels, std::memory_order_relaxed);
+  c->last_frames = m;
   return FDNN_OK;
 }
 
@@ -527,7 +602,7 @@ int upload_model(const uint8_t *host_view, const void *src, bool src_on_device, 
   }
   // Layer 0 for the certified tensor-core path (input_tc.cu): every weight row as a block-fixed-point integer vector
   // (|W_k| ≤ 2²², three 8-bit limbs, K padded with zeros to the plane pitch) plus scale, ‖w‖₂ and Σ|W_k| per node.
-  static const bool allow_input_tc = env_flag("FDNN_INPUT_TC", true);
+  const bool allow_input_tc = env_flag("FDNN_INPUT_TC", true);  // read per load: a test loads the same network both ways
   if (allow_input_tc && !m->force_simt && input_tc_supported(m->hdr.in_dim, m->hdr.hidden)) {
     const int I0 = m->hdr.in_dim, H0 = m->hdr.hidden;
     m->w_plane_rows = round_up(H0, 64);
@@ -573,10 +648,14 @@ int upload_model(const uint8_t *host_view, const void *src, bool src_on_device, 
       s.f = ru((u * std::fabs(double(s.bc)) + 2.1 * u + 1e-9) * up);
       s.pad[0] = s.pad[1] = 0.0f;
     }
-    CUDA_TRY(cudaMalloc(&m->d_w0_limbs, limbs.size()));
-    CUDA_TRY(cudaMemcpy(m->d_w0_limbs, limbs.data(), limbs.size(), cudaMemcpyHostToDevice));
-    CUDA_TRY(cudaMalloc(&m->d_node_stats, stats.size() * sizeof(InputNodeStats)));
-    CUDA_TRY(cudaMemcpy(m->d_node_stats, stats.data(), stats.size() * sizeof(InputNodeStats), cudaMemcpyHostToDevice));
+    cudaError_t ue = cudaMalloc(&m->d_w0_limbs, limbs.size());
+    if (ue == cudaSuccess) ue = cudaMemcpy(m->d_w0_limbs, limbs.data(), limbs.size(), cudaMemcpyHostToDevice);
+    if (ue == cudaSuccess) ue = cudaMalloc(&m->d_node_stats, stats.size() * sizeof(InputNodeStats));
+    if (ue == cudaSuccess) ue = cudaMemcpy(m->d_node_stats, stats.data(), stats.size() * sizeof(InputNodeStats), cudaMemcpyHostToDevice);
+    if (ue != cudaSuccess) {
+      set_error(std::string("layer-0 limb upload: ") + cudaGetErrorString(ue));
+      return fail(FDNN_ECUDA);
+    }
     if (int rc = make_tmap(&m->w0map, m->d_w0_limbs, 3 * m->w_plane_rows, kInputTcPitch, 64)) return fail(rc);
     if (cudaError_t ce = input_tc_configure(); ce != cudaSuccess) {
       set_error(std::string("input_tc_configure: ") + cudaGetErrorString(ce));
@@ -695,10 +774,212 @@ int fdnn_load_blob(const void *blob, size_t size, int device, fdnn_model **out) 
   return upload_model(view, blob, on_device, size, dev, out);
 }
 
+// ---- device groups: one replica per GPU behind ONE handle ----------------------------------------------
+// The host parses and quantizes once, the packed blob goes to the first device, ONE ncclBroadcast (in-process communicator,
+// ncclCommInitAll) delivers it to the others, and every device builds its replica from its copy.  No collective afterwards:
+// fdnn_calculate cuts its frames into one contiguous shard per device.  NCCL is bound at run time (dlopen "libnccl.so.2"),
+// so a single-GPU JVM needs no NCCL installed; a device group without it fails loudly.
+}  // extern "C"
+
+namespace {
+
+struct NcclApi {
+  using Comm = void *;
+  int (*CommInitAll)(Comm *, int, const int *) = nullptr;
+  int (*CommDestroy)(Comm) = nullptr;
+  int (*GroupStart)() = nullptr;
+  int (*GroupEnd)() = nullptr;
+  int (*Broadcast)(const void *, void *, size_t, int, int, Comm, cudaStream_t) = nullptr;
+  const char *(*GetErrorString)(int) = nullptr;
+  bool ok = false;
+};
+
+const NcclApi &nccl_api() {
+  static const NcclApi api = [] {
+    NcclApi a;
+    void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) return a;
+    a.CommInitAll = reinterpret_cast<decltype(a.CommInitAll)>(dlsym(h, "ncclCommInitAll"));
+    a.CommDestroy = reinterpret_cast<decltype(a.CommDestroy)>(dlsym(h, "ncclCommDestroy"));
+    a.GroupStart = reinterpret_cast<decltype(a.GroupStart)>(dlsym(h, "ncclGroupStart"));
+    a.GroupEnd = reinterpret_cast<decltype(a.GroupEnd)>(dlsym(h, "ncclGroupEnd"));
+    a.Broadcast = reinterpret_cast<decltype(a.Broadcast)>(dlsym(h, "ncclBroadcast"));
+    a.GetErrorString = reinterpret_cast<decltype(a.GetErrorString)>(dlsym(h, "ncclGetErrorString"));
+    a.ok = a.CommInitAll && a.CommDestroy && a.GroupStart && a.GroupEnd && a.Broadcast && a.GetErrorString;
+    return a;
+  }();
+  return api;
+}
+
+std::atomic<long long> g_nccl_broadcasts{0};
+
+// blob (host) → one device buffer per device of `devs`; devs[0] gets it over PCIe, the rest by one ncclBroadcast
+int broadcast_blob(const std::vector<uint8_t> &blob, const std::vector<int> &devs, std::vector<uint8_t *> &d_out) {
+  const NcclApi &nccl = nccl_api();
+  if (!nccl.ok) {
+    set_error("a device group needs NCCL (libnccl.so.2 could not be loaded): the weight blob is delivered by one ncclBroadcast");
+    return FDNN_ECUDA;
+  }
+  const int n = int(devs.size());
+  d_out.assign(size_t(n), nullptr);
+  std::vector<cudaStream_t> streams(size_t(n), nullptr);
+  std::vector<NcclApi::Comm> comms(size_t(n), nullptr);
+  int rc = FDNN_OK;
+  auto cuda_ok = [&](cudaError_t e, const char *what) {
+    if (e != cudaSuccess && rc == FDNN_OK) {
+      set_error(std::string(what) + ": " + cudaGetErrorString(e));
+      rc = FDNN_ECUDA;
+    }
+    return e == cudaSuccess;
+  };
+  auto nccl_ok = [&](int e, const char *what) {
+    if (e != 0 && rc == FDNN_OK) {
+      set_error(std::string(what) + ": " + nccl.GetErrorString(e));
+      rc = FDNN_ECUDA;
+    }
+    return e == 0;
+  };
+  int prev = -1;
+  cudaGetDevice(&prev);
+  for (int i = 0; i < n && rc == FDNN_OK; ++i) {
+    cuda_ok(cudaSetDevice(devs[size_t(i)]), "cudaSetDevice");
+    cuda_ok(cudaMalloc(&d_out[size_t(i)], blob.size()), "cudaMalloc(blob)");
+    cuda_ok(cudaStreamCreateWithFlags(&streams[size_t(i)], cudaStreamNonBlocking), "cudaStreamCreate");
+  }
+  if (rc == FDNN_OK) {
+    cuda_ok(cudaSetDevice(devs[0]), "cudaSetDevice");
+    cuda_ok(cudaMemcpyAsync(d_out[0], blob.data(), blob.size(), cudaMemcpyHostToDevice, streams[0]), "blob upload");
+  }
+  if (rc == FDNN_OK && nccl_ok(nccl.CommInitAll(comms.data(), n, devs.data()), "ncclCommInitAll")) {
+    nccl_ok(nccl.GroupStart(), "ncclGroupStart");
+    for (int i = 0; i < n && rc == FDNN_OK; ++i) {
+      cuda_ok(cudaSetDevice(devs[size_t(i)]), "cudaSetDevice");
+      nccl_ok(nccl.Broadcast(d_out[0], d_out[size_t(i)], blob.size(), /*ncclUint8*/ 1, /*root*/ 0, comms[size_t(i)], streams[size_t(i)]),
+              "ncclBroadcast");
+    }
+    nccl_ok(nccl.GroupEnd(), "ncclGroupEnd");
+    if (rc == FDNN_OK) g_nccl_broadcasts.fetch_add(1, std::memory_order_relaxed);
+  }
+  for (int i = 0; i < n; ++i) {
+    if (streams[size_t(i)]) {
+      cudaSetDevice(devs[size_t(i)]);
+      cuda_ok(cudaStreamSynchronize(streams[size_t(i)]), "blob broadcast");
+    }
+  }
+  for (int i = 0; i < n; ++i) {
+    if (comms[size_t(i)]) nccl.CommDestroy(comms[size_t(i)]);
+    if (streams[size_t(i)]) {
+      cudaSetDevice(devs[size_t(i)]);
+      cudaStreamDestroy(streams[size_t(i)]);
+    }
+  }
+  if (rc != FDNN_OK)
+    for (int i = 0; i < n; ++i)
+      if (d_out[size_t(i)]) {
+        cudaSetDevice(devs[size_t(i)]);
+        cudaFree(d_out[size_t(i)]);
+        d_out[size_t(i)] = nullptr;
+      }
+  if (prev >= 0) cudaSetDevice(prev);
+  return rc;
+}
+
+// "all", "0,1,2,3", "4" (a count) → device list; empty = not a group
+std::vector<int> parse_device_list(const char *text) {
+  std::vector<int> devs;
+  if (!text || !text[0]) return devs;
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess) {
+    cudaGetLastError();
+    return devs;
+  }
+  const std::string t(text);
+  if (t == "all" || t == "ALL") {
+    for (int i = 0; i < count; ++i) devs.push_back(i);
+    return devs;
+  }
+  size_t pos = 0;
+  while (pos < t.size()) {
+    size_t end = t.find(',', pos);
+    if (end == std::string::npos) end = t.size();
+    const std::string item = t.substr(pos, end - pos);
+    if (!item.empty()) devs.push_back(std::atoi(item.c_str()));
+    pos = end + 1;
+  }
+  return devs;
+}
+
+void release_group(fdnn_model *model) {
+  // pooled contexts first (each holds a reference on its replica), then the replicas' handle references
+  std::vector<fdnn_model *> members = model->group.empty() ? std::vector<fdnn_model *>{model} : model->group;
+  for (fdnn_model *r : members) {
+    std::vector<fdnn_ctx *> pooled;
+    {
+      std::lock_guard<std::mutex> lk(r->pool_mu);
+      pooled.swap(r->pool);
+    }
+    for (fdnn_ctx *c : pooled) destroy_ctx(c);
+  }
+  for (fdnn_model *r : members)
+    if (r != model) model_release(r);
+  model_release(model);
+}
+
+}  // namespace
+
+extern "C" {
+
+int fdnn_load_devices(const char *path, float cutoff, const int *devices, int n_devices, fdnn_model **out) {
+  if (!out || !devices || n_devices <= 0) {
+    set_error("bad argument to fdnn_load_devices");
+    return FDNN_EINVAL;
+  }
+  std::vector<int> devs;
+  for (int i = 0; i < n_devices; ++i) {
+    int dev = 0;
+    if (int rc = usable_device(devices[i], &dev)) return rc;
+    if (std::find(devs.begin(), devs.end(), dev) != devs.end()) {
+      set_error("device " + std::to_string(dev) + " is listed twice");
+      return FDNN_EINVAL;
+    }
+    devs.push_back(dev);
+  }
+  std::vector<uint8_t> v;
+  if (int rc = pack_model(path, cutoff, v)) return rc;
+  if (devs.size() == 1) return upload_model(v.data(), v.data(), false, v.size(), devs[0], out);
+  std::vector<uint8_t *> d_blobs;
+  if (int rc = broadcast_blob(v, devs, d_blobs)) return rc;
+  std::vector<fdnn_model *> reps;
+  int rc = FDNN_OK;
+  for (size_t i = 0; i < devs.size() && rc == FDNN_OK; ++i) {
+    fdnn_model *r = nullptr;
+    rc = upload_model(v.data(), d_blobs[i], true, v.size(), devs[i], &r);  // index sections from the host copy, weights device → device
+    if (rc == FDNN_OK) reps.push_back(r);
+  }
+  for (size_t i = 0; i < devs.size(); ++i) {
+    DeviceGuard g(devs[i]);
+    cudaFree(d_blobs[i]);
+  }
+  if (rc != FDNN_OK) {
+    for (fdnn_model *r : reps) model_release(r);
+    return rc;
+  }
+  reps[0]->group = reps;
+  *out = reps[0];
+  return FDNN_OK;
+}
+
 int fdnn_load(const char *path, float cutoff, int device, fdnn_model **out) {
   if (!out) {
     set_error("null output pointer");
     return FDNN_EINVAL;
+  }
+  // The JNI surface has no device argument (jni_dnn.cc:7-18): FDNN_DEVICES=all | 0,1,2,3 makes the handle that
+  // Java_suskun_nn_QuantizedDnn_initialize returns a device group.
+  if (device < 0) {
+    const std::vector<int> devs = parse_device_list(std::getenv("FDNN_DEVICES"));
+    if (!devs.empty()) return fdnn_load_devices(path, cutoff, devs.data(), int(devs.size()), out);
   }
   int dev = 0;
   if (int rc = usable_device(device, &dev)) return rc;
@@ -709,14 +990,16 @@ int fdnn_load(const char *path, float cutoff, int device, fdnn_model **out) {
 
 int fdnn_free(fdnn_model *model) {
   if (!model) return FDNN_OK;
-  for (fdnn_ctx *c : model->pool) destroy_ctx(c);
-  DeviceGuard g(model->device);
-  cudaFree(model->d_blob);
-  cudaFree(model->d_w0_limbs);
-  cudaFree(model->d_node_stats);
-  delete model;
+  release_group(model);
   return FDNN_OK;
 }
+
+int fdnn_device_count(const fdnn_model *m) { return m ? (m->group.empty() ? 1 : int(m->group.size())) : FDNN_EINVAL; }
+int fdnn_device_at(const fdnn_model *m, int i) {
+  if (!m || i < 0 || i >= fdnn_device_count(m)) return FDNN_EINVAL;
+  return m->group.empty() ? m->device : m->group[size_t(i)]->device;
+}
+long long fdnn_nccl_broadcast_count(void) { return g_nccl_broadcasts.load(std::memory_order_relaxed); }
 
 int fdnn_input_dim(const fdnn_model *m) { return m ? m->hdr.in_dim : FDNN_EINVAL; }
 int fdnn_output_dim(const fdnn_model *m) { return m ? m->hdr.out_dim : FDNN_EINVAL; }
@@ -728,6 +1011,7 @@ int fdnn_set_tile_policy(fdnn_model *m, int policy) {
     return FDNN_EINVAL;
   }
   m->tile_policy.store(policy, std::memory_order_relaxed);
+  for (fdnn_model *r : m->group) r->tile_policy.store(policy, std::memory_order_relaxed);
   return FDNN_OK;
 }
 int fdnn_layer_count(const fdnn_model *m) { return m ? m->hdr.n_qlayers + 1 : FDNN_EINVAL; }
@@ -786,7 +1070,9 @@ int fdnn_ctx_new(fdnn_model *model, int n, int batch_hint, fdnn_ctx **out) {
     set_error("null argument");
     return FDNN_EINVAL;
   }
-  return create_ctx(model, n, out);
+  // a device group hands its contexts out round-robin: one context lives on one GPU
+  fdnn_model *home = model->group.empty() ? model : model->group[model->next_ctx.fetch_add(1, std::memory_order_relaxed) % model->group.size()];
+  return create_ctx(home, n, out);
 }
 
 int fdnn_ctx_free(fdnn_ctx *ctx) {
@@ -892,11 +1178,17 @@ int fdnn_ctx_lazy(fdnn_ctx *ctx, int idx, const int8_t *mask, float *out) {
   }
   DeviceGuard g(ctx->model->device);
   const int O = ctx->model->hdr.out_dim;
-  if (!ctx->d_masks) CUDA_TRY(cudaMalloc(&ctx->d_masks, size_t(ctx->cap) * size_t(O)));
-  CUDA_TRY(cudaMemcpyAsync(ctx->d_masks, mask, size_t(O), cudaMemcpyHostToDevice, ctx->stream));
-  if (int rc = enqueue_softmax(ctx, ctx->d_logits + size_t(idx) * size_t(O), ctx->d_masks, 1, ctx->d_row, ctx->stream)) return rc;
-  CUDA_TRY(cudaMemcpyAsync(out, ctx->d_row, size_t(O) * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  // One frame per call is a latency path (the Java side calls this once per frame, QuantizedDnn.java:88-93): no copy
+  // engine round trips.  The mask sits in mapped page-locked memory the kernel reads over PCIe, the kernel writes the
+  // row straight into mapped page-locked memory, and the only host↔device handshake is one stream synchronise.
+  if (!ctx->h_mask) {
+    CUDA_TRY(cudaHostAlloc(reinterpret_cast<void **>(&ctx->h_mask), size_t(O), cudaHostAllocMapped));
+    CUDA_TRY(cudaHostAlloc(reinterpret_cast<void **>(&ctx->h_row), size_t(O) * 4, cudaHostAllocMapped));
+  }
+  std::memcpy(ctx->h_mask, mask, size_t(O));
+  if (int rc = enqueue_softmax(ctx, ctx->d_logits + size_t(idx) * size_t(O), ctx->h_mask, 1, ctx->h_row, ctx->stream)) return rc;
   CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  std::memcpy(out, ctx->h_row, size_t(O) * 4);
   return FDNN_OK;
 }
 
@@ -940,6 +1232,38 @@ int fdnn_ctx_hidden(fdnn_ctx *ctx, int layer, int n_frames, uint8_t *out) {
   }
   std::lock_guard<std::mutex> lk(ctx->model->cuda_mu);
   CUDA_TRY(cudaMemcpy(out, src, size_t(n_frames) * size_t(H), cudaMemcpyDeviceToHost));
+  return FDNN_OK;
+}
+
+int fdnn_ctx_hidden_digest(fdnn_ctx *ctx, int layer, int n_frames, unsigned long long *digest) {
+  if (!ctx || !digest) return FDNN_EINVAL;
+  const int nq = ctx->model->hdr.n_qlayers, H = ctx->model->hdr.hidden;
+  if (layer < 0 || layer > nq - 1 || n_frames < 0 || n_frames > ctx->last_frames) {
+    set_error("bad layer or frame count");
+    return FDNN_EINVAL;
+  }
+  const uint8_t *src = nullptr;
+  if (layer == nq - 1)
+    src = ctx->d_act[(nq - 1) & 1];
+  else if (ctx->trace && ctx->d_trace)
+    src = ctx->d_trace + size_t(layer) * size_t(ctx->cap) * size_t(H);
+  else {
+    set_error("only the last hidden layer is retained unless trace mode was enabled before the forward pass");
+    return FDNN_EINVAL;
+  }
+  DeviceGuard g(ctx->model->device);
+  std::lock_guard<std::mutex> lk(ctx->model->cuda_mu);
+  unsigned long long *d_sum = nullptr;
+  CUDA_TRY(cudaDeviceSynchronize());
+  CUDA_TRY(cudaMalloc(&d_sum, sizeof(unsigned long long)));
+  cudaMemset(d_sum, 0, sizeof(unsigned long long));
+  digest_kernel<<<ctx->model->num_sms * 8, 256>>>(src, size_t(n_frames) * size_t(H), d_sum);
+  cudaError_t e = cudaMemcpy(digest, d_sum, sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+  cudaFree(d_sum);
+  if (e != cudaSuccess) {
+    set_error(std::string("hidden digest: ") + cudaGetErrorString(e));
+    return FDNN_ECUDA;
+  }
   return FDNN_OK;
 }
 
@@ -1016,15 +1340,31 @@ int chunk_frames() {
   return v;
 }
 
+constexpr int kSubRows = 128;  // rows per result sub-chunk on the staged (pageable) path: 4 MB of scores at 8000 outputs
+
+// Workspace sizes come in buckets (128 · 2^k frames up to the streaming chunk): callers with variable-length utterances
+// then reuse a handful of pooled contexts instead of allocating one per distinct frame count.
+int bucket_cap(int n) {
+  const int chunk = chunk_frames();
+  if (n >= chunk) return chunk;
+  int c = 128;
+  while (c < n) c *= 2;
+  return std::min(c, chunk);
+}
+
+// smallest pooled context that holds `cap` frames (none larger than 4× what is needed: a 4096-frame workspace should
+// not be tied up by 100-frame calls)
 fdnn_ctx *pool_take(fdnn_model *m, int cap) {
   std::lock_guard<std::mutex> lk(m->pool_mu);
-  for (size_t i = 0; i < m->pool.size(); ++i)
-    if (m->pool[i]->cap == cap) {
-      fdnn_ctx *c = m->pool[i];
-      m->pool.erase(m->pool.begin() + long(i));
-      return c;
-    }
-  return nullptr;
+  size_t best = m->pool.size();
+  for (size_t i = 0; i < m->pool.size(); ++i) {
+    const int c = m->pool[i]->cap;
+    if (c >= cap && c <= 4 * cap && (best == m->pool.size() || c < m->pool[best]->cap)) best = i;
+  }
+  if (best == m->pool.size()) return nullptr;
+  fdnn_ctx *c = m->pool[best];
+  m->pool.erase(m->pool.begin() + long(best));
+  return c;
 }
 
 void pool_give(fdnn_model *m, fdnn_ctx *c) {
@@ -1032,18 +1372,114 @@ void pool_give(fdnn_model *m, fdnn_ctx *c) {
   {
     std::lock_guard<std::mutex> lk(m->pool_mu);
     m->pool.push_back(c);
-    if (m->pool.size() > 8) {
-      evict = m->pool.front();
+    if (m->pool.size() > 16) {
+      evict = m->pool.front();  // least recently returned
       m->pool.erase(m->pool.begin());
     }
   }
-  destroy_ctx(evict);
+  destroy_ctx(evict);  // outside pool_mu; takes cuda_mu for the frees only
 }
 
-}  // namespace
+bool host_pinned(const void *p) {
+  cudaPointerAttributes attr{};
+  const bool pinned = cudaPointerGetAttributes(&attr, p) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+  cudaGetLastError();
+  return pinned;
+}
 
-int fdnn_calculate(fdnn_model *model, const float *in, int n, int dim, int batch_hint, float *out) {
-  (void) batch_hint;
+// FDNN_SYNC=spin: wait for results by spinning on the stream (lowest latency for one caller); default: sleep on a
+// blocking-sync event, so that callers waiting for PCIe do not occupy the host cores other callers need.
+bool sync_by_spinning() {
+  static const bool spin = [] {
+    const char *e = std::getenv("FDNN_SYNC");
+    return e && std::string(e) == "spin";
+  }();
+  return spin;
+}
+
+int ensure_events(fdnn_ctx *x, size_t count) {
+  while (x->events.size() < count) {
+    cudaEvent_t e;
+    CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming | (sync_by_spinning() ? 0 : cudaEventBlockingSync)));
+    x->events.push_back(e);
+  }
+  return FDNN_OK;
+}
+
+// One device's share of a fdnn_calculate call: frames [f0, f0 + n), processed in chunks of at most `cap` on two pooled
+// contexts (two streams: while one chunk computes, the next one's input goes up and the previous result comes down).
+struct Share {
+  fdnn_model *m = nullptr;
+  int f0 = 0, n = 0, cap = 0, n_chunks = 0, n_slots = 0;
+  fdnn_ctx *slot[2] = {nullptr, nullptr};
+  int enqueued = 0, drained = 0;
+};
+
+struct CalcCall {
+  const float *in;
+  bool in_pinned;
+  float *out;        // direct destination (may be null when sink is set)
+  bool out_direct;   // D2H straight into `out` (page-locked caller memory)
+  fdnn_sink_fn sink;
+  void *user;
+  int I, O;
+};
+
+int enqueue_chunk(const CalcCall &call, Share &s, int c) {
+  fdnn_ctx *x = s.slot[c % s.n_slots];
+  const int f = s.f0 + c * s.cap, m = std::min(s.cap, s.n - c * s.cap);
+  const size_t I = size_t(call.I), O = size_t(call.O);
+  CUDA_TRY(cudaSetDevice(s.m->device));
+  const int subs = call.out_direct ? 0 : (m + kSubRows - 1) / kSubRows;
+  if (int rc = ensure_events(x, size_t(1 + subs))) return rc;
+  const float *src = call.in + size_t(f) * I;
+  if (!call.in_pinned) {
+    if (!x->h_in) CUDA_TRY(cudaHostAlloc(reinterpret_cast<void **>(&x->h_in), size_t(x->cap) * I * 4, cudaHostAllocPortable));
+    std::memcpy(x->h_in, src, size_t(m) * I * 4);
+    src = x->h_in;
+  }
+  CUDA_TRY(cudaMemcpyAsync(x->d_in, src, size_t(m) * I * 4, cudaMemcpyHostToDevice, x->stream));
+  if (int rc = run_pass(x, x->d_in, m, x->d_logits, true, x->stream)) return rc;
+  x->have_logits = false;
+  if (call.out_direct) {
+    CUDA_TRY(cudaMemcpyAsync(call.out + size_t(f) * O, x->d_logits, size_t(m) * O * 4, cudaMemcpyDeviceToHost, x->stream));
+  } else {
+    if (!x->h_out) CUDA_TRY(cudaHostAlloc(reinterpret_cast<void **>(&x->h_out), size_t(x->cap) * O * 4, cudaHostAllocPortable));
+    for (int k = 0; k < subs; ++k) {
+      const int r0 = k * kSubRows, rows = std::min(kSubRows, m - r0);
+      CUDA_TRY(cudaMemcpyAsync(x->h_out + size_t(r0) * O, x->d_logits + size_t(r0) * O, size_t(rows) * O * 4, cudaMemcpyDeviceToHost, x->stream));
+      CUDA_TRY(cudaEventRecord(x->events[size_t(1 + k)], x->stream));
+    }
+  }
+  CUDA_TRY(cudaEventRecord(x->events[0], x->stream));
+  return FDNN_OK;
+}
+
+int drain_chunk(const CalcCall &call, Share &s, int c) {
+  fdnn_ctx *x = s.slot[c % s.n_slots];
+  const int f = s.f0 + c * s.cap, m = std::min(s.cap, s.n - c * s.cap);
+  const size_t O = size_t(call.O);
+  CUDA_TRY(cudaSetDevice(s.m->device));
+  if (!call.out_direct) {
+    const int subs = (m + kSubRows - 1) / kSubRows;
+    for (int k = 0; k < subs; ++k) {
+      const int r0 = k * kSubRows, rows = std::min(kSubRows, m - r0);
+      CUDA_TRY(cudaEventSynchronize(x->events[size_t(1 + k)]));
+      if (call.sink) {
+        if (call.sink(call.user, f + r0, rows, x->h_out + size_t(r0) * O) != 0) {
+          set_error("the result sink reported a failure");
+          return FDNN_EINVAL;
+        }
+      } else {
+        std::memcpy(call.out + size_t(f + r0) * O, x->h_out + size_t(r0) * O, size_t(rows) * O * 4);
+      }
+    }
+  }
+  CUDA_TRY(cudaEventSynchronize(x->events[0]));
+  return FDNN_OK;
+}
+
+int calculate_impl(fdnn_model *model, const float *in, int n, int dim, float *out, fdnn_sink_fn sink, void *user) {
   if (!model || n < 0) {
     set_error("bad argument to fdnn_calculate");
     return FDNN_EINVAL;
@@ -1053,7 +1489,7 @@ int fdnn_calculate(fdnn_model *model, const float *in, int n, int dim, int batch
     return FDNN_EINVAL;
   }
   if (n == 0) return FDNN_OK;  // QuantizedDnn.java:154-156
-  if (!in || !out) {
+  if (!in || (!out && !sink)) {
     set_error("null buffer");
     return FDNN_EINVAL;
   }
@@ -1062,49 +1498,89 @@ int fdnn_calculate(fdnn_model *model, const float *in, int n, int dim, int batch
     set_error("cudaSetDevice failed");
     return FDNN_ECUDA;
   }
-  const int I = model->hdr.in_dim, O = model->hdr.out_dim;
-  const int cap = std::min(n, chunk_frames());
-  const int n_chunks = (n + cap - 1) / cap;
-  const int n_slots = n_chunks > 1 ? 2 : 1;
-  fdnn_ctx *slot[2] = {nullptr, nullptr};
+  CalcCall call{};
+  call.in = in;
+  call.in_pinned = host_pinned(in);
+  call.out = out;
+  call.out_direct = sink == nullptr && host_pinned(out);
+  call.sink = sink;
+  call.user = user;
+  call.I = model->hdr.in_dim;
+  call.O = model->hdr.out_dim;
+
+  // one contiguous shard per device of the group (frames are independent: no collective), whole tiles of 128 frames each
+  const int n_dev = model->group.empty() ? 1 : int(model->group.size());
+  const int used = std::max(1, std::min(n_dev, (n + 127) / 128));
+  std::vector<Share> shares{size_t(used)};
   int rc = FDNN_OK;
-  for (int s = 0; s < n_slots && rc == FDNN_OK; ++s) {
-    slot[s] = pool_take(model, cap);
-    if (!slot[s]) rc = create_ctx(model, cap, &slot[s]);
-  }
-  // Two contexts on two streams: while one chunk computes, the other's input goes up and the
-  // previous result comes down.  Softmax runs in place in the context's logits buffer.
-  for (int c = 0; c < n_chunks && rc == FDNN_OK; ++c) {
-    fdnn_ctx *x = slot[c % n_slots];
-    const int f0 = c * cap, m = std::min(cap, n - f0);
-    cudaError_t e = cudaMemcpyAsync(x->d_in, in + size_t(f0) * size_t(I), size_t(m) * size_t(I) * 4, cudaMemcpyHostToDevice, x->stream);
-    if (e == cudaSuccess) {
-      rc = run_pass(x, x->d_in, m, x->d_logits, true, x->stream);
-      x->have_logits = false;
-      if (rc == FDNN_OK)
-        e = cudaMemcpyAsync(out + size_t(f0) * size_t(O), x->d_logits, size_t(m) * size_t(O) * 4, cudaMemcpyDeviceToHost, x->stream);
-    }
-    if (e != cudaSuccess) {
-      set_error(std::string("fdnn_calculate copy: ") + cudaGetErrorString(e));
-      rc = FDNN_ECUDA;
-    }
-  }
-  for (int s = 0; s < n_slots; ++s)
-    if (slot[s]) {
-      cudaError_t e = cudaStreamSynchronize(slot[s]->stream);
-      if (e != cudaSuccess && rc == FDNN_OK) {
-        set_error(std::string("fdnn_calculate: ") + cudaGetErrorString(e));
-        rc = FDNN_ECUDA;
+  {
+    const int units = (n + 127) / 128;
+    int f = 0;
+    for (int d = 0; d < used; ++d) {
+      Share &s = shares[size_t(d)];
+      s.m = model->group.empty() ? model : model->group[size_t(d)];
+      const int u = units / used + (d < units % used ? 1 : 0);
+      s.f0 = f;
+      s.n = std::min(n - f, u * 128);
+      f += s.n;
+      s.cap = bucket_cap(s.n);
+      s.n_chunks = (s.n + s.cap - 1) / s.cap;
+      s.n_slots = s.n_chunks > 1 ? 2 : 1;
+      for (int k = 0; k < s.n_slots && rc == FDNN_OK; ++k) {
+        s.slot[k] = pool_take(s.m, s.cap);
+        if (!s.slot[k]) rc = create_ctx(s.m, s.cap, &s.slot[k]);
       }
     }
-  for (int s = 0; s < n_slots; ++s)
-    if (slot[s]) {
-      if (rc == FDNN_OK)
-        pool_give(model, slot[s]);
-      else
-        destroy_ctx(slot[s]);
+  }
+  // One host thread drives every device: all work is asynchronous, so the calling thread enqueues round-robin and then
+  // collects in the same order; the sink (JNI: SetFloatArrayRegion) is only ever called from the calling thread.
+  int max_chunks = 0;
+  for (const Share &s : shares) max_chunks = std::max(max_chunks, s.n_chunks);
+  for (int c = 0; c < max_chunks + 2 && rc == FDNN_OK; ++c) {
+    for (Share &s : shares) {
+      // a slot is reused by chunk c only after chunk c − 2 has been collected (its staging buffers are free again)
+      if (c >= 2 && c - 2 < s.n_chunks && rc == FDNN_OK) {
+        rc = drain_chunk(call, s, c - 2);
+        s.drained = c - 1;
+      }
+      if (c < s.n_chunks && rc == FDNN_OK) {
+        rc = enqueue_chunk(call, s, c);
+        s.enqueued = c + 1;
+      }
     }
+  }
+  for (Share &s : shares) {
+    if (rc != FDNN_OK)  // let whatever was enqueued finish before the workspaces go away
+      for (int k = 0; k < s.n_slots; ++k)
+        if (s.slot[k]) {
+          cudaSetDevice(s.m->device);
+          cudaStreamSynchronize(s.slot[k]->stream);
+        }
+    for (int k = 0; k < s.n_slots; ++k)
+      if (s.slot[k]) {
+        if (rc == FDNN_OK)
+          pool_give(s.m, s.slot[k]);
+        else
+          destroy_ctx(s.slot[k]);
+      }
+  }
+  if (rc != FDNN_OK) cudaGetLastError();
   return rc;
+}
+
+}  // namespace
+
+int fdnn_calculate(fdnn_model *model, const float *in, int n, int dim, int batch_hint, float *out) {
+  (void) batch_hint;
+  return calculate_impl(model, in, n, dim, out, nullptr, nullptr);
+}
+
+int fdnn_calculate_sink(fdnn_model *model, const float *in, int n, int dim, fdnn_sink_fn sink, void *user) {
+  if (!sink) {
+    set_error("null sink");
+    return FDNN_EINVAL;
+  }
+  return calculate_impl(model, in, n, dim, nullptr, sink, user);
 }
 
 // ---- misc ---------------------------------------------------------------------------------------------

@@ -64,32 +64,50 @@ FDNN_JNIEXPORT jint Java_suskun_nn_QuantizedDnn_outputDimension(JNIEnvPtr, jobje
   return fdnn_output_dim(reinterpret_cast<fdnn_model *>(handle));
 }
 
-// jni_dnn.cc:35-62: the Java array is read, never written back (JNI_ABORT)
+// jni_dnn.cc:35-62: the Java array is read, never written back (JNI_ABORT).  The reference mallocs a result buffer,
+// computes into it and copies it into a new float[]; here the scores go from the library's page-locked transfer buffer
+// straight into the float[] (SetFloatArrayRegion per 128-frame piece, on this thread, while later pieces are still
+// crossing PCIe) — one host copy instead of two, and no pageable-memory staging inside the driver.
+namespace {
+struct JavaSink {
+  JNIEnvPtr env;
+  jfloatArray array;
+  int out_dim;
+};
+int java_sink(void *user, int first_frame, int n_frames, const float *rows) {
+  auto *js = static_cast<JavaSink *>(user);
+  auto set = slot<void (*)(JNIEnvPtr, jfloatArray, jsize, jsize, const jfloat *)>(js->env, kJniSetFloatArrayRegion);
+  set(js->env, js->array, jsize(first_frame) * js->out_dim, jsize(n_frames) * js->out_dim, rows);
+  return 0;
+}
+}  // namespace
+
 FDNN_JNIEXPORT jfloatArray Java_suskun_nn_QuantizedDnn_calculate(JNIEnvPtr env, jobject, jlong handle, jfloatArray input, jint count, jint dim,
                                                                  jint batch) {
   auto get = slot<jfloat *(*) (JNIEnvPtr, jfloatArray, jboolean *)>(env, kJniGetFloatArrayElements);
   auto rel = slot<void (*)(JNIEnvPtr, jfloatArray, jfloat *, jint)>(env, kJniReleaseFloatArrayElements);
+  auto mk = slot<jfloatArray (*)(JNIEnvPtr, jsize)>(env, kJniNewFloatArray);
+  (void) batch;  // the reference's CPU cache-blocking batch size
   fdnn_model *model = reinterpret_cast<fdnn_model *>(handle);
   const int O = fdnn_output_dim(model);
   if (count < 0 || O <= 0) {
     throw_state(env, "bad handle or frame count");
     return nullptr;
   }
-  const size_t len = size_t(count) * size_t(O);
-  float *out = static_cast<float *>(std::malloc(len ? len * sizeof(float) : 1));
-  if (!out) {
-    throw_state(env, "out of host memory");
+  if (double(count) * double(O) > 2147483647.0) {  // a Java array holds at most 2^31 − 1 elements
+    throw_state(env, "result does not fit a Java float[]");
     return nullptr;
   }
+  jfloatArray result = mk(env, jsize(count) * jsize(O));
+  if (!result) return nullptr;  // OutOfMemoryError is already pending
   jfloat *elements = get(env, input, nullptr);
-  int rc = fdnn_calculate(model, elements, count, dim, batch, out);
+  JavaSink sink{env, result, O};
+  const int rc = count == 0 ? FDNN_OK : fdnn_calculate_sink(model, elements, count, dim, java_sink, &sink);
   rel(env, input, elements, JNI_ABORT_MODE);
-  jfloatArray result = nullptr;
-  if (rc == FDNN_OK)
-    result = to_java(env, out, jsize(len));
-  else
+  if (rc != FDNN_OK) {
     throw_state(env, fdnn_last_error());
-  std::free(out);
+    return nullptr;
+  }
   return result;
 }
 

@@ -25,12 +25,15 @@ constexpr int kMaxSmemFloats = 56 * 1024;  // 224 KB of exponentials; wider rows
 
 // e^x.  t = RN(x·log2e_hi) goes to ex2.approx; r = (x·log2e − t) is recovered exactly with one fma
 // plus the low part of log2e, and 2^r ≈ 1 + r·ln2 (|r| < 2^-17).  Overflows to +inf above 88.72 like
-// the reference's expf does (there is no max subtraction, dnn.cc:534-544); NaN stays NaN.
+// the reference's expf does (there is no max subtraction, dnn.cc:534-544), underflows to 0, NaN stays NaN.
 __device__ __forceinline__ float exp_fast(float x) {
   const float t = __fmul_rn(x, 1.4426950216293335f);
   const float r = fmaf(x, 1.9259629911e-8f, fmaf(x, 1.4426950216293335f, -t));
   float p;
   asm("ex2.approx.f32 %0, %1;" : "=f"(p) : "f"(t));
+  // 0 and +inf are final (x = ±inf makes r = inf − inf = NaN, and inf · r is NaN for r ≤ 0): expf(−inf) = 0 keeps a class
+  // that a −inf bias switched off at exactly 0, expf(x > 88.72) = +inf gives the reference's zeros-and-one-NaN row
+  if (p == 0.0f || p == __int_as_float(0x7f800000)) return p;
   return fmaf(p, r * 0.6931471805599453f, p);
 }
 

@@ -39,6 +39,10 @@ SIGNATURES = {
     "fdnn_last_error": (C.c_char_p, []),
     "fdnn_version": (C.c_char_p, []),
     "fdnn_load": (_I, [C.c_char_p, _F, _I, C.POINTER(_P)]),
+    "fdnn_load_devices": (_I, [C.c_char_p, _F, C.POINTER(_I), _I, C.POINTER(_P)]),
+    "fdnn_device_count": (_I, [_P]),
+    "fdnn_device_at": (_I, [_P, _I]),
+    "fdnn_nccl_broadcast_count": (_LL, []),
     "fdnn_pack": (_I, [C.c_char_p, _F, C.POINTER(_P), C.POINTER(_SZ)]),
     "fdnn_blob_free": (None, [_P]),
     "fdnn_load_blob": (_I, [_P, _SZ, _I, C.POINTER(_P)]),
@@ -56,6 +60,7 @@ SIGNATURES = {
     "fdnn_hidden_dim": (_I, [_P]),
     "fdnn_device": (_I, [_P]),
     "fdnn_calculate": (_I, [_P, _P, _I, _I, _I, _P]),
+    "fdnn_calculate_sink": (_I, [_P, _P, _I, _I, _P, _P]),
     "fdnn_ctx_new": (_I, [_P, _I, _I, C.POINTER(_P)]),
     "fdnn_ctx_free": (_I, [_P]),
     "fdnn_ctx_frames": (_I, [_P]),
@@ -71,6 +76,7 @@ SIGNATURES = {
     "fdnn_ctx_input_undecided": (_I, [_P, C.POINTER(C.c_uint)]),
     "fdnn_ctx_set_trace": (_I, [_P, _I]),
     "fdnn_ctx_hidden": (_I, [_P, _I, _I, _P]),
+    "fdnn_ctx_hidden_digest": (_I, [_P, _I, _I, C.POINTER(C.c_ulonglong)]),
     "fdnn_ctx_logits": (_I, [_P, _I, _P]),
     "fdnn_model_qlayer": (_I, [_P, _I, C.POINTER(_I), C.POINTER(_I), C.POINTER(_F), _P, _P]),
     "fdnn_model_fixup_count": (_I, [_P, _I]),
@@ -207,6 +213,18 @@ class QuantizedDnn:
     loadFromFile = load_from_file
 
     @classmethod
+    def load_on_devices(cls, dnn_file, devices, weight_cut_off_value: float = 3.0) -> "QuantizedDnn":
+        """One handle over several GPUs (no counterpart in the reference): one ncclBroadcast of the packed weights at load,
+        calculate() shards its frames over the devices, lazy contexts are handed out round-robin."""
+        devs = (C.c_int * len(devices))(*devices)
+        h = C.c_void_p()
+        _check(lib().fdnn_load_devices(os.fsencode(os.path.abspath(os.fspath(dnn_file))), weight_cut_off_value, devs, len(devices), C.byref(h)))
+        return cls(h.value)
+
+    def devices(self):
+        return [lib().fdnn_device_at(self._h, i) for i in range(lib().fdnn_device_count(self._h))]
+
+    @classmethod
     def load_from_blob(cls, blob, device: int = -1, size: int | None = None) -> "QuantizedDnn":
         """blob: numpy uint8 array (host) or an integer device pointer with `size` (e.g. the NCCL
         receive buffer of the load-time weight broadcast)."""
@@ -239,7 +257,8 @@ class QuantizedDnn:
 
     def set_tile_policy(self, policy: str) -> None:
         """'latency' (default: shortest pass for one caller) or 'throughput' (least SM time per frame, for several contexts in
-        flight on this model); results are identical.  Applies to contexts created afterwards."""
+        flight on this model); results are identical.  A context (get_new_lazy_context, and the workspaces calculate() pools)
+        takes the policy in force when it is created and keeps it."""
         _check(lib().fdnn_set_tile_policy(self._h, {"latency": 0, "throughput": 1}[policy]))
 
     inputDimension, outputDimension, layerCount, layerDimension = input_dimension, output_dimension, layer_count, layer_dimension
@@ -339,6 +358,15 @@ class LazyContext:
         out = np.empty((n, self.dnn.hidden_dimension()), dtype=np.uint8)
         _check(lib().fdnn_ctx_hidden(self._h, layer, n, _ptr(out)))
         return out
+
+    def hidden_digest(self, layer: int | None = None, n_frames: int | None = None) -> int:
+        """64-bit position-weighted checksum of hidden(layer) computed on the device (soak tests)"""
+        n = self.input_vector_count if n_frames is None else n_frames
+        if layer is None:
+            layer = self.dnn.layer_count() - 2
+        d = C.c_ulonglong()
+        _check(lib().fdnn_ctx_hidden_digest(self._h, layer, n, C.byref(d)))
+        return int(d.value)
 
     def logits(self, n_frames: int | None = None) -> np.ndarray:
         n = self.input_vector_count if n_frames is None else n_frames

@@ -49,6 +49,19 @@ const char *fdnn_version(void);
  * (−1 = the calling thread's current device). */
 int fdnn_load(const char *path, float cutoff, int device, fdnn_model **out);
 
+/* Device group behind ONE handle (no counterpart in the reference, which is single-threaded CPU code):
+ * the host parses and quantizes once, the packed blob is uploaded to devices[0] and delivered to the other devices by ONE
+ * in-process ncclBroadcast (libnccl.so.2 is bound at run time; a group without it fails with FDNN_ECUDA), and every device
+ * builds a replica.  fdnn_calculate on the returned handle shards its frames contiguously over the devices (whole tiles of
+ * 128 frames, no per-frame collective); fdnn_ctx_new hands contexts out round-robin, one context lives on one device.
+ * fdnn_load(path, cutoff, -1, …) does the same for the devices named by the environment variable FDNN_DEVICES
+ * ("all" or "0,1,2,3"), which is how the JNI entry point — whose signature has no device argument, jni_dnn.cc:7-18 —
+ * gets more than one GPU. */
+int fdnn_load_devices(const char *path, float cutoff, const int *devices, int n_devices, fdnn_model **out);
+int fdnn_device_count(const fdnn_model *model);      /* 1 unless the handle is a device group */
+int fdnn_device_at(const fdnn_model *model, int i);  /* CUDA ordinal of the i-th device of the group */
+long long fdnn_nccl_broadcast_count(void);           /* ncclBroadcast collectives issued by this library since load */
+
 /* Host-only half of fdnn_load: parse + quantize into one relocatable blob (weights, biases,
  * multipliers, sigmoid LUT, saturation fix-up lists).  In a multi-GPU job rank 0 packs, the blob
  * is broadcast once (NCCL), and every rank calls fdnn_load_blob — SURVEY.md §8e. */
@@ -92,8 +105,8 @@ int fdnn_device(const fdnn_model *model);
  * the CPU cache).  FDNN_POLICY_LATENCY (default): the narrowest tiles that fill the GPU in one wave — shortest time for
  * one caller.  FDNN_POLICY_THROUGHPUT: one step wider tiles, half as many CTAs that each move fewer operand bytes per
  * result — less SM time per frame, for callers that keep several contexts in flight on one model (the pattern of
- * MultiThreadedStressTest.java:48-61).  Results are identical.  Set it before the contexts that should use it exist
- * (a context caches the launch sequence of the first pass of each shape). */
+ * MultiThreadedStressTest.java:48-61).  Results are identical.  A context takes the policy in force when it is CREATED
+ * (fdnn_ctx_new; the workspaces fdnn_calculate pools are contexts too) and keeps it for life. */
 #define FDNN_POLICY_LATENCY 0
 #define FDNN_POLICY_THROUGHPUT 1
 int fdnn_set_tile_policy(fdnn_model *model, int policy);
@@ -106,6 +119,13 @@ int fdnn_set_tile_policy(fdnn_model *model, int policy);
  * reference's CPU cache-blocking batchSize; results do not depend on it and it is ignored.
  * Re-entrant: concurrent calls on one model each use a private workspace. n == 0 is a no-op. */
 int fdnn_calculate(fdnn_model *model, const float *in, int n, int dim, int batch_hint, float *out);
+/* Same computation, results delivered piecewise: `sink` is called on the CALLING thread, in frame order, with
+ * rows [first_frame, first_frame + n_frames) in page-locked memory that is only valid during the call; a non-zero return
+ * aborts.  This is what Java_suskun_nn_QuantizedDnn_calculate uses to move scores from the transfer buffer straight into
+ * the Java array (SetFloatArrayRegion) while the next sub-chunk is still crossing PCIe, instead of the reference's
+ * malloc + copy + copy (jni_dnn.cc:49-58). */
+typedef int (*fdnn_sink_fn)(void *user, int first_frame, int n_frames, const float *rows);
+int fdnn_calculate_sink(fdnn_model *model, const float *in, int n, int dim, fdnn_sink_fn sink, void *user);
 
 /* ---- contexts: lazy output + device-resident pipelines --------------------------------------
  * Java_suskun_nn_QuantizedDnn_getContext (jni_dnn.cc:64-77): workspace for exactly n frames. */
@@ -138,6 +158,9 @@ int fdnn_ctx_lazy_batch_device(fdnn_ctx *ctx, const int8_t *d_masks, int n_frame
  * is retained unless the context was put in trace mode before the forward. */
 int fdnn_ctx_set_trace(fdnn_ctx *ctx, int enable);
 int fdnn_ctx_hidden(fdnn_ctx *ctx, int layer, int n_frames, uint8_t *out);
+/* position-weighted 64-bit checksum of the same bytes, computed on the device (soak tests over more frames than are
+ * worth copying back): equal digests ⇔ equal bytes up to a 2^-64 coincidence; any single-byte change changes it */
+int fdnn_ctx_hidden_digest(fdnn_ctx *ctx, int layer, int n_frames, unsigned long long *digest);
 /* dense output logits (dequantized + bias, before softmax) of the most recent until_output */
 int fdnn_ctx_logits(fdnn_ctx *ctx, int n_frames, float *out);
 /* quantized layer i (0-based among int8 layers): any of the out pointers may be NULL */

@@ -220,8 +220,41 @@ class Ref:
             L.ref_hidden_trace.argtypes = [C.c_void_p, _f32p, C.c_int, C.c_int, _u8p]
             L.ref_time_calculate.argtypes = [C.c_void_p, _f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
             L.ref_time_calculate.restype = C.c_double
+            L.ref_float_load.restype = C.c_void_p
+            L.ref_float_load.argtypes = [C.c_char_p]
+            L.ref_float_free.argtypes = [C.c_void_p]
+            for name in ("ref_float_layer_count",):
+                getattr(L, name).argtypes = [C.c_void_p]
+                getattr(L, name).restype = C.c_int
+            for name in ("ref_float_layer_inputs", "ref_float_layer_nodes"):
+                getattr(L, name).argtypes = [C.c_void_p, C.c_int]
+                getattr(L, name).restype = C.c_int
+            L.ref_float_layer.argtypes = [C.c_void_p, C.c_int, _f32p, _f32p]
+            L.ref_float_shift_scale.argtypes = [C.c_void_p, _f32p, _f32p]
             cls._lib = L
         return cls._lib
+
+    @classmethod
+    def load_float_network(cls, path: str):
+        """dnn.bin through the reference's own fp32 loader (FloatDnn, float_dnn.cc:18-69) →
+        ([(W [nodes][inputs], bias)], shift, scale); layer-0 inputs padded to ×4 as the loader does."""
+        L = cls.lib()
+        if not os.path.exists(path):
+            raise IOError(path)
+        h = L.ref_float_load(os.fsencode(path))
+        try:
+            layers = []
+            for i in range(L.ref_float_layer_count(h)):
+                n, k = L.ref_float_layer_nodes(h, i), L.ref_float_layer_inputs(h, i)
+                w, b = np.zeros((n, k), dtype=np.float32), np.zeros(n, dtype=np.float32)
+                L.ref_float_layer(h, i, w, b)
+                layers.append((w, b))
+            I = layers[0][0].shape[1]
+            shift, scale = np.zeros(I, dtype=np.float32), np.zeros(I, dtype=np.float32)
+            L.ref_float_shift_scale(h, shift, scale)
+            return layers, shift, scale
+        finally:
+            L.ref_float_free(h)
 
     def __init__(self, path: str, cutoff: float = 3.0):
         self.L = self.lib()

@@ -58,6 +58,24 @@ void *ref_load(const char *path, float cutoff) {
 
 void ref_free(void *h) { delete reinterpret_cast<dnn::QuantizedDnn *>(h); }
 
+// The reference's own fp32 loader on its own (float_dnn.cc:18-69): what it reads back from a dnn.bin that OUR
+// aligner / Kaldi importer wrote.
+void *ref_float_load(const char *path) { return new dnn::FloatDnn(std::string(path)); }
+void ref_float_free(void *h) { delete reinterpret_cast<dnn::FloatDnn *>(h); }
+int ref_float_layer_count(void *h) { return (int) reinterpret_cast<dnn::FloatDnn *>(h)->layer_count(); }
+int ref_float_layer_inputs(void *h, int i) { return (int) reinterpret_cast<dnn::FloatDnn *>(h)->layers()[i]->input_dimension(); }
+int ref_float_layer_nodes(void *h, int i) { return (int) reinterpret_cast<dnn::FloatDnn *>(h)->layers()[i]->node_count(); }
+void ref_float_layer(void *h, int i, float *w_out /*[nodes][inputs]*/, float *bias_out) {
+  dnn::FloatLayer *l = reinterpret_cast<dnn::FloatDnn *>(h)->layers()[i];
+  for (size_t n = 0; n < l->node_count(); ++n) std::memcpy(w_out + n * l->input_dimension(), l->weights()[n], l->input_dimension() * sizeof(float));
+  std::memcpy(bias_out, l->bias(), l->node_count() * sizeof(float));
+}
+void ref_float_shift_scale(void *h, float *shift_out, float *scale_out) {
+  auto *f = reinterpret_cast<dnn::FloatDnn *>(h);
+  std::memcpy(shift_out, f->shift(), f->input_dimension() * sizeof(float));
+  std::memcpy(scale_out, f->scale(), f->input_dimension() * sizeof(float));
+}
+
 int ref_input_dim(void *h) { return (int) reinterpret_cast<dnn::QuantizedDnn *>(h)->input_dimension(); }
 int ref_output_dim(void *h) { return (int) reinterpret_cast<dnn::QuantizedDnn *>(h)->output_dimension(); }
 // number of int8 layers (file layers − 1)

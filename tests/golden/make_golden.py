@@ -58,6 +58,33 @@ def main():
         np.savez_compressed(os.path.join(HERE, f"{name}.npz"), **out)
         print(name, {k: v.shape for k, v in out.items()})
     np.save(os.path.join(HERE, "sigmoid_lut.npy"), oracle_py.Ref.sigmoid_lut())
+    make_cfg0()
+
+
+def make_cfg0():
+    """BASELINE configs[0]: the reference's shipped FEATURE files (data/8khz.aligned.bin rows 0-99, data/16khz.bin; both
+    432-dim, real speech features, range ≈ [−73, 126] with three zero pad columns) through the synthetic 432-input network P
+    on the unmodified reference.  The frames themselves are stored (they cannot be regenerated on the GPU box, where
+    /root/reference does not exist) together with the reference's bytes for them."""
+    from fast_dnn_b200 import formats
+    ref = oracle_py.Ref(synth.network_file("P"))
+    out = {}
+    for key, name, rows in (("khz8", "8khz.aligned.bin", 100), ("khz16", "16khz.bin", 100)):
+        x = formats.read_feature_bin(os.path.join("/root/reference/data", name))[:rows]
+        trace = ref.hidden_trace(x)
+        ctx = ref.lazy_context(rows)
+        ctx.until_output(x)
+        lin = ctx.output_linear()
+        ctx.close()
+        sm = ref.calculate(x)
+        out[key] = x
+        out[key + "_hidden_first"] = trace[0]
+        out[key + "_hidden_last"] = trace[-1]
+        out[key + "_argmax"] = sm.argmax(axis=1).astype(np.int32)
+        out[key + "_softmax_rows"] = sm[::10]            # every tenth row in full
+        out[key + "_linear_rows"] = lin[::10]            # pre-bias dequantized output-layer sums of the same rows
+    np.savez_compressed(os.path.join(HERE, "cfg0.npz"), **out)
+    print("cfg0", {k: v.shape for k, v in out.items()})
 
 
 if __name__ == "__main__":

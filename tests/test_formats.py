@@ -136,3 +136,63 @@ def test_kaldi_nnet1_text_importer(tmp_path, with_splice):
     assert qd.lib().fdnn_import_kaldi_nnet1(b"/nonexistent/x", trans.encode(), got.encode()) == qd.FDNN_EIO
     open(nnet, "w").write("<Nnet>\n</Nnet>\n")
     assert qd.lib().fdnn_import_kaldi_nnet1(nnet.encode(), trans.encode(), got.encode()) == qd.FDNN_EFORMAT
+
+
+needs_ref = pytest.mark.skipif(not (os.path.isdir(REFERENCE_ROOT)), reason="needs the compiled reference (/root/reference)")
+
+
+def _assert_same_network(got, want):
+    (gl, gsh, gsc), (wl, wsh, wsc) = got, want
+    assert [w.shape for w, _ in gl] == [w.shape for w, _ in wl]
+    for (gw, gb), (ww, wb) in zip(gl, wl):
+        assert np.array_equal(gw.view(np.uint32), ww.view(np.uint32)) and np.array_equal(gb.view(np.uint32), wb.view(np.uint32))
+    assert np.array_equal(gsh.view(np.uint32), wsh.view(np.uint32)) and np.array_equal(gsc.view(np.uint32), wsc.view(np.uint32))
+
+
+@needs_ref
+def test_aligned_file_read_back_by_the_reference_loader(tmp_path):
+    """SURVEY.md §8f row 1, pinned on the reference side: what fdnn_align_dnn_bin writes is read back by the reference's own
+    FloatDnn (float_dnn.cc:18-69) with the dimensions, every weight and bias, shift and scale FeedForwardNetwork.align
+    (FeedForwardNetwork.java:50-58,264-281) prescribes, and the compiled reference then computes on it what the port computes."""
+    layers, shift, scale = synth.make_network((10, 40, 3, 7), seed=5)
+    raw, aligned = str(tmp_path / "raw.bin"), str(tmp_path / "aligned.bin")
+    formats.write_dnn_bin(raw, layers, shift, scale)
+    qd.align_dnn_bin(raw, aligned, 4, 16)
+    got = oracle_py.Ref.load_float_network(aligned)
+    want = formats.align_network(layers, shift, scale, 4, 16)
+    _assert_same_network(got, want)
+    assert [w.shape for w, _ in got[0]] == [(48, 12), (48, 48), (48, 48), (7, 48)]
+    # padded rows/columns and biases are exact zeros; the real block is the original
+    assert np.array_equal(got[0][0][0][:40, :10], layers[0][0]) and not got[0][0][0][40:].any() and not got[0][1][0][:, 40:].any()
+    ref, port = oracle_py.Ref(aligned), oracle_py.Port(aligned)
+    frames = synth.make_frames(23, 12, seed=3)
+    frames[:, 10:] = 0
+    assert np.array_equal(ref.calculate(frames, batch=10).view(np.uint32), port.calculate(frames).view(np.uint32))
+    assert np.array_equal(ref.hidden_trace(frames), port.hidden_trace(frames))
+    # an already aligned network passes through unchanged (idempotence)
+    again = str(tmp_path / "again.bin")
+    qd.align_dnn_bin(aligned, again, 4, 16)
+    assert open(again, "rb").read() == open(aligned, "rb").read()
+
+
+@needs_ref
+@pytest.mark.parametrize("with_splice", [True, False])
+def test_kaldi_import_read_back_by_the_reference_loader(tmp_path, with_splice):
+    """SURVEY.md §8f row 3, pinned on the reference side: Kaldi nnet1 text → fdnn_import_kaldi_nnet1 → fdnn_align_dnn_bin →
+    the reference's FloatDnn returns the numbers that were in the text (float32(repr) is exact), and the compiled reference's
+    forward on the imported file equals the port's."""
+    layers, shift, scale = synth.make_network((22, 40, 3, 7), seed=9)
+    nnet, trans, imported, aligned = (str(tmp_path / n) for n in ("final.nnet.txt", "final.feature_transform", "imported.bin", "aligned.bin"))
+    open(nnet, "w").write(_kaldi_text(layers))
+    open(trans, "w").write(_transform_text(shift, scale, with_splice))
+    qd.import_kaldi_nnet1(nnet, trans, imported)
+    # the unaligned import, read by the reference loader: layer-0 inputs padded to ×4 (22 → 24) by the loader itself
+    got = oracle_py.Ref.load_float_network(imported)
+    want = formats.align_network(layers, shift, scale, 4, 1)
+    _assert_same_network(got, want)
+    qd.align_dnn_bin(imported, aligned, 4, 16)
+    _assert_same_network(oracle_py.Ref.load_float_network(aligned), formats.align_network(layers, shift, scale, 4, 16))
+    ref, port = oracle_py.Ref(aligned), oracle_py.Port(aligned)
+    frames = synth.make_frames(17, 24, seed=4)
+    frames[:, 22:] = 0
+    assert np.array_equal(ref.calculate(frames, batch=10).view(np.uint32), port.calculate(frames).view(np.uint32))

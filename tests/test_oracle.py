@@ -149,3 +149,18 @@ def test_config0_shipped_features_through_synthetic_network(net_file):
     assert np.array_equal(port.calculate(x).view(np.uint32), ref.calculate(x, batch=10).view(np.uint32))
     short = formats.read_feature_bin(os.path.join(REFERENCE_ROOT, "data", "16khz.bin"))
     assert short.shape == (100, 432)  # the file holds a 101st row that the header does not count
+
+
+@pytest.mark.parametrize("key", ["khz8", "khz16"])
+def test_config0_golden_real_features(key, net_file):
+    """BASELINE configs[0] without /root/reference: the committed shipped-feature rows and the bytes the unmodified
+    reference produced for them (tests/golden/cfg0.npz, make_golden.py) against the port"""
+    g = np.load(os.path.join(GOLDEN, "cfg0.npz"))
+    x = g[key]
+    port = oracle_py.Port(net_file("P"))
+    trace = port.hidden_trace(x)
+    assert np.array_equal(trace[0], g[key + "_hidden_first"]) and np.array_equal(trace[-1], g[key + "_hidden_last"])
+    assert np.array_equal(port.output_linear(trace[-1])[::10].view(np.uint32), g[key + "_linear_rows"].view(np.uint32))
+    sm = port.calculate(x)
+    assert np.array_equal(sm[::10].view(np.uint32), g[key + "_softmax_rows"].view(np.uint32))
+    assert np.array_equal(sm.argmax(axis=1), g[key + "_argmax"])
