@@ -15,9 +15,11 @@
 #include <algorithm>
 #include <array>
 #include <atomic>
+#include <chrono>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <ctime>
 #include <functional>
 #include <memory>
 #include <mutex>
@@ -217,7 +219,7 @@ struct fdnn_ctx {
   // owned by the context, results come down in sub-chunks with one event each so that the copy-out overlaps the transfer
   float *h_in = nullptr;    // [cap][I]
   float *h_out = nullptr;   // [cap][O]
-  std::vector<cudaEvent_t> events;  // blocking-sync events: [0] = whole chunk done, [1 + k] = sub-chunk k has landed in h_out
+  std::vector<cudaEvent_t> events;  // polled events (wait_event): [0] = whole chunk done, [1 + k] = sub-chunk k has landed in h_out
   int8_t *h_mask = nullptr;  // single-row lazy path: mapped page-locked mask [O] and result row [O]
   float *h_row = nullptr;
   bool trace = false;
@@ -233,6 +235,7 @@ struct fdnn_ctx {
     int m;
     bool softmax;
     cudaGraphExec_t exec;  // nullptr: this combination has been seen once and ran un-captured; the next use captures
+    int kernels;           // kernel launches one replay stands for
   };
   std::vector<PassGraph> graphs;
 };
@@ -322,6 +325,8 @@ int create_ctx(fdnn_model *m, int n, fdnn_ctx **out) {
   CUDA_TRY(cudaMemsetAsync(c->d_act[1], 0, act_bytes, c->stream));
   CUDA_TRY(cudaMalloc(&c->d_logits, size_t(n) * O * 4));
   CUDA_TRY(cudaMalloc(&c->d_row, size_t(O) * 4));
+  CUDA_TRY(cudaMalloc(&c->d_fused, kFusedSyncWords * sizeof(uint32_t)));
+  CUDA_TRY(cudaMemsetAsync(c->d_fused, 0, kFusedSyncWords * sizeof(uint32_t), c->stream));
   if (H % 128 == 0 && !m->force_simt) {
     for (int b = 0; b < 2; ++b)
       for (int v = 0; v < 3; ++v)
@@ -349,8 +354,11 @@ int create_ctx(fdnn_model *m, int n, fdnn_ctx **out) {
 
 // Enqueue one forward pass over frames [0, m) of `d_in` on `stream`.  Logits (lin + bias of the
 // output layer) go to `d_logits` with row pitch O.
+// `want_softmax`: the caller will normalise d_logits in place right after; when the fused kernel takes the pass it does that
+// itself and sets *softmax_done.
 int enqueue_until_logits(fdnn_ctx *c, const float *d_in, int m, float *d_logits, cudaStream_t stream,
-                         const std::function<void(int)> &after_stage = nullptr) {
+                         const std::function<void(int)> &after_stage = nullptr, bool want_softmax = false, bool *softmax_done = nullptr,
+                         bool allow_fused = true) {
   fdnn_model *mod = c->model;
   const BlobHeader &h = mod->hdr;
   const int nq = h.n_qlayers;
@@ -408,6 +416,66 @@ int enqueue_until_logits(fdnn_ctx *c, const float *d_in, int m, float *d_logits,
   if (after_stage) after_stage(0);
   const size_t act_bytes = size_t(m) * size_t(h.hidden);
   if (c->trace) CUDA_TRY(cudaMemcpyAsync(c->d_trace, c->d_act[0], act_bytes, cudaMemcpyDeviceToDevice, stream));
+
+  // One persistent kernel for all int8 layers (+ softmax) when the batch is a single wave of tiles (qlayer_fused.cu)
+  if (allow_fused && c->amap_ok && !c->trace && nq >= 2 && nq <= kFusedMaxLayers &&
+      std::all_of(mod->tc_ok.begin(), mod->tc_ok.end(), [](bool b) { return b; })) {
+    int grid = 0;
+    const int bnh = qlayer_fused_plan(m, h.hidden, h.out_dim, mod->num_sms, c->policy, &grid);
+    if (bnh != 0) {
+      FusedArgs fa{};
+      fa.act[0] = c->amap[0][0];
+      fa.act[1] = c->amap[1][0];
+      uint32_t done = 0, tiles_so_far = 0;
+      for (int j = 0; j < nq; ++j) {
+        const BlobQLayer &ql = mod->q[size_t(j)];
+        const bool logits = j == nq - 1;
+        const int bn = logits ? 256 : bnh;
+        const int variant = bn == 64 ? 0 : (bn == 128 ? 1 : 2);
+        fa.w[j] = mod->wmaps[size_t(j)][size_t(variant)];
+        FusedLayer &L = fa.layer[j];
+        L.bias = mod->at<float>(ql.off_bias);
+        L.fix_ptr = mod->at<uint32_t>(ql.off_fix_ptr[variant]);
+        L.fix_ent = mod->at<FixEntry>(ql.off_fix_ent[variant]);
+        L.coeff = ql.coeff;
+        L.rcp = ql.rcp_coeff;
+        L.fast_div = int(ql.fast_div);
+        L.fast_tail = mod->fast_tail[size_t(j)];
+        L.N = ql.nodes;
+        L.K = ql.inputs;
+        L.need = done;
+        L.n_blocks = uint32_t((ql.nodes + bn - 1) / bn);
+        L.tile_begin = tiles_so_far;
+        tiles_so_far += L.n_blocks * uint32_t((m + 127) / 128);
+        done += L.n_blocks;
+      }
+      fa.n_layers = nq;
+      fa.M = m;
+      fa.act_buf[0] = c->d_act[0];
+      fa.act_buf[1] = c->d_act[1];
+      fa.out = d_logits;
+      fa.out_ld = h.out_dim;
+      fa.do_softmax = (want_softmax && h.out_dim <= qlayer_fused_max_softmax_width() && qlayer_fused_softmax_pays(m, grid)) ? 1 : 0;
+      fa.lut = mod->at<uint8_t>(h.off_lut);
+      fa.one = 1.0f;
+      fa.neg_zero = -0.0f;
+      fa.sync = c->d_fused;
+      fa.tiles_per_row_block = done;
+      fa.total_tiles = tiles_so_far;
+      {
+        const char *e = std::getenv("FDNN_FUSED_DEBUG");
+        fa.debug_flags = e ? std::atoi(e) : 0;
+      }
+      fa.timeline = c->d_timeline;
+      CUDA_TRY(launch_qlayer_fused(fa, bnh, grid, stream));
+      g_launches.fetch_add(1, std::memory_order_relaxed);
+      if (after_stage)
+        for (int j = 0; j < nq; ++j) after_stage(j + 1);
+      if (softmax_done) *softmax_done = fa.do_softmax != 0;
+      c->last_frames = m;
+      return FDNN_OK;
+    }
+  }
 
   for (int j = 0; j < nq; ++j) {
     const BlobQLayer &ql = mod->q[size_t(j)];
@@ -483,13 +551,15 @@ int enqueue_softmax(fdnn_ctx *c, const float *d_logits, const int8_t *d_masks, i
 
 // One whole pass (input layer … output layer [→ softmax in place]) on `stream`, replayed from a
 // cached CUDA graph when possible.
+int enqueue_pass(fdnn_ctx *c, const float *d_in, int m, float *d_out, bool softmax, cudaStream_t stream) {
+  bool done = false;
+  if (int rc = enqueue_until_logits(c, d_in, m, d_out, stream, nullptr, softmax, &done)) return rc;
+  return (softmax && !done) ? enqueue_softmax(c, d_out, nullptr, m, d_out, stream) : FDNN_OK;
+}
+
 int run_pass(fdnn_ctx *c, const float *d_in, int m, float *d_out, bool softmax, cudaStream_t stream) {
   static const bool use_graphs = env_flag("FDNN_GRAPHS", true);
-  const int kernels = c->model->hdr.n_qlayers + (c->input_tc ? 3 : 1) + (softmax ? 1 : 0);
-  if (!use_graphs || c->trace || c->d_timeline != nullptr || m <= 0) {
-    if (int rc = enqueue_until_logits(c, d_in, m, d_out, stream)) return rc;
-    return softmax ? enqueue_softmax(c, d_out, nullptr, m, d_out, stream) : FDNN_OK;
-  }
+  if (!use_graphs || c->trace || c->d_timeline != nullptr || m <= 0) return enqueue_pass(c, d_in, m, d_out, softmax, stream);
   // A launch sequence is captured the SECOND time a (input, output, frames, softmax) combination shows up: callers with
   // variable-length utterances (every fdnn_calculate with a new frame count) then pay direct launches once instead of a
   // capture + instantiate per call; steady-state callers replay from their second call on.  LRU over 64 entries.
@@ -501,10 +571,6 @@ int run_pass(fdnn_ctx *c, const float *d_in, int m, float *d_out, bool softmax, 
       break;
     }
   }
-  auto run_direct = [&]() -> int {
-    if (int rc = enqueue_until_logits(c, d_in, m, d_out, stream)) return rc;
-    return softmax ? enqueue_softmax(c, d_out, nullptr, m, d_out, stream) : FDNN_OK;
-  };
   if (hit < c->graphs.size() && c->graphs[hit].exec != nullptr) {
     const fdnn_ctx::PassGraph g = c->graphs[hit];
     if (hit + 1 != c->graphs.size()) {  // most recently used last
@@ -512,7 +578,7 @@ int run_pass(fdnn_ctx *c, const float *d_in, int m, float *d_out, bool softmax, 
       c->graphs.push_back(g);
     }
     CUDA_TRY(cudaGraphLaunch(g.exec, stream));
-    g_launches.fetch_add(kernels, std::memory_order_relaxed);
+    g_launches.fetch_add(g.kernels, std::memory_order_relaxed);
     c->last_frames = m;
     return FDNN_OK;
   }
@@ -521,31 +587,33 @@ int run_pass(fdnn_ctx *c, const float *d_in, int m, float *d_out, bool softmax, 
       if (c->graphs.front().exec) cudaGraphExecDestroy(c->graphs.front().exec);
       c->graphs.erase(c->graphs.begin());
     }
-    c->graphs.push_back({d_in, d_out, m, softmax, nullptr});
-    return run_direct();
+    c->graphs.push_back({d_in, d_out, m, softmax, nullptr, 0});
+    return enqueue_pass(c, d_in, m, d_out, softmax, stream);
   }
   // Capture on the context's own stream (thread-local mode: other threads keep using CUDA freely).
   // If the capture is broken by something outside our control (another library synchronising the
   // device from a different thread), this call simply runs un-captured.
-  const long long before = g_launches.load(std::memory_order_relaxed);
   cudaGraphExec_t exec = nullptr;
+  long long kernels = 0;
   {
     std::lock_guard<std::mutex> lk(c->model->cuda_mu);
+    const long long before = g_launches.load(std::memory_order_relaxed);
     cudaGraph_t graph = nullptr;
     int rc = FDNN_ECUDA;
     if (cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
-      rc = enqueue_until_logits(c, d_in, m, d_out, c->stream);
-      if (rc == FDNN_OK && softmax) rc = enqueue_softmax(c, d_out, nullptr, m, d_out, c->stream);
+      rc = enqueue_pass(c, d_in, m, d_out, softmax, c->stream);
       if (cudaStreamEndCapture(c->stream, &graph) != cudaSuccess) rc = FDNN_ECUDA;
     }
-    g_launches.store(before, std::memory_order_relaxed);  // capturing is not launching
+    // capturing is not launching (other threads' launches during the capture are taken off the tally too: it is a statistic)
+    kernels = g_launches.exchange(before, std::memory_order_relaxed) - before;
     if (rc == FDNN_OK && graph != nullptr && cudaGraphInstantiate(&exec, graph, 0) != cudaSuccess) exec = nullptr;
     if (graph) cudaGraphDestroy(graph);
     if (rc != FDNN_OK) exec = nullptr;
     cudaGetLastError();
   }
-  if (exec == nullptr) return run_direct();
+  if (exec == nullptr) return enqueue_pass(c, d_in, m, d_out, softmax, stream);
   c->graphs[hit].exec = exec;
+  c->graphs[hit].kernels = int(kernels);
   CUDA_TRY(cudaGraphLaunch(exec, stream));
   g_launches.fetch_add(kernels, std::memory_order_relaxed);
   c->last_frames = m;
@@ -594,6 +662,10 @@ int upload_model(const uint8_t *host_view, const void *src, bool src_on_device, 
   }
   if (cudaError_t ce = qlayer_pair_configure(); ce != cudaSuccess) {
     set_error(std::string("qlayer_pair_configure: ") + cudaGetErrorString(ce));
+    return fail(FDNN_ECUDA);
+  }
+  if (cudaError_t ce = qlayer_fused_configure(); ce != cudaSuccess) {
+    set_error(std::string("qlayer_fused_configure: ") + cudaGetErrorString(ce));
     return fail(FDNN_ECUDA);
   }
   if (cudaError_t ce = softmax_configure(); ce != cudaSuccess) {
@@ -1308,7 +1380,8 @@ int fdnn_ctx_profile_stages(fdnn_ctx *ctx, const float *d_in, int n_frames, floa
   int rc = FDNN_OK;
   for (int it = 0; it < iters && rc == FDNN_OK; ++it) {
     cudaEventRecord(ev[0], ctx->stream);
-    rc = enqueue_until_logits(ctx, d_in, n_frames, d_out, ctx->stream, [&](int stage) { cudaEventRecord(ev[size_t(stage) + 1], ctx->stream); });
+    rc = enqueue_until_logits(ctx, d_in, n_frames, d_out, ctx->stream, [&](int stage) { cudaEventRecord(ev[size_t(stage) + 1], ctx->stream); },
+                              false, nullptr, /*allow_fused=*/false);
     if (rc == FDNN_OK) rc = enqueue_softmax(ctx, d_out, nullptr, n_frames, d_out, ctx->stream);
     cudaEventRecord(ev[size_t(stages)], ctx->stream);
     if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
@@ -1324,6 +1397,54 @@ int fdnn_ctx_profile_stages(fdnn_ctx *ctx, const float *d_in, int n_frames, floa
   ctx->have_logits = false;
   for (auto &e : ev) cudaEventDestroy(e);
   for (int s = 0; s < stages; ++s) ms[s] = float(total[size_t(s)] / iters);
+  return rc;
+}
+
+// Bench/profiling aid: the pass as it normally runs (fused kernel where it applies), `iters` times on the context's stream
+// with CUDA events after the input layer and at the end.  ms[0] = fp32 input layer, ms[1] = everything after it (the fused
+// int8 stack + softmax: ONE kernel when *fused = 1); averages in milliseconds.
+int fdnn_ctx_profile_pass(fdnn_ctx *ctx, const float *d_in, int n_frames, float *d_out, int iters, float *ms, int *fused) {
+  if (!ctx || !d_in || !d_out || !ms || iters <= 0 || n_frames <= 0 || n_frames > ctx->cap) {
+    set_error("bad argument to fdnn_ctx_profile_pass");
+    return FDNN_EINVAL;
+  }
+  DeviceGuard g(ctx->model->device);
+  cudaEvent_t ev[3];
+  for (auto &e : ev) CUDA_TRY(cudaEventCreate(&e));
+  double total[2] = {0.0, 0.0};
+  int rc = FDNN_OK;
+  bool took_fused = false;
+  for (int it = 0; it < iters && rc == FDNN_OK; ++it) {
+    const long long before = g_launches.load(std::memory_order_relaxed);
+    long long after_input = before;
+    bool done = false;
+    cudaEventRecord(ev[0], ctx->stream);
+    rc = enqueue_until_logits(ctx, d_in, n_frames, d_out, ctx->stream,
+                              [&](int stage) {
+                                if (stage == 0) {
+                                  cudaEventRecord(ev[1], ctx->stream);
+                                  after_input = g_launches.load(std::memory_order_relaxed);
+                                }
+                              },
+                              true, &done);
+    if (rc == FDNN_OK && !done) rc = enqueue_softmax(ctx, d_out, nullptr, n_frames, d_out, ctx->stream);
+    cudaEventRecord(ev[2], ctx->stream);
+    if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
+      set_error("profile_pass: stream synchronize failed");
+      rc = FDNN_ECUDA;
+    }
+    took_fused = g_launches.load(std::memory_order_relaxed) - after_input == 1;
+    for (int s2 = 0; s2 < 2 && rc == FDNN_OK; ++s2) {
+      float t = 0;
+      cudaEventElapsedTime(&t, ev[s2], ev[s2 + 1]);
+      total[s2] += t;
+    }
+  }
+  ctx->have_logits = false;
+  for (auto &e : ev) cudaEventDestroy(e);
+  ms[0] = float(total[0] / iters);
+  ms[1] = float(total[1] / iters);
+  if (fused) *fused = took_fused ? 1 : 0;
   return rc;
 }
 
@@ -1387,8 +1508,11 @@ bool host_pinned(const void *p) {
   return pinned;
 }
 
-// FDNN_SYNC=spin: wait for results by spinning on the stream (lowest latency for one caller); default: sleep on a
-// blocking-sync event, so that callers waiting for PCIe do not occupy the host cores other callers need.
+// How a host thread waits for its results.  Spinning (cudaStreamSynchronize's default) keeps a core busy per caller — with
+// several callers per GPU and eight GPUs that starves the callers that have work to do; the driver's blocking sync sleeps on
+// an interrupt, which on virtualised hosts wakes up hundreds of microseconds late (measured here: +0.5 ms per call).
+// So: poll the event, yielding the core between polls with a short sleep once the wait has lasted longer than a kernel
+// launch.  FDNN_SYNC=spin polls without sleeping (lowest latency for one caller on an idle host).
 bool sync_by_spinning() {
   static const bool spin = [] {
     const char *e = std::getenv("FDNN_SYNC");
@@ -1397,10 +1521,23 @@ bool sync_by_spinning() {
   return spin;
 }
 
+cudaError_t wait_event(cudaEvent_t ev) {
+  const bool spin = sync_by_spinning();
+  const auto t0 = std::chrono::steady_clock::now();
+  for (;;) {
+    const cudaError_t e = cudaEventQuery(ev);
+    if (e != cudaErrorNotReady) return e;
+    if (!spin && std::chrono::steady_clock::now() - t0 > std::chrono::microseconds(20)) {
+      timespec ts{0, 25000};  // 25 us; the kernel's timer slack makes it ≈ 80 us
+      nanosleep(&ts, nullptr);
+    }
+  }
+}
+
 int ensure_events(fdnn_ctx *x, size_t count) {
   while (x->events.size() < count) {
     cudaEvent_t e;
-    CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming | (sync_by_spinning() ? 0 : cudaEventBlockingSync)));
+    CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     x->events.push_back(e);
   }
   return FDNN_OK;
@@ -1464,7 +1601,7 @@ int drain_chunk(const CalcCall &call, Share &s, int c) {
     const int subs = (m + kSubRows - 1) / kSubRows;
     for (int k = 0; k < subs; ++k) {
       const int r0 = k * kSubRows, rows = std::min(kSubRows, m - r0);
-      CUDA_TRY(cudaEventSynchronize(x->events[size_t(1 + k)]));
+      CUDA_TRY(wait_event(x->events[size_t(1 + k)]));
       if (call.sink) {
         if (call.sink(call.user, f + r0, rows, x->h_out + size_t(r0) * O) != 0) {
           set_error("the result sink reported a failure");
@@ -1475,7 +1612,7 @@ int drain_chunk(const CalcCall &call, Share &s, int c) {
       }
     }
   }
-  CUDA_TRY(cudaEventSynchronize(x->events[0]));
+  CUDA_TRY(wait_event(x->events[0]));
   return FDNN_OK;
 }
 

@@ -118,6 +118,45 @@ cudaError_t launch_qlayer_tc(const CUtensorMap &tmap_act, const CUtensorMap &tma
 cudaError_t qlayer_pair_configure();
 cudaError_t launch_qlayer_pair(const CUtensorMap &tmap_act, const CUtensorMap &tmap_w, const QLayerArgs &a, bool logits, int block_n, int num_sms,
                                cudaStream_t stream);
+// Fused path (qlayer_fused.cu): every int8 layer of the pass and the softmax in one persistent, cooperatively launched kernel,
+// for batches whose layers are a single wave of tiles.
+constexpr int kFusedMaxLayers = 16;     // int8 layers per network the fused kernel takes
+constexpr int kFusedMaxRowBlocks = 64;  // 128-frame row blocks per launch (one progress counter each)
+constexpr int kFusedSyncWords = kFusedMaxRowBlocks + 2;  // + exit counter + tile counter
+struct FusedLayer {
+  const float *bias;        // [N]
+  const uint32_t *fix_ptr;  // risk list grouped by this layer's tile width (fdnn_internal.h)
+  const FixEntry *fix_ent;
+  float coeff, rcp;
+  int fast_div, fast_tail;
+  int N, K;
+  uint32_t need;            // tiles of a row block that must have been finished (all earlier layers) before this layer reads it
+  uint32_t tile_begin;      // number of this layer's first tile in the global (layer, row block, column block) order
+  uint32_t n_blocks;        // column blocks of this layer at its tile width
+};
+struct FusedArgs {
+  CUtensorMap act[2];                 // the two u8 activation buffers [M][H], box 128 rows × 128 bytes
+  CUtensorMap w[kFusedMaxLayers];     // s8 weights [N][K]: box BNH rows (hidden layers), 256 rows (output layer)
+  FusedLayer layer[kFusedMaxLayers];
+  int n_layers, M;
+  uint8_t *act_buf[2];
+  float *out;                         // [M][out_ld]: logits, normalised in place when do_softmax
+  int out_ld;
+  int do_softmax;
+  const uint8_t *lut;
+  float one, neg_zero;
+  uint32_t *sync;                     // [kFusedSyncWords] zero-initialised; the kernel leaves it zeroed
+  uint32_t total_tiles;
+  uint32_t tiles_per_row_block;       // Σ over layers of the number of N tiles: a row block has left the output layer
+  int debug_flags;                    // FDNN_FUSED_DEBUG: timing experiments (2 no proxy fences, 4 no extra fence before the release, 8 poll without sleeping, 16 spin on the accumulator barrier)
+  unsigned long long *timeline;       // optional [layers][1024][8] nanosecond stamps (fdnn_ctx_timeline)
+};
+cudaError_t qlayer_fused_configure();
+int qlayer_fused_plan(int M, int H, int O, int num_sms, int policy, int *grid);  // → hidden tile width (64 / 128) or 0 = not applicable
+int qlayer_fused_max_softmax_width();
+bool qlayer_fused_softmax_pays(int M, int grid);
+cudaError_t launch_qlayer_fused(const FusedArgs &a, int bnh, int grid, cudaStream_t stream);
+
 // dp4a path (qlayer_simt.cu): any legal network (K a multiple of 16); used for narrow layers.
 cudaError_t launch_qlayer_simt(const QLayerArgs &a, bool logits, cudaStream_t stream);
 

@@ -72,6 +72,7 @@ SIGNATURES = {
     "fdnn_ctx_until_output_device": (_I, [_P, _P, _I, _P]),
     "fdnn_ctx_lazy_batch_device": (_I, [_P, _P, _I, _P, _P]),
     "fdnn_ctx_profile_stages": (_I, [_P, _P, _I, _P, _I, _P]),
+    "fdnn_ctx_profile_pass": (_I, [_P, _P, _I, _P, _I, _P, C.POINTER(_I)]),
     "fdnn_ctx_timeline": (_I, [_P, _I, _P]),
     "fdnn_ctx_input_undecided": (_I, [_P, C.POINTER(C.c_uint)]),
     "fdnn_ctx_set_trace": (_I, [_P, _I]),
@@ -404,6 +405,13 @@ class LazyContext:
         ms = np.zeros(self.dnn.layer_count() + 1, dtype=np.float32)
         _check(lib().fdnn_ctx_profile_stages(self._h, C.c_void_p(d_in), n_frames, C.c_void_p(d_out), iters, _ptr(ms)))
         return ms
+
+    def profile_pass(self, d_in: int, n_frames: int, d_out: int, iters: int = 20):
+        """(input-layer ms, rest-of-pass ms, fused?) of the pass as it normally runs (bench aid)"""
+        ms = np.zeros(2, dtype=np.float32)
+        fused = C.c_int()
+        _check(lib().fdnn_ctx_profile_pass(self._h, C.c_void_p(d_in), n_frames, C.c_void_p(d_out), iters, _ptr(ms), C.byref(fused)))
+        return float(ms[0]), float(ms[1]), bool(fused.value)
 
     def delete(self) -> None:
         """delete() — :95-97."""

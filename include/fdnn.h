@@ -181,6 +181,11 @@ int fdnn_sigmoid_lut(uint8_t out[1280]);
  * averages in milliseconds, synchronised on return. */
 int fdnn_ctx_profile_stages(fdnn_ctx *ctx, const float *d_in, int n_frames, float *d_out, int iters, float *ms);
 
+/* The pass as it normally runs (for batches that are one wave of tiles: input layer + ONE fused kernel for all int8 layers and
+ * the softmax, csrc/qlayer_fused.cu): ms[0] = fp32 input layer, ms[1] = everything after it; *fused = 1 when that was the
+ * single fused kernel.  fdnn_ctx_profile_stages above always times the layer-by-layer kernels. */
+int fdnn_ctx_profile_pass(fdnn_ctx *ctx, const float *d_in, int n_frames, float *d_out, int iters, float *ms, int *fused);
+
 /* Diagnostics of the certified tensor-core input layer (csrc/input_tc.cu): how many (frame, node) elements of the last pass
  * the error-bound certificate left to the exact CUDA-core path; *undecided = 0xffffffff when the context uses the plain
  * exact kernel.  Synchronises the context's stream. */

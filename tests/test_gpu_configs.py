@@ -218,6 +218,34 @@ def test_soak_digest_detects_a_single_byte(net_file):
         dnn.delete()
 
 
+@pytest.mark.parametrize("shape,stress,policy", [("S", False, "latency"), ("S", True, "latency"), ("L", False, "latency"), ("L", False, "throughput"),
+                                                 ("ragged", False, "latency")])
+def test_fused_kernel_equals_layer_by_layer(net_file, shape, stress, policy):
+    """csrc/qlayer_fused.cu (all int8 layers + softmax in one persistent kernel, the default for batches that are one wave of
+    tiles) against the layer-by-layer kernels (FDNN_FUSED=0) on the same context: last-hidden bytes, logits and softmax
+    scores identical, for ragged batch sizes, several tiles per CTA in the output layer, and dense saturation"""
+    dnn = qd.QuantizedDnn.load_from_file(net_file(shape, stress=stress))
+    dnn.set_tile_policy(policy)
+    dim = dnn.input_dimension()
+    sizes = (1, 100, 128, 129, 512, 1000) if shape != "S" else (1, 100, 129, 512, 1000, 2500, 4096)
+    try:
+        for n in sizes:
+            frames = synth.make_frames(n, dim, seed=60 + n)
+            outs = []
+            for flag in ("2", "0"):  # 2 = fused wherever it is applicable, also where the default plan prefers layer by layer
+                os.environ["FDNN_FUSED"] = flag
+                ctx = dnn.get_new_lazy_context(n)
+                ctx.calculate_until_output(frames)
+                outs.append((ctx.hidden().copy(), ctx.logits().copy(), dnn.calculate(frames).copy()))
+                ctx.delete()
+            assert np.array_equal(outs[0][0], outs[1][0]), f"{n} frames: last-hidden bytes differ"
+            assert np.array_equal(outs[0][1].view(np.uint32), outs[1][1].view(np.uint32)), f"{n} frames: logits differ"
+            assert np.array_equal(outs[0][2].view(np.uint32), outs[1][2].view(np.uint32)), f"{n} frames: softmax scores differ"
+    finally:
+        os.environ.pop("FDNN_FUSED", None)
+        dnn.delete()
+
+
 def test_softmax_overflow_and_switched_off_class(tmp_path):
     """SoftMax::apply has no max subtraction (dnn.cc:534-544): a logit above 88.7 overflows expf to +inf and the row becomes
     zeros and one NaN; a −inf bias gives exp = 0 and a valid distribution.  Same here."""
