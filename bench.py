@@ -1,19 +1,23 @@
 #!/usr/bin/env python
 """bench.py — frames/sec of the quantized inference hot path (BASELINE.json metric).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W]            our CUDA path
-  python bench.py --impl reference [--gpus N] [--steps K] ...     the reference's own SSE4.1 CPU path
-  (N > 1: launched by torchrun, one rank per GPU)
+  python bench.py [--gpus N] [--steps K] [--warmup W]            our CUDA path, BASELINE configs[2] (+ short configs[3]/[4] legs)
+  python bench.py --config lazy | stream1m [...]                  configs[3] / configs[4] as the headline of the line
+  python bench.py --impl reference [--config ...] [...]           the reference's own SSE4.1 CPU path on the host cores
+  python bench.py --single-process --gpus N                       N GPUs behind ONE handle (fdnn_load_devices), no torchrun
+  (N > 1 otherwise: launched by torchrun, one rank per GPU)
 
-A step = one pass of the hot path over one batch of synthetic frames: the 7×2048-hidden /
-8000-output / 440-input network of BASELINE.json configs[2] at batch 512 (per GPU; weak scaling).
-Prints ONE JSON line (rank 0).  See DESIGN.md §Measurement for what every field means.
+A step = one pass of the hot path over one batch of synthetic frames: the 7×2048-hidden / 8000-output / 440-input network of
+BASELINE.json configs[2] at batch 512 (per GPU; weak scaling).  Prints ONE JSON line (rank 0).  DESIGN.md §6 says what
+every field means.
 """
 from __future__ import annotations
 
 import argparse
+import ctypes as C
 import json
 import os
+import subprocess
 import sys
 import threading
 import time
@@ -22,12 +26,29 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tools"))
 
 METRIC = "frames/sec (7x2048 hidden, 8000 out)"
-SHAPE = "L"            # 440-[2048x7]-8000, SURVEY.md §8d
+SHAPE = os.environ.get("FDNN_BENCH_SHAPE_FOR_TEST", "L")  # 440-[2048x7]-8000, SURVEY.md §8d (tests shrink it)
 BATCH = 512
-I_DIM, H_DIM, O_DIM, N_HIDDEN = 440, 2048, 8000, 7
-INT8_OPS_PER_FRAME = 2 * ((N_HIDDEN - 1) * H_DIM * H_DIM + O_DIM * H_DIM)  # 83 099 648 − layer 0 is fp32
+STREAM_CHUNK = 16384
+WORKLOADS = {
+    "batch512": "BASELINE configs[2]: 440-7x2048-8000 synthetic network, batch 512 synthetic frames per step and GPU",
+    "lazy": "BASELINE configs[3]: 440-7x2048-8000 synthetic network, LazyContext masked output, 40% active-output mask "
+            "(3% drift per frame), batch 512 synthetic frames per step and GPU",
+    "stream1m": "BASELINE configs[4]: 440-7x2048-8000 synthetic network, 1M-frame synthetic stream sharded across the GPUs",
+}
+
+
+def shape_dims():
+    from fast_dnn_b200 import synth
+    i, h, nh, o = synth.SHAPES[SHAPE]
+    return i, h, nh, o
+
+
+def int8_ops_per_frame():
+    i, h, nh, o = shape_dims()
+    return 2 * ((nh - 1) * h * h + o * h)  # layer 0 is fp32
 
 
 def env_int(name, default):
@@ -41,9 +62,29 @@ def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         with open(p) as f:
-            d = json.load(f)
-        return d, "measured (MEASURED_PEAKS.json)"
+            return json.load(f), "measured (MEASURED_PEAKS.json)"
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback (B200_PROFILING.md)"
+
+
+def int8_peak(run_live: bool):
+    """Calibrated dense int8 rate (tools/int8_peak.cu: a UTCIMMA-only loop, pseudo-random operands resident in shared memory).
+    Measured live on this GPU when the binary is there, else the committed measurement, else 2 x the bf16 figure."""
+    exe = os.path.join(ROOT, "tools", "int8_peak")
+    if run_live and os.path.exists(exe):
+        try:
+            out = subprocess.run([exe, "1.5"], capture_output=True, text=True, timeout=120, check=True).stdout.strip().splitlines()[-1]
+            d = json.loads(out)
+            return d, "tools/int8_peak run inside this bench (tcgen05.mma kind::i8 loop, operands resident in shared memory)"
+        except Exception:
+            pass
+    p = os.path.join(ROOT, "profiles", "r2_int8_peak.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f), "profiles/r2_int8_peak.json (tools/int8_peak on a B200 of this pool, earlier in the round)"
+    peaks, src = measured_peaks()
+    v = 2.0 * float(peaks["bf16_tflops"])
+    return {"cta_group_1": {"burst_tops": v, "sustained_tops": 2.0 * float(peaks.get("bf16_tflops_sustained", v / 2))},
+            "cta_group_2": {"burst_tops": v, "sustained_tops": 2.0 * float(peaks.get("bf16_tflops_sustained", v / 2))}}, f"2 x bf16_tflops {src}"
 
 
 class ClockSampler:
@@ -101,6 +142,12 @@ class ClockSampler:
                 "samples": len(self.samples)}
 
 
+def plain(o):
+    if isinstance(o, (np.floating, np.integer)):
+        return o.item()
+    raise TypeError(type(o).__name__)
+
+
 # ---------------------------------------------------------------------------------------------------
 # reference arm: the unmodified reference C++ (oracle/_ref) on the host cores
 # ---------------------------------------------------------------------------------------------------
@@ -120,28 +167,64 @@ def time_cpu(model, kind, frames, threads):
     return model.time_calculate(frames, threads=threads)
 
 
+def time_cpu_lazy(model, kind, frames, masks, threads):
+    """CalculateUntilLastHiddenLayer + one LazyOutputActivations per frame (FuncTest.java:92-133), `threads` contexts"""
+    if kind == "reference":
+        return model.time_lazy(frames, masks, batch=8, threads=threads)
+    t0 = time.perf_counter()  # the port has no threaded lazy driver: one thread
+    hidden = model.until_output(frames, threads=threads)
+    for i in range(frames.shape[0]):
+        model.lazy(hidden[i], masks[i])
+    return time.perf_counter() - t0
+
+
+def cpu_sample(model, kind, config, cores, i_dim, o_dim):
+    """a bounded sample (≈ 10 CPU-seconds in total) of the workload on all host cores → (frames/s, description)"""
+    from fast_dnn_b200 import synth
+    per = max(8, min(BATCH, 4096 // cores))
+    n = per * cores
+    frames = synth.make_frames(n, i_dim, seed=7)
+    if config == "lazy":
+        masks = synth.make_masks(n, o_dim, seed=11)
+        time_cpu_lazy(model, kind, frames[: cores * 2], masks[: cores * 2], cores)
+        secs = time_cpu_lazy(model, kind, frames, masks, cores)
+        what = "CalculateUntilLastHiddenLayer + LazyOutputActivations per frame (40% masks), batchSize 8"
+    else:
+        time_cpu(model, kind, frames[: cores * 4], cores)
+        secs = time_cpu(model, kind, frames, cores)
+        what = "CalculationContext::Calculate, batchSize 10"
+    return n / secs, f"{n} frames of the same workload, {per} per thread on {cores} threads, one pass, {secs:.2f} s wall; {what}"
+
+
 def run_reference_arm(args):
     rank = env_int("RANK", 0)
     if rank != 0:
         return
     from fast_dnn_b200 import synth
+    i_dim, _, _, o_dim = shape_dims()
     path = synth.network_file(SHAPE)
     model, kind = load_cpu_reference(path)
     cores = os.cpu_count() or 1
     n = BATCH * max(1, args.gpus)
-    frames = synth.make_frames(n, I_DIM, seed=7)
+    frames = synth.make_frames(n, i_dim, seed=7)
+    masks = synth.make_masks(n, o_dim, seed=11) if args.config == "lazy" else None
+
+    def one():
+        return time_cpu_lazy(model, kind, frames, masks, cores) if args.config == "lazy" else time_cpu(model, kind, frames, cores)
+
     for _ in range(max(args.warmup, 1)):
-        time_cpu(model, kind, frames, cores)
-    t = [time_cpu(model, kind, frames, cores) for _ in range(args.steps)]
+        one()
+    t = [one() for _ in range(args.steps)]
     total = float(np.sum(t))
     value = n * args.steps / total
-    sample = f"{args.steps} steps x {n} frames (one batch of {BATCH} per GPU of the GPU arm) split over {cores} threads"
+    sample = (f"{args.steps} steps x {n} frames (one batch of {BATCH} per GPU of the GPU arm) split over {cores} threads; reference C++ "
+              f"(dnn.cc) compiled -O2 -msse4.1, " + ("lazy protocol, batchSize 8" if args.config == "lazy" else "batchSize 10") +
+              ("; for the 1M-frame stream this is the per-batch rate (the CPU path has no per-stream state)" if args.config == "stream1m" else ""))
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "int8 weights x uint8 activations (SSE4.1 pmaddubsw), fp32 input layer", "data": "synthetic",
-        "config": {"workload": f"440-7x2048-8000 synthetic network, batch {BATCH} synthetic frames per step and GPU, "
-                               "reference C++ (dnn.cc) compiled -O2 -msse4.1, batchSize 10"},
+        "config": {"workload": WORKLOADS[args.config]},
         "cpu_baseline": {"value": value, "unit": "frames/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -151,248 +234,525 @@ def run_reference_arm(args):
 # ---------------------------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------------------------
-def run_gpu_arm(args):
-    import torch
-    import torch.distributed as dist
-    from fast_dnn_b200 import quantized_dnn as qd, synth
+class Bench:
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
+        from fast_dnn_b200 import quantized_dnn as qd, synth
+        self.torch, self.dist, self.qd, self.synth, self.args = torch, dist, qd, synth, args
+        self.world = 1 if args.single_process else env_int("WORLD_SIZE", 1)
+        self.rank = 0 if args.single_process else env_int("RANK", 0)
+        self.local = 0 if args.single_process else env_int("LOCAL_RANK", 0)
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py: no CUDA device — the hot path has no CPU implementation (use --impl reference for the CPU arm)")
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device("cuda", self.local)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=self.dev)
+        self.I, self.H, self.NH, self.O = shape_dims()
+        self.path = synth.network_file(SHAPE)
+        # ---- load: rank 0 parses + quantizes, ONE broadcast of the packed blob, every rank uploads ----
+        if args.single_process and args.gpus > 1:
+            self.dnn = qd.QuantizedDnn.load_on_devices(self.path, list(range(args.gpus)))  # one in-process ncclBroadcast
+        elif self.world > 1:
+            from fast_dnn_b200 import sharding
+            blob = sharding.broadcast_blob(qd.pack(self.path) if self.rank == 0 else None, src=0, device=self.dev)
+            self.dnn = qd.QuantizedDnn.load_from_blob(blob.data_ptr(), device=self.local, size=blob.numel())
+            del blob
+        else:
+            self.dnn = qd.QuantizedDnn.load_from_file(self.path, device=self.local)
+        self.n_layers = self.dnn.layer_count()
+        assert all(self.dnn.uses_tensor_cores(i) for i in range(self.n_layers - 1)), "tcgen05 path not selected"
+        self.stream = torch.cuda.current_stream()
+        self.sampler = ClockSampler(self.local)
+        self.host_cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
 
-    world = env_int("WORLD_SIZE", 1)
-    rank = env_int("RANK", 0)
-    local = env_int("LOCAL_RANK", 0)
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device — the hot path has no CPU implementation (use --impl reference for the CPU arm)")
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+    # -- helpers ---------------------------------------------------------------------------------
+    def barrier(self):
+        self.torch.cuda.synchronize()
+        if self.world > 1:
+            self.dist.barrier()
+            self.torch.cuda.synchronize()
 
-    # ---- load: rank 0 parses + quantizes, ONE broadcast of the packed blob, every rank uploads ----
-    path = synth.network_file(SHAPE)
-    if world > 1:
+    def max_over_ranks(self, v: float) -> float:
+        if self.world == 1:
+            return v
+        t = self.torch.tensor([v], dtype=self.torch.float64, device=self.dev)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def repeat_timed(self, timed_once, min_total_ms=60.0, max_repeats=400):
+        """timed_once() → device ms of exactly K steps.  Repeats it until ≥ min_total_ms have been timed (a 1.4 ms region is
+        one scheduler hiccup from noise) and returns (median ms of K steps, repeats, all)"""
+        first = self.max_over_ranks(timed_once())
+        runs = [first]
+        repeats = int(min(max_repeats, max(3, np.ceil(min_total_ms / max(first, 1e-3)))))
+        for _ in range(repeats - 1):
+            self.barrier()
+            runs.append(self.max_over_ranks(timed_once()))
+        return float(np.median(runs)), len(runs), runs
+
+    # -- configs[2]: batch 512, device-resident ----------------------------------------------------
+    def device_resident(self):
+        torch, qd, synth, args, dnn = self.torch, self.qd, self.synth, self.args, self.dnn
+        pool = 16  # inputs + outputs rotate over more than the L2 (126 MB)
+        seeds = 1000 + self.rank * pool
+        d_in = [torch.from_numpy(synth.make_frames(BATCH, self.I, seed=seeds + i)).to(self.dev) for i in range(pool)]
+        d_out = [torch.empty(BATCH, self.O, dtype=torch.float32, device=self.dev) for _ in range(pool)]
+        # Steps are independent batches, so — like the reference's own multi-caller pattern (several callers share one immutable
+        # model, each with its own context: MultiThreadedStressTest.java:48-61) — INFLIGHT contexts take the steps round-robin on
+        # their own streams with the library's "throughput" tile policy.  single_stream = one context, one stream, default
+        # ("latency") policy: input layer + ONE fused kernel per pass.
+        INFLIGHT = 4
+        ctx = dnn.get_new_lazy_context(BATCH)
+        dnn.set_tile_policy("throughput")
+        flight = [dnn.get_new_lazy_context(BATCH) for _ in range(INFLIGHT)]
+        dnn.set_tile_policy("latency")
+        streams = [self.stream] + [torch.cuda.Stream(device=self.dev) for _ in range(INFLIGHT - 1)]
+
+        def step(i, lanes):
+            k = i % lanes
+            c = ctx if lanes == 1 else flight[k]
+            c.forward_device(d_in[i % pool].data_ptr(), BATCH, d_out[i % pool].data_ptr(), streams[k].cuda_stream)
+
+        def timed(steps, lanes):
+            ev0 = torch.cuda.Event(enable_timing=True)
+            ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(lanes)]
+            ev0.record(self.stream)
+            for s in streams[1:lanes]:
+                s.wait_event(ev0)
+            for i in range(steps):
+                step(i, lanes)
+            for s, e in zip(streams[:lanes], ev1):
+                e.record(s)
+            torch.cuda.synchronize()
+            return max(ev0.elapsed_time(e) for e in ev1)
+
+        warm = max(args.warmup, 3)
+        for i in range(max(warm, 3 * pool // INFLIGHT) * INFLIGHT):  # every (context, buffer pair) captures its graph on second sight
+            step(i, INFLIGHT)
+        for i in range(max(warm, 3 * pool)):
+            step(i, 1)
+        self.barrier()
+        ms_single, rep_single, _ = self.repeat_timed(lambda: timed(args.steps, 1))
+        self.barrier()
+        self.sampler.start()
+        launches0 = qd.launch_count()
+        ms_total, repeats, runs = self.repeat_timed(lambda: timed(args.steps, INFLIGHT))
+        launches = (qd.launch_count() - launches0) // repeats
+        self.barrier()
+        # keep the device busy with the same loop long enough for NVML to see clocks under load
+        t_end = time.time() + 1.0
+        i = 0
+        while time.time() < t_end:
+            step(i, INFLIGHT)
+            i += 1
+            if i % 64 == 0:
+                torch.cuda.synchronize()
+        torch.cuda.synchronize()
+
+        # ---- per-kernel times (CUDA events on the launching stream) ----
+        iters = max(args.steps, 20)
+        thr_ms = flight[0].profile_stages(d_in[0].data_ptr(), BATCH, d_out[0].data_ptr(), iters=iters)  # what the timed region launches
+        lat_ms = ctx.profile_stages(d_in[0].data_ptr(), BATCH, d_out[0].data_ptr(), iters=iters)
+        t_in, t_rest, fused = ctx.profile_pass(d_in[0].data_ptr(), BATCH, d_out[0].data_ptr(), iters=iters)
+        und = ctx.input_undecided()
+        out = {"pool": pool, "inflight": INFLIGHT, "ms_total": ms_total, "repeats": repeats, "runs_ms": runs, "ms_single": ms_single,
+               "repeats_single": rep_single, "launches": int(launches), "thr_ms": thr_ms, "lat_ms": lat_ms, "pass_ms": (t_in, t_rest, fused),
+               "undecided": und}
+        for c in flight + [ctx]:
+            c.delete()
+        del d_in, d_out
+        return out
+
+    # -- the same kernels on a long stream (configs[4] regime: 16384-frame chunks) ---------------------
+    def stream_regime(self, peak_tops):
+        torch, synth, dnn = self.torch, self.synth, self.dnn
+        m_big = STREAM_CHUNK
+        big_in = torch.from_numpy(synth.make_frames(m_big, self.I, seed=99)).to(self.dev)
+        big_out = torch.empty(m_big, self.O, dtype=torch.float32, device=self.dev)
+        big_ctx = dnn.get_new_lazy_context(m_big)
+        big_ms = big_ctx.profile_stages(big_in.data_ptr(), m_big, big_out.data_ptr(), iters=5)
+        for _ in range(3):
+            big_ctx.forward_device(big_in.data_ptr(), m_big, big_out.data_ptr(), self.stream.cuda_stream)
+        b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        b0.record(self.stream)
+        reps = 40  # ≈ 55 ms
+        for _ in range(reps):
+            big_ctx.forward_device(big_in.data_ptr(), m_big, big_out.data_ptr(), self.stream.cuda_stream)
+        b1.record(self.stream)
+        torch.cuda.synchronize()
+        nl = self.n_layers
+        big_hidden = float(np.mean(big_ms[1:nl - 1]))
+        big_tops = 2.0 * m_big * self.H * self.H / (big_hidden * 1e-3) / 1e12
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "r2_stream_kernel_traffic.json")
+        if os.path.exists(tpath):
+            with open(tpath) as f:
+                traffic = json.load(f)
+        info = {"frames_per_pass": m_big, "frames_per_s": m_big * reps / (b0.elapsed_time(b1) * 1e-3), "timed_ms": b0.elapsed_time(b1),
+                "hidden_kernel_ms": big_hidden, "hidden_kernel_tops": big_tops, "hidden_kernel_frac_of_peak": big_tops / peak_tops,
+                "input_ms": float(big_ms[0]), "output_ms": float(big_ms[nl - 1]), "softmax_ms": float(big_ms[nl]),
+                "roofline": {"kernel": "qlayer_pair_kernel<256, hidden> (tcgen05 cta_group::2, one 2048x2048 layer over 16384 frames)",
+                             "bound": "tensor", "achieved": big_tops, "peak": peak_tops, "unit": "TOP/s (int8, 2*M*N*K per launch)",
+                             "frac": big_tops / peak_tops, "avg_launch_ms": big_hidden,
+                             "traffic": traffic.get("dram_bytes_per_launch") if traffic else None,
+                             "l2_to_sm_bytes_per_launch": traffic.get("xbar2l1tex_bytes_per_launch") if traffic else None}}
+        big_ctx.delete()
+        del big_in, big_out
+        return info
+
+    # -- end to end through the public call (fdnn_calculate): pinned HOST buffers, H2D + D2H inside ---
+    def e2e(self, steps):
+        torch, qd, synth, dnn = self.torch, self.qd, self.synth, self.dnn
+        ranks_here = self.args.gpus if self.args.single_process else self.world
+        n_call = BATCH * (self.args.gpus if self.args.single_process else 1)  # a device group shards one call over its GPUs
+        callers = max(1, min(3, self.host_cores // max(ranks_here, 1)))
+        e2e_pool = 2
+        h_in = [[qd.PinnedArray((n_call, self.I), np.float32) for _ in range(e2e_pool)] for _ in range(callers)]
+        h_out = [[qd.PinnedArray((n_call, self.O), np.float32) for _ in range(e2e_pool)] for _ in range(callers)]
+        for t_ in range(callers):
+            for j in range(e2e_pool):
+                h_in[t_][j].array[:] = synth.make_frames(n_call, self.I, seed=5000 + self.rank * 100 + t_ * 10 + j)
+        per_thread = [steps // callers + (1 if t_ < steps % callers else 0) for t_ in range(callers)]
+
+        def worker(t_, count):
+            torch.cuda.set_device(self.local)
+            for k in range(count):
+                dnn.calculate(h_in[t_][k % e2e_pool].array, 10, out=h_out[t_][k % e2e_pool].array)
+
+        def run(counts):
+            ws = [threading.Thread(target=worker, args=(t_, counts[t_])) for t_ in range(callers)]
+            [w.start() for w in ws]
+            [w.join() for w in ws]
+
+        for _ in range(2):  # every pooled workspace (and its captured graph) exists before the clock starts
+            run([4] * callers)
+        self.barrier()
+        t0 = time.perf_counter()
+        run(per_thread)
+        torch.cuda.synchronize()
+        secs = self.max_over_ranks(time.perf_counter() - t0)
+        t0 = time.perf_counter()
+        for k in range(10):
+            dnn.calculate(h_in[0][k % e2e_pool].array, 10, out=h_out[0][k % e2e_pool].array)
+        serial_ms = (time.perf_counter() - t0) / 10 * 1e3
+        # what the box can move: D2H of the same 16 MB results into pinned memory, all ranks at once, nothing else running
+        ceiling = None
+        try:
+            import d2h_ceiling
+            self.barrier()
+            if self.args.single_process and self.args.gpus > 1:
+                res, lock = [], threading.Lock()
+
+                def probe(d):
+                    torch.cuda.set_device(d)
+                    g, _ = d2h_ceiling.measure(torch, torch.device("cuda", d), seconds=0.4, h2d_bytes=BATCH * self.I * 4)
+                    with lock:
+                        res.append(g)
+                ts = [threading.Thread(target=probe, args=(d,)) for d in range(self.args.gpus)]
+                [t.start() for t in ts]
+                [t.join() for t in ts]
+                gbs_total = float(sum(res))
+            else:
+                gbs, _ = d2h_ceiling.measure(torch, self.dev, seconds=0.4, h2d_bytes=BATCH * self.I * 4)
+                t = torch.tensor([gbs], dtype=torch.float64, device=self.dev)
+                if self.world > 1:
+                    self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+                gbs_total = float(t.item())
+            ceiling = {"d2h_pinned_gbs_all_gpus": gbs_total, "frames_per_s": gbs_total * 1e9 / (self.O * 4.0),
+                       "how": "tools/d2h_ceiling.py: 16 MB device->pinned-host copies (+ the 0.9 MB input upload), 4 in flight per GPU, "
+                              "every GPU of the run at the same time, nothing else running"}
+        except Exception as e:  # the ceiling is an annotation, never a reason to lose the line
+            ceiling = {"error": repr(e)}
+        total_frames = n_call * steps if self.args.single_process else ranks_here * BATCH * steps
+        value = total_frames / secs
+        out = {"value": value, "unit": "frames/s", "h2d_bytes_per_step": n_call * self.I * 4, "d2h_bytes_per_step": n_call * self.O * 4,
+               "steps": steps, "wall_s": secs,
+               "mode": f"QuantizedDnn.calculate (fdnn_calculate) on pinned host buffers, {callers} host threads per process sharing one model "
+                       "(MultiThreadedStressTest pattern) so copies overlap compute; wall clock, max over ranks",
+               "single_caller_ms_per_step": serial_ms, "host_cores": self.host_cores, "ceiling": ceiling}
+        if ceiling and "frames_per_s" in ceiling:
+            out["frac_of_d2h_ceiling"] = value / ceiling["frames_per_s"]
+        return out
+
+    def e2e_jni(self, iters=40):
+        """the same loop through the JNI symbol itself: Java_suskun_nn_QuantizedDnn_calculate on pageable 'Java' arrays, driven by
+        tools/jni_harness.c (a JVM stand-in: Get<Float>ArrayElements copies, NewFloatArray zero-fills, SetFloatArrayRegion memcpy)"""
+        so = os.path.join(ROOT, "tools", "libjni_harness.so")
+        if not os.path.exists(so):
+            return {"unavailable": "tools/libjni_harness.so not built"}
+        h = C.CDLL(so)
+        h.jni_harness_calculate.restype = C.c_double
+        h.jni_harness_calculate.argtypes = [C.c_char_p, C.c_char_p, C.c_float, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int]
+        frames = self.synth.make_frames(BATCH, self.I, seed=4242)
+        first = np.zeros((BATCH, self.O), np.float32)
+        threads = max(1, min(6, self.host_cores // max(self.world, 1)))
+        self.barrier()
+        secs = h.jni_harness_calculate(self.qd.LIB_PATH.encode(), self.path.encode(), 3.0, frames.ctypes.data_as(C.c_void_p), BATCH, self.I,
+                                       iters * threads, threads, first.ctypes.data_as(C.c_void_p), first.size)
+        if secs <= 0:
+            return {"unavailable": f"jni_harness_calculate returned {secs}"}
+        secs = self.max_over_ranks(secs)
+        same = bool(np.array_equal(first, self.dnn.calculate(frames)))
+        return {"value": self.world * BATCH * iters * threads / secs, "unit": "frames/s", "threads_per_process": threads, "calls": iters * threads,
+                "frames_per_call": BATCH, "wall_s": secs, "same_bytes_as_calculate": same,
+                "mode": "Java_suskun_nn_QuantizedDnn_calculate through a C JVM stand-in (tools/jni_harness.c): pageable float[] in and out, "
+                        "per call a copy of the input array, a zero-filled new float[], SetFloatArrayRegion from the transfer buffer"}
+
+    # -- configs[3]: lazy masked output --------------------------------------------------------------
+    def lazy(self, steps):
+        torch, synth, dnn = self.torch, self.synth, self.dnn
+        frames = synth.make_frames(BATCH, self.I, seed=7 + self.rank)
+        masks = synth.make_masks(BATCH, self.O, ratio=0.40, drift=0.03, seed=11)
+        d_in = torch.from_numpy(frames).to(self.dev)
+        d_masks = torch.from_numpy(masks).to(self.dev)
+        d_out = torch.empty(BATCH, self.O, dtype=torch.float32, device=self.dev)
+        ctx = dnn.get_new_lazy_context(BATCH)
+        for _ in range(3):
+            ctx.until_output_device(d_in.data_ptr(), BATCH, self.stream.cuda_stream)
+            ctx.lazy_batch_device(d_masks.data_ptr(), BATCH, d_out.data_ptr(), self.stream.cuda_stream)
+        torch.cuda.synchronize()
+
+        def timed():
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(self.stream)
+            for _ in range(steps):
+                ctx.until_output_device(d_in.data_ptr(), BATCH, self.stream.cuda_stream)
+                ctx.lazy_batch_device(d_masks.data_ptr(), BATCH, d_out.data_ptr(), self.stream.cuda_stream)
+            e1.record(self.stream)
+            torch.cuda.synchronize()
+            return e0.elapsed_time(e1)
+
+        ms, repeats, _ = self.repeat_timed(timed)
+        # host protocol of the reference (FuncTest.java:92-133): calculateUntilOutput once, calculateForOutputNodes per frame
+        ctx.calculate_until_output(frames)
+        ctx.calculate_for_output_nodes(masks[0])
+        t0 = time.perf_counter()
+        reps = 3
+        for _ in range(reps):
+            ctx.calculate_until_output(frames)
+            for i in range(BATCH):
+                ctx.calculate_for_output_nodes(masks[i])
+        per_frame_s = (time.perf_counter() - t0) / reps
+        lat = []
+        ctx.calculate_until_output(frames)
+        for i in range(200):
+            t1 = time.perf_counter()
+            ctx.calculate_for_output_nodes(masks[i])
+            lat.append(time.perf_counter() - t1)
+        t0 = time.perf_counter()
+        for _ in range(10):
+            ctx.calculate_until_output(frames)
+            ctx.calculate_for_output_nodes_batch(masks)
+        batch_s = (time.perf_counter() - t0) / 10
+        ctx.delete()
+        return {"workload": WORKLOADS["lazy"], "device_resident": {"value": self.world * BATCH * steps / (ms * 1e-3), "unit": "frames/s",
+                                                                  "ms_per_step": ms / steps, "repeats": repeats,
+                                                                  "what": "fdnn_ctx_until_output_device + fdnn_ctx_lazy_batch_device (512 masked softmax rows)"},
+                "per_frame_protocol": {"value": BATCH / per_frame_s, "unit": "frames/s", "ms_per_512_frames": per_frame_s * 1e3,
+                                       "calculateLazy_latency_us_median": float(np.median(lat)) * 1e6,
+                                       "what": "calculateUntilOutput (H2D inside) + 512 x calculateForOutputNodes, one host thread, through the "
+                                               "Python mirror of the Java class (ctypes call overhead included); mask 8 KB up, 32 KB row down per call"},
+                "batched_host": {"value": BATCH / batch_s, "unit": "frames/s",
+                                 "what": "calculateUntilOutput + fdnn_ctx_lazy_batch on pageable host arrays (masks 4 MB up, scores 16 MB down)"},
+                "note": "the output layer is computed densely once per batch on the tensor cores (16.4 M MAC/frame) and every lazy call is a masked "
+                        "softmax over resident logits: 40% masks differ per frame and drift, their union over a batch is nearly every node, and a "
+                        "row-gathered sparse GEMM would forgo the tensor cores for 0.6 x of one layer's work (DESIGN.md §4)"}
+
+    # -- configs[4]: a 1M-frame stream -----------------------------------------------------------------
+    def stream1m(self, total_frames=1_000_000):
+        torch, qd, synth, dnn = self.torch, self.qd, self.synth, self.dnn
         from fast_dnn_b200 import sharding
-        blob = sharding.broadcast_blob(qd.pack(path) if rank == 0 else None, src=0, device=dev)
-        dnn = qd.QuantizedDnn.load_from_blob(blob.data_ptr(), device=local, size=blob.numel())
-        del blob
-    else:
-        dnn = qd.QuantizedDnn.load_from_file(path, device=local)
-    n_layers = dnn.layer_count()
-    assert all(dnn.uses_tensor_cores(i) for i in range(n_layers - 1)), "tcgen05 path not selected"
-
-    # ---- device-resident pool: inputs + outputs rotate over more than the L2 (126 MB) -------------
-    pool = 16
-    seeds = 1000 + rank * pool
-    d_in = [torch.from_numpy(synth.make_frames(BATCH, I_DIM, seed=seeds + i)).to(dev) for i in range(pool)]
-    d_out = [torch.empty(BATCH, O_DIM, dtype=torch.float32, device=dev) for _ in range(pool)]
-    ctx = dnn.get_new_lazy_context(BATCH)
-    stream = torch.cuda.current_stream()
-    sampler = ClockSampler(local)
-    # Steps are independent batches, so — like the reference's own multi-caller pattern (several callers share one
-    # immutable model, each with its own context: MultiThreadedStressTest.java:48-61, and the e2e leg below) — INFLIGHT
-    # contexts take the steps round-robin on their own streams; kernels of neighbouring steps fill each other's tails and
-    # the SMs a 128-CTA kernel leaves idle (measured on B200: 144 → 124 → 115 → 112 us per step for 1 → 2 → 3 → 4).
-    # Several callers in flight is what the library's "throughput" tile policy is for (include/fdnn.h): same results,
-    # wider tiles, less SM time per frame.  The single-stream figure reported beside it uses the default "latency" policy.
-    INFLIGHT = 4
-    dnn.set_tile_policy("throughput")
-    flight = [dnn.get_new_lazy_context(BATCH) for _ in range(INFLIGHT)]
-    dnn.set_tile_policy("latency")
-    streams = [stream] + [torch.cuda.Stream(device=dev) for _ in range(INFLIGHT - 1)]
-
-    def step(i, lanes=INFLIGHT):
-        k = i % lanes
-        c = ctx if lanes == 1 else flight[k]
-        c.forward_device(d_in[i % pool].data_ptr(), BATCH, d_out[i % pool].data_ptr(), streams[k].cuda_stream)
-
-    def timed(steps, lanes):
-        """device time of `steps` steps over `lanes` streams: from one start event every stream waits on to the last stream's end"""
-        ev0 = torch.cuda.Event(enable_timing=True)
-        ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(lanes)]
-        ev0.record(stream)
-        for s in streams[1:lanes]:
-            s.wait_event(ev0)
-        for i in range(steps):
-            step(i, lanes)
-        for s, e in zip(streams[:lanes], ev1):
-            e.record(s)
+        group = self.args.gpus if self.args.single_process else 1
+        lo, hi = (0, total_frames) if self.args.single_process else sharding.shard_range(total_frames, self.rank, self.world)
+        # device-resident: the shard in 16384-frame passes through one context; four distinct resident chunks rotate
+        # (4 x (29 MB in + 524 MB out) is far beyond the L2; regenerating 1M frames per chunk would measure numpy)
+        n_buf = 4
+        bufs_in = [torch.from_numpy(synth.make_frames(STREAM_CHUNK, self.I, seed=300 + self.rank * 10 + b)).to(self.dev) for b in range(n_buf)]
+        bufs_out = [torch.empty(STREAM_CHUNK, self.O, dtype=torch.float32, device=self.dev) for _ in range(n_buf)]
+        ctx = dnn.get_new_lazy_context(STREAM_CHUNK)
+        my_frames = (hi - lo) // group
+        spans = list(sharding.chunk_ranges(0, my_frames, STREAM_CHUNK))
+        for k in range(n_buf * 2):
+            ctx.forward_device(bufs_in[k % n_buf].data_ptr(), STREAM_CHUNK, bufs_out[k % n_buf].data_ptr(), self.stream.cuda_stream)
+        self.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(self.stream)
+        for k, (a, bb) in enumerate(spans):
+            ctx.forward_device(bufs_in[k % n_buf].data_ptr(), bb - a, bufs_out[k % n_buf].data_ptr(), self.stream.cuda_stream)
+        e1.record(self.stream)
         torch.cuda.synchronize()
-        return max(ev0.elapsed_time(e) for e in ev1)
+        dev_ms = self.max_over_ranks(e0.elapsed_time(e1))
+        ctx.delete()
+        del bufs_in, bufs_out
+        # end to end: the shard through QuantizedDnn.calculate in 16384-frame (per GPU) calls on alternating pinned buffer pairs
+        chunk = STREAM_CHUNK * group
+        n_threads = 2
+        h_in = [qd.PinnedArray((chunk, self.I), np.float32) for _ in range(n_threads)]
+        h_out = [qd.PinnedArray((chunk, self.O), np.float32) for _ in range(n_threads)]
+        for j in range(n_threads):
+            h_in[j].array[:] = synth.make_frames(chunk, self.I, seed=400 + self.rank * 10 + j)
+            dnn.calculate(h_in[j].array, 10, out=h_out[j].array)
+            dnn.calculate(h_in[j].array, 10, out=h_out[j].array)
+        spans = list(sharding.chunk_ranges(lo, hi, chunk))
 
-    def barrier():
+        def worker(t_):
+            torch.cuda.set_device(self.local)
+            for k in range(t_, len(spans), n_threads):
+                a, bb = spans[k]
+                dnn.calculate(h_in[t_].array[: bb - a], 10, out=h_out[t_].array[: bb - a])
+
+        self.barrier()
+        t0 = time.perf_counter()
+        ws = [threading.Thread(target=worker, args=(t_,)) for t_ in range(n_threads)]
+        [w.start() for w in ws]
+        [w.join() for w in ws]
         torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-            torch.cuda.synchronize()
+        secs = self.max_over_ranks(time.perf_counter() - t0)
+        n_gpus = self.args.gpus if self.args.single_process else self.world
+        dev_frames = my_frames * group if self.args.single_process else total_frames
+        return {"workload": WORKLOADS["stream1m"], "frames": total_frames, "n_gpus": n_gpus, "chunk_frames_per_gpu": STREAM_CHUNK,
+                "device_resident": {"value": (my_frames if self.args.single_process else dev_frames) / (dev_ms * 1e-3), "unit": "frames/s", "ms": dev_ms,
+                                    "what": ("one GPU's share of the stream" if self.args.single_process else "each GPU's shard") +
+                                            " in 16384-frame passes, inputs/outputs rotating over 4 resident chunk buffers; device time, max over ranks"},
+                "e2e": {"value": total_frames / secs, "unit": "frames/s", "wall_s": secs, "h2d_bytes": total_frames * self.I * 4,
+                        "d2h_bytes": total_frames * self.O * 4,
+                        "what": "the stream through QuantizedDnn.calculate in 16384-frame-per-GPU calls on pinned host buffers, 2 host threads per "
+                                "process; wall clock, max over ranks"}}
 
-    dnn.set_tile_policy("throughput")  # (a context caches its launch sequence per shape on first use)
-    for i in range(max(args.warmup, 3, 3 * pool // INFLIGHT) * INFLIGHT):  # every context captures its graphs (on second sight) before the clock starts
-        step(i)
-    barrier()
-    dnn.set_tile_policy("latency")
-    for i in range(max(args.warmup, 3, 3 * pool)):  # one graph per (input, output) pair of the pool, captured on second sight
-        step(i, 1)
-    barrier()
-    ms_single = timed(args.steps, 1)  # one context, one stream: reported beside the headline value
-    barrier()
-    sampler.start()
-    launches0 = qd.launch_count()
-    ms_total = timed(args.steps, INFLIGHT)
-    launches = qd.launch_count() - launches0
-    if world > 1:
-        t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total = float(t.item())
-    barrier()
-    value = world * BATCH * args.steps / (ms_total * 1e-3)
 
-    # keep the device busy with the same loop long enough for NVML to see clocks under load
-    t_end = time.time() + 1.0
-    i = 0
-    while time.time() < t_end:
-        step(i)
-        i += 1
-        if i % 64 == 0:
-            torch.cuda.synchronize()
-    torch.cuda.synchronize()
+def run_group_arm(args):
+    """--single-process --gpus N: the N GPUs behind ONE model handle (fdnn_load_devices: one in-process ncclBroadcast at load,
+    fdnn_calculate shards every call over the devices).  There is no device-resident entry point for a group (a context lives on
+    one GPU), so `value` here IS the end-to-end figure; the per-GPU kernel numbers are those of the N = 1 line."""
+    b = Bench(args)
+    e2e = b.e2e(max(args.steps, 60))
+    stream1m = b.stream1m(env_int("FDNN_BENCH_STREAM_FRAMES", 1_000_000)) if not args.no_extra else None
+    b.sampler.stop()
+    print(json.dumps({
+        "metric": METRIC, "value": e2e["value"], "unit": "frames/s", "n_gpus": args.gpus, "steps": e2e["steps"], "warmup": max(args.warmup, 3),
+        "ms_per_step": 1e3 * e2e["wall_s"] / e2e["steps"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u8 activations x s8 weights -> s32 (tcgen05 kind::i8); fp32 input layer and softmax", "data": "synthetic",
+        "config": {"workload": WORKLOADS["batch512"].replace("per step and GPU", f"per GPU: {BATCH * args.gpus} frames per call"),
+                   "parallelism": f"one process, ONE handle over {args.gpus} GPUs (fdnn_load_devices): one in-process ncclBroadcast of the weight "
+                                  f"blob at load ({b.qd.lib().fdnn_nccl_broadcast_count()} issued), every call sharded over the devices, no per-frame collective",
+                   "value_is": "end to end through fdnn_calculate (host buffers, copies inside the timed region)"},
+        "e2e": e2e, "stream1m": stream1m, "gpu_launches": int(b.qd.launch_count()), "clocks": b.sampler.summary(), "roofline": None,
+        "cpu_baseline": None}, default=plain))
+    b.dnn.delete()
 
-    # ---- per-kernel times (CUDA events on the launching stream) → roofline of the hidden kernel --
-    stage_ms = ctx.profile_stages(d_in[0].data_ptr(), BATCH, d_out[0].data_ptr(), iters=max(args.steps, 20))
-    hidden_ms = [float(x) for x in stage_ms[1:n_layers - 1]]
-    hid_avg = float(np.mean(hidden_ms))
-    peaks, peak_src = measured_peaks()
-    int8_peak = 2.0 * float(peaks["bf16_tflops"])  # dense int8 tensor rate = 2 × bf16 on sm_100 (4.5 vs 2.25 P nominal)
-    hid_ops = 2.0 * BATCH * H_DIM * H_DIM
-    achieved = hid_ops / (hid_avg * 1e-3) / 1e12
+
+def run_gpu_arm(args):
+    if args.single_process:
+        return run_group_arm(args)
+    b = Bench(args)
+    i8, i8_src = int8_peak(run_live=(b.rank == 0 and not args.no_peak))
+    peak1, peak2 = float(i8["cta_group_1"]["burst_tops"]), float(i8["cta_group_2"]["burst_tops"])
+    ops_frame = int8_ops_per_frame()
+
+    res = b.device_resident()
+    world = b.world
+    n_gpus = args.gpus if args.single_process else world
+    value = world * BATCH * args.steps / (res["ms_total"] * 1e-3)
+    nl = b.n_layers
+    thr, lat = res["thr_ms"], res["lat_ms"]
+    hid_thr = float(np.mean(thr[1:nl - 1]))
+    hid_ops = 2.0 * BATCH * b.H * b.H
+    t_in, t_rest, fused = res["pass_ms"]
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "hidden_kernel_traffic.json")
     if os.path.exists(tpath):
         with open(tpath) as f:
-            traffic = json.load(f).get("dram_bytes_per_launch")
-    total_stage = float(np.sum(stage_ms))
+            traffic = json.load(f)
+    achieved = hid_ops / (hid_thr * 1e-3) / 1e12
+    step_tops = ops_frame * BATCH / (res["ms_total"] / args.steps * 1e-3) / 1e12
+    feed_bytes = 64 * (128 + 128) * b.H
     roofline = {
-        "kernel": "qlayer_tc_kernel<hidden> (tcgen05 kind::i8, one 2048x2048 layer over 512 frames)", "bound": "tensor",
-        "achieved": achieved, "peak": int8_peak, "unit": "TOP/s (int8, 2*M*N*K per launch)", "frac": achieved / int8_peak,
-        "traffic": traffic, "peak_source": f"2 x bf16_tflops {peak_src}; the file has no int8 entry, nominal dense int8 is 4500",
-        "avg_launch_ms": hid_avg, "share_of_step": float(np.sum(hidden_ms)) / total_stage,
+        "kernel": "qlayer_tc_kernel<128, hidden> (tcgen05 kind::i8, one 2048x2048 layer over 512 frames: the tile policy the timed region "
+                  "runs; 6 of the 11 launches of a step)",
+        "bound": "tensor", "achieved": achieved, "peak": peak1, "unit": "TOP/s (int8, 2*M*N*K per launch)", "frac": achieved / peak1,
+        "traffic": traffic.get("dram_bytes_per_launch") if traffic else None, "peak_source": i8_src,
+        "avg_launch_ms": hid_thr, "share_of_step": float(np.sum(thr[1:nl - 1])) / float(np.sum(thr)),
+        "how": "CUDA events around every launch of one pass on the launching stream (fdnn_ctx_profile_stages), same tile policy as the timed "
+               "region, one pass at a time; in the timed region four passes overlap",
+        "whole_step_in_timed_region": {"int8_tops": step_tops, "frac": step_tops / peak1,
+                                       "what": "all int8 ops of a step / ms_per_step (input layer and softmax time included)"},
+        "operand_feed": {"l2_to_sm_bytes_per_launch": feed_bytes, "achieved_gbs": feed_bytes / (hid_thr * 1e-3) / 1e9,
+                         "what": "what bounds a 512-frame layer: 64 CTAs x (128 activation + 128 weight rows) x 2048 B through L2 -> shared "
+                                 "memory (≈ 36 B/clk per SM measured, DESIGN.md §5), not the tensor pipe"},
     }
-    und = ctx.input_undecided()
-    stages = {"input_layer": ("input_tc.cu: fixed-point dot products on tcgen05 int8 + rounding-error certificate, exact CUDA-core arithmetic for the "
-                              f"{100.0 * und / (BATCH * H_DIM):.2f} % of the elements it leaves undecided (3 kernels)") if und is not None
+    fused_tops = ops_frame * BATCH / (t_rest * 1e-3) / 1e12
+    single = {"value": world * BATCH * args.steps / (res["ms_single"] * 1e-3), "ms_per_step": res["ms_single"] / args.steps,
+              "repeats": res["repeats_single"],
+              "pass": {"input_layer_ms": t_in, "fused_int8_stack_and_softmax_ms": t_rest, "fused_kernel": fused},
+              "roofline": {"kernel": "qlayer_fused_kernel<64> (all 7 int8 layers + softmax of a 512-frame pass in one persistent kernel)"
+                           if fused else "layer-by-layer kernels", "bound": "tensor", "achieved": fused_tops, "peak": peak1, "unit": "TOP/s (int8)",
+                           "frac": fused_tops / peak1, "avg_launch_ms": t_rest}}
+    und = res["undecided"]
+    stages = {"policy_throughput_ms": {"input_fp32": float(thr[0]), "hidden_int8": [float(x) for x in thr[1:nl - 1]],
+                                       "output_int8": float(thr[nl - 1]), "softmax": float(thr[nl]), "sum": float(np.sum(thr))},
+              "policy_latency_layer_by_layer_ms": {"input_fp32": float(lat[0]), "hidden_int8": [float(x) for x in lat[1:nl - 1]],
+                                                   "output_int8": float(lat[nl - 1]), "softmax": float(lat[nl]), "sum": float(np.sum(lat))},
+              "input_layer": ("input_tc.cu: fixed-point dot products on tcgen05 int8 + rounding-error certificate, exact CUDA-core arithmetic "
+                              f"for the {100.0 * und / (BATCH * b.H):.2f} % of the elements it leaves undecided (3 kernels)") if und is not None
               else "input_layer.cu: exact CUDA-core arithmetic for every element (1 kernel)",
-              "input_fp32_ms": float(stage_ms[0]), "hidden_int8_ms": hidden_ms, "output_int8_ms": float(stage_ms[n_layers - 1]),
-              "softmax_ms": float(stage_ms[n_layers]), "sum_ms": total_stage,
-              "output_plus_softmax_hbm_gbs": (BATCH * O_DIM * 4 * 3 + O_DIM * H_DIM) / ((stage_ms[n_layers - 1] + stage_ms[n_layers]) * 1e-3) / 1e9}
+              "output_plus_softmax_hbm_gbs": (BATCH * b.O * 4 * 3 + b.O * b.H) / ((thr[nl - 1] + thr[nl]) * 1e-3) / 1e9}
 
-    # ---- the same kernels on a long stream (BASELINE configs[4] regime: 16384-frame chunks) ----------
-    stream_info = None
-    if rank == 0 and not args.no_stream:
-        m_big = 16384
-        big_in = torch.from_numpy(synth.make_frames(m_big, I_DIM, seed=99)).to(dev)
-        big_out = torch.empty(m_big, O_DIM, dtype=torch.float32, device=dev)
-        big_ctx = dnn.get_new_lazy_context(m_big)
-        big_ms = big_ctx.profile_stages(big_in.data_ptr(), m_big, big_out.data_ptr(), iters=5)
-        for _ in range(3):
-            big_ctx.forward_device(big_in.data_ptr(), m_big, big_out.data_ptr(), stream.cuda_stream)
-        b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        b0.record(stream)
-        for _ in range(5):
-            big_ctx.forward_device(big_in.data_ptr(), m_big, big_out.data_ptr(), stream.cuda_stream)
-        b1.record(stream)
-        torch.cuda.synchronize()
-        big_hidden = float(np.mean(big_ms[1:n_layers - 1]))
-        big_tops = 2.0 * m_big * H_DIM * H_DIM / (big_hidden * 1e-3) / 1e12
-        stream_info = {"frames_per_pass": m_big, "frames_per_s": m_big * 5 / (b0.elapsed_time(b1) * 1e-3),
-                       "hidden_kernel_ms": big_hidden, "hidden_kernel_tops": big_tops, "hidden_kernel_frac_of_peak": big_tops / int8_peak,
-                       "input_ms": float(big_ms[0]), "output_ms": float(big_ms[n_layers - 1]), "softmax_ms": float(big_ms[n_layers])}
-        big_ctx.delete()
-        del big_in, big_out
+    stream_info = b.stream_regime(peak2) if (b.rank == 0 and not args.no_stream) else None
+    e2e = b.e2e(max(args.steps, 60))
+    e2e_jni = b.e2e_jni() if not (args.no_jni or args.single_process) else None
+    lazy = b.lazy(max(20, min(args.steps, 100))) if not (args.no_extra or args.single_process) else None
+    stream1m = b.stream1m(env_int("FDNN_BENCH_STREAM_FRAMES", 1_000_000)) if not args.no_extra else None
+    b.sampler.stop()
 
-    # ---- end to end through the public call (fdnn_calculate): pinned HOST buffers, H2D + D2H inside
-    # three callers per GPU overlap copies and compute; with many ranks on one host leave every caller a core of its own
-    # (8 ranks x 3 spinning callers on 16 cores: 2.9 M frames/s at 8 GPUs against 5.0 M at 4)
-    host_cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
-    e2e_threads = max(1, min(3, host_cores // max(world, 1)))
-    e2e_pool = 2
-    h_in = [[qd.PinnedArray((BATCH, I_DIM), np.float32) for _ in range(e2e_pool)] for _ in range(e2e_threads)]
-    h_out = [[qd.PinnedArray((BATCH, O_DIM), np.float32) for _ in range(e2e_pool)] for _ in range(e2e_threads)]
-    for t_ in range(e2e_threads):
-        for j in range(e2e_pool):
-            h_in[t_][j].array[:] = synth.make_frames(BATCH, I_DIM, seed=5000 + rank * 100 + t_ * 10 + j)
-    e2e_steps = max(args.steps, 30)
-    per_thread = [e2e_steps // e2e_threads + (1 if t_ < e2e_steps % e2e_threads else 0) for t_ in range(e2e_threads)]
-
-    def e2e_worker(t_, count):
-        torch.cuda.set_device(local)
-        for k in range(count):
-            dnn.calculate(h_in[t_][k % e2e_pool].array, 10, out=h_out[t_][k % e2e_pool].array)
-
-    # warm-up with the same concurrency as the timed region, so that every pooled context (and its
-    # captured graph) exists before the clock starts
-    for _ in range(2):
-        workers = [threading.Thread(target=e2e_worker, args=(t_, 4)) for t_ in range(e2e_threads)]
-        [w.start() for w in workers]
-        [w.join() for w in workers]
-    barrier()
-    t0 = time.perf_counter()
-    workers = [threading.Thread(target=e2e_worker, args=(t_, per_thread[t_])) for t_ in range(e2e_threads)]
-    [w.start() for w in workers]
-    [w.join() for w in workers]
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    if world > 1:
-        t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
-    # single-caller latency for reference
-    t0 = time.perf_counter()
-    for k in range(10):
-        dnn.calculate(h_in[0][k % e2e_pool].array, 10, out=h_out[0][k % e2e_pool].array)
-    e2e_serial_ms = (time.perf_counter() - t0) / 10 * 1e3
-    sampler.stop()
-    e2e = {"value": world * BATCH * e2e_steps / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": BATCH * I_DIM * 4,
-           "d2h_bytes_per_step": BATCH * O_DIM * 4, "steps": e2e_steps,
-           "mode": f"QuantizedDnn.calculate (fdnn_calculate) on pinned host buffers, {e2e_threads} host threads sharing one model "
-                   "(MultiThreadedStressTest pattern) so copies overlap compute; wall clock",
-           "single_caller_ms_per_step": e2e_serial_ms}
-
-    # ---- CPU baseline on this box's host cores (rank 0, N = 1 only; bounded sample) ------------------
-    cpu_baseline = None
-    if rank == 0 and world == 1 and not args.no_cpu:
-        model, kind = load_cpu_reference(path)
+    # ---- CPU baseline on this box's host cores (rank 0, N = 1 only; bounded samples) ------------------
+    cpu_baseline = cpu_lazy = None
+    if b.rank == 0 and n_gpus == 1 and not args.no_cpu:
+        model, kind = load_cpu_reference(b.path)
         cores = os.cpu_count() or 1
-        frames = synth.make_frames(BATCH, I_DIM, seed=7)
-        per = max(8, min(BATCH, 4096 // cores))  # ≈ 4096 frames ≈ 12 CPU-seconds in total
-        big = np.concatenate([frames] * ((per * cores + BATCH - 1) // BATCH))[: per * cores]
-        time_cpu(model, kind, big[: cores * 4], cores)
-        secs = time_cpu(model, kind, big, cores)
-        cpu_baseline = {"value": per * cores / secs, "unit": "frames/s", "cores": cores, "kind": kind,
-                        "sample": f"{per * cores} frames of the same workload, {per} per thread on {cores} threads, one pass, "
-                                  f"{secs:.2f} s wall; batchSize 10"}
+        v, sample = cpu_sample(model, kind, "batch512", cores, b.I, b.O)
+        cpu_baseline = {"value": v, "unit": "frames/s", "cores": cores, "kind": kind, "sample": sample}
+        if lazy is not None:
+            v, sample = cpu_sample(model, kind, "lazy", cores, b.I, b.O)
+            cpu_lazy = {"value": v, "unit": "frames/s", "cores": cores, "kind": kind, "sample": sample}
+            lazy["cpu_baseline"] = cpu_lazy
 
-    if rank == 0:
-        def plain(o):
-            if isinstance(o, (np.floating, np.integer)):
-                return o.item()
-            raise TypeError(type(o).__name__)
-
+    if b.rank == 0:
+        headline = {"value": value, "ms_per_step": res["ms_total"] / args.steps, "workload": WORKLOADS["batch512"], "e2e": e2e, "cpu": cpu_baseline}
+        if args.config == "lazy" and lazy is not None:
+            headline = {"value": lazy["device_resident"]["value"], "ms_per_step": lazy["device_resident"]["ms_per_step"], "workload": WORKLOADS["lazy"],
+                        "cpu": cpu_lazy,
+                        "e2e": {"value": lazy["batched_host"]["value"], "unit": "frames/s", "h2d_bytes_per_step": BATCH * (b.I * 4 + b.O),
+                                "d2h_bytes_per_step": BATCH * b.O * 4, "mode": lazy["batched_host"]["what"]}}
+        if args.config == "stream1m" and stream1m is not None:
+            headline = {"value": stream1m["device_resident"]["value"] * (n_gpus if args.single_process else 1),
+                        "ms_per_step": stream1m["device_resident"]["ms"] / max(1, len(range(0, stream1m["frames"] // n_gpus, STREAM_CHUNK))),
+                        "workload": WORKLOADS["stream1m"], "cpu": cpu_baseline,
+                        "e2e": {"value": stream1m["e2e"]["value"], "unit": "frames/s", "h2d_bytes_per_step": STREAM_CHUNK * b.I * 4,
+                                "d2h_bytes_per_step": STREAM_CHUNK * b.O * 4, "mode": stream1m["e2e"]["what"]}}
         print(json.dumps({
-            "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "metric": METRIC, "value": headline["value"], "unit": "frames/s", "n_gpus": n_gpus, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": headline["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u8 activations x s8 weights -> s32 (tcgen05 kind::i8); fp32 input layer and softmax", "data": "synthetic",
-            "config": {"workload": f"BASELINE configs[2]: 440-7x2048-8000 synthetic network, batch {BATCH} synthetic frames per step and GPU",
-                       "l2": f"inputs and outputs rotate over a {pool}-deep pool ({pool * BATCH * (I_DIM + O_DIM) * 4 / 1e6:.0f} MB > 126 MB L2); "
+            "config": {"workload": headline["workload"],
+                       "l2": f"inputs and outputs rotate over a {res['pool']}-deep pool ({res['pool'] * BATCH * (b.I + b.O) * 4 / 1e6:.0f} MB > 126 MB L2); "
                              "the 45 MB of weights stay L2-resident as in steady-state serving",
-                       "inflight": f"{INFLIGHT} contexts on {INFLIGHT} streams take the steps round-robin (independent batches; one shared model; "
-                                   "tile policy 'throughput'); single_stream = one context, one stream, tile policy 'latency'",
-                       "parallelism": f"frames sharded over {world} GPU(s), one NCCL broadcast of the weight blob at load, no per-frame collective"},
-            "single_stream": {"value": world * BATCH * args.steps / (ms_single * 1e-3), "ms_per_step": ms_single / args.steps},
-            "e2e": e2e, "gpu_launches": int(launches), "clocks": sampler.summary(), "roofline": roofline, "stages": stages,
-            "cpu_baseline": cpu_baseline, "stream_regime": stream_info,
+                       "inflight": f"{res['inflight']} contexts on {res['inflight']} streams take the steps round-robin (independent batches; one shared "
+                                   "model; tile policy 'throughput'); single_stream = one context, one stream, tile policy 'latency' (fused kernel)",
+                       "timing": f"exactly --steps steps between CUDA events, repeated {res['repeats']} times (≥ 60 ms in total); value is the median",
+                       "parallelism": f"frames sharded over {n_gpus} GPU(s), one NCCL broadcast of the weight blob at load, no per-frame collective" +
+                                      (" (one process, one handle over all GPUs: fdnn_load_devices)" if args.single_process else "")},
+            "timed": {"repeats": res["repeats"], "ms_of_k_steps_min_median_max": [float(np.min(res["runs_ms"])), float(np.median(res["runs_ms"])),
+                                                                                float(np.max(res["runs_ms"]))]},
+            "single_stream": single, "e2e": headline["e2e"], "e2e_jni": e2e_jni, "gpu_launches": res["launches"],
+            "clocks": b.sampler.summary(), "roofline": roofline, "roofline_stream": stream_info["roofline"] if stream_info else None,
+            "stages": stages, "cpu_baseline": headline["cpu"], "stream_regime": stream_info, "lazy": lazy, "stream1m": stream1m,
+            "int8_peak_calibration": i8,
         }, default=plain))
-    for c in flight + [ctx]:
-        c.delete()
-    dnn.delete()
+    b.dnn.delete()
     if world > 1:
-        dist.destroy_process_group()
+        b.dist.destroy_process_group()
 
 
 def main():
@@ -401,8 +761,14 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--no-stream", action="store_true", help="skip the extra long-stream measurement")
+    ap.add_argument("--config", default="batch512", choices=["batch512", "lazy", "stream1m"],
+                    help="which BASELINE config the headline value/e2e of the line describe (all are measured and reported either way)")
+    ap.add_argument("--single-process", action="store_true", help="--gpus N behind one handle in this process (fdnn_load_devices) instead of torchrun ranks")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline legs")
+    ap.add_argument("--no-stream", action="store_true", help="skip the 16384-frame stream-regime measurement")
+    ap.add_argument("--no-extra", action="store_true", help="skip the configs[3] / configs[4] legs")
+    ap.add_argument("--no-jni", action="store_true", help="skip the e2e_jni leg")
+    ap.add_argument("--no-peak", action="store_true", help="do not run tools/int8_peak live (use the committed calibration)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

@@ -220,6 +220,8 @@ class Ref:
             L.ref_hidden_trace.argtypes = [C.c_void_p, _f32p, C.c_int, C.c_int, _u8p]
             L.ref_time_calculate.argtypes = [C.c_void_p, _f32p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
             L.ref_time_calculate.restype = C.c_double
+            L.ref_time_lazy.argtypes = [C.c_void_p, _f32p, C.c_int, C.c_int, C.c_int, _i8p, C.c_int, C.c_void_p]
+            L.ref_time_lazy.restype = C.c_double
             L.ref_float_load.restype = C.c_void_p
             L.ref_float_load.argtypes = [C.c_char_p]
             L.ref_float_free.argtypes = [C.c_void_p]
@@ -324,6 +326,14 @@ class Ref:
         x = _f32(frames)
         ptr = out.ctypes.data_as(C.c_void_p) if out is not None else None
         return float(self.L.ref_time_calculate(self.h, x, x.shape[0], x.shape[1], batch, threads, ptr))
+
+
+    def time_lazy(self, frames, masks, batch=8, threads=1) -> float:
+        """wall seconds of the lazy protocol (until_output + one LazyOutputActivations per frame) over `threads` host threads"""
+        x = _f32(frames)
+        m = np.ascontiguousarray(masks, dtype=np.int8)
+        assert m.shape == (x.shape[0], self.output_dim)
+        return float(self.L.ref_time_lazy(self.h, x, x.shape[0], x.shape[1], batch, m, threads, None))
 
 
 class RefContext:

@@ -224,4 +224,46 @@ double ref_time_calculate(void *h, const float *in, int n, int dim, int batch, i
   return std::chrono::duration<double>(t1 - t0).count();
 }
 
+// CPU baseline of the lazy path (BASELINE config 3): T threads, each with its own context over a disjoint frame shard
+// of one shared QuantizedDnn; timed region per thread = context construction + CalculateUntilLastHiddenLayer + one
+// LazyOutputActivations per frame with that frame's mask (the protocol of test/java/suskun/nn/FuncTest.java:92-133).
+// masks = [n][O] bytes.  Returns wall seconds of the slowest thread.
+double ref_time_lazy(void *h, const float *in, int n, int dim, int batch, const int8_t *masks, int threads, float *out) {
+  auto *q = reinterpret_cast<dnn::QuantizedDnn *>(h);
+  if (threads < 1) threads = 1;
+  if (threads > n) threads = n;
+  size_t O = q->output_dimension();
+  std::vector<float *> copies(threads);
+  std::vector<int> begin(threads + 1);
+  for (int t = 0; t <= threads; ++t) begin[t] = (int) ((long long) n * t / threads);
+  for (int t = 0; t < threads; ++t)
+    copies[t] = aligned_copy(in + (size_t) begin[t] * dim, (size_t) (begin[t + 1] - begin[t]) * dim);
+  std::atomic<int> ready{0};
+  std::atomic<bool> go{false};
+  std::vector<std::thread> pool;
+  for (int t = 0; t < threads; ++t) {
+    pool.emplace_back([&, t]() {
+      ready.fetch_add(1);
+      while (!go.load()) std::this_thread::yield();
+      size_t cnt = (size_t) (begin[t + 1] - begin[t]);
+      dnn::BatchData data(copies[t], cnt, (size_t) dim, true);
+      dnn::CalculationContext ctx(q, cnt, (size_t) batch);
+      ctx.CalculateUntilLastHiddenLayer(data);
+      float sink = 0;
+      for (size_t i = 0; i < cnt; ++i) {
+        float *r = ctx.LazyOutputActivations(i, reinterpret_cast<const char *>(masks + ((size_t) begin[t] + i) * O));
+        if (out) std::memcpy(out + ((size_t) begin[t] + i) * O, r, O * sizeof(float));
+        sink += r[0];
+      }
+      if (sink == 12345.678f) std::abort();
+    });
+  }
+  while (ready.load() < threads) std::this_thread::yield();
+  auto t0 = std::chrono::steady_clock::now();
+  go.store(true);
+  for (auto &th : pool) th.join();
+  auto t1 = std::chrono::steady_clock::now();
+  return std::chrono::duration<double>(t1 - t0).count();
+}
+
 }  // extern "C"

@@ -27,7 +27,7 @@ constexpr int kGroup = 16;      // MMAs per commit
 constexpr int kThreads = 128;
 
 template <int kCtaGroup>
-__global__ void __launch_bounds__(kThreads, 1) mma_loop_kernel(int groups, unsigned long long *sink) {
+__global__ void __launch_bounds__(kThreads, 1) mma_loop_kernel(int groups, int random_fill, unsigned long long *sink) {
   extern __shared__ __align__(1024) uint8_t smem[];
   // A: 128 rows × 128 bytes; B: 256 (cta_group::1) or 128 (this CTA's half, cta_group::2) rows × 128 bytes; contents are
   // irrelevant to the rate (zeros), the layout is the K-major 128B-swizzled one the layer kernels use
@@ -36,7 +36,17 @@ __global__ void __launch_bounds__(kThreads, 1) mma_loop_kernel(int groups, unsig
   __shared__ uint64_t bars[2];
   __shared__ uint32_t tmem_slot;
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
-  for (int i = threadIdx.x; i < (128 + kN) * kStageK / 16; i += kThreads) reinterpret_cast<uint4 *>(smem)[i] = make_uint4(0, 0, 0, 0);
+  for (int i = threadIdx.x; i < (128 + kN) * kStageK / 16; i += kThreads) {
+    // operand bytes: zeros, or pseudo-random bytes (what real activations and weights look like to the multipliers: the
+    // power drawn, and with it the clock the chip sustains, depends on how much the operands toggle)
+    uint32_t h = uint32_t(i) * 2654435761u + blockIdx.x * 40503u;
+    uint4 v;
+    h ^= h >> 15; h *= 2246822519u; v.x = h;
+    h ^= h >> 13; h *= 3266489917u; v.y = h;
+    h ^= h >> 16; h *= 668265263u; v.z = h;
+    h ^= h >> 15; h *= 374761393u; v.w = h;
+    reinterpret_cast<uint4 *>(smem)[i] = random_fill ? v : make_uint4(0, 0, 0, 0);
+  }
   if (threadIdx.x == 0) {
     ptx::mbar_init(&bars[0], 1);
     ptx::mbar_init(&bars[1], 1);
@@ -110,7 +120,7 @@ __global__ void __launch_bounds__(kThreads, 1) mma_loop_kernel(int groups, unsig
   } while (0)
 
 template <int kCtaGroup>
-cudaError_t launch(int ctas, int groups, cudaStream_t s) {
+cudaError_t launch(int ctas, int groups, int random_fill, cudaStream_t s) {
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(unsigned(ctas));
   cfg.blockDim = dim3(kThreads);
@@ -123,11 +133,11 @@ cudaError_t launch(int ctas, int groups, cudaStream_t s) {
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = kCtaGroup > 1 ? 1 : 0;
-  return cudaLaunchKernelEx(&cfg, mma_loop_kernel<kCtaGroup>, groups, static_cast<unsigned long long *>(nullptr));
+  return cudaLaunchKernelEx(&cfg, mma_loop_kernel<kCtaGroup>, groups, random_fill, static_cast<unsigned long long *>(nullptr));
 }
 
 template <int kCtaGroup>
-void measure(int sms, double seconds, double *burst, double *sustained, double *sustained_first, double *sustained_last) {
+void measure(int sms, double seconds, int random_fill, double *burst, double *sustained, double *sustained_first, double *sustained_last) {
   CK(cudaFuncSetAttribute(mma_loop_kernel<kCtaGroup>, cudaFuncAttributeMaxDynamicSharedMemorySize, (128 + kN) * kStageK));
   const int ctas = sms / kCtaGroup * kCtaGroup;
   // ops per instruction and issuing CTA: 2 · M · N · K with M = 128 per CTA of the group
@@ -137,12 +147,12 @@ void measure(int sms, double seconds, double *burst, double *sustained, double *
   CK(cudaEventCreate(&e0));
   CK(cudaEventCreate(&e1));
   const int groups = 2000;  // 32 000 MMAs per issuer ≈ 2 ms
-  for (int i = 0; i < 3; ++i) CK(launch<kCtaGroup>(ctas, groups, nullptr));
+  for (int i = 0; i < 3; ++i) CK(launch<kCtaGroup>(ctas, groups, random_fill, nullptr));
   CK(cudaDeviceSynchronize());
   double best = 0;
   for (int i = 0; i < 10; ++i) {
     CK(cudaEventRecord(e0));
-    CK(launch<kCtaGroup>(ctas, groups, nullptr));
+    CK(launch<kCtaGroup>(ctas, groups, random_fill, nullptr));
     CK(cudaEventRecord(e1));
     CK(cudaEventSynchronize(e1));
     float ms = 0;
@@ -158,7 +168,7 @@ void measure(int sms, double seconds, double *burst, double *sustained, double *
   CK(cudaEventRecord(first));
   ev.push_back(first);
   while (std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() < seconds) {
-    for (int i = 0; i < 8; ++i) CK(launch<kCtaGroup>(ctas, groups, nullptr));
+    for (int i = 0; i < 8; ++i) CK(launch<kCtaGroup>(ctas, groups, random_fill, nullptr));
     cudaEvent_t e;
     CK(cudaEventCreate(&e));
     CK(cudaEventRecord(e));
@@ -187,17 +197,22 @@ int main(int argc, char **argv) {
   CK(cudaDeviceGetAttribute(&clock_khz, cudaDevAttrClockRate, dev));
   cudaDeviceProp prop;
   CK(cudaGetDeviceProperties(&prop, dev));
-  double b1, s1, f1, l1, b2, s2, f2, l2;
-  measure<1>(sms, seconds, &b1, &s1, &f1, &l1);
-  measure<2>(sms, seconds, &b2, &s2, &f2, &l2);
+  double r[4][4];
+  measure<1>(sms, seconds, 1, &r[0][0], &r[0][1], &r[0][2], &r[0][3]);
+  measure<2>(sms, seconds, 1, &r[1][0], &r[1][1], &r[1][2], &r[1][3]);
+  measure<1>(sms, seconds / 2, 0, &r[2][0], &r[2][1], &r[2][2], &r[2][3]);
+  measure<2>(sms, seconds / 2, 0, &r[3][0], &r[3][1], &r[3][2], &r[3][3]);
   // what the instruction rate would give at the maximum SM clock: 128·256·32 MACs per 128 cycles and SM
   const double nominal = 2.0 * 8192.0 * sms * (clock_khz * 1e3) / 1e12;
-  std::printf(
-      "{\"gpu\": \"%s\", \"sms\": %d, \"sm_max_mhz\": %.0f, \"int8_tops_at_max_clock_8192_mac_per_clk_sm\": %.1f, "
-      "\"cta_group_1\": {\"burst_tops\": %.1f, \"sustained_tops\": %.1f, \"sustained_first_tenth\": %.1f, \"sustained_last_tenth\": %.1f}, "
-      "\"cta_group_2\": {\"burst_tops\": %.1f, \"sustained_tops\": %.1f, \"sustained_first_tenth\": %.1f, \"sustained_last_tenth\": %.1f}, "
-      "\"sustained_seconds\": %.1f, \"how\": \"tcgen05.mma kind::i8 (u8 x s8 -> s32), operands resident in shared memory, "
-      "%d MMAs per commit, 2 commits in flight, one CTA (pair) per SM; ops = 2*M*N*K\"}\n",
-      prop.name, sms, clock_khz / 1e3, nominal, b1, s1, f1, l1, b2, s2, f2, l2, seconds, kGroup);
+  const char *names[4] = {"cta_group_1", "cta_group_2", "cta_group_1_zero_operands", "cta_group_2_zero_operands"};
+  std::printf("{\"gpu\": \"%s\", \"sms\": %d, \"sm_max_mhz\": %.0f, \"int8_tops_at_max_clock_8192_mac_per_clk_sm\": %.1f", prop.name, sms,
+              clock_khz / 1e3, nominal);
+  for (int i = 0; i < 4; ++i)
+    std::printf(", \"%s\": {\"burst_tops\": %.1f, \"sustained_tops\": %.1f, \"sustained_first_tenth\": %.1f, \"sustained_last_tenth\": %.1f}", names[i],
+                r[i][0], r[i][1], r[i][2], r[i][3]);
+  std::printf(", \"sustained_seconds\": %.1f, \"how\": \"tcgen05.mma kind::i8 (u8 x s8 -> s32), operands resident in shared memory "
+              "(pseudo-random bytes; zeros for the *_zero_operands entries), %d MMAs per commit, 2 commits in flight, one CTA (pair) per SM; "
+              "ops = 2*M*N*K\"}\n",
+              seconds, kGroup);
   return 0;
 }
