@@ -121,7 +121,7 @@ class ClockSampler:
                         self.reasons.add(name)
             except Exception:
                 pass
-            time.sleep(0.004)
+            time.sleep(0.02)  # NVML calls take driver locks: a tight poll slows the very CUDA calls being measured
 
     def start(self):
         if self.nv:
@@ -350,6 +350,7 @@ class Bench:
             if i % 64 == 0:
                 torch.cuda.synchronize()
         torch.cuda.synchronize()
+        self.sampler.stop()  # the end-to-end legs below are host-driven: no NVML polling beside them
 
         # ---- per-kernel times (CUDA events on the launching stream) ----
         iters = max(args.steps, 20)

@@ -29,6 +29,7 @@ struct QLayerArgs {
   int fast_tail;
   float one, neg_zero;  // 1.0f and −0.0f as run-time values: keeps ptxas from rewriting fma(a, 1, b) / fma(a, b, −0) into FADD2 / FMUL2
   int M, N, K;
+  int row0;         // first row of this launch (CTA-pair kernel only; a multiple of 256): rows [row0, M) are computed
   FixList fix;      // this layer's saturation risk entries
   uint8_t *out_u8;  // hidden mode: u8 activations [M][N]
   float *out_f32;   // logits mode: lin + bias, fp32 [M][out_ld]

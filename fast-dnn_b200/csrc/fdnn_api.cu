@@ -47,6 +47,13 @@ std::atomic<long long> g_launches{0};
 
 int round_up(int v, int m) { return (v + m - 1) / m * m; }
 
+// rows of logits per output-layer/softmax sub-chunk on long batches (FDNN_OUTPUT_SUB_ROWS; 0 = no sub-chunks)
+const int kOutputSubRows = [] {
+  const char *e = std::getenv("FDNN_OUTPUT_SUB_ROWS");
+  const int v = e ? std::atoi(e) : 0;  // measured on B200 (profiles/r2_experiments.md): sub-chunks lose; off unless asked for
+  return v <= 0 ? (1 << 30) : std::max(256, v / 256 * 256);
+}();
+
 bool env_flag(const char *name, bool dflt) {
   const char *e = std::getenv(name);
   if (!e || !e[0]) return dflt;
@@ -354,6 +361,8 @@ int create_ctx(fdnn_model *m, int n, fdnn_ctx **out) {
 
 // Enqueue one forward pass over frames [0, m) of `d_in` on `stream`.  Logits (lin + bias of the
 // output layer) go to `d_logits` with row pitch O.
+int enqueue_softmax(fdnn_ctx *c, const float *d_logits, const int8_t *d_masks, int rows, float *d_out, cudaStream_t stream);
+
 // `want_softmax`: the caller will normalise d_logits in place right after; when the fused kernel takes the pass it does that
 // itself and sets *softmax_done.
 int enqueue_until_logits(fdnn_ctx *c, const float *d_in, int m, float *d_logits, cudaStream_t stream,
@@ -516,6 +525,28 @@ int enqueue_until_logits(fdnn_ctx *c, const float *d_in, int m, float *d_logits,
       const int act_box = plan.share_a ? (plan.cluster == 4 ? 2 : (plan.cluster == 2 ? 1 : 0)) : 0;
       const int w_rows = plan.share_a ? plan.block_n : plan.block_n / plan.cluster;
       const int w_box = w_rows == 64 ? 0 : (w_rows == 128 ? 1 : (w_rows == 256 ? 2 : 3));
+      if (plan.pair && logits && want_softmax && softmax_done != nullptr && !after_stage && m > kOutputSubRows) {
+        // Long batches: output layer and softmax in sub-chunks of rows whose logits (32 KB per frame at 8000 outputs) still sit in the
+        // L2 when the softmax reads and overwrites them — one HBM write of the scores instead of write + read + write.  Sub-chunks
+        // are whole waves of 256×256 pair tiles (9 row pairs × 32 column blocks ≈ 3.9 waves of 74 pairs for the headline network).
+        const int m_pairs = (m + 255) / 256;
+        const int per = std::max(1, kOutputSubRows / 256);
+        const int n_sub = std::max(1, (m_pairs + per / 2) / per);
+        int done_pairs = 0;
+        for (int sc = 0; sc < n_sub; ++sc) {
+          const int take = (m_pairs - done_pairs) / (n_sub - sc);
+          QLayerArgs as = a;
+          as.row0 = done_pairs * 256;
+          as.M = std::min(m, (done_pairs + take) * 256);
+          CUDA_TRY(launch_qlayer_pair(c->amap[j & 1][0], mod->wmaps[size_t(j)][size_t(w_box)], as, true, plan.block_n, mod->num_sms, stream));
+          g_launches.fetch_add(1, std::memory_order_relaxed);
+          if (int rc = enqueue_softmax(c, d_logits + size_t(as.row0) * size_t(ql.nodes), nullptr, as.M - as.row0, d_logits + size_t(as.row0) * size_t(ql.nodes), stream)) return rc;
+          done_pairs += take;
+        }
+        *softmax_done = true;
+        c->last_frames = m;
+        return FDNN_OK;
+      }
       if (plan.pair)
         CUDA_TRY(launch_qlayer_pair(c->amap[j & 1][0], mod->wmaps[size_t(j)][size_t(w_box)], a, logits, plan.block_n, mod->num_sms, stream));
       else

@@ -56,11 +56,11 @@ constexpr int kEpilogueThreads = kEpilogueWarps * 32;
 constexpr int kFirstScanWarp = 4, kFirstEpilogueWarp = kFirstScanWarp + kScanWarps;
 constexpr int kThreads = (kFirstEpilogueWarp + kEpilogueWarps) * 32;  // 896
 constexpr int kAccStages = 2;
-constexpr int kEntCap = 1024;   // risk entries of the tile staged (packed) in shared memory; the rest is read from global
+constexpr int kEntCap = 512;    // risk entries of the tile staged (packed) in shared memory; the rest is read from global
 constexpr int kPtrSlots = 132;  // ≥ k_blocks + 1 → K ≤ 16768
 constexpr int kRowEvents = 4;    // overflow events kept per tile row (third and later event of one 16-column chunk)
-constexpr int kCellSlots = 2;    // events a (chunk, row) cell holds
-constexpr int kListCap = 64;     // events a scan warp collects per tile; the epilogue warps file them into the cells
+constexpr int kCellSlots = 1;    // events a (chunk, row) cell holds (1: 16 KB of cells per CTA instead of 32 — the difference is a sixth pipeline stage)
+constexpr int kListCap = 32;     // events a scan warp collects per tile; the epilogue warps file them into the cells
 
 static_assert(kBlockK == kFixKBlock, "risk-list order is tied to the tiling");
 
@@ -78,7 +78,9 @@ __device__ __forceinline__ void file_event(uint32_t *cell, uint32_t *flag_s, uin
   constexpr int kAllChunks = BN / 16;
   const uint32_t word = (uint32_t(d) & 0xfffffu) | ((node_local & 15u) << 20);
   uint32_t *c0 = cell + (node_local >> 4) * kBlockM + row;
-  if (atomicCAS(c0, 0u, word) != 0u && atomicCAS(c0 + kAllChunks * kBlockM, 0u, word) != 0u) {
+  bool filed = atomicCAS(c0, 0u, word) == 0u;
+  if (kCellSlots > 1 && !filed) filed = atomicCAS(c0 + kAllChunks * kBlockM, 0u, word) == 0u;
+  if (!filed) {
     const uint32_t slot = atomicAdd(flag_s + row, 0x10000u) >> 16;
     if (slot >= 0x8000u) atomicSub(flag_s + row, 0x10000u);  // dense risk lists: the count must not wrap (such a row recomputes anyway)
     atomicOr(flag_s + row, 1u << (node_local >> 4));
@@ -91,7 +93,7 @@ struct PairConfig {
   static constexpr int kABytes = kBlockM * kBlockK;     // this CTA's 128 activation rows
   static constexpr int kBBytes = (BN / 2) * kBlockK;    // this CTA's half of the weight rows
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = BN == 256 ? 5 : (BN == 128 ? 7 : 8);
+  static constexpr int kStages = BN == 256 ? 6 : (BN == 128 ? 8 : 9);
   static constexpr int kAllChunks = BN / 16;
   static constexpr int kCellWords = kCellSlots * kAllChunks * kBlockM;  // per accumulator stage
   static constexpr int kCellBytes = kAccStages * kCellWords * 4;
@@ -139,8 +141,9 @@ qlayer_pair_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_co
   const int warp = int(threadIdx.x) / 32, lane = int(threadIdx.x) % 32;
   auto tstamp = [&](int slot) { stamp(args.timeline, slot); };
   if (threadIdx.x == 0) tstamp(0);
-  const int M = args.M, N = args.N, K = args.K;
-  const int m_pairs = (M + 2 * kBlockM - 1) / (2 * kBlockM);
+  const int M = args.M, N = args.N, K = args.K;  // rows [args.row0, M) of the activation / output buffers
+  const int row0 = args.row0;
+  const int m_pairs = (M - row0 + 2 * kBlockM - 1) / (2 * kBlockM);
   const int n_blocks = (N + BN - 1) / BN;
   const int tiles_total = m_pairs * n_blocks;
   const int k_blocks = (K + kBlockK - 1) / kBlockK;
@@ -199,7 +202,7 @@ qlayer_pair_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_co
           uint8_t *sb = sa + Cfg::kABytes;
           if (leader) ptx::mbar_arrive_expect_tx(full_bar + stage, 2 * Cfg::kStageBytes);  // both CTAs' bytes land on this barrier
           const uint32_t bar = ptx::mapa_u32(ptx::smem_u32(full_bar + stage), 0);
-          ptx::tma_load_2d_pair(&tmap_act, bar, sa, kb * kBlockK, m_blk * kBlockM);
+          ptx::tma_load_2d_pair(&tmap_act, bar, sa, kb * kBlockK, row0 + m_blk * kBlockM);
           ptx::tma_load_2d_pair(&tmap_w, bar, sb, kb * kBlockK, n_blk * BN + int(rank) * (BN / 2));
           if (++stage == Cfg::kStages) {
             stage = 0;
@@ -425,7 +428,7 @@ qlayer_pair_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_co
       int m_blk, n_blk;
       decode(ct, m_blk, n_blk);
       const int n0 = n_blk * BN;
-      const int row = m_blk * kBlockM + row_local;
+      const int row = row0 + m_blk * kBlockM + row_local;
       const bool row_ok = row < M;
       const int col0 = n0 + col_group * Cfg::kColsPerWarp;
       const int n_valid = max(0, min(Cfg::kChunks, (N - col0 + 15) / 16));  // warp-uniform
@@ -474,7 +477,7 @@ qlayer_pair_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_co
       for (int j = 0; j < Cfg::kChunks; ++j) {
         if (j < n_valid) {
           const int chunk = col_group * Cfg::kChunks + j;
-          uint32_t e0 = cell[chunk * kBlockM], e1 = cell[(Cfg::kAllChunks + chunk) * kBlockM];
+          uint32_t e0 = cell[chunk * kBlockM], e1 = kCellSlots > 1 ? cell[(Cfg::kAllChunks + chunk) * kBlockM] : 0u;
           uint32_t raw[16];
           ptx::tmem_ld_32x16(t_addr + uint32_t(j * 16), raw);
           ptx::tmem_ld_wait();
@@ -543,7 +546,7 @@ qlayer_pair_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_co
 template <int BN, bool kLogits>
 cudaError_t launch_one(const CUtensorMap &ta, const CUtensorMap &tw, const QLayerArgs &a, int num_sms, cudaStream_t stream) {
   using Cfg = PairConfig<BN>;
-  const int m_pairs = (a.M + 2 * kBlockM - 1) / (2 * kBlockM), n_blocks = (a.N + BN - 1) / BN;
+  const int m_pairs = (a.M - a.row0 + 2 * kBlockM - 1) / (2 * kBlockM), n_blocks = (a.N + BN - 1) / BN;
   const int pair_tiles = m_pairs * n_blocks;
   const int max_pairs = num_sms / 2;
   const int pairs = pair_tiles < max_pairs ? pair_tiles : max_pairs;
@@ -588,7 +591,7 @@ cudaError_t qlayer_pair_configure() {
 // `tmap_act`: box of 128 rows; `tmap_w`: box of block_n / 2 rows.
 cudaError_t launch_qlayer_pair(const CUtensorMap &tmap_act, const CUtensorMap &tmap_w, const QLayerArgs &a, bool logits, int block_n, int num_sms,
                                cudaStream_t stream) {
-  if (a.M <= 0) return cudaSuccess;
+  if (a.M - a.row0 <= 0 || a.row0 % (2 * kBlockM) != 0) return a.M - a.row0 <= 0 ? cudaSuccess : cudaErrorInvalidValue;
   switch (block_n) {
     case 64: return logits ? launch_one<64, true>(tmap_act, tmap_w, a, num_sms, stream) : launch_one<64, false>(tmap_act, tmap_w, a, num_sms, stream);
     case 128: return logits ? launch_one<128, true>(tmap_act, tmap_w, a, num_sms, stream) : launch_one<128, false>(tmap_act, tmap_w, a, num_sms, stream);
