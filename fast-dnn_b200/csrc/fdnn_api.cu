@@ -227,6 +227,7 @@ struct fdnn_ctx {
   float *h_in = nullptr;    // [cap][I]
   float *h_out = nullptr;   // [cap][O]
   std::vector<cudaEvent_t> events;  // polled events (wait_event): [0] = whole chunk done, [1 + k] = sub-chunk k has landed in h_out
+  int8_t *h_maskbuf = nullptr;  // batched lazy path on pageable masks: page-locked staging [cap][O]
   int8_t *h_mask = nullptr;  // single-row lazy path: mapped page-locked mask [O] and result row [O]
   float *h_row = nullptr;
   bool trace = false;
@@ -286,6 +287,7 @@ void destroy_ctx(fdnn_ctx *c) {
     cudaFree(c->d_fused);
     if (c->h_in) cudaFreeHost(c->h_in);
     if (c->h_out) cudaFreeHost(c->h_out);
+    if (c->h_maskbuf) cudaFreeHost(c->h_maskbuf);
     if (c->h_mask) cudaFreeHost(c->h_mask);
     if (c->h_row) cudaFreeHost(c->h_row);
     for (cudaEvent_t e : c->events) cudaEventDestroy(e);
@@ -1295,27 +1297,6 @@ int fdnn_ctx_lazy(fdnn_ctx *ctx, int idx, const int8_t *mask, float *out) {
   return FDNN_OK;
 }
 
-int fdnn_ctx_lazy_batch(fdnn_ctx *ctx, const int8_t *masks, float *out) {
-  if (!ctx || !masks || !out) {
-    set_error("null argument");
-    return FDNN_EINVAL;
-  }
-  if (!ctx->have_logits) {
-    set_error("calculateUntilOutput has not been run on this context");
-    return FDNN_EINVAL;
-  }
-  DeviceGuard g(ctx->model->device);
-  const int O = ctx->model->hdr.out_dim, n = ctx->last_frames;
-  if (!ctx->d_masks) CUDA_TRY(cudaMalloc(&ctx->d_masks, size_t(ctx->cap) * size_t(O)));
-  CUDA_TRY(cudaMemcpyAsync(ctx->d_masks, masks, size_t(n) * size_t(O), cudaMemcpyHostToDevice, ctx->stream));
-  // the masked softmax must not overwrite the resident logits (later lazy calls need them)
-  if (!ctx->d_lazy) CUDA_TRY(cudaMalloc(&ctx->d_lazy, size_t(ctx->cap) * size_t(O) * 4));
-  if (int rc = enqueue_softmax(ctx, ctx->d_logits, ctx->d_masks, n, ctx->d_lazy, ctx->stream)) return rc;
-  CUDA_TRY(cudaMemcpyAsync(out, ctx->d_lazy, size_t(n) * size_t(O) * 4, cudaMemcpyDeviceToHost, ctx->stream));
-  CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-  return FDNN_OK;
-}
-
 int fdnn_ctx_hidden(fdnn_ctx *ctx, int layer, int n_frames, uint8_t *out) {
   if (!ctx || !out) return FDNN_EINVAL;
   const int nq = ctx->model->hdr.n_qlayers, H = ctx->model->hdr.hidden;
@@ -1737,6 +1718,58 @@ int calculate_impl(fdnn_model *model, const float *in, int n, int dim, float *ou
 }
 
 }  // namespace
+
+// All frames of the context at once (BASELINE config 3).  Page-locked caller memory: masks up, one masked-softmax launch,
+// scores down, all asynchronous.  Pageable caller memory (what a JVM hands us): masks through the context's page-locked
+// staging buffer, scores come down in 128-row pieces with an event each, and the calling thread copies piece k out while
+// piece k+1 is still crossing PCIe.
+int fdnn_ctx_lazy_batch(fdnn_ctx *ctx, const int8_t *masks, float *out) {
+  if (!ctx || !masks || !out) {
+    set_error("null argument");
+    return FDNN_EINVAL;
+  }
+  if (!ctx->have_logits) {
+    set_error("calculateUntilOutput has not been run on this context");
+    return FDNN_EINVAL;
+  }
+  DeviceGuard g(ctx->model->device);
+  const size_t O = size_t(ctx->model->hdr.out_dim);
+  const int n = ctx->last_frames;
+  if (!ctx->d_masks) CUDA_TRY(cudaMalloc(&ctx->d_masks, size_t(ctx->cap) * O));
+  // the masked softmax must not overwrite the resident logits (later lazy calls need them)
+  if (!ctx->d_lazy) CUDA_TRY(cudaMalloc(&ctx->d_lazy, size_t(ctx->cap) * O * 4));
+  const int8_t *src = masks;
+  if (!host_pinned(masks)) {
+    if (!ctx->h_maskbuf) CUDA_TRY(cudaHostAlloc(reinterpret_cast<void **>(&ctx->h_maskbuf), size_t(ctx->cap) * O, cudaHostAllocPortable));
+    std::memcpy(ctx->h_maskbuf, masks, size_t(n) * O);
+    src = ctx->h_maskbuf;
+  }
+  CUDA_TRY(cudaMemcpyAsync(ctx->d_masks, src, size_t(n) * O, cudaMemcpyHostToDevice, ctx->stream));
+  if (host_pinned(out)) {
+    if (int rc = enqueue_softmax(ctx, ctx->d_logits, ctx->d_masks, n, ctx->d_lazy, ctx->stream)) return rc;
+    CUDA_TRY(cudaMemcpyAsync(out, ctx->d_lazy, size_t(n) * O * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (int rc = ensure_events(ctx, 1)) return rc;
+    CUDA_TRY(cudaEventRecord(ctx->events[0], ctx->stream));
+    CUDA_TRY(wait_event(ctx->events[0]));
+    return FDNN_OK;
+  }
+  if (!ctx->h_out) CUDA_TRY(cudaHostAlloc(reinterpret_cast<void **>(&ctx->h_out), size_t(ctx->cap) * O * 4, cudaHostAllocPortable));
+  const int subs = (n + kSubRows - 1) / kSubRows;
+  if (int rc = ensure_events(ctx, size_t(1 + subs))) return rc;
+  for (int k = 0; k < subs; ++k) {
+    const int r0 = k * kSubRows, rows = std::min(kSubRows, n - r0);
+    if (int rc = enqueue_softmax(ctx, ctx->d_logits + size_t(r0) * O, ctx->d_masks + size_t(r0) * O, rows, ctx->d_lazy + size_t(r0) * O, ctx->stream))
+      return rc;
+    CUDA_TRY(cudaMemcpyAsync(ctx->h_out + size_t(r0) * O, ctx->d_lazy + size_t(r0) * O, size_t(rows) * O * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaEventRecord(ctx->events[size_t(1 + k)], ctx->stream));
+  }
+  for (int k = 0; k < subs; ++k) {
+    const int r0 = k * kSubRows, rows = std::min(kSubRows, n - r0);
+    CUDA_TRY(wait_event(ctx->events[size_t(1 + k)]));
+    std::memcpy(out + size_t(r0) * O, ctx->h_out + size_t(r0) * O, size_t(rows) * O * 4);
+  }
+  return FDNN_OK;
+}
 
 int fdnn_calculate(fdnn_model *model, const float *in, int n, int dim, int batch_hint, float *out) {
   (void) batch_hint;
