@@ -59,6 +59,7 @@ constexpr int kMaxStages = 8;
 constexpr int kRingBytes = 192 * 1024;
 constexpr int kLogitsBN = 256;
 constexpr int kTmemCols = 512;
+constexpr int kPrepThreads = 64;  // warps 2 and 3
 constexpr int kSched = 4;  // depth of the claimed-tile ring between the producer and the other roles
 constexpr int kSoftmaxGroups = 4;                                   // groups of kSoftmaxThreads threads, a row each
 constexpr int kSoftmaxRowFloats = kRingBytes / kSoftmaxGroups / 4;  // 12288: widest row the fused softmax takes
@@ -84,7 +85,7 @@ constexpr int kSmemPtr = kSmemEnt + kAccStages * kEntCap * 4;
 constexpr int kSmemRowEv = kSmemPtr + kAccStages * kPtrSlots * 4;
 constexpr int kSmemRowCnt = kSmemRowEv + kAccStages * kBlockM * kRowEvents * 4;
 constexpr int kSmemBars = kSmemRowCnt + kAccStages * kBlockM * 4;
-constexpr int kNumBars = 2 * kMaxStages + 3 * kAccStages + 2 * kSched;
+constexpr int kNumBars = 2 * kMaxStages + 4 * kAccStages + 2 * kSched;
 constexpr int kSmemRed = kSmemBars + kNumBars * 8 + 16 + kSched * 4;
 constexpr int kSmemTotal = kSmemRed + kSoftmaxGroups * (kSoftmaxThreads / 32) * 4;
 static_assert(kSmemBars % 8 == 0 && kSmemTotal <= 232448, "shared memory budget");
@@ -135,7 +136,7 @@ struct Shared {
   float *bias;
   uint8_t *lut;
   uint32_t *ent, *ptr, *rowev, *rowcnt;
-  uint64_t *full_bar, *empty_bar, *tmem_full_bar, *tmem_empty_bar, *scan_done_bar;
+  uint64_t *full_bar, *empty_bar, *tmem_full_bar, *tmem_empty_bar, *scan_done_bar, *prep_bar;
   uint64_t *sched_full_bar, *sched_empty_bar;
   uint32_t *tmem_slot;
   int *tile_ring;
@@ -262,6 +263,34 @@ __device__ __forceinline__ void mma_tile(const FusedArgs &p, const Tile &t, cons
   advance_acc(f);
 }
 
+// The per-tile state of the saturation scan, staged by warps 2-3 ahead of the scan warps: entry offsets per K block, packed
+// entry words (w0 | w1 << 8 | (node − n0) << 16 | byte offset of the pair in its K block << 24), zeroed event counters.
+template <int BN>
+__device__ __forceinline__ void prep_tile(const FusedArgs &p, const Tile &t, const Shared &sh, Flow &f, int pt, int lane) {
+  const FusedLayer &L = p.layer[t.layer];
+  const int kbn = L.K / kBlockK;
+  const uint32_t acc = f.acc;
+  const uint32_t *gp = L.fix_ptr + size_t(t.n_blk) * kbn;
+  uint32_t *P = sh.ptr + acc * kPtrSlots;
+  uint32_t *E = sh.ent + acc * kEntCap;
+  // the event slots and lists of this accumulator stage are free once its previous tile has been drained
+  ptx::mbar_wait(sh.tmem_empty_bar + acc, bit(f.acc_ph, acc) ^ 1u);
+  const bool scan_on = !(p.debug_flags & 1);
+  const uint32_t ent_begin = __ldg(gp);
+  for (int i = pt; i <= kbn; i += kPrepThreads) P[i] = scan_on ? __ldg(gp + i) - ent_begin : 0u;
+  const uint32_t n_ent = scan_on ? __ldg(gp + kbn) - ent_begin : 0u;
+  const uint32_t staged = min(n_ent, uint32_t(kEntCap));
+  const uint2 *gent = reinterpret_cast<const uint2 *>(L.fix_ent) + ent_begin;
+  for (uint32_t e = uint32_t(pt); e < staged; e += kPrepThreads) {
+    const uint2 fe = __ldg(gent + e);
+    E[e] = (fe.x >> 16) | ((fe.y - uint32_t(t.n_blk * BN)) << 16) | (((2u * (fe.x & 0xffffu)) & 127u) << 24);
+  }
+  for (int i = pt; i < kBlockM; i += kPrepThreads) sh.rowcnt[acc * kBlockM + i] = 0;
+  __syncwarp();
+  if (lane == 0) ptx::mbar_arrive(sh.prep_bar + acc);
+  advance_acc(f);
+}
+
 template <int BN>
 __device__ __forceinline__ void scan_tile(const FusedArgs &p, const Tile &t, const Shared &sh, Flow &f, int st, int lane) {
   using G = Geo<BN>;
@@ -282,22 +311,12 @@ __device__ __forceinline__ void scan_tile(const FusedArgs &p, const Tile &t, con
     const uint32_t *gp = fix_ptr + size_t(n_blk) * kbn;
     uint32_t *P = sh.ptr + acc * kPtrSlots;
     uint32_t *E = sh.ent + acc * kEntCap;
-    // the event slots of this accumulator stage are free once its previous tile has been drained
-    ptx::mbar_wait(sh.tmem_empty_bar + acc, bit(f.acc_ph, acc) ^ 1u);
-    const bool scan_on = !(p.debug_flags & 1);
-    const uint32_t ent_begin = __ldg(gp);
-    for (int i = st; i <= kbn; i += kScanThreads) P[i] = scan_on ? __ldg(gp + i) - ent_begin : 0u;
-    const uint32_t n_ent = scan_on ? __ldg(gp + kbn) - ent_begin : 0u;
-    const uint32_t staged = min(n_ent, uint32_t(kEntCap));
-    const uint2 *gent = reinterpret_cast<const uint2 *>(fix_ent) + ent_begin;
-    for (uint32_t e = uint32_t(st); e < staged; e += kScanThreads) {
-      const uint2 fe = __ldg(gent + e);
-      E[e] = (fe.x >> 16) | ((fe.y - uint32_t(n_blk * BN)) << 16) | (((2u * (fe.x & 0xffffu)) & 127u) << 24);
-    }
+    // the two prep warps have staged this tile's entry offsets (P) and packed entries (E) and zeroed the event counters of
+    // this accumulator stage — one or more tiles ahead, so no global-memory latency sits between two tiles of a CTA
+    ptx::mbar_wait(sh.prep_bar + acc, bit(f.acc_ph, acc));
+    const uint32_t staged = min(P[kbn], uint32_t(kEntCap));
     uint32_t *cnt_s = sh.rowcnt + acc * kBlockM;
     uint32_t *ev_s = sh.rowev + acc * kBlockM * kRowEvents;
-    if (st < kBlockM) cnt_s[st] = 0;
-    ptx::named_bar_sync(2, kScanThreads);
     auto record = [&](int row, int v, uint32_t node_local) {
       const int d = max(min(v, 32767), -32768) - v;
       const uint32_t slot = atomicAdd(cnt_s + row, 1u);
@@ -349,6 +368,7 @@ __device__ __forceinline__ void scan_tile(const FusedArgs &p, const Tile &t, con
         }
       }
       for (uint32_t e = max(r0, staged); e < r1; ++e) {  // beyond the staging capacity (dense risk lists)
+        const uint2 *gent = reinterpret_cast<const uint2 *>(fix_ent) + __ldg(gp);
         const uint2 fe = __ldg(gent + e);
         const uint32_t b = (2u * (fe.x & 0xffffu)) & 127u;
         const int row = (st % kBlockM);
@@ -502,7 +522,8 @@ __global__ void __launch_bounds__(kThreads, 1) qlayer_fused_kernel(const __grid_
   sh.tmem_full_bar = sh.empty_bar + kMaxStages;
   sh.tmem_empty_bar = sh.tmem_full_bar + kAccStages;
   sh.scan_done_bar = sh.tmem_empty_bar + kAccStages;
-  sh.sched_full_bar = sh.scan_done_bar + kAccStages;
+  sh.prep_bar = sh.scan_done_bar + kAccStages;
+  sh.sched_full_bar = sh.prep_bar + kAccStages;
   sh.sched_empty_bar = sh.sched_full_bar + kSched;
   sh.tmem_slot = reinterpret_cast<uint32_t *>(sh.sched_empty_bar + kSched);
   sh.tile_ring = reinterpret_cast<int *>(sh.tmem_slot + 4);
@@ -525,10 +546,11 @@ __global__ void __launch_bounds__(kThreads, 1) qlayer_fused_kernel(const __grid_
       ptx::mbar_init(sh.tmem_full_bar + i, 1);
       ptx::mbar_init(sh.tmem_empty_bar + i, kEpilogueThreads);
       ptx::mbar_init(sh.scan_done_bar + i, kScanThreads);
+      ptx::mbar_init(sh.prep_bar + i, kPrepThreads / 32);
     }
     for (int i = 0; i < kSched; ++i) {
       ptx::mbar_init(sh.sched_full_bar + i, 1);
-      ptx::mbar_init(sh.sched_empty_bar + i, 1 + kScanWarps + kEpilogueWarps);  // one lane of the MMA warp and of every scan / epilogue warp
+      ptx::mbar_init(sh.sched_empty_bar + i, 1 + 2 + kScanWarps + kEpilogueWarps);  // one lane of the MMA warp and of every prep / scan / epilogue warp
     }
     ptx::fence_barrier_init();
   }
@@ -553,6 +575,8 @@ __global__ void __launch_bounds__(kThreads, 1) qlayer_fused_kernel(const __grid_
   if (warp == 0) {
     if (lane == 0) {
       const int total = int(p.total_tiles);
+      // (Claiming one tile ahead, to take the atomic's round trip off the path between two tiles, was measured and dropped: no gain
+      // at 512 frames, a loss at 1024 — it changes who gets which tile.  profiles/r2_experiments.md)
       for (;;) {
         ptx::mbar_wait(sh.sched_empty_bar + sc.q, bit(sc.ph, sc.q) ^ 1u);
         int id = int(atomicAdd(p.sync + kSyncTile, 1u));
@@ -592,6 +616,17 @@ __global__ void __launch_bounds__(kThreads, 1) qlayer_fused_kernel(const __grid_
       } else {
         mma_tile<BNH>(p, t, sh, f, tmem_base, lane);
       }
+    }
+  } else if (warp == 2 || warp == 3) {
+    const int pt = int(threadIdx.x) - 64;
+    for (;;) {
+      const int id = next_tile(sh, sc, lane == 0);
+      if (id < 0) break;
+      const Tile t = decode_tile(p, id);
+      if (t.layer == last)
+        prep_tile<kLogitsBN>(p, t, sh, f, pt, lane);
+      else
+        prep_tile<BNH>(p, t, sh, f, pt, lane);
     }
   } else if (warp >= kFirstScanWarp && warp < kFirstEpilogueWarp) {
     const int st = int(threadIdx.x) - kFirstScanWarp * 32;
@@ -719,7 +754,7 @@ int qlayer_fused_plan(int M, int H, int O, int num_sms, int policy, int *grid) {
   const char *force = std::getenv("FDNN_FUSED");
   const bool forced = force && force[0] == '2';
   int bnh = 0;
-  if (tiles(H, 64) <= num_sms && policy != 1)
+  if (tiles(H, 64) <= num_sms)
     bnh = 64;
   else if (tiles(H, 128) <= num_sms)
     bnh = 128;
@@ -727,6 +762,17 @@ int qlayer_fused_plan(int M, int H, int O, int num_sms, int policy, int *grid) {
   if (!forced && (policy == 1 || tiles(H, bnh) < num_sms / 3)) return 0;
   // the output layer may take several rounds of 128×256 tiles on the same CTAs
   *grid = std::min(num_sms, std::max(tiles(H, bnh), tiles(O, kLogitsBN)));
+  if (policy == 1) {
+    // (FDNN_FUSED=2 only.)  Several contexts in flight: a kernel that takes every SM serialises the passes; with fewer CTAs
+    // than tiles the fused kernels of several contexts share the GPU.  Measured on B200 (profiles/r2_experiments.md): 74.5 us per
+    // step at best (grid 64, 4 contexts) against 68.5 us layer by layer, so the "throughput" policy stays layer by layer.
+    static const int tgrid = [] {
+      const char *e = std::getenv("FDNN_FUSED_TGRID");
+      const int v = e ? std::atoi(e) : 64;
+      return v > 0 ? v : 64;
+    }();
+    *grid = std::min(*grid, tgrid);
+  }
   return bnh;
 }
 

@@ -15,6 +15,7 @@ shape = sys.argv[1] if len(sys.argv) > 1 else "L"
 m = int(sys.argv[2]) if len(sys.argv) > 2 else 512
 dev = torch.device("cuda", 0)
 dnn = qd.QuantizedDnn.load_from_file(synth.network_file(shape), device=0)
+dnn.set_tile_policy(os.environ.get("TIMELINE_POLICY", "latency"))
 I, O = dnn.input_dimension(), dnn.output_dimension()
 x = torch.from_numpy(synth.make_frames(m, I, seed=3)).to(dev)
 y = torch.empty(m, O, dtype=torch.float32, device=dev)
