@@ -67,6 +67,25 @@ def test_no_gpu_means_no_compute(net_file):
         qd.QuantizedDnn.load_from_blob(blob)
     with pytest.raises(qd.FdnnError):
         qd.PinnedArray((4, 4), np.float32)
+    with pytest.raises(qd.NoGpuError):  # a device group is no way around it either
+        qd.QuantizedDnn.load_on_devices(net_file("tiny"), [0, 1])
+    os.environ["FDNN_DEVICES"] = "all"
+    try:
+        with pytest.raises(qd.NoGpuError):
+            qd.QuantizedDnn.load_from_file(net_file("tiny"))
+    finally:
+        os.environ.pop("FDNN_DEVICES", None)
+    assert qd.lib().fdnn_device_count(None) == qd.FDNN_EINVAL and qd.lib().fdnn_nccl_broadcast_count() == 0
+
+
+def test_bad_arguments_are_refused_not_crashed_on(net_file):
+    L = qd.lib()
+    h = C.c_void_p()
+    assert L.fdnn_load_devices(net_file("tiny").encode(), 3.0, None, 2, C.byref(h)) == qd.FDNN_EINVAL
+    assert L.fdnn_load_devices(net_file("tiny").encode(), 3.0, (C.c_int * 1)(0), 0, C.byref(h)) == qd.FDNN_EINVAL
+    assert L.fdnn_calculate_sink(None, None, 4, 12, None, None) == qd.FDNN_EINVAL
+    assert L.fdnn_ctx_hidden_digest(None, 0, 0, None) == qd.FDNN_EINVAL
+    assert L.fdnn_ctx_profile_pass(None, None, 1, None, 1, None, None) == qd.FDNN_EINVAL
 
 
 def test_cutoff_must_be_positive(net_file):

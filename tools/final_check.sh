@@ -1,6 +1,8 @@
+#!/bin/bash
+# what the driver runs at round end, in one call: smoke, the GPU suite, both bench arms
+set -u
+TAG=${1:-r2z}
 mkdir -p gpurun_out
-timeout 400 python -m pytest tests -m gpu -x -q > gpurun_out/final_tests.log 2>&1; tail -2 gpurun_out/final_tests.log
-timeout 200 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
-timeout 600 python bench.py --steps 200 --warmup 10 > gpurun_out/final_bench.json 2> gpurun_out/final_bench.err; python -c "
-import json; d=json.load(open('gpurun_out/final_bench.json')); print(d['value'], d['ms_per_step'], d['single_stream']['value'], d['e2e']['value'], d['stream_regime']['frames_per_s'], d['roofline']['frac'], d['gpu_launches'])"
-timeout 300 python bench.py --impl reference --steps 3 --warmup 1 2>/dev/null | tail -1 | cut -c1-200
+python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/${TAG}_smoke.log 2>&1; echo "smoke rc=$?"; tail -2 gpurun_out/${TAG}_smoke.log
+timeout 1500 python -m pytest tests -m gpu -x -q --durations=8 > gpurun_out/${TAG}_pytest.log 2>&1; echo "pytest rc=$?"; tail -14 gpurun_out/${TAG}_pytest.log
+bash tools/r2_bench.sh ${TAG}
