@@ -227,7 +227,6 @@ struct fdnn_ctx {
   float *h_in = nullptr;    // [cap][I]
   float *h_out = nullptr;   // [cap][O]
   std::vector<cudaEvent_t> events;  // polled events (wait_event): [0] = whole chunk done, [1 + k] = sub-chunk k has landed in h_out
-  int8_t *h_maskbuf = nullptr;  // batched lazy path on pageable masks: page-locked staging [cap][O]
   int8_t *h_mask = nullptr;  // single-row lazy path: mapped page-locked mask [O] and result row [O]
   float *h_row = nullptr;
   bool trace = false;
@@ -287,7 +286,6 @@ void destroy_ctx(fdnn_ctx *c) {
     cudaFree(c->d_fused);
     if (c->h_in) cudaFreeHost(c->h_in);
     if (c->h_out) cudaFreeHost(c->h_out);
-    if (c->h_maskbuf) cudaFreeHost(c->h_maskbuf);
     if (c->h_mask) cudaFreeHost(c->h_mask);
     if (c->h_row) cudaFreeHost(c->h_row);
     for (cudaEvent_t e : c->events) cudaEventDestroy(e);
@@ -1719,10 +1717,9 @@ int calculate_impl(fdnn_model *model, const float *in, int n, int dim, float *ou
 
 }  // namespace
 
-// All frames of the context at once (BASELINE config 3).  Page-locked caller memory: masks up, one masked-softmax launch,
-// scores down, all asynchronous.  Pageable caller memory (what a JVM hands us): masks through the context's page-locked
-// staging buffer, scores come down in 128-row pieces with an event each, and the calling thread copies piece k out while
-// piece k+1 is still crossing PCIe.
+// All frames of the context at once (BASELINE config 3): masks up, one masked-softmax launch, scores down.  With page-locked caller
+// memory all three are asynchronous and the thread naps until they are done; pageable memory goes through the driver's own
+// staging (measured on B200: faster than staging it here — 152 k against 123 k frames/s at batch 512, profiles/r2_experiments.md).
 int fdnn_ctx_lazy_batch(fdnn_ctx *ctx, const int8_t *masks, float *out) {
   if (!ctx || !masks || !out) {
     set_error("null argument");
@@ -1738,36 +1735,12 @@ int fdnn_ctx_lazy_batch(fdnn_ctx *ctx, const int8_t *masks, float *out) {
   if (!ctx->d_masks) CUDA_TRY(cudaMalloc(&ctx->d_masks, size_t(ctx->cap) * O));
   // the masked softmax must not overwrite the resident logits (later lazy calls need them)
   if (!ctx->d_lazy) CUDA_TRY(cudaMalloc(&ctx->d_lazy, size_t(ctx->cap) * O * 4));
-  const int8_t *src = masks;
-  if (!host_pinned(masks)) {
-    if (!ctx->h_maskbuf) CUDA_TRY(cudaHostAlloc(reinterpret_cast<void **>(&ctx->h_maskbuf), size_t(ctx->cap) * O, cudaHostAllocPortable));
-    std::memcpy(ctx->h_maskbuf, masks, size_t(n) * O);
-    src = ctx->h_maskbuf;
-  }
-  CUDA_TRY(cudaMemcpyAsync(ctx->d_masks, src, size_t(n) * O, cudaMemcpyHostToDevice, ctx->stream));
-  if (host_pinned(out)) {
-    if (int rc = enqueue_softmax(ctx, ctx->d_logits, ctx->d_masks, n, ctx->d_lazy, ctx->stream)) return rc;
-    CUDA_TRY(cudaMemcpyAsync(out, ctx->d_lazy, size_t(n) * O * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    if (int rc = ensure_events(ctx, 1)) return rc;
-    CUDA_TRY(cudaEventRecord(ctx->events[0], ctx->stream));
-    CUDA_TRY(wait_event(ctx->events[0]));
-    return FDNN_OK;
-  }
-  if (!ctx->h_out) CUDA_TRY(cudaHostAlloc(reinterpret_cast<void **>(&ctx->h_out), size_t(ctx->cap) * O * 4, cudaHostAllocPortable));
-  const int subs = (n + kSubRows - 1) / kSubRows;
-  if (int rc = ensure_events(ctx, size_t(1 + subs))) return rc;
-  for (int k = 0; k < subs; ++k) {
-    const int r0 = k * kSubRows, rows = std::min(kSubRows, n - r0);
-    if (int rc = enqueue_softmax(ctx, ctx->d_logits + size_t(r0) * O, ctx->d_masks + size_t(r0) * O, rows, ctx->d_lazy + size_t(r0) * O, ctx->stream))
-      return rc;
-    CUDA_TRY(cudaMemcpyAsync(ctx->h_out + size_t(r0) * O, ctx->d_lazy + size_t(r0) * O, size_t(rows) * O * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_TRY(cudaEventRecord(ctx->events[size_t(1 + k)], ctx->stream));
-  }
-  for (int k = 0; k < subs; ++k) {
-    const int r0 = k * kSubRows, rows = std::min(kSubRows, n - r0);
-    CUDA_TRY(wait_event(ctx->events[size_t(1 + k)]));
-    std::memcpy(out + size_t(r0) * O, ctx->h_out + size_t(r0) * O, size_t(rows) * O * 4);
-  }
+  CUDA_TRY(cudaMemcpyAsync(ctx->d_masks, masks, size_t(n) * O, cudaMemcpyHostToDevice, ctx->stream));
+  if (int rc = enqueue_softmax(ctx, ctx->d_logits, ctx->d_masks, n, ctx->d_lazy, ctx->stream)) return rc;
+  CUDA_TRY(cudaMemcpyAsync(out, ctx->d_lazy, size_t(n) * O * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  if (int rc = ensure_events(ctx, 1)) return rc;
+  CUDA_TRY(cudaEventRecord(ctx->events[0], ctx->stream));
+  CUDA_TRY(wait_event(ctx->events[0]));
   return FDNN_OK;
 }
 
