@@ -11,6 +11,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <dlfcn.h>
+#include <emmintrin.h>
 
 #include <algorithm>
 #include <array>
@@ -1471,6 +1472,7 @@ int chunk_frames() {
   return v;
 }
 
+constexpr int kStagedChunk = 512;  // frames per pass when results go through the page-locked staging buffers
 constexpr int kSubRows = 128;  // rows per result sub-chunk on the staged (pageable) path: 4 MB of scores at 8000 outputs
 
 // Workspace sizes come in buckets (128 · 2^k frames up to the streaming chunk): callers with variable-length utterances
@@ -1509,6 +1511,37 @@ void pool_give(fdnn_model *m, fdnn_ctx *c) {
     }
   }
   destroy_ctx(evict);  // outside pool_mu; takes cuda_mu for the frees only
+}
+
+// Copy out of the page-locked transfer buffer into caller memory with non-temporal stores: the destination is megabytes of
+// memory nobody will read before the caller does, so ordinary stores would first READ every destination line into the cache
+// (read-for-ownership) and evict what the caller's other threads are using.  Source lines were just written by DMA: not
+// cached either way.  (Measured on the B200 host: profiles/r2_experiments.md.)
+void stream_copy(void *dst, const void *src, size_t bytes) {
+  uint8_t *d = static_cast<uint8_t *>(dst);
+  const uint8_t *s = static_cast<const uint8_t *>(src);
+  const size_t head = (16 - (reinterpret_cast<uintptr_t>(d) & 15)) & 15;
+  if (bytes < 4096 || head > bytes) {
+    std::memcpy(d, s, bytes);
+    return;
+  }
+  std::memcpy(d, s, head);
+  d += head;
+  s += head;
+  bytes -= head;
+  const size_t blocks = bytes / 64;
+  for (size_t i = 0; i < blocks; ++i) {
+    const __m128i a = _mm_loadu_si128(reinterpret_cast<const __m128i *>(s) + 0), b = _mm_loadu_si128(reinterpret_cast<const __m128i *>(s) + 1),
+                  c = _mm_loadu_si128(reinterpret_cast<const __m128i *>(s) + 2), e = _mm_loadu_si128(reinterpret_cast<const __m128i *>(s) + 3);
+    _mm_stream_si128(reinterpret_cast<__m128i *>(d) + 0, a);
+    _mm_stream_si128(reinterpret_cast<__m128i *>(d) + 1, b);
+    _mm_stream_si128(reinterpret_cast<__m128i *>(d) + 2, c);
+    _mm_stream_si128(reinterpret_cast<__m128i *>(d) + 3, e);
+    s += 64;
+    d += 64;
+  }
+  _mm_sfence();
+  std::memcpy(d, s, bytes - blocks * 64);
 }
 
 bool host_pinned(const void *p) {
@@ -1618,7 +1651,7 @@ int drain_chunk(const CalcCall &call, Share &s, int c) {
           return FDNN_EINVAL;
         }
       } else {
-        std::memcpy(call.out + size_t(f + r0) * O, x->h_out + size_t(r0) * O, size_t(rows) * O * 4);
+        stream_copy(call.out + size_t(f + r0) * O, x->h_out + size_t(r0) * O, size_t(rows) * O * 4);
       }
     }
   }
@@ -1647,9 +1680,11 @@ int calculate_impl(fdnn_model *model, const float *in, int n, int dim, float *ou
   }
   CalcCall call{};
   call.in = in;
-  call.in_pinned = host_pinned(in);
+  // FDNN_STAGE=0 (experiments): pageable caller memory straight into cudaMemcpyAsync (the driver stages it, synchronously)
+  static const bool stage = env_flag("FDNN_STAGE", true);
+  call.in_pinned = !stage || host_pinned(in);
   call.out = out;
-  call.out_direct = sink == nullptr && host_pinned(out);
+  call.out_direct = sink == nullptr && (!stage || host_pinned(out));
   call.sink = sink;
   call.user = user;
   call.I = model->hdr.in_dim;
@@ -1670,7 +1705,10 @@ int calculate_impl(fdnn_model *model, const float *in, int n, int dim, float *ou
       s.f0 = f;
       s.n = std::min(n - f, u * 128);
       f += s.n;
-      s.cap = bucket_cap(s.n);
+      // Staged (pageable) callers: the calling thread's copy-out, not the GPU, is the slow stage (≈ 10-15 GB/s per host thread), and
+      // it runs at its best out of transfer buffers small enough to still sit in the last-level cache the DMA wrote them to — chunks
+      // of 512 frames (16 MB of scores), which also lets upload, compute, download and copy-out of one call overlap.
+      s.cap = call.out_direct ? bucket_cap(s.n) : std::min(bucket_cap(s.n), kStagedChunk);
       s.n_chunks = (s.n + s.cap - 1) / s.cap;
       s.n_slots = s.n_chunks > 1 ? 2 : 1;
       for (int k = 0; k < s.n_slots && rc == FDNN_OK; ++k) {
