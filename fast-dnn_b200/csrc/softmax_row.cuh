@@ -21,7 +21,7 @@ namespace fdnn {
 
 constexpr int kSoftmaxThreads = 224;  // threads that work on one row (the shape of the summation tree depends on it): 7 warps,
                                       // so that the 28 warps of the fused layer kernel are exactly four row groups
-constexpr int kSoftmaxUnroll = 4;
+constexpr int kSoftmaxUnroll = 4;  // (9 — the whole 8000-wide row in flight — measured: 12.4 vs 12.5 us at 512 rows, 240 vs 211 us at 16384)
 
 // e^x.  t = RN(x·log2e_hi) goes to ex2.approx; r = (x·log2e − t) is recovered exactly with one fma
 // plus the low part of log2e, and 2^r ≈ 1 + r·ln2 (|r| < 2^-17).  Overflows to +inf above 88.72 like
