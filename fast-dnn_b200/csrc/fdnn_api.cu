@@ -1461,6 +1461,26 @@ int fdnn_ctx_profile_pass(fdnn_ctx *ctx, const float *d_in, int n_frames, float 
 
 // ---- full forward over host buffers -------------------------------------------------------------
 
+// How a call of n frames is cut over the devices of a group: contiguous shards in device order, whole tiles of 128 frames
+// (the row block of every layer kernel), sizes differing by at most one tile, no device used for less than a tile; the
+// last shard takes the ragged end.  Host-only (also what tests/test_multirank.py checks without a GPU).
+int fdnn_shard_plan(int n_frames, int n_devices, int *first, int *count) {
+  if (n_frames < 0 || n_devices <= 0 || !first || !count) return FDNN_EINVAL;
+  const int units = (n_frames + 127) / 128;
+  const int used = std::max(1, std::min(n_devices, units));
+  int f = 0;
+  for (int d = 0; d < n_devices; ++d) {
+    first[d] = f;
+    count[d] = 0;
+    if (d < used) {
+      const int u = units / used + (d < units % used ? 1 : 0);
+      count[d] = std::min(n_frames - f, u * 128);
+      f += count[d];
+    }
+  }
+  return used;
+}
+
 namespace {
 
 int chunk_frames() {
@@ -1692,29 +1712,24 @@ int calculate_impl(fdnn_model *model, const float *in, int n, int dim, float *ou
 
   // one contiguous shard per device of the group (frames are independent: no collective), whole tiles of 128 frames each
   const int n_dev = model->group.empty() ? 1 : int(model->group.size());
-  const int used = std::max(1, std::min(n_dev, (n + 127) / 128));
+  std::vector<int> first(size_t(n_dev), 0), count(size_t(n_dev), 0);
+  const int used = fdnn_shard_plan(n, n_dev, first.data(), count.data());
   std::vector<Share> shares{size_t(used)};
   int rc = FDNN_OK;
-  {
-    const int units = (n + 127) / 128;
-    int f = 0;
-    for (int d = 0; d < used; ++d) {
-      Share &s = shares[size_t(d)];
-      s.m = model->group.empty() ? model : model->group[size_t(d)];
-      const int u = units / used + (d < units % used ? 1 : 0);
-      s.f0 = f;
-      s.n = std::min(n - f, u * 128);
-      f += s.n;
-      // Staged (pageable) callers: the calling thread's copy-out, not the GPU, is the slow stage (≈ 10-15 GB/s per host thread), and
-      // it runs at its best out of transfer buffers small enough to still sit in the last-level cache the DMA wrote them to — chunks
-      // of 512 frames (16 MB of scores), which also lets upload, compute, download and copy-out of one call overlap.
-      s.cap = call.out_direct ? bucket_cap(s.n) : std::min(bucket_cap(s.n), kStagedChunk);
-      s.n_chunks = (s.n + s.cap - 1) / s.cap;
-      s.n_slots = s.n_chunks > 1 ? 2 : 1;
-      for (int k = 0; k < s.n_slots && rc == FDNN_OK; ++k) {
-        s.slot[k] = pool_take(s.m, s.cap);
-        if (!s.slot[k]) rc = create_ctx(s.m, s.cap, &s.slot[k]);
-      }
+  for (int d = 0; d < used; ++d) {
+    Share &s = shares[size_t(d)];
+    s.m = model->group.empty() ? model : model->group[size_t(d)];
+    s.f0 = first[size_t(d)];
+    s.n = count[size_t(d)];
+    // Staged (pageable) callers: the calling thread's copy-out, not the GPU, is the slow stage (≈ 10-15 GB/s per host thread), and
+    // it runs at its best out of transfer buffers small enough to still sit in the last-level cache the DMA wrote them to — chunks
+    // of 512 frames (16 MB of scores), which also lets upload, compute, download and copy-out of one call overlap.
+    s.cap = call.out_direct ? bucket_cap(s.n) : std::min(bucket_cap(s.n), kStagedChunk);
+    s.n_chunks = (s.n + s.cap - 1) / s.cap;
+    s.n_slots = s.n_chunks > 1 ? 2 : 1;
+    for (int k = 0; k < s.n_slots && rc == FDNN_OK; ++k) {
+      s.slot[k] = pool_take(s.m, s.cap);
+      if (!s.slot[k]) rc = create_ctx(s.m, s.cap, &s.slot[k]);
     }
   }
   // One host thread drives every device: all work is asynchronous, so the calling thread enqueues round-robin and then

@@ -43,6 +43,7 @@ SIGNATURES = {
     "fdnn_device_count": (_I, [_P]),
     "fdnn_device_at": (_I, [_P, _I]),
     "fdnn_nccl_broadcast_count": (_LL, []),
+    "fdnn_shard_plan": (_I, [_I, _I, C.POINTER(_I), C.POINTER(_I)]),
     "fdnn_pack": (_I, [C.c_char_p, _F, C.POINTER(_P), C.POINTER(_SZ)]),
     "fdnn_blob_free": (None, [_P]),
     "fdnn_load_blob": (_I, [_P, _SZ, _I, C.POINTER(_P)]),
@@ -138,6 +139,15 @@ def pack(path: str, cutoff: float = 3.0) -> np.ndarray:
         return np.ctypeslib.as_array(C.cast(blob, C.POINTER(C.c_uint8)), shape=(size.value,)).copy()
     finally:
         lib().fdnn_blob_free(blob)
+
+
+def shard_plan(n_frames: int, n_devices: int):
+    """[(first, count)] per device: how calculate() on a device group cuts a call (host only)."""
+    first, count = (C.c_int * n_devices)(), (C.c_int * n_devices)()
+    used = lib().fdnn_shard_plan(n_frames, n_devices, first, count)
+    if used < 0:
+        raise ValueError("bad shard request")
+    return [(first[d], count[d]) for d in range(n_devices)], used
 
 
 def align_dnn_bin(in_path, out_path, input_alignment: int = 4, hidden_alignment: int = 16) -> None:

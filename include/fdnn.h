@@ -61,6 +61,10 @@ int fdnn_load_devices(const char *path, float cutoff, const int *devices, int n_
 int fdnn_device_count(const fdnn_model *model);      /* 1 unless the handle is a device group */
 int fdnn_device_at(const fdnn_model *model, int i);  /* CUDA ordinal of the i-th device of the group */
 long long fdnn_nccl_broadcast_count(void);           /* ncclBroadcast collectives issued by this library since load */
+/* Host-only: how fdnn_calculate cuts a call of n_frames over n_devices — contiguous shards in device order, whole tiles of
+ * 128 frames, sizes differing by at most one tile; first[d], count[d] for every device (count 0 = unused); returns the number
+ * of devices used. */
+int fdnn_shard_plan(int n_frames, int n_devices, int *first, int *count);
 
 /* Host-only half of fdnn_load: parse + quantize into one relocatable blob (weights, biases,
  * multipliers, sigmoid LUT, saturation fix-up lists).  In a multi-GPU job rank 0 packs, the blob

@@ -28,6 +28,28 @@ def test_shard_ranges_partition_the_stream():
         sharding.shard_range(10, 2, 2)
 
 
+def test_device_group_shard_plan_partitions_a_call():
+    """fdnn_shard_plan (what fdnn_calculate does on a device group, host-only): contiguous, ordered, whole 128-frame tiles, balanced
+    to one tile, nobody used for less than a tile, ragged end on the last used device"""
+    for n in (0, 1, 127, 128, 129, 512, 1000, 4096, 9001, 1_000_000):
+        for devs in (1, 2, 3, 8):
+            plan, used = qd.shard_plan(n, devs)
+            assert 1 <= used <= devs and len(plan) == devs
+            pos = 0
+            for d, (first, count) in enumerate(plan):
+                assert first == pos and count >= 0
+                assert (count > 0) == (d < used) or n == 0
+                if d + 1 < used:
+                    assert count % 128 == 0 and count > 0
+                pos += count
+            assert pos == n
+            tiles = [(c + 127) // 128 for _, c in plan[:used]]
+            assert max(tiles) - min(tiles) <= 1
+    assert qd.shard_plan(512, 8)[1] == 4 and qd.shard_plan(100, 8)[1] == 1
+    with pytest.raises(ValueError):
+        qd.shard_plan(-1, 2)
+
+
 def _free_port():
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
