@@ -193,44 +193,55 @@ __device__ __forceinline__ void advance_acc(Flow &f) {
 
 // ---- one layer, one role each ---------------------------------------------------------------------------------------------
 
+// The whole producer warp, converged.  One thread gets a 128-row TMA box accepted only every ≈ 225 ns (71 GB/s per SM); boxes issued
+// by several lanes in the SAME instruction go out together (two lanes 101 GB/s, four 146 GB/s, tools/feed_bench.cu) — the issue rate of
+// a single lane, not the L2, was what capped the operand feed of every layer at batch 512.  So: the first `pre` stages of a tile are
+// issued by `pre` lanes at once (lane i owns stage i: its weight box first, its activation box once the row block is ready), the
+// remaining K blocks by two lanes per stage (lane 0 the activation box and the barrier, lane 1 the weight box).
 template <int BN>
-__device__ __forceinline__ void produce_tile(const FusedArgs &p, const Tile &t, const Shared &sh, Flow &f) {
+__device__ __forceinline__ void produce_tile(const FusedArgs &p, const Tile &t, const Shared &sh, Flow &f, int lane) {
   using G = Geo<BN>;
   const int j = t.layer, m_blk = t.m_blk, n_blk = t.n_blk;
   const FusedLayer &L = p.layer[j];
   const int k_blocks = L.K / kBlockK;
   const CUtensorMap *amap = &p.act[j & 1];
   const CUtensorMap *wmap = &p.w[j];
-  int kb = first_k_block(m_blk, n_blk, k_blocks);
-  // Weight tiles first, for as many stages as the ring has: they do not depend on the previous layer.  Then wait for this
-  // row block's activations, then send the activation tiles after them.
+  const int kb0 = first_k_block(m_blk, n_blk, k_blocks);
   const int pre = min(G::kStages, k_blocks);
-  fstamp(p, j, 7);
-  Flow g = f;
-  int kb2 = kb;
-  for (int i = 0; i < pre; ++i, kb2 = (kb2 + 1 == k_blocks ? 0 : kb2 + 1)) {
-    ptx::mbar_wait(sh.empty_bar + g.slot, bit(g.ring_ph, g.slot) ^ 1u);
-    uint8_t *sa = sh.ring + g.slot * G::kStageBytes;
-    ptx::mbar_arrive_expect_tx(sh.full_bar + g.slot, G::kStageBytes);
-    ptx::tma_load_2d(wmap, sh.full_bar + g.slot, sa + G::kABytes, kb2 * kBlockK, n_blk * BN);
-    advance<BN>(g);
+  if (lane == 0) fstamp(p, j, 7);
+  // Weight tiles first: they do not depend on the previous layer.
+  const uint32_t my_slot = (f.slot + uint32_t(lane)) % uint32_t(G::kStages);
+  const int my_kb = (kb0 + lane) % k_blocks;
+  uint8_t *my_stage = sh.ring + my_slot * G::kStageBytes;
+  if (lane < pre) {
+    ptx::mbar_wait(sh.empty_bar + my_slot, bit(f.ring_ph, my_slot) ^ 1u);
+    ptx::mbar_arrive_expect_tx(sh.full_bar + my_slot, G::kStageBytes);
+    ptx::tma_load_2d(wmap, sh.full_bar + my_slot, my_stage + G::kABytes, my_kb * kBlockK, n_blk * BN);
   }
-  fstamp(p, j, 6);
-  if (j > 0) {
-    wait_counter(p.sync + m_blk, L.need, (p.debug_flags & 8) == 0);
-    if (!(p.debug_flags & 2)) fence_proxy_async_global();
+  if (lane == 0) {
+    fstamp(p, j, 6);
+    if (j > 0) {
+      wait_counter(p.sync + m_blk, L.need, (p.debug_flags & 8) == 0);
+      if (!(p.debug_flags & 2)) fence_proxy_async_global();
+    }
+    fstamp(p, j, 0);
   }
-  fstamp(p, j, 0);
-  for (int i = 0; i < pre; ++i, kb = (kb + 1 == k_blocks ? 0 : kb + 1)) {
-    ptx::tma_load_2d(amap, sh.full_bar + f.slot, sh.ring + f.slot * G::kStageBytes, kb * kBlockK, m_blk * kBlockM);
-    advance<BN>(f);
+  __syncwarp();
+  if (lane < pre) {
+    if (j > 0 && !(p.debug_flags & 2)) fence_proxy_async_global();
+    ptx::tma_load_2d(amap, sh.full_bar + my_slot, my_stage, my_kb * kBlockK, m_blk * kBlockM);
   }
+  for (int i = 0; i < pre; ++i) advance<BN>(f);
+  int kb = (kb0 + pre) % k_blocks;
   for (int i = pre; i < k_blocks; ++i, kb = (kb + 1 == k_blocks ? 0 : kb + 1)) {
-    ptx::mbar_wait(sh.empty_bar + f.slot, bit(f.ring_ph, f.slot) ^ 1u);
-    uint8_t *sa = sh.ring + f.slot * G::kStageBytes;
-    ptx::mbar_arrive_expect_tx(sh.full_bar + f.slot, G::kStageBytes);
-    ptx::tma_load_2d(amap, sh.full_bar + f.slot, sa, kb * kBlockK, m_blk * kBlockM);
-    ptx::tma_load_2d(wmap, sh.full_bar + f.slot, sa + G::kABytes, kb * kBlockK, n_blk * BN);
+    if (lane < 2) {
+      ptx::mbar_wait(sh.empty_bar + f.slot, bit(f.ring_ph, f.slot) ^ 1u);
+      uint8_t *sa = sh.ring + f.slot * G::kStageBytes;
+      if (lane == 0) ptx::mbar_arrive_expect_tx(sh.full_bar + f.slot, G::kStageBytes);
+      // one instruction, two boxes: per-lane tensor map, destination and row coordinate
+      ptx::tma_load_2d(lane == 0 ? amap : wmap, sh.full_bar + f.slot, lane == 0 ? sa : sa + G::kABytes, kb * kBlockK,
+                       lane == 0 ? m_blk * kBlockM : n_blk * BN);
+    }
     advance<BN>(f);
   }
 }
@@ -573,30 +584,36 @@ __global__ void __launch_bounds__(kThreads, 1) qlayer_fused_kernel(const __grid_
   bool recut = false;  // the ring has been re-cut for the output layer
   const int last = nl - 1;
   if (warp == 0) {
-    if (lane == 0) {
+    {  // the whole warp, converged (produce_tile)
       const int total = int(p.total_tiles);
       // (Claiming one tile ahead, to take the atomic's round trip off the path between two tiles, was measured and dropped: no gain
       // at 512 frames, a loss at 1024 — it changes who gets which tile.  profiles/r2_experiments.md)
       for (;;) {
-        ptx::mbar_wait(sh.sched_empty_bar + sc.q, bit(sc.ph, sc.q) ^ 1u);
-        int id = int(atomicAdd(p.sync + kSyncTile, 1u));
-        if (id >= total) id = -1;
-        sh.tile_ring[sc.q] = id;
-        ptx::mbar_arrive(sh.sched_full_bar + sc.q);
+        int id = 0;
+        if (lane == 0) {
+          ptx::mbar_wait(sh.sched_empty_bar + sc.q, bit(sc.ph, sc.q) ^ 1u);
+          id = int(atomicAdd(p.sync + kSyncTile, 1u));
+          if (id >= total) id = -1;
+          sh.tile_ring[sc.q] = id;
+          ptx::mbar_arrive(sh.sched_full_bar + sc.q);
+        }
+        id = __shfl_sync(0xffffffffu, id, 0);
         sc.ph ^= 1u << sc.q;
         sc.q = sc.q + 1 == uint32_t(kSched) ? 0u : sc.q + 1;
         if (id < 0) break;
         const Tile t = decode_tile(p, id);
         if (t.layer == last) {
           if (!recut) {  // every stage of the old cut must have been released
-            for (uint32_t s2 = 0; s2 < uint32_t(kMaxStages); ++s2) ptx::mbar_wait(sh.empty_bar + s2, bit(f.ring_ph, s2) ^ 1u);
+            if (lane == 0)
+              for (uint32_t s2 = 0; s2 < uint32_t(kMaxStages); ++s2) ptx::mbar_wait(sh.empty_bar + s2, bit(f.ring_ph, s2) ^ 1u);
+            __syncwarp();
             f.slot = 0;
             f.turn = 0;
             recut = true;
           }
-          produce_tile<kLogitsBN>(p, t, sh, f);
+          produce_tile<kLogitsBN>(p, t, sh, f, lane);
         } else {
-          produce_tile<BNH>(p, t, sh, f);
+          produce_tile<BNH>(p, t, sh, f, lane);
         }
       }
     }

@@ -189,7 +189,9 @@ qlayer_pair_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_co
 
   if (warp == 0) {
     // ===== TMA producer (both CTAs): my 128 activation rows + my half of the weight rows =====
-    if (lane == 0) {
+    // TWO lanes issue, one box each: a thread gets a 128-row box accepted only every ≈ 225 ns (71 GB/s per SM from one lane,
+    // 101 GB/s from two, tools/feed_bench.cu) — a single issuing lane, not the L2, was what capped the operand feed.
+    if (lane < 2) {
       int stage = 0;
       uint32_t phase = 0;
       for (int ct = first_ct; ct < tiles_total; ct += ct_step) {
@@ -200,10 +202,11 @@ qlayer_pair_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_co
           ptx::mbar_wait_parked(empty_bar + stage, phase ^ 1);
           uint8_t *sa = tiles + stage * Cfg::kStageBytes;
           uint8_t *sb = sa + Cfg::kABytes;
-          if (leader) ptx::mbar_arrive_expect_tx(full_bar + stage, 2 * Cfg::kStageBytes);  // both CTAs' bytes land on this barrier
+          if (leader && lane == 0) ptx::mbar_arrive_expect_tx(full_bar + stage, 2 * Cfg::kStageBytes);  // both CTAs' bytes land on this barrier
           const uint32_t bar = ptx::mapa_u32(ptx::smem_u32(full_bar + stage), 0);
-          ptx::tma_load_2d_pair(&tmap_act, bar, sa, kb * kBlockK, row0 + m_blk * kBlockM);
-          ptx::tma_load_2d_pair(&tmap_w, bar, sb, kb * kBlockK, n_blk * BN + int(rank) * (BN / 2));
+          // one instruction, two boxes: per-lane tensor map, destination and row coordinate
+          ptx::tma_load_2d_pair(lane == 0 ? &tmap_act : &tmap_w, bar, lane == 0 ? sa : sb, kb * kBlockK,
+                                lane == 0 ? row0 + m_blk * kBlockM : n_blk * BN + int(rank) * (BN / 2));
           if (++stage == Cfg::kStages) {
             stage = 0;
             phase ^= 1;

@@ -192,7 +192,9 @@ qlayer_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_cons
 
   if (warp == 0) {
     // ===== TMA producer =====
-    if (lane == 0) {
+    // Without clusters TWO lanes issue, one box each (lane 0 the activation box and the barrier, lane 1 the weight box): one thread
+    // gets a 128-row box accepted only every ≈ 225 ns — 71 GB/s per SM from one lane, 101 GB/s from two (tools/feed_bench.cu).
+    if (lane < (C == 1 ? 2 : 1)) {
       int stage = 0;
       uint32_t phase = 0;
       for (int ct = first_ct; ct < tiles_total; ct += ct_step) {
@@ -206,10 +208,12 @@ qlayer_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_cons
             ptx::mbar_wait_cluster(empty_bar + stage, phase ^ 1);
           uint8_t *sa = tiles + stage * Cfg::kStageBytes;
           uint8_t *sb = sa + Cfg::kABytes;
-          ptx::mbar_arrive_expect_tx(full_bar + stage, Cfg::kStageBytes);
+          if (lane == 0) ptx::mbar_arrive_expect_tx(full_bar + stage, Cfg::kStageBytes);
           if (C == 1) {
-            ptx::tma_load_2d(&tmap_act, full_bar + stage, sa, kb * kBlockK, m_blk * kBlockM);
-            ptx::tma_load_2d(&tmap_w, full_bar + stage, sb, kb * kBlockK, n_blk * BN);
+            // (the weight box may land before lane 0's expect_tx: the transaction count dips below zero, the phase cannot complete
+            // before lane 0 has arrived)
+            // one instruction, two boxes: per-lane tensor map, destination and row coordinate
+            ptx::tma_load_2d(lane == 0 ? &tmap_act : &tmap_w, full_bar + stage, lane == 0 ? sa : sb, kb * kBlockK, lane == 0 ? m_blk * kBlockM : n_blk * BN);
           } else if (kShareA) {
             // my quarter (half) of the activation tile, to everybody; my own weight tile
             constexpr int kRows = kBlockM / C;

@@ -38,7 +38,7 @@ __device__ __forceinline__ void cp_async_arrive_noinc(uint64_t *bar) {
 
 // mode: 0 tma, 1 ldgsts, 2 mixed
 __global__ void __launch_bounds__(kThreads, 1) feed_kernel(const __grid_constant__ CUtensorMap tmap, const uint8_t *base, int rows, int turns, int mode,
-                                                            unsigned long long *sink) {
+                                                            unsigned long long *sink, int box_rows = 128, int issuers = 1) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t full_bar[kStages], empty_bar[kStages];
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
@@ -56,15 +56,18 @@ __global__ void __launch_bounds__(kThreads, 1) feed_kernel(const __grid_constant
   const int row_tiles = rows / 128, k_tiles = kK / 128;
   const int total_tiles = row_tiles * k_tiles;
   if (warp == 0) {
-    if (lane == 0 && tma_tiles) {
+    if (lane < issuers && tma_tiles) {
+      // `issuers` lanes share the boxes of a stage (lane 0 arms the barrier): does one thread's issue rate matter?
       int stage = 0;
       uint32_t phase = 0;
+      const int box_bytes = box_rows * 128, boxes = tma_tiles * kTileBytes / box_bytes;
       for (int t = 0; t < turns; ++t) {
         ptx::mbar_wait(empty_bar + stage, phase ^ 1);
-        ptx::mbar_arrive_expect_tx(full_bar + stage, tma_tiles * kTileBytes);
-        for (int j = 0; j < tma_tiles; ++j) {
-          const int tile = int((uint64_t(blockIdx.x) * 7919u + uint64_t(t) * 2 + j) % uint64_t(total_tiles));
-          ptx::tma_load_2d(&tmap, full_bar + stage, smem + stage * kStageBytes + j * kTileBytes, (tile % k_tiles) * 128, (tile / k_tiles) * 128);
+        if (lane == 0) ptx::mbar_arrive_expect_tx(full_bar + stage, tma_tiles * kTileBytes);
+        __syncwarp((1u << issuers) - 1u);
+        for (int j = lane; j < boxes; j += issuers) {
+          const int tile = int((uint64_t(blockIdx.x) * 7919u + uint64_t(t) * 8 + j) % uint64_t(total_tiles - 2));
+          ptx::tma_load_2d(&tmap, full_bar + stage, smem + stage * kStageBytes + j * box_bytes, (tile % k_tiles) * 128, (tile / k_tiles) * 128);
         }
         if (++stage == kStages) { stage = 0; phase ^= 1; }
       }
@@ -103,6 +106,54 @@ __global__ void __launch_bounds__(kThreads, 1) feed_kernel(const __grid_constant
       if (++stage == kStages) { stage = 0; phase ^= 1; }
     }
     asm volatile("cp.async.wait_all;" ::: "memory");
+  }
+}
+
+// TMA only, everything a parameter: rows per box, how many lanes of the producer warp issue boxes, stage size, stages in flight.
+__global__ void __launch_bounds__(64, 1) tma_rate_kernel(const __grid_constant__ CUtensorMap tmap, int rows, int turns, int box_rows, int issuers, int stage_bytes,
+                                                         int stages, unsigned long long *sink) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t full_bar[8], empty_bar[8];
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < stages; ++i) {
+      ptx::mbar_init(full_bar + i, 1);
+      ptx::mbar_init(empty_bar + i, 1);
+    }
+    ptx::fence_barrier_init();
+  }
+  __syncthreads();
+  const int k_tiles = kK / 128, row_boxes = rows / box_rows, total = row_boxes * k_tiles;
+  const int box_bytes = box_rows * 128, boxes = stage_bytes / box_bytes;
+  if (warp == 0) {
+    if (lane < issuers) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = 0; t < turns; ++t) {
+        ptx::mbar_wait(empty_bar + stage, phase ^ 1);
+        if (lane == 0) ptx::mbar_arrive_expect_tx(full_bar + stage, uint32_t(stage_bytes));
+        __syncwarp((1u << issuers) - 1u);
+        for (int j = lane; j < boxes; j += issuers) {
+          const int tile = int((uint64_t(blockIdx.x) * 7919u + uint64_t(t) * 16 + j) % uint64_t(total));
+          ptx::tma_load_2d(&tmap, full_bar + stage, smem + stage * stage_bytes + j * box_bytes, (tile % k_tiles) * 128, (tile / k_tiles) * box_rows);
+        }
+        if (++stage == stages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else {
+    int stage = 0;
+    uint32_t phase = 0;
+    unsigned long long acc = 0;
+    for (int t = 0; t < turns; ++t) {
+      ptx::mbar_wait(full_bar + stage, phase);
+      if (lane == 0) {
+        acc += smem[stage * stage_bytes + (t & 1023)];
+        ptx::mbar_arrive(empty_bar + stage);
+      }
+      __syncwarp();
+      if (++stage == stages) { stage = 0; phase ^= 1; }
+    }
+    if (lane == 0 && sink) sink[blockIdx.x] = acc;
   }
 }
 
@@ -245,6 +296,64 @@ int main() {
       std::printf("%s{\"ctas\": %d, \"mode\": \"%s\", \"ms\": %.3f, \"total_gbs\": %.1f, \"per_sm_gbs\": %.1f}", first ? "" : ", ", ctas, names[mode], ms,
                   bytes / (ms * 1e-3) / 1e9, bytes / (ms * 1e-3) / 1e9 / ctas);
       first = false;
+    }
+  }
+  // TMA variants: box height, number of issuing lanes, stage size
+  CK(cudaFuncSetAttribute(tma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 196608));
+  for (int box_rows : {32, 64, 128, 256}) {
+    CUtensorMap mb;
+    cuuint32_t boxb[2] = {128u, cuuint32_t(box_rows)};
+    if (reinterpret_cast<EncodeFn>(fnp)(&mb, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, d, dims, strides, boxb, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      continue;
+    for (int stage_bytes : {32768, 49152, 65536}) {
+      const int stages = 196608 / stage_bytes > 8 ? 8 : 196608 / stage_bytes;
+      for (int issuers : {1, 2, 4, 8}) {
+        if (stage_bytes % (box_rows * 128) != 0 || stage_bytes / (box_rows * 128) < issuers) continue;
+        const int tn = turns * 32768 / stage_bytes;
+        tma_rate_kernel<<<sms, 64, stages * stage_bytes>>>(mb, rows, 200, box_rows, issuers, stage_bytes, stages, sink);
+        CK(cudaDeviceSynchronize());
+        CK(cudaEventRecord(e0));
+        tma_rate_kernel<<<sms, 64, stages * stage_bytes>>>(mb, rows, tn, box_rows, issuers, stage_bytes, stages, sink);
+        CK(cudaEventRecord(e1));
+        CK(cudaEventSynchronize(e1));
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, e0, e1));
+        std::printf(", {\"ctas\": %d, \"mode\": \"tma\", \"box_rows\": %d, \"issuing_lanes\": %d, \"stage_bytes\": %d, \"stages\": %d, \"per_sm_gbs\": %.1f}", sms, box_rows,
+                    issuers, stage_bytes, stages, double(sms) * tn * stage_bytes / (ms * 1e-3) / 1e9 / sms);
+      }
+    }
+  }
+  {  // no swizzle, 128-row boxes
+    CUtensorMap mn;
+    if (reinterpret_cast<EncodeFn>(fnp)(&mn, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, d, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                        CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS) {
+      feed_kernel<<<sms, kThreads, kStages * kStageBytes>>>(mn, d, rows, 200, 0, sink, 128, 1);
+      CK(cudaDeviceSynchronize());
+      CK(cudaEventRecord(e0));
+      feed_kernel<<<sms, kThreads, kStages * kStageBytes>>>(mn, d, rows, turns, 0, sink, 128, 1);
+      CK(cudaEventRecord(e1));
+      CK(cudaEventSynchronize(e1));
+      float ms = 0;
+      CK(cudaEventElapsedTime(&ms, e0, e1));
+      std::printf(", {\"ctas\": %d, \"mode\": \"tma no swizzle\", \"ms\": %.3f, \"per_sm_gbs\": %.1f}", sms, ms, double(sms) * turns * kStageBytes / (ms * 1e-3) / 1e9 / sms);
+    }
+  }
+  {  // a wide 2-D box: 256 bytes of K per row is not expressible with 128B swizzle; instead a matrix viewed as [rows/2][4096]: rows twice as long
+    CUtensorMap mw;
+    cuuint64_t dims2[2] = {cuuint64_t(2 * kK), cuuint64_t(rows / 2)};
+    cuuint64_t strides2[1] = {cuuint64_t(2 * kK)};
+    if (reinterpret_cast<EncodeFn>(fnp)(&mw, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, d, dims2, strides2, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS) {
+      feed_kernel<<<sms, kThreads, kStages * kStageBytes>>>(mw, d, rows / 2, 200, 0, sink, 128, 1);
+      CK(cudaDeviceSynchronize());
+      CK(cudaEventRecord(e0));
+      feed_kernel<<<sms, kThreads, kStages * kStageBytes>>>(mw, d, rows / 2, turns, 0, sink, 128, 1);
+      CK(cudaEventRecord(e1));
+      CK(cudaEventSynchronize(e1));
+      float ms = 0;
+      CK(cudaEventElapsedTime(&ms, e0, e1));
+      std::printf(", {\"ctas\": %d, \"mode\": \"tma rows 4096 bytes apart\", \"ms\": %.3f, \"per_sm_gbs\": %.1f}", sms, ms, double(sms) * turns * kStageBytes / (ms * 1e-3) / 1e9 / sms);
     }
   }
   // multicast: tensor maps with boxes of 256/C rows

@@ -27,7 +27,7 @@ constexpr int kGroup = 16;      // MMAs per commit
 constexpr int kThreads = 128;
 
 template <int kCtaGroup>
-__global__ void __launch_bounds__(kThreads, 1) mma_loop_kernel(int groups, int random_fill, unsigned long long *sink) {
+__global__ void __launch_bounds__(kThreads, 1) mma_loop_kernel(int groups, int random_fill, unsigned long long *sink, int n_cols) {
   extern __shared__ __align__(1024) uint8_t smem[];
   // A: 128 rows × 128 bytes; B: 256 (cta_group::1) or 128 (this CTA's half, cta_group::2) rows × 128 bytes; contents are
   // irrelevant to the rate (zeros), the layout is the K-major 128B-swizzled one the layer kernels use
@@ -66,7 +66,7 @@ __global__ void __launch_bounds__(kThreads, 1) mma_loop_kernel(int groups, int r
   const uint32_t tmem_base = tmem_slot;
   const bool issuer = warp == 0 && (kCtaGroup == 1 || ptx::cluster_ctarank() == 0);
   if (issuer) {
-    const uint32_t idesc = kCtaGroup == 1 ? ptx::idesc_i8_u8s8(kN) : ptx::idesc_i8_u8s8_pair(kN);
+    const uint32_t idesc = kCtaGroup == 1 ? ptx::idesc_i8_u8s8(uint32_t(n_cols)) : ptx::idesc_i8_u8s8_pair(uint32_t(n_cols));
     const uint64_t da = ptx::smem_desc_k_sw128(ptx::smem_u32(a_tile)), db = ptx::smem_desc_k_sw128(ptx::smem_u32(b_tile));
     uint32_t phase[2] = {0, 0};
     for (int g = 0; g < groups; ++g) {
@@ -133,7 +133,7 @@ cudaError_t launch(int ctas, int groups, int random_fill, cudaStream_t s) {
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = kCtaGroup > 1 ? 1 : 0;
-  return cudaLaunchKernelEx(&cfg, mma_loop_kernel<kCtaGroup>, groups, random_fill, static_cast<unsigned long long *>(nullptr));
+  return cudaLaunchKernelEx(&cfg, mma_loop_kernel<kCtaGroup>, groups, random_fill, static_cast<unsigned long long *>(nullptr), int(kN));
 }
 
 template <int kCtaGroup>
@@ -210,6 +210,35 @@ int main(int argc, char **argv) {
   for (int i = 0; i < 4; ++i)
     std::printf(", \"%s\": {\"burst_tops\": %.1f, \"sustained_tops\": %.1f, \"sustained_first_tenth\": %.1f, \"sustained_last_tenth\": %.1f}", names[i],
                 r[i][0], r[i][1], r[i][2], r[i][3]);
+  // instruction rate at narrower tiles (cta_group::1, M = 128): is a layer with 64- or 128-wide tiles bound by how fast one thread
+  // can issue tcgen05.mma rather than by the tensor pipe?
+  {
+    CK(cudaFuncSetAttribute(mma_loop_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (128 + kN) * kStageK));
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    std::printf(", \"narrow_tiles\": [");
+    bool first = true;
+    for (int n : {32, 64, 128, 256}) {
+      cudaLaunchConfig_t cfg{};
+      cfg.gridDim = dim3(unsigned(sms));
+      cfg.blockDim = dim3(kThreads);
+      cfg.dynamicSmemBytes = (128 + kN) * kStageK;
+      const int groups = 4000;
+      CK(cudaLaunchKernelEx(&cfg, mma_loop_kernel<1>, 200, 1, static_cast<unsigned long long *>(nullptr), n));
+      CK(cudaDeviceSynchronize());
+      CK(cudaEventRecord(e0));
+      CK(cudaLaunchKernelEx(&cfg, mma_loop_kernel<1>, groups, 1, static_cast<unsigned long long *>(nullptr), n));
+      CK(cudaEventRecord(e1));
+      CK(cudaEventSynchronize(e1));
+      float ms = 0;
+      CK(cudaEventElapsedTime(&ms, e0, e1));
+      const double mmas = double(groups) * kGroup;
+      std::printf("%s{\"n\": %d, \"ns_per_mma\": %.1f, \"tops\": %.1f}", first ? "" : ", ", n, ms * 1e6 / mmas, 2.0 * 128 * n * 32 * mmas * sms / (ms * 1e-3) / 1e12);
+      first = false;
+    }
+    std::printf("]");
+  }
   std::printf(", \"sustained_seconds\": %.1f, \"how\": \"tcgen05.mma kind::i8 (u8 x s8 -> s32), operands resident in shared memory "
               "(pseudo-random bytes; zeros for the *_zero_operands entries), %d MMAs per commit, 2 commits in flight, one CTA (pair) per SM; "
               "ops = 2*M*N*K\"}\n",
