@@ -102,6 +102,27 @@ int make_tmap(CUtensorMap *map, const void *base, int rows, int K, int box_rows)
   return FDNN_OK;
 }
 
+// The same matrix as a 3-D tensor: (128 bytes of K, row, 128-byte K block).  One box = `box_rows` rows × `box_kb` consecutive K blocks,
+// delivered as box_kb consecutive 128B-swizzled tiles (the fused kernel's two-K-block pipeline stages, csrc/qlayer_fused.cu).
+int make_tmap3(CUtensorMap *map, const void *base, int rows, int K, int box_rows, int box_kb) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (!fn) {
+    set_error("cuTensorMapEncodeTiled is not available from this driver");
+    return FDNN_ECUDA;
+  }
+  cuuint64_t dims[3] = {128u, cuuint64_t(rows), cuuint64_t(K / 128)};
+  cuuint64_t strides[2] = {cuuint64_t(K), 128u};
+  cuuint32_t box[3] = {128u, cuuint32_t(box_rows), cuuint32_t(box_kb)};
+  cuuint32_t estr[3] = {1u, 1u, 1u};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (3-D) failed with CUresult " + std::to_string(int(r)));
+    return FDNN_ECUDA;
+  }
+  return FDNN_OK;
+}
+
 struct DeviceGuard {
   int prev = -1;
   bool ok = false;
@@ -169,6 +190,8 @@ struct fdnn_model {
   BlobHeader hdr{};
   std::vector<BlobQLayer> q;
   std::vector<std::array<CUtensorMap, 4>> wmaps;  // per int8 layer, box rows 64 / 128 / 256 / 32
+  std::vector<std::array<CUtensorMap, 3>> wmaps3;  // … as 3-D maps with boxes of 64 / 128 / 256 rows × 2 K blocks (fused kernel)
+  bool fused_ok = false;                           // every int8 layer has such maps (K a multiple of 256)
   std::vector<bool> tc_ok;
   std::vector<int> fast_tail;  // per int8 layer: the packed-f32x2 epilogue is provably bit-identical (device_common.cuh)
   // certified tensor-core input layer (input_tc.cu): fixed-point limb planes and per-node statistics of layer 0
@@ -220,6 +243,7 @@ struct fdnn_ctx {
   CUtensorMap xmap;
   bool input_tc = false;
   CUtensorMap amap[2][3];  // per activation buffer: TMA box of 128 / 64 / 32 rows (cluster 1 / 2 / 4 sharing the tile)
+  CUtensorMap amap3[2];    // per activation buffer: 3-D box of 128 rows × 2 K blocks (fused kernel)
   bool amap_ok = false;
   cudaStream_t stream = nullptr;
   int policy = FDNN_POLICY_LATENCY;  // tile policy of the model when the context was created (part of every cached launch sequence)
@@ -339,6 +363,9 @@ int create_ctx(fdnn_model *m, int n, fdnn_ctx **out) {
     for (int b = 0; b < 2; ++b)
       for (int v = 0; v < 3; ++v)
         if (int rc = make_tmap(&c->amap[b][v], c->d_act[b], n, H, 128 >> v)) return rc;
+    if (m->fused_ok)
+      for (int b = 0; b < 2; ++b)
+        if (int rc = make_tmap3(&c->amap3[b], c->d_act[b], n, H, 128, 2)) return rc;
     c->amap_ok = true;
   }
   if (m->input_tc) {
@@ -428,21 +455,20 @@ int enqueue_until_logits(fdnn_ctx *c, const float *d_in, int m, float *d_logits,
   if (c->trace) CUDA_TRY(cudaMemcpyAsync(c->d_trace, c->d_act[0], act_bytes, cudaMemcpyDeviceToDevice, stream));
 
   // One persistent kernel for all int8 layers (+ softmax) when the batch is a single wave of tiles (qlayer_fused.cu)
-  if (allow_fused && c->amap_ok && !c->trace && nq >= 2 && nq <= kFusedMaxLayers &&
-      std::all_of(mod->tc_ok.begin(), mod->tc_ok.end(), [](bool b) { return b; })) {
+  if (allow_fused && c->amap_ok && mod->fused_ok && !c->trace && nq >= 2 && nq <= kFusedMaxLayers) {
     int grid = 0;
     const int bnh = qlayer_fused_plan(m, h.hidden, h.out_dim, mod->num_sms, c->policy, &grid);
     if (bnh != 0) {
       FusedArgs fa{};
-      fa.act[0] = c->amap[0][0];
-      fa.act[1] = c->amap[1][0];
+      fa.act[0] = c->amap3[0];
+      fa.act[1] = c->amap3[1];
       uint32_t done = 0, tiles_so_far = 0;
       for (int j = 0; j < nq; ++j) {
         const BlobQLayer &ql = mod->q[size_t(j)];
         const bool logits = j == nq - 1;
         const int bn = logits ? 256 : bnh;
         const int variant = bn == 64 ? 0 : (bn == 128 ? 1 : 2);
-        fa.w[j] = mod->wmaps[size_t(j)][size_t(variant)];
+        fa.w[j] = mod->wmaps3[size_t(j)][size_t(variant)];
         FusedLayer &L = fa.layer[j];
         L.bias = mod->at<float>(ql.off_bias);
         L.fix_ptr = mod->at<uint32_t>(ql.off_fix_ptr[variant]);
@@ -793,6 +819,17 @@ int upload_model(const uint8_t *host_view, const void *src, bool src_on_device, 
     for (int b = 0; b < 4; ++b)
       if (int rc = make_tmap(&m->wmaps[j][size_t(b)], m->d_blob + ql.off_w, ql.nodes, ql.inputs, boxes[b])) return fail(rc);
     m->tc_ok[j] = true;
+  }
+  m->wmaps3.resize(m->q.size());
+  m->fused_ok = !m->q.empty();
+  for (size_t j = 0; j < m->q.size(); ++j) {
+    const BlobQLayer &ql = m->q[j];
+    if (!m->tc_ok[j] || ql.inputs % 256 != 0) {
+      m->fused_ok = false;
+      break;
+    }
+    for (int b = 0; b < 3; ++b)
+      if (int rc = make_tmap3(&m->wmaps3[j][size_t(b)], m->d_blob + ql.off_w, ql.nodes, ql.inputs, 64 << b, 2)) return fail(rc);
   }
   *out = m.release();
   return FDNN_OK;

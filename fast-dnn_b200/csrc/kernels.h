@@ -135,8 +135,8 @@ struct FusedLayer {
   uint32_t n_blocks;        // column blocks of this layer at its tile width
 };
 struct FusedArgs {
-  CUtensorMap act[2];                 // the two u8 activation buffers [M][H], box 128 rows × 128 bytes
-  CUtensorMap w[kFusedMaxLayers];     // s8 weights [N][K]: box BNH rows (hidden layers), 256 rows (output layer)
+  CUtensorMap act[2];                 // the two u8 activation buffers [M][H] as 3-D maps (128 B of K, row, K block): box 128 rows × 2 K blocks
+  CUtensorMap w[kFusedMaxLayers];     // s8 weights [N][K], 3-D likewise: box BNH rows (hidden layers) / 256 rows (output layer) × 2 K blocks
   FusedLayer layer[kFusedMaxLayers];
   int n_layers, M;
   uint8_t *act_buf[2];
@@ -148,7 +148,7 @@ struct FusedArgs {
   uint32_t *sync;                     // [kFusedSyncWords] zero-initialised; the kernel leaves it zeroed
   uint32_t total_tiles;
   uint32_t tiles_per_row_block;       // Σ over layers of the number of N tiles: a row block has left the output layer
-  int debug_flags;                    // FDNN_FUSED_DEBUG: timing experiments (2 no proxy fences, 4 no extra fence before the release, 8 poll without sleeping, 16 spin on the accumulator barrier)
+  int debug_flags;                    // FDNN_FUSED_DEBUG: timing experiments (2 no proxy fences, 4 no extra fence before the release, 8 poll without sleeping, 16 spin on the accumulator barrier; RESULTS WRONG: 1 no scan entries, 32 no MMAs, 64 no activation tiles)
   unsigned long long *timeline;       // optional [layers][1024][8] nanosecond stamps (fdnn_ctx_timeline)
 };
 cudaError_t qlayer_fused_configure();

@@ -111,6 +111,15 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap *map, uint64_t *ba
       : "memory");
 }
 
+// 3D tile load: a u8 matrix [rows][K] viewed as (128 bytes of K, row, 128-byte K block) — one instruction brings `box_kb` consecutive K
+// blocks of `box_rows` rows, landing as box_kb consecutive 128B-swizzled tiles.  Coordinates (c0 = 0, c1 = row, c2 = K block).
+__device__ __forceinline__ void tma_load_3d(const CUtensorMap *map, uint64_t *bar, void *smem_dst, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+
 // Plain bulk copy global → shared memory (no tensor map): `bytes` a multiple of 16, both addresses 16-byte aligned;
 // completes on `bar` like a TMA tile.
 __device__ __forceinline__ void bulk_load(void *smem_dst, const void *gmem_src, uint32_t bytes, uint64_t *bar) {

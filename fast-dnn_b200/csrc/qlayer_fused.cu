@@ -67,11 +67,17 @@ constexpr int kSoftmaxRowFloats = kRingBytes / kSoftmaxGroups / 4;  // 12288: wi
 static_assert(kBlockK == kFixKBlock, "risk-list order is tied to the tiling");
 static_assert(kSoftmaxGroups * kSoftmaxThreads == kThreads, "softmax groups");
 
+// A pipeline stage is TWO 128-byte K blocks of both operands, each operand brought by ONE 3-D TMA box: what a stage costs the
+// producer is a fixed ≈ 300-350 ns of barrier and TMA instruction issue whatever it carries (tools/feed_bench.cu: 24 / 32 / 48 KB
+// stages → 80 / 107 / 160 GB/s per SM), so the bytes per stage, not the stage count, decide how fast a tile's operands arrive.
+constexpr int kKbPerStage = 2;
 template <int BN>
 struct Geo {
-  static constexpr int kABytes = kBlockM * kBlockK;
-  static constexpr int kStageBytes = kABytes + BN * kBlockK;
-  static constexpr int kStages = BN == 256 ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int kATile = kBlockM * kBlockK;   // one K block of the activation rows
+  static constexpr int kWTile = BN * kBlockK;        // … of the weight rows
+  static constexpr int kABytes = kKbPerStage * kATile;
+  static constexpr int kStageBytes = kABytes + kKbPerStage * kWTile;
+  static constexpr int kStages = BN == 256 ? 2 : (BN == 128 ? 2 : 4);
   static constexpr int kColsPerWarp = BN / 4;
   static constexpr int kChunks = kColsPerWarp / 16;
   static_assert(kStages * kStageBytes <= kRingBytes && kStages <= kMaxStages && kStages % kScanSets == 0, "ring");
@@ -127,7 +133,8 @@ __device__ __forceinline__ void fstamp(const FusedArgs &p, int layer, int slot) 
   if (p.timeline != nullptr) p.timeline[(size_t(layer) * 1024 + blockIdx.x) * 8 + slot] = global_ns();
 }
 
-__device__ __forceinline__ int first_k_block(int m_blk, int n_blk, int k_blocks) { return (n_blk + 5 * m_blk) % k_blocks; }
+// first stage (pair of K blocks) of a tile's rotated K loop, in stages: CTAs that share an operand start at different K blocks
+__device__ __forceinline__ int first_k_stage(int m_blk, int n_blk, int k_stages) { return (n_blk + 5 * m_blk) % k_stages; }
 
 __device__ __forceinline__ uint32_t bit(uint32_t word, uint32_t i) { return (word >> i) & 1u; }
 
@@ -193,30 +200,28 @@ __device__ __forceinline__ void advance_acc(Flow &f) {
 
 // ---- one layer, one role each ---------------------------------------------------------------------------------------------
 
-// The whole producer warp, converged.  One thread gets a 128-row TMA box accepted only every ≈ 225 ns (71 GB/s per SM); boxes issued
-// by several lanes in the SAME instruction go out together (two lanes 101 GB/s, four 146 GB/s, tools/feed_bench.cu) — the issue rate of
-// a single lane, not the L2, was what capped the operand feed of every layer at batch 512.  So: the first `pre` stages of a tile are
-// issued by `pre` lanes at once (lane i owns stage i: its weight box first, its activation box once the row block is ready), the
-// remaining K blocks by two lanes per stage (lane 0 the activation box and the barrier, lane 1 the weight box).
+// The whole producer warp, converged.  The first `pre` stages of a tile are issued by `pre` lanes at once (lane i owns stage i: its
+// weight box first — weights do not depend on the previous layer — its activation box once the row block is ready), the remaining
+// stages by two lanes (lane 0 the activation box and the barrier, lane 1 the weight box).
 template <int BN>
 __device__ __forceinline__ void produce_tile(const FusedArgs &p, const Tile &t, const Shared &sh, Flow &f, int lane) {
   using G = Geo<BN>;
   const int j = t.layer, m_blk = t.m_blk, n_blk = t.n_blk;
   const FusedLayer &L = p.layer[j];
-  const int k_blocks = L.K / kBlockK;
+  const int k_stages = L.K / (kBlockK * kKbPerStage);
   const CUtensorMap *amap = &p.act[j & 1];
   const CUtensorMap *wmap = &p.w[j];
-  const int kb0 = first_k_block(m_blk, n_blk, k_blocks);
-  const int pre = min(G::kStages, k_blocks);
+  const int ks0 = first_k_stage(m_blk, n_blk, k_stages);
+  const int pre = min(G::kStages, k_stages);
   if (lane == 0) fstamp(p, j, 7);
-  // Weight tiles first: they do not depend on the previous layer.
   const uint32_t my_slot = (f.slot + uint32_t(lane)) % uint32_t(G::kStages);
-  const int my_kb = (kb0 + lane) % k_blocks;
+  const int my_kb = ((ks0 + lane) % k_stages) * kKbPerStage;
   uint8_t *my_stage = sh.ring + my_slot * G::kStageBytes;
   if (lane < pre) {
     ptx::mbar_wait(sh.empty_bar + my_slot, bit(f.ring_ph, my_slot) ^ 1u);
-    ptx::mbar_arrive_expect_tx(sh.full_bar + my_slot, G::kStageBytes);
-    ptx::tma_load_2d(wmap, sh.full_bar + my_slot, my_stage + G::kABytes, my_kb * kBlockK, n_blk * BN);
+    // (a weight box may land before … no: the same lane posts the expect_tx first)
+    ptx::mbar_arrive_expect_tx(sh.full_bar + my_slot, (p.debug_flags & 64) ? G::kStageBytes - G::kABytes : G::kStageBytes);
+    ptx::tma_load_3d(wmap, sh.full_bar + my_slot, my_stage + G::kABytes, 0, n_blk * BN, my_kb);
   }
   if (lane == 0) {
     fstamp(p, j, 6);
@@ -229,18 +234,20 @@ __device__ __forceinline__ void produce_tile(const FusedArgs &p, const Tile &t, 
   __syncwarp();
   if (lane < pre) {
     if (j > 0 && !(p.debug_flags & 2)) fence_proxy_async_global();
-    ptx::tma_load_2d(amap, sh.full_bar + my_slot, my_stage, my_kb * kBlockK, m_blk * kBlockM);
+    if (!(p.debug_flags & 64)) ptx::tma_load_3d(amap, sh.full_bar + my_slot, my_stage, 0, m_blk * kBlockM, my_kb);
   }
   for (int i = 0; i < pre; ++i) advance<BN>(f);
-  int kb = (kb0 + pre) % k_blocks;
-  for (int i = pre; i < k_blocks; ++i, kb = (kb + 1 == k_blocks ? 0 : kb + 1)) {
+  int ks = (ks0 + pre) % k_stages;
+  for (int i = pre; i < k_stages; ++i, ks = (ks + 1 == k_stages ? 0 : ks + 1)) {
     if (lane < 2) {
       ptx::mbar_wait(sh.empty_bar + f.slot, bit(f.ring_ph, f.slot) ^ 1u);
       uint8_t *sa = sh.ring + f.slot * G::kStageBytes;
-      if (lane == 0) ptx::mbar_arrive_expect_tx(sh.full_bar + f.slot, G::kStageBytes);
-      // one instruction, two boxes: per-lane tensor map, destination and row coordinate
-      ptx::tma_load_2d(lane == 0 ? amap : wmap, sh.full_bar + f.slot, lane == 0 ? sa : sa + G::kABytes, kb * kBlockK,
-                       lane == 0 ? m_blk * kBlockM : n_blk * BN);
+      if (lane == 0) ptx::mbar_arrive_expect_tx(sh.full_bar + f.slot, (p.debug_flags & 64) ? G::kStageBytes - G::kABytes : G::kStageBytes);
+      // one instruction, two boxes: per-lane tensor map, destination and row coordinate (the weight box may land before lane 0's
+      // expect_tx is visible: the transaction count dips below zero, the phase cannot complete before lane 0 has arrived)
+      if (!(p.debug_flags & 64) || lane == 1)
+        ptx::tma_load_3d(lane == 0 ? amap : wmap, sh.full_bar + f.slot, lane == 0 ? sa : sa + G::kABytes, 0, lane == 0 ? m_blk * kBlockM : n_blk * BN,
+                         ks * kKbPerStage);
     }
     advance<BN>(f);
   }
@@ -250,23 +257,29 @@ template <int BN>
 __device__ __forceinline__ void mma_tile(const FusedArgs &p, const Tile &t, const Shared &sh, Flow &f, uint32_t tmem_base, int lane) {
   using G = Geo<BN>;
   const int j = t.layer;
-  const int k_blocks = p.layer[j].K / kBlockK;
+  const int k_stages = p.layer[j].K / (kBlockK * kKbPerStage);
   constexpr uint32_t idesc = ptx::idesc_i8_u8s8(BN);
   ptx::mbar_wait(sh.tmem_empty_bar + f.acc, bit(f.acc_ph, f.acc) ^ 1u);
   ptx::tc_fence_after_sync();
   const uint32_t d_tmem = tmem_base + f.acc * uint32_t(BN);
-  for (int kb = 0; kb < k_blocks; ++kb) {
+  for (int ks = 0; ks < k_stages; ++ks) {
     ptx::mbar_wait(sh.full_bar + f.slot, bit(f.ring_ph, f.slot));
     ptx::tc_fence_after_sync();
     if (lane == 0) {
-      if (kb == 0) fstamp(p, j, 1);
-      const uint32_t a_addr = ptx::smem_u32(sh.ring + f.slot * G::kStageBytes);
-      const uint64_t da = ptx::smem_desc_k_sw128(a_addr), db = ptx::smem_desc_k_sw128(a_addr + G::kABytes);
+      if (ks == 0) fstamp(p, j, 1);
+      const uint32_t s_addr = ptx::smem_u32(sh.ring + f.slot * G::kStageBytes);
+      if (!(p.debug_flags & 32)) {
 #pragma unroll
-      for (int k = 0; k < kBlockK / kUmmaK; ++k)
-        ptx::mma_i8_ss(d_tmem, da + uint64_t(k * (kUmmaK / 16)), db + uint64_t(k * (kUmmaK / 16)), idesc, uint32_t((kb | k) != 0));
+        for (int kt = 0; kt < kKbPerStage; ++kt) {
+          const uint64_t da = ptx::smem_desc_k_sw128(s_addr + uint32_t(kt * G::kATile));
+          const uint64_t db = ptx::smem_desc_k_sw128(s_addr + uint32_t(G::kABytes + kt * G::kWTile));
+#pragma unroll
+          for (int k = 0; k < kBlockK / kUmmaK; ++k)
+            ptx::mma_i8_ss(d_tmem, da + uint64_t(k * (kUmmaK / 16)), db + uint64_t(k * (kUmmaK / 16)), idesc, uint32_t((ks | kt | k) != 0));
+        }
+      }
       ptx::mma_commit(sh.empty_bar + f.slot);
-      if (kb == k_blocks - 1) ptx::mma_commit(sh.tmem_full_bar + f.acc);
+      if (ks == k_stages - 1) ptx::mma_commit(sh.tmem_full_bar + f.acc);
     }
     __syncwarp();
     advance<BN>(f);
@@ -275,7 +288,7 @@ __device__ __forceinline__ void mma_tile(const FusedArgs &p, const Tile &t, cons
 }
 
 // The per-tile state of the saturation scan, staged by warps 2-3 ahead of the scan warps: entry offsets per K block, packed
-// entry words (w0 | w1 << 8 | (node − n0) << 16 | byte offset of the pair in its K block << 24), zeroed event counters.
+// entry words (w0 | w1 << 8 | (node − n0) << 16 | byte offset of the pair in its stage's 256 bytes of K << 24), zeroed event counters.
 template <int BN>
 __device__ __forceinline__ void prep_tile(const FusedArgs &p, const Tile &t, const Shared &sh, Flow &f, int pt, int lane) {
   const FusedLayer &L = p.layer[t.layer];
@@ -294,7 +307,8 @@ __device__ __forceinline__ void prep_tile(const FusedArgs &p, const Tile &t, con
   const uint2 *gent = reinterpret_cast<const uint2 *>(L.fix_ent) + ent_begin;
   for (uint32_t e = uint32_t(pt); e < staged; e += kPrepThreads) {
     const uint2 fe = __ldg(gent + e);
-    E[e] = (fe.x >> 16) | ((fe.y - uint32_t(t.n_blk * BN)) << 16) | (((2u * (fe.x & 0xffffu)) & 127u) << 24);
+    // bits 24-30: byte offset of the pair in its K block; bit 31: which of the stage's two K blocks (stages start at even K blocks)
+    E[e] = (fe.x >> 16) | ((fe.y - uint32_t(t.n_blk * BN)) << 16) | (((2u * (fe.x & 0xffffu)) & 255u) << 24);
   }
   for (int i = pt; i < kBlockM; i += kPrepThreads) sh.rowcnt[acc * kBlockM + i] = 0;
   __syncwarp();
@@ -306,7 +320,7 @@ template <int BN>
 __device__ __forceinline__ void scan_tile(const FusedArgs &p, const Tile &t, const Shared &sh, Flow &f, int st, int lane) {
   using G = Geo<BN>;
   const FusedLayer &L = p.layer[t.layer];
-  const int k_blocks = L.K / kBlockK;
+  const int k_blocks = L.K / kBlockK, k_stages = k_blocks / kKbPerStage;
   const int sset = st / kBlockM;
   const int row_sub = lane & 7, ent_sub = lane >> 3;
   const int row_base = ((st % kBlockM) / 32) * 32 + row_sub;
@@ -316,8 +330,8 @@ __device__ __forceinline__ void scan_tile(const FusedArgs &p, const Tile &t, con
   const FixEntry *fix_ent = L.fix_ent;
   {
     const int m_blk = t.m_blk, n_blk = t.n_blk;
-    const int kb0 = first_k_block(m_blk, n_blk, k_blocks);
-    auto k_block_of = [&](int turn) { return (kb0 + turn) % k_blocks; };
+    const int ks0 = first_k_stage(m_blk, n_blk, k_stages);
+    auto k_block_of = [&](int turn) { return ((ks0 + turn) % k_stages) * kKbPerStage; };  // first K block of pipeline turn `turn`
     const uint32_t acc = f.acc;
     const uint32_t *gp = fix_ptr + size_t(n_blk) * kbn;
     uint32_t *P = sh.ptr + acc * kPtrSlots;
@@ -339,27 +353,29 @@ __device__ __forceinline__ void scan_tile(const FusedArgs &p, const Tile &t, con
       w0 = E[min(r0 + uint32_t(ent_sub), last)];
       w1 = E[min(r0 + 4u + uint32_t(ent_sub), last)];
     };
-    // this set's first pipeline turn of the tile; every role counts turns identically, so ring slot and scan set follow from it
-    int kb = int((uint32_t(sset) + kScanSets - f.turn % kScanSets) % kScanSets);
+    // this set's first pipeline turn (stage) of the tile; every role counts turns identically, so ring slot and scan set follow from it
+    int turn = int((uint32_t(sset) + kScanSets - f.turn % kScanSets) % kScanSets);
     uint32_t r0 = 0, r1 = 0;
-    if (kb < k_blocks) {
-      r0 = P[k_block_of(kb)];
-      r1 = P[k_block_of(kb) + 1];
+    if (turn < k_stages) {
+      r0 = P[k_block_of(turn)];
+      r1 = P[k_block_of(turn) + kKbPerStage];
       fetch(r0, min(r1, staged));
     }
-    for (; kb < k_blocks; kb += kScanSets) {
-      const uint32_t slot = (f.slot + uint32_t(kb)) % uint32_t(G::kStages);
+    for (; turn < k_stages; turn += kScanSets) {
+      const uint32_t slot = (f.slot + uint32_t(turn)) % uint32_t(G::kStages);
       ptx::mbar_wait(sh.full_bar + slot, bit(f.ring_ph, slot));
       f.ring_ph ^= 1u << slot;
+      // activation bytes of the stage: two 128B-swizzled tiles of 128 rows, one per K block (entry word bit 31 says which)
       const uint32_t a_swz = (ptx::smem_u32(sh.ring + slot * G::kStageBytes) + uint32_t(row_base) * 128u) ^ swz;
       const uint32_t fast_end = min(r1, staged);
       for (uint32_t e = r0; e < fast_end; e += 8) {
         if (e != r0) fetch(e, fast_end);
+        const uint32_t o0 = (w0 >> 24) & 127u, t0 = (w0 >> 31) * uint32_t(G::kATile), o1 = (w1 >> 24) & 127u, t1 = (w1 >> 31) * uint32_t(G::kATile);
         uint32_t a0[4], a1[4];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-          a0[q] = ptx::lds_u16((a_swz + uint32_t(q) * 1024u) ^ (w0 >> 24));
-          a1[q] = ptx::lds_u16((a_swz + uint32_t(q) * 1024u) ^ (w1 >> 24));
+          a0[q] = ptx::lds_u16(((a_swz + uint32_t(q) * 1024u) ^ o0) + t0);
+          a1[q] = ptx::lds_u16(((a_swz + uint32_t(q) * 1024u) ^ o1) + t1);
         }
         int v0[4], v1[4];
         uint32_t fired = 0;
@@ -381,24 +397,24 @@ __device__ __forceinline__ void scan_tile(const FusedArgs &p, const Tile &t, con
       for (uint32_t e = max(r0, staged); e < r1; ++e) {  // beyond the staging capacity (dense risk lists)
         const uint2 *gent = reinterpret_cast<const uint2 *>(fix_ent) + __ldg(gp);
         const uint2 fe = __ldg(gent + e);
-        const uint32_t b = (2u * (fe.x & 0xffffu)) & 127u;
+        const uint32_t b2 = (2u * (fe.x & 0xffffu)) & 255u, b = b2 & 127u;
         const int row = (st % kBlockM);
-        const uint32_t a_addr = ptx::smem_u32(sh.ring + slot * G::kStageBytes) + uint32_t(row) * 128u;
+        const uint32_t a_addr = ptx::smem_u32(sh.ring + slot * G::kStageBytes) + (b2 >> 7) * uint32_t(G::kATile) + uint32_t(row) * 128u;
         const uint32_t a01s = ptx::lds_u16(a_addr + (((b & 0x70u) ^ (uint32_t(row & 7) << 4)) | (b & 15u)));
         const int v = dp4a_u8s8(a01s, fe.x >> 16, 0);
         if (uint32_t(v + 32768) > 65535u) record(row, v, fe.y - uint32_t(n_blk * BN));
       }
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(sh.empty_bar + slot);
-      if (kb + kScanSets < k_blocks) {
-        r0 = P[k_block_of(kb + kScanSets)];
-        r1 = P[k_block_of(kb + kScanSets) + 1];
+      if (turn + kScanSets < k_stages) {
+        r0 = P[k_block_of(turn + kScanSets)];
+        r1 = P[k_block_of(turn + kScanSets) + kKbPerStage];
         fetch(r0, min(r1, staged));
       }
     }
     // account for the whole tile's turns (the phase bits of this set's own slots were flipped above, one by one)
-    f.slot = (f.slot + uint32_t(k_blocks)) % uint32_t(G::kStages);
-    f.turn += uint32_t(k_blocks);
+    f.slot = (f.slot + uint32_t(k_stages)) % uint32_t(G::kStages);
+    f.turn += uint32_t(k_stages);
     ptx::mbar_arrive(sh.scan_done_bar + acc);
     advance_acc(f);
   }

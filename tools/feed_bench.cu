@@ -157,6 +157,78 @@ __global__ void __launch_bounds__(64, 1) tma_rate_kernel(const __grid_constant__
   }
 }
 
+// The layer kernels' stage: one 128-row box from one tensor map (activations) + one w_rows-row box from ANOTHER map (weights).
+// lanes = 1: one lane issues both boxes; lanes = 2: lane 0 the activation box, lane 1 the weight box, in one instruction.
+__global__ void __launch_bounds__(96, 1) two_map_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, int rows,
+                                                        int turns, int w_rows, int lanes, int stages, unsigned long long *sink) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t full_bar[8], empty_bar[8];
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+  const int stage_bytes = (128 + w_rows) * 128;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < stages; ++i) {
+      ptx::mbar_init(full_bar + i, 1);
+      ptx::mbar_init(empty_bar + i, 1);
+    }
+    ptx::fence_barrier_init();
+  }
+  __syncthreads();
+  const int k_tiles = kK / 128;
+  if (lanes == 3 && (warp == 0 || warp == 2)) {
+    if (lane == 0) {  // two warps, one box each
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = 0; t < turns; ++t) {
+        ptx::mbar_wait(empty_bar + stage, phase ^ 1);
+        uint8_t *sa = smem + stage * stage_bytes;
+        const int ta = int((uint64_t(blockIdx.x % 4) * 16 + uint64_t(t)) % uint64_t(k_tiles));
+        const int tw = int((uint64_t(blockIdx.x) * 7919u + uint64_t(t)) % uint64_t((rows / w_rows) * k_tiles));
+        if (warp == 0) {
+          ptx::mbar_arrive_expect_tx(full_bar + stage, uint32_t(stage_bytes));
+          ptx::tma_load_2d(&map_a, full_bar + stage, sa, ta * 128, int(blockIdx.x % 4) * 128);
+        } else {
+          ptx::tma_load_2d(&map_w, full_bar + stage, sa + 128 * 128, (tw % k_tiles) * 128, (tw / k_tiles) * w_rows);
+        }
+        if (++stage == stages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 0) {
+    if (lane < lanes) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = 0; t < turns; ++t) {
+        ptx::mbar_wait(empty_bar + stage, phase ^ 1);
+        uint8_t *sa = smem + stage * stage_bytes;
+        if (lane == 0) ptx::mbar_arrive_expect_tx(full_bar + stage, uint32_t(stage_bytes));
+        const int ta = int((uint64_t(blockIdx.x % 4) * 16 + uint64_t(t)) % uint64_t(k_tiles));         // 4 row blocks shared by many CTAs, K walks
+        const int tw = int((uint64_t(blockIdx.x) * 7919u + uint64_t(t)) % uint64_t((rows / w_rows) * k_tiles));
+        if (lanes == 1) {
+          ptx::tma_load_2d(&map_a, full_bar + stage, sa, ta * 128, int(blockIdx.x % 4) * 128);
+          ptx::tma_load_2d(&map_w, full_bar + stage, sa + 128 * 128, (tw % k_tiles) * 128, (tw / k_tiles) * w_rows);
+        } else {
+          ptx::tma_load_2d(lane == 0 ? &map_a : &map_w, full_bar + stage, lane == 0 ? sa : sa + 128 * 128, lane == 0 ? ta * 128 : (tw % k_tiles) * 128,
+                           lane == 0 ? int(blockIdx.x % 4) * 128 : (tw / k_tiles) * w_rows);
+        }
+        if (++stage == stages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    int stage = 0;
+    uint32_t phase = 0;
+    unsigned long long acc = 0;
+    for (int t = 0; t < turns; ++t) {
+      ptx::mbar_wait(full_bar + stage, phase);
+      if (lane == 0) {
+        acc += smem[stage * stage_bytes + (t & 1023)];
+        ptx::mbar_arrive(empty_bar + stage);
+      }
+      __syncwarp();
+      if (++stage == stages) { stage = 0; phase ^= 1; }
+    }
+    if (lane == 0 && sink) sink[blockIdx.x] = acc;
+  }
+}
+
 // mode "multicast": clusters of C CTAs; every CTA issues 1/C of each stage's bytes and multicasts them to all C CTAs, so each CTA
 // RECEIVES a whole 32 KB stage while its TMA unit only ISSUES 32/C KB.  A stage is free when all C consumers have released it.
 template <int C>
@@ -321,6 +393,30 @@ int main() {
         CK(cudaEventElapsedTime(&ms, e0, e1));
         std::printf(", {\"ctas\": %d, \"mode\": \"tma\", \"box_rows\": %d, \"issuing_lanes\": %d, \"stage_bytes\": %d, \"stages\": %d, \"per_sm_gbs\": %.1f}", sms, box_rows,
                     issuers, stage_bytes, stages, double(sms) * tn * stage_bytes / (ms * 1e-3) / 1e9 / sms);
+      }
+    }
+  }
+  // the layer kernels' stage shape: activation box + weight box from two tensor maps
+  CK(cudaFuncSetAttribute(two_map_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 196608));
+  for (int w_rows : {64, 128, 256}) {
+    CUtensorMap mw2;
+    cuuint32_t boxw[2] = {128u, cuuint32_t(w_rows)};
+    if (reinterpret_cast<EncodeFn>(fnp)(&mw2, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, d, dims, strides, boxw, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      continue;
+    const int stage_bytes = (128 + w_rows) * 128, stages = 196608 / stage_bytes > 8 ? 8 : 196608 / stage_bytes;
+    for (int ctas : {128, 64}) {
+      for (int lanes : {1, 2, 3}) {
+        two_map_kernel<<<ctas, 96, stages * stage_bytes>>>(map, mw2, rows, 200, w_rows, lanes, stages, sink);
+        CK(cudaDeviceSynchronize());
+        CK(cudaEventRecord(e0));
+        two_map_kernel<<<ctas, 96, stages * stage_bytes>>>(map, mw2, rows, turns, w_rows, lanes, stages, sink);
+        CK(cudaEventRecord(e1));
+        CK(cudaEventSynchronize(e1));
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, e0, e1));
+        std::printf(", {\"ctas\": %d, \"mode\": \"two maps: 128-row box + %d-row box, issue mode %d (1 one lane, 2 two lanes, 3 two warps), %d stages\", \"per_sm_gbs\": %.1f}", ctas, w_rows, lanes,
+                    stages, double(turns) * stage_bytes / (ms * 1e-3) / 1e9);
       }
     }
   }
