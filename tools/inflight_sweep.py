@@ -6,7 +6,7 @@ import os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 from fast_dnn_b200 import quantized_dnn as qd, synth
-B, I, O = 512, 440, 8000
+B, I, O = int(os.environ.get("B", "512")), 440, 8000
 dnn = qd.QuantizedDnn.load_from_file(synth.network_file("L"), device=0)
 if os.environ.get("POLICY"):
     dnn.set_tile_policy(os.environ["POLICY"])
