@@ -6,8 +6,9 @@
 // contraction, same saturation scan, same verified tail in device_common.cuh) and of softmax_row.cuh: results are
 // bit-identical to the layer-by-layer path.
 //
-// Why.  At batch 512 a 2048×2048 layer is 128 tiles of 128×64 and ≈ 4 us of operand streaming (48 MB through the L2 → SM
-// fabric at its ≈ 6.3 kB/clk cap), but as a kernel of its own it took 14-15 us: launch ramp, barrier and tensor-memory set-up,
+// Why.  At batch 512 a 2048×2048 layer is 128 tiles of 128×64 and ≈ 4 us of operand streaming (48 MB from the L2 at 12 TB/s:
+// 192 KB in flight per SM over a ≈ 2 us round trip TMA → MMA issue → scan → release; tools/feed_bench.cu reaches 22 TB/s with
+// the same bytes in flight when nothing holds a stage), but as a kernel of its own it took 14-15 us: launch ramp, barrier and tensor-memory set-up,
 // table loads, the first TMA round trip and the drain were paid seven times per pass (profiles/r1f_summary.md).  Here they are
 // paid once: a CTA keeps its tensor memory, barriers, tables and TMA ring across layers, and between layers waits only for the
 // DATA it needs — the 128 frames of its tile's row block must have left the previous layer, which is a counter per row block

@@ -371,3 +371,38 @@ def test_block_fixup_wide_layer_long_batch_dense_blocks(net_file):
         assert rows.size == 0, (f"layer-0 bytes differ ({name}): {rows.size} elements, rows {np.unique(rows)[:20]} "
                                 f"(blocks {np.unique(rows // 32)[:20]}), cols {np.unique(cols)[:20]} … {np.unique(cols)[-5:]}")
         assert np.array_equal(outs["exact"][1].view(np.uint32), outs[name][1].view(np.uint32)), f"logits differ ({name})"
+
+
+@pytest.mark.parametrize("hidden", [128, 256, 384, 768])
+@pytest.mark.parametrize("stress", [False, True])
+def test_pipeline_geometries_bit_exact(net_file, hidden, stress):
+    """Hidden widths of 1, 2, 3 and 6 K blocks of 128 bytes: one K block per tile (shorter than any ring), the fused kernel's
+    two-K-block stages with a single stage (256) and with an odd number of stages (768), and a width the fused kernel does not take
+    (384 = 1.5 stages → layer by layer).  Traced stages against the oracle with the layer-by-layer kernels; the fused kernel and
+    CTA pairs, where they apply, against those; dense pmaddubsw saturation with the heavy-tailed weights."""
+    shape = (40, hidden, 3, 300)
+    path = net_file(shape, stress=stress)
+    dnn, port = qd.QuantizedDnn.load_from_file(path), oracle_py.Port(path)
+    try:
+        assert all(dnn.uses_tensor_cores(i) for i in range(dnn.layer_count() - 1))
+        for n in (1, 129, 640):
+            frames = synth.make_frames(n, dnn.input_dimension(), seed=700 + n)
+            os.environ["FDNN_FUSED"] = "0"
+            logits = stage_parity(dnn, port, frames)
+            scores = dnn.calculate(frames)
+            softmax_close(scores, port.calculate(frames))
+            for env in ({"FDNN_FUSED": "2"}, {"FDNN_FUSED": "0", "FDNN_PAIR": "64"}, {"FDNN_FUSED": "0", "FDNN_PAIR": "256"}):
+                os.environ.update(env)
+                ctx = dnn.get_new_lazy_context(n)
+                try:
+                    ctx.calculate_until_output(frames)
+                    assert np.array_equal(ctx.hidden(), port.until_output(frames)), f"{env}: last-hidden bytes, {n} frames"
+                    assert np.array_equal(ctx.logits().view(np.uint32), logits.view(np.uint32)), f"{env}: logits, {n} frames"
+                finally:
+                    ctx.delete()
+                assert np.array_equal(dnn.calculate(frames).view(np.uint32), scores.view(np.uint32)), f"{env}: scores, {n} frames"
+                os.environ.pop("FDNN_PAIR", None)
+    finally:
+        os.environ.pop("FDNN_FUSED", None)
+        os.environ.pop("FDNN_PAIR", None)
+        dnn.delete()
