@@ -38,7 +38,7 @@ def raw(rep):
 
 
 kernels = []
-for name in ("hidden", "input", "fixup", "fixup_stream", "hidden_stream", "output_stream"):
+for name in ("fused", "hidden_throughput", "hidden", "input", "fixup", "fixup_stream", "hidden_stream", "output_stream"):
     rep = os.path.join(OUT, f"{tag}_{name}.ncu-rep")
     if not os.path.exists(rep):
         continue
@@ -56,7 +56,8 @@ with open(os.path.join(PROF, f"{tag}_kernels.csv"), "w", newline="") as f:
     for d in kernels:
         w.writerow(d)
 
-for suffix in ("launches.csv", "launches_warm.csv", "bench.json", "bench_reference.json", "stage_times.log"):
+for suffix in ("launches.csv", "launches_warm.csv", "launches_latency.csv", "launches_throughput.csv", "launches_throughput_warm.csv", "launches_stream.csv",
+               "bench.json", "bench_reference.json", "stage_times.log"):
     src = os.path.join(OUT, f"{tag}_{suffix}")
     if os.path.exists(src):
         shutil.copy(src, os.path.join(PROF, f"{tag}_{suffix}"))
