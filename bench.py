@@ -680,8 +680,9 @@ def run_gpu_arm(args):
         "whole_step_in_timed_region": {"int8_tops": step_tops, "frac": step_tops / peak1,
                                        "what": "all int8 ops of a step / ms_per_step (input layer and softmax time included)"},
         "operand_feed": {"l2_to_sm_bytes_per_launch": feed_bytes, "achieved_gbs": feed_bytes / (hid_thr * 1e-3) / 1e9,
-                         "what": "what bounds a 512-frame layer: 64 CTAs x (128 activation + 128 weight rows) x 2048 B through L2 -> shared "
-                                 "memory (≈ 36 B/clk per SM measured, DESIGN.md §5), not the tensor pipe"},
+                         "what": "operand tiles of a 512-frame layer: 64 CTAs x (128 activation + 128 weight rows) x 2048 B from the L2 into "
+                                 "shared memory over the kernel's duration; what bounds it is 192 KB of ring per SM over a stage's round trip "
+                                 "(TMA -> MMA issue -> scan -> release), not the L2 (22 TB/s in tools/feed_bench) nor the tensor pipe (DESIGN.md §5)"},
     }
     fused_tops = ops_frame * BATCH / (t_rest * 1e-3) / 1e12
     single = {"value": world * BATCH * args.steps / (res["ms_single"] * 1e-3), "ms_per_step": res["ms_single"] / args.steps,
