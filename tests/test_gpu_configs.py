@@ -335,9 +335,18 @@ def test_jni_calculate_long_input_through_the_sink(net_file):
 # ---- multi-GPU parity (SURVEY.md §4 v: sharded results equal the 1-GPU results bit for bit) -------------------------------
 
 def _free_port():
-    with socket.socket() as s:
-        s.bind(("127.0.0.1", 0))
-        return s.getsockname()[1]
+    """a port below the kernel's ephemeral range (an ephemeral one can be handed to somebody's outgoing connection between this
+    probe and the rendezvous binding it — seen once on a GPU box: EADDRINUSE)"""
+    import random
+    for _ in range(200):
+        port = random.randint(15000, 29999)
+        with socket.socket() as s:
+            try:
+                s.bind(("127.0.0.1", port))
+                return port
+            except OSError:
+                continue
+    raise RuntimeError("no free port found")
 
 
 RANK_SCRIPT = r"""
@@ -377,8 +386,12 @@ def test_two_ranks_sharded_output_equals_single_gpu(tmp_path, net_file):
     path, n = net_file("S"), 5003
     script = tmp_path / "rank.py"
     script.write_text(RANK_SCRIPT.format(root=ROOT, path=path, n=n, out=str(tmp_path)))
-    subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
-                    "--master-port", str(_free_port()), str(script)], check=True, timeout=600)
+    for attempt in range(3):  # a rendezvous port can still be lost to a race: try another one
+        r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                            "--master-port", str(_free_port()), str(script)], timeout=600, capture_output=True, text=True)
+        if r.returncode == 0 or "EADDRINUSE" not in r.stderr:
+            break
+    assert r.returncode == 0, r.stderr[-3000:]
     shards = np.concatenate([np.load(tmp_path / f"rank{r}.npy") for r in range(2)])
     dnn = qd.QuantizedDnn.load_from_file(path)
     want = dnn.calculate(synth.make_frames(n, 440, seed=7))

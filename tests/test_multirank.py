@@ -51,9 +51,18 @@ def test_device_group_shard_plan_partitions_a_call():
 
 
 def _free_port():
-    with socket.socket() as s:
-        s.bind(("127.0.0.1", 0))
-        return s.getsockname()[1]
+    """a port below the kernel's ephemeral range (an ephemeral one can be handed to somebody's outgoing connection between this
+    probe and the rendezvous binding it — seen once on a GPU box: EADDRINUSE)"""
+    import random
+    for _ in range(200):
+        port = random.randint(15000, 29999)
+        with socket.socket() as s:
+            try:
+                s.bind(("127.0.0.1", port))
+                return port
+            except OSError:
+                continue
+    raise RuntimeError("no free port found")
 
 
 def _worker(rank, world, port, path, n_frames, result_dir):
