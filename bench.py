@@ -501,6 +501,43 @@ class Bench:
                 "mode": "Java_suskun_nn_QuantizedDnn_calculate through a C JVM stand-in (tools/jni_harness.c): pageable float[] in and out, "
                         "per call a copy of the input array, a zero-filled new float[], SetFloatArrayRegion from the transfer buffer"}
 
+    # -- configs[1]: 440-4x512-2000, batch 128 -----------------------------------------------------------
+    def small_config(self, steps=400):
+        """BASELINE configs[1] on this GPU: device-resident passes of 128 frames through the small network, one caller and four"""
+        torch, qd, synth = self.torch, self.qd, self.synth
+        i_dim, _, _, o_dim = synth.SHAPES["S"]
+        n = 128
+        dnn = qd.QuantizedDnn.load_from_file(synth.network_file("S"), device=self.local)
+        pool = 8
+        d_in = [torch.from_numpy(synth.make_frames(n, i_dim, seed=300 + i)).to(self.dev) for i in range(pool)]
+        d_out = [torch.empty(n, o_dim, dtype=torch.float32, device=self.dev) for _ in range(pool)]
+        out = {"workload": "BASELINE configs[1]: 440-4x512-2000 synthetic network, batch 128 synthetic frames per step"}
+        for lanes, key in ((1, "one_caller"), (4, "four_callers")):
+            ctxs = [dnn.get_new_lazy_context(n) for _ in range(lanes)]
+            streams = [self.stream] + [torch.cuda.Stream(device=self.dev) for _ in range(lanes - 1)]
+
+            def run(k):
+                for i in range(k):
+                    ctxs[i % lanes].forward_device(d_in[i % pool].data_ptr(), n, d_out[i % pool].data_ptr(), streams[i % lanes].cuda_stream)
+            run(4 * pool * lanes)
+            torch.cuda.synchronize()
+            ev0 = torch.cuda.Event(enable_timing=True)
+            ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(lanes)]
+            ev0.record(self.stream)
+            for st in streams[1:]:
+                st.wait_event(ev0)
+            run(steps)
+            for st, e in zip(streams, ev1):
+                e.record(st)
+            torch.cuda.synchronize()
+            ms = max(ev0.elapsed_time(e) for e in ev1)
+            out[key] = {"value": n * steps / (ms * 1e-3), "unit": "frames/s", "us_per_step": ms / steps * 1e3,
+                        "real_time_factor_at_100_frames_per_s": n * steps / (ms * 1e-3) / 100.0}
+            for c in ctxs:
+                c.delete()
+        dnn.delete()
+        return out
+
     # -- configs[3]: lazy masked output --------------------------------------------------------------
     def lazy(self, steps):
         torch, synth, dnn = self.torch, self.synth, self.dnn
@@ -706,6 +743,7 @@ def run_gpu_arm(args):
     e2e_jni = b.e2e_jni() if not (args.no_jni or args.single_process) else None
     lazy = b.lazy(max(20, min(args.steps, 100))) if not (args.no_extra or args.single_process) else None
     stream1m = b.stream1m(env_int("FDNN_BENCH_STREAM_FRAMES", 1_000_000)) if not args.no_extra else None
+    small = b.small_config() if (b.rank == 0 and n_gpus == 1 and not args.no_extra) else None
     b.sampler.stop()
 
     # ---- CPU baseline on this box's host cores (rank 0, N = 1 only; bounded samples) ------------------
@@ -750,7 +788,7 @@ def run_gpu_arm(args):
             "single_stream": single, "e2e": headline["e2e"], "e2e_jni": e2e_jni, "gpu_launches": res["launches"],
             "clocks": b.sampler.summary(), "roofline": roofline, "roofline_stream": stream_info["roofline"] if stream_info else None,
             "stages": stages, "cpu_baseline": headline["cpu"], "stream_regime": stream_info, "lazy": lazy, "stream1m": stream1m,
-            "int8_peak_calibration": i8,
+            "configs1": small, "int8_peak_calibration": i8,
         }, default=plain))
     b.dnn.delete()
     if world > 1:

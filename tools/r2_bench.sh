@@ -16,6 +16,7 @@ print('roofline', {k:v for k,v in d['roofline'].items() if k not in ('kernel','h
 print('roofline_stream', d['roofline_stream'])
 print('lazy', json.dumps(d['lazy'])[:1500])
 print('stream1m', json.dumps(d['stream1m'])[:900])
+print('configs1', d.get('configs1'))
 print('cpu', d['cpu_baseline'])
 print('i8', d['int8_peak_calibration'])
 PY
