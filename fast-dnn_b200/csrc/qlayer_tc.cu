@@ -184,6 +184,19 @@ qlayer_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_cons
   if (C > 1) ptx::cluster_sync_all();  // peers' barriers must exist before anything is multicast into them
   ptx::tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
+  // Weights are model constants: the weight boxes of the first tile's first stages go out BEFORE the wait for the previous kernel, so
+  // they arrive while this CTA (launched early, programmatic dependent launch) would only sit there; after the wait the same stages
+  // need their activation boxes only.  (Not in a cluster: a stage's multicast halves come from different CTAs.)
+  const int pre_w = (C == 1 && first_ct < tiles_total) ? min(Cfg::kStages, k_blocks) : 0;  // stages whose weight box is in flight
+  if (warp == 0 && lane == 0 && pre_w > 0) {
+    int m_blk, n_blk;
+    tmap.decode(first_ct, rank, m_blk, n_blk);
+    int kb = first_k_block<C>(m_blk, n_blk, k_blocks);
+    for (int s = 0; s < pre_w; ++s, kb = (kb + 1 == k_blocks ? 0 : kb + 1)) {
+      ptx::mbar_arrive_expect_tx(full_bar + s, Cfg::kStageBytes);
+      ptx::tma_load_2d(&tmap_w, full_bar + s, tiles + s * Cfg::kStageBytes + Cfg::kABytes, kb * kBlockK, n_blk * BN);
+    }
+  }
   // everything above touched only constants and this CTA's own shared/tensor memory; from here on
   // we read the previous kernel's activations and write buffers it may still be reading
   ptx::griddep_wait();
@@ -202,12 +215,21 @@ qlayer_tc_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_cons
         tmap.decode(ct, rank, m_blk, n_blk);
         int kb = first_k_block<C>(m_blk, n_blk, k_blocks);
         for (int i = 0; i < k_blocks; ++i, kb = (kb + 1 == k_blocks ? 0 : kb + 1)) {
+          uint8_t *sa = tiles + stage * Cfg::kStageBytes;
+          uint8_t *sb = sa + Cfg::kABytes;
+          if (C == 1 && ct == first_ct && i < pre_w) {
+            // armed and its weight box issued before the wait for the previous kernel (above): the activation box completes it
+            if (lane == 0) ptx::tma_load_2d(&tmap_act, full_bar + stage, sa, kb * kBlockK, m_blk * kBlockM);
+            if (++stage == Cfg::kStages) {
+              stage = 0;
+              phase ^= 1;
+            }
+            continue;
+          }
           if (C == 1)
             ptx::mbar_wait(empty_bar + stage, phase ^ 1);
           else
             ptx::mbar_wait_cluster(empty_bar + stage, phase ^ 1);
-          uint8_t *sa = tiles + stage * Cfg::kStageBytes;
-          uint8_t *sb = sa + Cfg::kABytes;
           if (lane == 0) ptx::mbar_arrive_expect_tx(full_bar + stage, Cfg::kStageBytes);
           if (C == 1) {
             // (the weight box may land before lane 0's expect_tx: the transaction count dips below zero, the phase cannot complete
