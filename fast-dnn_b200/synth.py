@@ -125,3 +125,22 @@ def network_file(shape, seed: int = 1234, stress: bool = False, cache_dir: str |
         formats.write_dnn_bin(tmp, layers, shift, scale)
         os.replace(tmp, path)
     return path
+
+
+def make_hostile_frames(n: int, dim: int, seed: int = 31) -> np.ndarray:
+    """Ordinary frames with the rows the reference was never written for mixed in: NaN, ±inf, huge, tiny, all-zero and constant rows,
+    single hostile elements (what happens to them is defined by x86 arithmetic, dnn.h:35-42: NaN and out-of-range products convert
+    to INT_MIN and land in bucket 0)."""
+    x = make_frames(n, dim, seed=seed)
+    if n >= 24:
+        x[3, 7 % dim] = np.nan
+        x[5, :] = 0.0
+        x[9, 100 % dim] = np.inf
+        x[11, 5 % dim] = -np.inf
+        x[13, :] = 1e30
+        x[15, :] = -1e30
+        x[17, :] = 1e-30
+        x[19, :] = 3.0
+        x[21, 0] = 3e38
+        x[23, :] = np.nan
+    return x

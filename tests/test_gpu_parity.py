@@ -406,3 +406,33 @@ def test_pipeline_geometries_bit_exact(net_file, hidden, stress):
         os.environ.pop("FDNN_FUSED", None)
         os.environ.pop("FDNN_PAIR", None)
         dnn.delete()
+
+
+@pytest.mark.parametrize("shape,policy", [("tiny", "latency"), ("S", "latency"), ("L", "latency"), ("L", "throughput")])
+def test_hostile_frames_match_oracle(net_file, shape, policy):
+    """NaN, ±inf, huge, tiny, zero and constant rows against the oracle (which tests/test_oracle.py pins on the compiled reference for
+    the same frames): every hidden layer's bytes, the logits' bits (NaN for NaN), the scores within tolerance where they are finite"""
+    path = net_file(shape)
+    dnn, port = qd.QuantizedDnn.load_from_file(path), oracle_py.Port(path)
+    dnn.set_tile_policy(policy)
+    try:
+        frames = synth.make_hostile_frames(40, dnn.input_dimension())
+        ctx = dnn.get_new_lazy_context(frames.shape[0])
+        try:
+            ctx.calculate_until_output(frames)
+            hidden = port.until_output(frames)
+            assert np.array_equal(ctx.hidden(), hidden)
+            _, bias, _ = port.qlayer(port.qlayer_count - 1)
+            want_logits = (port.output_linear(hidden) + bias).astype(np.float32)
+            got_logits = ctx.logits()
+            assert np.array_equal(np.isnan(got_logits), np.isnan(want_logits))
+            ok = ~np.isnan(want_logits)
+            assert np.array_equal(got_logits[ok].view(np.uint32), want_logits[ok].view(np.uint32))
+        finally:
+            ctx.delete()
+        got, want = dnn.calculate(frames), port.calculate(frames)
+        assert np.array_equal(np.isnan(got), np.isnan(want))
+        ok = ~np.isnan(want)
+        softmax_close(got[ok], want[ok])
+    finally:
+        dnn.delete()

@@ -130,6 +130,20 @@ def test_port_equals_compiled_reference(shape, stress, n, net_file):
 
 
 @needs_ref
+@pytest.mark.parametrize("shape", ["tiny", "S"])
+def test_port_equals_compiled_reference_on_hostile_frames(shape, net_file):
+    """NaN, ±inf, huge, tiny, zero and constant rows: what the reference does with them is x86 arithmetic (cvttss2si's INT_MIN for NaN
+    and out-of-range products → bucket 0, dnn.h:35-42); the restatement must do the same, byte for byte and NaN for NaN"""
+    path = net_file(shape)
+    port, ref = oracle_py.Port(path), oracle_py.Ref(path)
+    frames = synth.make_hostile_frames(40, port.input_dim)
+    assert np.array_equal(port.hidden_trace(frames), ref.hidden_trace(frames, batch=10))
+    got, want = port.calculate(frames), ref.calculate(frames, batch=10)
+    assert np.array_equal(np.isnan(got), np.isnan(want))
+    assert np.array_equal(got[~np.isnan(got)].view(np.uint32), want[~np.isnan(want)].view(np.uint32))
+
+
+@needs_ref
 def test_lut_and_qsigmoid_equal_compiled_reference():
     assert np.array_equal(oracle_py.Port.sigmoid_lut(), oracle_py.Ref.sigmoid_lut())
     xs = np.concatenate([np.linspace(-7, 7, 2801, dtype=np.float32), np.float32([1e9, -1e9, 3e7, 2.1474836e7, np.inf, -np.inf, np.nan, 0.005, -0.005, 0.015])])
