@@ -436,3 +436,35 @@ def test_hostile_frames_match_oracle(net_file, shape, policy):
         softmax_close(got[ok], want[ok])
     finally:
         dnn.delete()
+
+
+def test_lazy_mask_edge_cases(loaded):
+    """LazyOutputActivations (dnn.cc:355-392) at the edges of its mask argument: nothing active (every score 1/O exactly as the
+    reference computes it: exp(0) summed O times), everything active (the same scores as calculate()), negative and large mask
+    bytes (any non-zero byte is active), a single active node, and the per-frame index running through the whole context"""
+    dnn, port = loaded("S")
+    n, O = 6, dnn.output_dimension()
+    frames = synth.make_frames(n, dnn.input_dimension(), seed=17)
+    hidden = port.until_output(frames)
+    masks = np.zeros((n, O), np.int8)
+    masks[1, :] = 1
+    masks[2, :] = -1
+    masks[3, ::3] = -128
+    masks[3, 1::3] = 127
+    masks[4, 1234] = 1
+    masks[5, :] = np.where(np.arange(O) % 2 == 0, 5, 0)
+    full = dnn.calculate(frames)
+    ctx = dnn.get_new_lazy_context(n)
+    try:
+        ctx.calculate_until_output(frames)
+        rows = [ctx.calculate_for_output_nodes(masks[i]) for i in range(n)]
+        batch = ctx.calculate_for_output_nodes_batch(masks)
+    finally:
+        ctx.delete()
+    for i in range(n):
+        want = port.lazy(hidden[i], masks[i])
+        softmax_close(rows[i], want)
+        assert np.array_equal(rows[i].view(np.uint32), batch[i].view(np.uint32))
+    assert np.all(rows[0] == rows[0][0]) and abs(float(rows[0][0]) * O - 1.0) < 1e-5
+    assert np.array_equal(rows[1].view(np.uint32), full[1].view(np.uint32)), "all-active mask must give calculate()'s scores"
+    assert np.array_equal(rows[2].view(np.uint32), full[2].view(np.uint32)), "negative mask bytes are active"
