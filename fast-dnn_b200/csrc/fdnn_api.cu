@@ -758,12 +758,15 @@ int upload_model(const uint8_t *host_view, const void *src, bool src_on_device, 
       double sum_abs = 0.0, sum_low = 0.0;
       for (int k = 0; k < I0 && !bad; ++k) {
         const int W = int(std::lrint(std::ldexp(double(w[k]), 22 - e)));  // exact scaling, round to nearest
+        // balanced base-256 digits, every one an s8: W = d0 + 256·d1 + 65536·d2 exactly (the tensor-core kernel multiplies a frame
+        // limb with all three weight limbs in one instruction, so they must share their signedness)
+        const int d0 = ((W + 128) & 255) - 128, r1 = (W - d0) / 256, d1 = ((r1 + 128) & 255) - 128, d2 = (r1 - d1) / 256;
         sum_abs += std::abs(W);
-        sum_low += double(W & 255);
+        sum_low += double(std::abs(d0));
         const size_t o = size_t(n) * kInputTcPitch + size_t(k);
-        limbs[o] = uint8_t(W & 255);
-        limbs[plane + o] = uint8_t((W >> 8) & 255);
-        limbs[2 * plane + o] = uint8_t((W >> 16) & 255);
+        limbs[o] = uint8_t(int8_t(d0));
+        limbs[plane + o] = uint8_t(int8_t(d1));
+        limbs[2 * plane + o] = uint8_t(int8_t(d2));
       }
       // certificate constants, every bound rounded up (derivation in input_tc.cu)
       const double u = 5.9604644775390625e-8, up = 1.0 + 1e-6;

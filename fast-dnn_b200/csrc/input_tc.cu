@@ -11,10 +11,13 @@
 //   1. input_prep_kernel    x' = fl(fl(x + shift)·scale) exactly as the reference; each row is written as a
 //                           block-fixed-point integer vector X (|X_k| ≤ 2²², three 8-bit limbs) together with
 //                           its scale, Σ|X_k| and ‖x'‖₂.  W0 gets the same treatment once, at model upload.
-//   2. input_tc_kernel      Σ_k X_k·W_k EXACTLY up to the product of the two lowest limbs (bounded by 255·ΣW₀ and
-//                           put into ε_q): eight limb-pair products on tcgen05.mma kind::i8 (u8/s8 mixes, s32
-//                           accumulators in tensor memory, one per shift class s = i + j = 1 … 4, two sets so
-//                           that a tile's epilogue overlaps the next tile's MMAs).
+//   2. input_tc_kernel      Σ_k X_k·W_k EXACTLY up to the product of the two lowest limbs (bounded by 255·Σ|W₀| and
+//                           put into ε_q): the eight limb-pair products on tcgen05.mma kind::i8, s32 accumulators in tensor
+//                           memory, one per shift class s = i + j = 1 … 4, two sets so that a tile's epilogue overlaps the
+//                           next tile's MMAs.  The frame limbs are the bytes of the two's-complement integer (u8, u8, s8); the
+//                           weight limbs are BALANCED base-256 digits (all s8, W = W₀ + 256·W₁ + 65536·W₂ exactly), so that one
+//                           instruction multiplies a frame limb with all the weight limbs it needs (N = 192 or 128: three
+//                           instructions per K step instead of eight of N = 64 that cost the same ≈ 37 ns each).
 //                           z = (h_fix + bias)·100 is then evaluated in fp32 from the five class sums and
 //                             D = 100·(u·‖√c·x'‖₂·‖√c·w‖₂ + ε_q) + 100·7u·‖x'‖₂'·‖w‖₂' + 3.1u·|z| + u·|bias·100| + 2.1u
 //                           where u = 2⁻²⁴ and c_k counts the roundings term k goes through in the reference (its
@@ -59,11 +62,12 @@ constexpr int kAccSets = 2;               // two sets of accumulators: the next 
 constexpr int kStages = 3;
 constexpr int kXBytes = kTileM * kBlockK, kWBytes = kTileN * kBlockK;
 constexpr int kStageBytes = kLimbs * (kXBytes + kWBytes);  // 72 KB
-constexpr int kEpiWarps = 8;
+constexpr int kEpiWarps = 16;  // four per tensor-memory lane quarter, 16 of the tile's 64 columns each (the certificate is ≈ 40 instructions
+                               // per element and latency-bound: eight warps took 5.5 us per tile, more than the MMAs or the operand feed)
 constexpr int kTcThreads = (4 + kEpiWarps) * 32;
 constexpr int kTmemCols = kAccSets * kClasses * kTileN;  // 2 × 4 × 64 = 512
 constexpr int kBarRegion = 128;  // 2·kStages + 1 barriers, the TMEM address
-constexpr int kTcSmem = kStages * kStageBytes + kBarRegion + kLut2Padded + kTileN * int(sizeof(InputNodeStats));
+constexpr int kTcSmem = kStages * kStageBytes + kBarRegion + kLut2Padded + kTileN * int(sizeof(InputNodeStats)) + kTileM * 2 * 4;
 
 // ---- 1. prepare: transform, block-fixed-point limbs, row statistics ---------------------------------------
 __global__ void __launch_bounds__(256) input_prep_kernel(const InputTcArgs a) {
@@ -161,9 +165,9 @@ __device__ __forceinline__ void tmem_ld_32x8(uint32_t taddr, uint32_t (&r)[8]) {
                : "memory");
 }
 
-// instruction descriptor, kind::i8, D = s32, M = 128, N = 64, A/B each u8 (0) or s8 (1), both K-major
-__device__ __forceinline__ uint32_t idesc_limbs(bool a_signed, bool b_signed) {
-  return (2u << 4) | (uint32_t(a_signed) << 7) | (uint32_t(b_signed) << 10) | ((uint32_t(kTileN) >> 3) << 17) | ((128u >> 4) << 24);
+// instruction descriptor, kind::i8, D = s32, M = 128, N = n (a multiple of 16), A u8 (0) or s8 (1), B s8, both K-major
+__device__ __forceinline__ uint32_t idesc_limbs(bool a_signed, int n) {
+  return (2u << 4) | (uint32_t(a_signed) << 7) | (1u << 10) | ((uint32_t(n) >> 3) << 17) | ((128u >> 4) << 24);
 }
 
 __global__ void __launch_bounds__(kTcThreads, 1)
@@ -209,20 +213,27 @@ input_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
   ptx::griddep_launch_dependents();
 
   if (warp == 0) {
-    if (lane == 0) {
+    // SIX lanes issue, one box each, in one instruction (lanes 0-2 the frame limbs, 3-5 the weight limbs): one thread gets a box
+    // accepted only every ≈ 225 ns (tools/feed_bench.cu), and six boxes per 72 KB stage from one lane were what this kernel ran at
+    // (52 GB/s per SM, 5.5 us per tile — more than its MMAs or its epilogue take).
+    if (lane < 2 * kLimbs) {
+      const bool is_x = lane < kLimbs;
+      const int l = is_x ? lane : lane - kLimbs;
       uint32_t it = 0;  // K blocks issued so far: stage = it % kStages, use number = it / kStages
       for (int tile = int(blockIdx.x); tile < tiles_total; tile += int(gridDim.x)) {
         const int m_blk = tile / n_blocks, n_blk = tile % n_blocks;
-        for (int kb = 0; kb < k_blocks; ++kb, ++it) {
+        const int row = is_x ? l * a.x_plane_rows + m_blk * kTileM : l * a.w_plane_rows + n_blk * kTileN;
+        // K rotation: tiles start at different K blocks (integer accumulation is order-independent), so the CTAs do not all ask the
+        // L2 for the same 128-byte column of the 512-byte-pitch limb planes at the same time
+        int kb = (m_blk * 3 + n_blk) % k_blocks;
+        for (int turn = 0; turn < k_blocks; ++turn, ++it, kb = (kb + 1 == k_blocks ? 0 : kb + 1)) {
           const int stage = int(it % kStages);
           if (it >= uint32_t(kStages)) ptx::mbar_wait(empty_bar + stage, ((it / kStages) - 1u) & 1u);
           uint8_t *st = tiles + stage * kStageBytes;
-          ptx::mbar_arrive_expect_tx(full_bar + stage, kStageBytes);
-#pragma unroll
-          for (int l = 0; l < kLimbs; ++l) {
-            ptx::tma_load_2d(&tmap_x, full_bar + stage, st + l * kXBytes, kb * kBlockK, l * a.x_plane_rows + m_blk * kTileM);
-            ptx::tma_load_2d(&tmap_w, full_bar + stage, st + kLimbs * kXBytes + l * kWBytes, kb * kBlockK, l * a.w_plane_rows + n_blk * kTileN);
-          }
+          // (a box may land before lane 0's expect_tx is visible: the transaction count dips below zero, the phase cannot complete
+          // before lane 0 has arrived)
+          if (lane == 0) ptx::mbar_arrive_expect_tx(full_bar + stage, kStageBytes);
+          ptx::tma_load_2d(is_x ? &tmap_x : &tmap_w, full_bar + stage, is_x ? st + l * kXBytes : st + kLimbs * kXBytes + l * kWBytes, kb * kBlockK, row);
         }
       }
     }
@@ -240,24 +251,32 @@ input_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
       ptx::tc_fence_after_sync();
       if (lane == 0) {
         const uint32_t base = ptx::smem_u32(tiles + stage * kStageBytes);
+        // The weight limbs are BALANCED digits (every limb an s8, model upload), and the three limb tiles of a K block lie one after
+        // the other in the stage: one instruction multiplies a frame limb with all the weight limbs it needs — N = 192 or 128 instead
+        // of three or two instructions of N = 64, which cost the same 37 ns each (tools/int8_peak.cu) — and the products of
+        // consecutive shift classes land in consecutive accumulator columns.  Class s = i + j sits at columns (s − 1)·64:
+        //   X₁ · [W₀ W₁ W₂] → classes 1 2 3 (columns 0-191)     X₀ · [W₁ W₂] → classes 1 2 (0-127; X₀·W₀ is bounded, not computed)
+        //   X₂ · [W₀ W₁ W₂] → classes 2 3 4 (columns 64-255)
+        // The very first step of a tile overwrites: X₁ first (classes 1-3), and class 4 by an instruction of its own.
+        const uint32_t d0 = tmem_base + uint32_t(int(set) * kClasses * kTileN);
+        const uint32_t xa = base, wa = base + uint32_t(kLimbs * kXBytes);
 #pragma unroll
-        for (int i = 0; i < kLimbs; ++i)
-#pragma unroll
-          for (int j = 0; j < kLimbs; ++j) {
-            const uint64_t da = ptx::smem_desc_k_sw128(base + uint32_t(i * kXBytes));
-            const uint64_t db = ptx::smem_desc_k_sw128(base + uint32_t(kLimbs * kXBytes + j * kWBytes));
-            const uint32_t idesc = idesc_limbs(i == kLimbs - 1, j == kLimbs - 1);
-            // the first product of a shift class in this tile overwrites its accumulator: pairs with j == 0 or i == kLimbs−1
-            // come first in this loop order for their class only when (i == 0 || j == 0) … simpler: class s is first
-            // touched by the pair with the smallest i, which is (max(0, s − 2), s − max(0, s − 2))
-            const int s = i + j;
-            if (s == 0) continue;  // |Σ X₀·W₀| ≤ 255·ΣW₀ goes into the certificate's error bound instead (InputNodeStats::e)
-            const bool first_of_class = (i == (s > kLimbs - 1 ? s - (kLimbs - 1) : 0));
-#pragma unroll
-            for (int k = 0; k < kBlockK / kUmmaK; ++k)
-              ptx::mma_i8_ss(tmem_base + uint32_t(int(set) * kClasses * kTileN + (s - 1) * kTileN), da + uint64_t(k * (kUmmaK / 16)), db + uint64_t(k * (kUmmaK / 16)), idesc,
-                             uint32_t(!(kb == 0 && k == 0 && first_of_class)));
+        for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+          const uint64_t ko = uint64_t(k * (kUmmaK / 16));
+          const uint64_t dx0 = ptx::smem_desc_k_sw128(xa) + ko, dx1 = ptx::smem_desc_k_sw128(xa + uint32_t(kXBytes)) + ko,
+                         dx2 = ptx::smem_desc_k_sw128(xa + uint32_t(2 * kXBytes)) + ko;
+          const uint64_t dw0 = ptx::smem_desc_k_sw128(wa) + ko, dw1 = ptx::smem_desc_k_sw128(wa + uint32_t(kWBytes)) + ko,
+                         dw2 = ptx::smem_desc_k_sw128(wa + uint32_t(2 * kWBytes)) + ko;
+          const bool first = kb == 0 && k == 0;
+          ptx::mma_i8_ss(d0, dx1, dw0, idesc_limbs(false, 3 * kTileN), uint32_t(!first));
+          ptx::mma_i8_ss(d0, dx0, dw1, idesc_limbs(false, 2 * kTileN), 1u);
+          if (first) {
+            ptx::mma_i8_ss(d0 + uint32_t(3 * kTileN), dx2, dw2, idesc_limbs(true, kTileN), 0u);
+            ptx::mma_i8_ss(d0 + uint32_t(kTileN), dx2, dw0, idesc_limbs(true, 2 * kTileN), 1u);
+          } else {
+            ptx::mma_i8_ss(d0 + uint32_t(kTileN), dx2, dw0, idesc_limbs(true, 3 * kTileN), 1u);
           }
+        }
         ptx::mma_commit(empty_bar + stage);
         if (kb == k_blocks - 1) ptx::mma_commit(acc_bar + set);
       }
@@ -268,8 +287,9 @@ input_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
     const int et = int(threadIdx.x) - 128;
     for (int i = et; i < kLut2Padded / 16; i += kEpiWarps * 32) reinterpret_cast<uint4 *>(s_lut)[i] = __ldg(reinterpret_cast<const uint4 *>(a.lut) + i);
     ptx::named_bar_sync(1, kEpiWarps * 32);
-    const int quarter = warp & 3, half = (warp - 4) >> 2;
+    const int quarter = warp & 3, cq = (warp - 4) >> 2, half = cq >> 1;  // column quarter (16 columns), bitmap word (32 columns)
     InputNodeStats *s_node = reinterpret_cast<InputNodeStats *>(s_lut + kLut2Padded);
+    uint32_t *s_unc = reinterpret_cast<uint32_t *>(s_node + kTileN);  // [tile row][word]: the odd column quarters' half words
     uint32_t tile_no = 0;
     for (int tile = int(blockIdx.x); tile < tiles_total; tile += int(gridDim.x), ++tile_no) {
     const int m_blk = tile / n_blocks, n_blk = tile % n_blocks;
@@ -290,17 +310,17 @@ input_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
     if (warp == 4) ptx::mbar_wait_parked(acc_bar + set, use & 1u);
     ptx::named_bar_sync(1, kEpiWarps * 32);
     ptx::tc_fence_after_sync();
-    uint32_t unc_mask = 0;  // bit c: column (half·32 + c) of this row is uncertain
+    uint32_t unc_mask = 0;  // bit c: column (half·32 + c) of this row is uncertain (this warp fills 16 of the word's bits)
     const int col_base = n_blk * kTileN + half * 32;
     const bool row_cert = row_ok && rs.a[0] > 0.0f;
 #pragma unroll 1
-    for (int g = 0; g < 4; ++g) {
+    for (int g = 2 * (cq & 1); g < 2 * (cq & 1) + 2; ++g) {
       uint32_t acc[kClasses][8];
 #pragma unroll
       for (int s = 0; s < kClasses; ++s)
         tmem_ld_32x8(tmem_base + uint32_t(int(set) * kClasses * kTileN + s * kTileN + half * 32 + g * 8) + (uint32_t(quarter * 32) << 16), acc[s]);
       ptx::tmem_ld_wait();
-      if (g == 3) {  // accumulators fully read by this warp: the next tile's MMAs may overwrite them
+      if (g == 2 * (cq & 1) + 1) {  // accumulators fully read by this warp: the next tile's MMAs may overwrite them
         ptx::tc_fence_before_sync();
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(acc_free + set);
@@ -331,6 +351,12 @@ input_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
       if (row_ok && col_base + g * 8 < a.H)  // hidden widths are multiples of 16: an 8-column group is whole or absent
         *reinterpret_cast<uint2 *>(a.out_u8 + size_t(row) * size_t(a.H) + col_base + g * 8) = make_uint2(bytes[0], bytes[1]);
     }
+    // the two warps of a bitmap word meet: the odd column quarter hands its 16 bits over and is done
+    uint32_t n_unc = uint32_t(__popc(unc_mask));
+    if (cq & 1) s_unc[(quarter * 32 + lane) * 2 + half] = unc_mask;
+    ptx::named_bar_sync(1, kEpiWarps * 32);
+    if (!(cq & 1)) {
+    unc_mask |= s_unc[(quarter * 32 + lane) * 2 + half];
     // undecided elements → one bitmap word per (frame, 32 nodes); every word of the bitmap has exactly one writer
     if (row_ok && col_base < a.H) a.unc_bits[size_t(row) * size_t(a.unc_words) + size_t(col_base / 32)] = unc_mask;
     // … and the same 32 frames × 32 nodes transposed (five butterfly steps over the warp): lane c ends up with the word of
@@ -346,7 +372,7 @@ input_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
       const int row0 = m_blk * kTileM + quarter * 32;
       if (row0 < a.M && col_base + lane < a.H) a.unc_t[size_t(row0 / 32) * size_t(a.H) + size_t(col_base + lane)] = t;
     }
-    uint32_t n_unc = uint32_t(__popc(unc_mask));
+    }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) n_unc += __shfl_xor_sync(0xffffffffu, n_unc, o);
     if (lane == 0 && n_unc != 0u) atomicAdd(a.unc_count, n_unc);

@@ -35,7 +35,8 @@ def certificate(x_raw, w, bias, shift, scale):
 
     X, sx = fixed(xq)
     W, sw = fixed(w)
-    low = (X & 255) @ (W & 255).T  # the product of the lowest limbs, which the kernel bounds instead of computing
+    w_low = ((W + 128) & 255) - 128  # the weights' lowest BALANCED digit (an s8; fdnn_api.cu: upload_model)
+    low = (X & 255) @ w_low.T  # the product of the lowest limbs, which the kernel bounds instead of computing
     total = X @ W.T - low
     z = (total * np.outer(sx, sw) + bias.astype(np.float64)[None, :]) * 100.0
     nxc = np.sqrt((c * xq.astype(np.float64) ** 2).sum(axis=1))
@@ -43,7 +44,7 @@ def certificate(x_raw, w, bias, shift, scale):
     nx = np.sqrt((xq.astype(np.float64) ** 2).sum(axis=1)) + sx * 131072.0 * np.sqrt(I)
     nw = np.sqrt((w.astype(np.float64) ** 2).sum(axis=1)) + sw * 131072.0 * np.sqrt(I)
     eps_q = np.outer(sx, sw) * (0.5 * np.abs(X).sum(axis=1)[:, None] + 0.5 * np.abs(W).sum(axis=1)[None, :] + 0.25 * I
-                                + 255.0 * (W & 255).sum(axis=1)[None, :])
+                                + 255.0 * np.abs(w_low).sum(axis=1)[None, :])
     bc = np.abs(bias.astype(np.float64) * 100.0)
     D = (100.0 * (U * 1.0001 * np.outer(nxc, nwc) + 7 * U * np.outer(nx, nw) + eps_q) + 3.1 * U * np.abs(z) + U * bc[None, :] + 2.1 * U + 1e-9) * 1.00001
     k = np.rint(z)
