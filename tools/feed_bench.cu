@@ -38,7 +38,7 @@ __device__ __forceinline__ void cp_async_arrive_noinc(uint64_t *bar) {
 
 // mode: 0 tma, 1 ldgsts, 2 mixed
 __global__ void __launch_bounds__(kThreads, 1) feed_kernel(const __grid_constant__ CUtensorMap tmap, const uint8_t *base, int rows, int turns, int mode,
-                                                            unsigned long long *sink, int box_rows = 128, int issuers = 1) {
+                                                            unsigned long long *sink, int box_rows = 128, int issuers = 1, int k_tiles_arg = kK / 128) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t full_bar[kStages], empty_bar[kStages];
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
@@ -53,7 +53,7 @@ __global__ void __launch_bounds__(kThreads, 1) feed_kernel(const __grid_constant
     ptx::fence_barrier_init();
   }
   __syncthreads();
-  const int row_tiles = rows / 128, k_tiles = kK / 128;
+  const int row_tiles = rows / 128, k_tiles = k_tiles_arg;
   const int total_tiles = row_tiles * k_tiles;
   if (warp == 0) {
     if (lane < issuers && tma_tiles) {
@@ -433,6 +433,26 @@ int main() {
       float ms = 0;
       CK(cudaEventElapsedTime(&ms, e0, e1));
       std::printf(", {\"ctas\": %d, \"mode\": \"tma no swizzle\", \"ms\": %.3f, \"per_sm_gbs\": %.1f}", sms, ms, double(sms) * turns * kStageBytes / (ms * 1e-3) / 1e9 / sms);
+    }
+  }
+  {  // rows only 512 bytes apart (the limb planes of the input layer's certificate kernel): the same buffer viewed as [rows·4][512]
+    CUtensorMap mp;
+    cuuint64_t dims5[2] = {512u, cuuint64_t(rows) * 4};
+    cuuint64_t strides5[1] = {512u};
+    if (reinterpret_cast<EncodeFn>(fnp)(&mp, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, d, dims5, strides5, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS) {
+      for (int issuers : {1, 2}) {
+        feed_kernel<<<sms, kThreads, kStages * kStageBytes>>>(mp, d, rows * 4, 200, 0, sink, 128, issuers, 4);
+        CK(cudaDeviceSynchronize());
+        CK(cudaEventRecord(e0));
+        feed_kernel<<<sms, kThreads, kStages * kStageBytes>>>(mp, d, rows * 4, turns, 0, sink, 128, issuers, 4);
+        CK(cudaEventRecord(e1));
+        CK(cudaEventSynchronize(e1));
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, e0, e1));
+        std::printf(", {\"ctas\": %d, \"mode\": \"tma rows 512 bytes apart\", \"issuing_lanes\": %d, \"ms\": %.3f, \"per_sm_gbs\": %.1f}", sms, issuers, ms,
+                    double(sms) * turns * kStageBytes / (ms * 1e-3) / 1e9 / sms);
+      }
     }
   }
   {  // a wide 2-D box: 256 bytes of K per row is not expressible with 128B swizzle; instead a matrix viewed as [rows/2][4096]: rows twice as long
