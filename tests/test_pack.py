@@ -172,3 +172,32 @@ def test_doubled_lut_trick_equals_reference_rounding(net_file):
     got = lut2[v + 1282]
     want = np.array([oracle_py.Port.qsigmoid(float(x)) for x in xs], dtype=np.uint8)
     assert np.array_equal(got, want), np.flatnonzero(got != want)[:10]
+
+
+def test_parser_survives_mutated_files(tmp_path, net_file):
+    """seeded mutations of a valid dnn.bin — header bytes, random bytes, truncations, extreme big-endian words (layer counts and
+    dimensions of 2³¹) — must come back as an error code or a packed model, never a crash or an allocation the file cannot back
+    (the reference's loader trusts every field, float_dnn.cc:18-69)"""
+    good = open(net_file("tiny"), "rb").read()
+    rng = np.random.default_rng(5)
+    case = tmp_path / "case.bin"
+    seen = set()
+    for it in range(300):
+        b = bytearray(good)
+        kind = it % 4
+        if kind == 0:
+            for _ in range(int(rng.integers(1, 4))):
+                b[int(rng.integers(0, 20))] = int(rng.integers(0, 256))
+        elif kind == 1:
+            for _ in range(int(rng.integers(1, 8))):
+                b[int(rng.integers(0, len(b)))] = int(rng.integers(0, 256))
+        elif kind == 2:
+            b = b[: int(rng.integers(0, len(b)))]
+        else:
+            pos = int(rng.integers(0, len(b) // 4)) * 4
+            b[pos:pos + 4] = int(rng.choice([0x7FFFFFFF, 0xFFFFFFFF, 0x80000000, 0, 1 << 24])).to_bytes(4, "big")
+        case.write_bytes(bytes(b))
+        rc, _ = _pack_rc(str(case))
+        assert rc in (0, qd.FDNN_EIO, qd.FDNN_EFORMAT, qd.FDNN_EINVAL, qd.FDNN_ENOMEM), rc
+        seen.add(rc)
+    assert 0 in seen and len(seen) >= 2
