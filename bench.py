@@ -660,6 +660,30 @@ class Bench:
                                 "process; wall clock, max over ranks"}}
 
 
+def file_stream_leg(dnn, qd, synth, i_dim, o_dim, frames=32768):
+    """The file-to-file front end (fdnn_calculate_file, csrc/stream_file.cc = the data path of the reference's command-line
+    driver, dnn.cc:55-78): a big-endian feature file through the GPU into /dev/null — reader thread, byte swap, PCIe both
+    ways and the kernels; what a real dump adds is the storage's write rate (32 000 B per frame)."""
+    import tempfile
+    try:
+        with tempfile.TemporaryDirectory() as d:
+            path = os.path.join(d, "features.bin")
+            block = synth.make_frames(4096, i_dim, seed=77).astype(">f4").tobytes()
+            with open(path, "wb") as f:
+                f.write(np.array([frames, i_dim], dtype=">i4").tobytes())
+                for _ in range(frames // 4096):
+                    f.write(block)
+            dnn.calculate_file(path, "/dev/null", chunk_frames=2048)
+            t0 = time.perf_counter()
+            n = dnn.calculate_file(path, "/dev/null", chunk_frames=2048)
+            secs = time.perf_counter() - t0
+        return {"value": n / secs, "unit": "frames/s", "frames": n, "wall_s": secs, "chunk_frames": 2048,
+                "what": "QuantizedDnn.calculate_file: big-endian feature file -> reader thread -> fdnn_calculate on page-locked chunks -> "
+                        "writer thread -> binary dump to /dev/null (wall clock, one pass after a warm-up pass)"}
+    except Exception as e:  # a bench line without this leg is better than no bench line
+        return {"error": repr(e)}
+
+
 def run_group_arm(args):
     """--single-process --gpus N: the N GPUs behind ONE model handle (fdnn_load_devices: one in-process ncclBroadcast at load,
     fdnn_calculate shards every call over the devices).  There is no device-resident entry point for a group (a context lives on
@@ -744,6 +768,7 @@ def run_gpu_arm(args):
     lazy = b.lazy(max(20, min(args.steps, 100))) if not (args.no_extra or args.single_process) else None
     stream1m = b.stream1m(env_int("FDNN_BENCH_STREAM_FRAMES", 1_000_000)) if not args.no_extra else None
     small = b.small_config() if (b.rank == 0 and n_gpus == 1 and not args.no_extra) else None
+    file_stream = file_stream_leg(b.dnn, b.qd, b.synth, b.I, b.O) if (b.rank == 0 and n_gpus == 1 and not args.no_extra) else None
     b.sampler.stop()
 
     # ---- CPU baseline on this box's host cores (rank 0, N = 1 only; bounded samples) ------------------
@@ -788,7 +813,7 @@ def run_gpu_arm(args):
             "single_stream": single, "e2e": headline["e2e"], "e2e_jni": e2e_jni, "gpu_launches": res["launches"],
             "clocks": b.sampler.summary(), "roofline": roofline, "roofline_stream": stream_info["roofline"] if stream_info else None,
             "stages": stages, "cpu_baseline": headline["cpu"], "stream_regime": stream_info, "lazy": lazy, "stream1m": stream1m,
-            "configs1": small, "int8_peak_calibration": i8,
+            "configs1": small, "file_stream": file_stream, "int8_peak_calibration": i8,
         }, default=plain))
     b.dnn.delete()
     if world > 1:

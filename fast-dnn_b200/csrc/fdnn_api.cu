@@ -1029,7 +1029,7 @@ int broadcast_blob(const std::vector<uint8_t> &blob, const std::vector<int> &dev
   return rc;
 }
 
-// "all", "0,1,2,3", "4" (a count) → device list; empty = not a group
+// "all", "0,1,2,3", "4" (device 4 alone) → device list; empty = not a group
 std::vector<int> parse_device_list(const char *text) {
   std::vector<int> devs;
   if (!text || !text[0]) return devs;

@@ -1,0 +1,308 @@
+// File-to-file front end ("feature .bin reader/writer + streaming front-end").
+//
+// The data path of the reference's command-line driver, src/cpp/dnn.cc:55-78 —
+//   BatchData input(path)  →  CalculationContext::Calculate(input)  →  output->dumpToFile(path, binary)
+// — holds the whole feature matrix and the whole score matrix in memory (float_dnn.cc:85-105 reads every
+// float of the file into one array, dnn.cc:451 allocates n × outputs floats).  For BASELINE config 4
+// (one million frames: 1.76 GB of features, 32 GB of scores) that is not an option, so here the
+// two files are streamed: a reader thread fills page-locked chunks from the big-endian feature file,
+// the CALLING thread pushes each chunk through fdnn_calculate (host → device, kernels, device → host),
+// a writer thread appends the scores to the dump, and the three overlap over a small ring of chunks.
+// Only the public C ABI is used below (include/fdnn.h): without a usable GPU fdnn_host_alloc fails
+// with FDNN_ENOGPU and so does this — there is no CPU path.
+//
+// File formats (both follow the reference exactly):
+//   features   big-endian int32 frames, int32 dim, fp32 rows       float_dnn.cc:85-105, BatchData.java:80-91
+//   BIN dump   native-endian uint32 frames, uint32 dim, fp32 rows   float_dnn.cc:128-164 (binary = true)
+//   TXT dump   one row per line, values printed by `ostream << float` (= "%g", six significant digits)
+//              and separated by one blank                           float_dnn.cc:128-164 (binary = false)
+
+#include <algorithm>
+#include <atomic>
+#include <condition_variable>
+#include <cstdio>
+#include <cstring>
+#include <deque>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/fdnn.h"
+#include "fdnn_internal.h"
+
+namespace {
+
+using fdnn::set_error;
+
+// slot indices handed from one pipeline stage to the next
+class Channel {
+ public:
+  void push(int v) {
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      q_.push_back(v);
+    }
+    cv_.notify_one();
+  }
+  // false: the channel was closed and is empty
+  bool pop(int *v) {
+    std::unique_lock<std::mutex> lk(mu_);
+    cv_.wait(lk, [&] { return !q_.empty() || closed_; });
+    if (q_.empty()) return false;
+    *v = q_.front();
+    q_.pop_front();
+    return true;
+  }
+  void close() {
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      closed_ = true;
+    }
+    cv_.notify_all();
+  }
+
+ private:
+  std::mutex mu_;
+  std::condition_variable cv_;
+  std::deque<int> q_;
+  bool closed_ = false;
+};
+
+struct Slot {
+  float *in = nullptr;   // [chunk][I] page-locked
+  float *out = nullptr;  // [chunk][O] page-locked
+  int frames = 0;
+};
+
+// the first failure of any stage; its text reaches fdnn_last_error() of the calling thread at the end
+struct Failure {
+  std::mutex mu;
+  int rc = FDNN_OK;
+  std::string text;
+  std::atomic<bool> any{false};
+  void set(int code, const std::string &msg) {
+    std::lock_guard<std::mutex> lk(mu);
+    if (rc == FDNN_OK) {
+      rc = code;
+      text = msg;
+    }
+    any.store(true, std::memory_order_release);
+  }
+};
+
+uint32_t be32(const uint8_t *p) { return (uint32_t(p[0]) << 24) | (uint32_t(p[1]) << 16) | (uint32_t(p[2]) << 8) | uint32_t(p[3]); }
+
+// `ostream << float` of the reference's text dump: printf's %g with the stream's default precision of 6
+void append_row_txt(std::string &line, const float *row, int dim) {
+  char buf[32];
+  for (int j = 0; j < dim; ++j) {
+    const int k = std::snprintf(buf, sizeof buf, "%g", double(row[j]));
+    line.append(buf, size_t(k));
+    if (j + 1 < dim) line.push_back(' ');
+  }
+  line.push_back('\n');
+}
+
+bool write_rows(std::FILE *f, int format, const float *rows, int frames, int dim, std::string &scratch) {
+  if (format == FDNN_DUMP_BIN) return std::fwrite(rows, sizeof(float) * size_t(dim), size_t(frames), f) == size_t(frames);
+  for (int r = 0; r < frames; ++r) {
+    scratch.clear();
+    append_row_txt(scratch, rows + size_t(r) * size_t(dim), dim);
+    if (std::fwrite(scratch.data(), 1, scratch.size(), f) != scratch.size()) return false;
+  }
+  return true;
+}
+
+bool write_header(std::FILE *f, int format, long long frames, int dim) {
+  if (format != FDNN_DUMP_BIN) return true;  // the text dump has no header
+  const uint32_t hdr[2] = {uint32_t(frames), uint32_t(dim)};
+  return std::fwrite(hdr, sizeof hdr, 1, f) == 1;
+}
+
+struct FileCloser {
+  std::FILE *f = nullptr;
+  ~FileCloser() {
+    if (f) std::fclose(f);
+  }
+};
+
+}  // namespace
+
+extern "C" {
+
+int fdnn_output_dump_write_txt(const char *path, const float *data, int frames, int dim) {
+  if (!path || (!data && frames > 0) || frames < 0 || dim <= 0) {
+    set_error("bad argument to fdnn_output_dump_write_txt");
+    return FDNN_EINVAL;
+  }
+  FileCloser out;
+  out.f = std::fopen(path, "wb");
+  if (!out.f) {
+    set_error(std::string("cannot open for writing: ") + path);
+    return FDNN_EIO;
+  }
+  std::string scratch;
+  const bool ok = write_rows(out.f, FDNN_DUMP_TXT, data, frames, dim, scratch);
+  const bool closed = std::fclose(out.f) == 0;
+  out.f = nullptr;
+  if (!ok || !closed) {
+    set_error(std::string("short write: ") + path);
+    return FDNN_EIO;
+  }
+  return FDNN_OK;
+}
+
+int fdnn_calculate_file(fdnn_model *model, const char *feature_bin_path, const char *out_path, int out_format, int chunk_frames,
+                        long long *frames_done) {
+  if (frames_done) *frames_done = 0;
+  if (!model || !feature_bin_path || !out_path || (out_format != FDNN_DUMP_BIN && out_format != FDNN_DUMP_TXT) || chunk_frames < 0) {
+    set_error("bad argument to fdnn_calculate_file");
+    return FDNN_EINVAL;
+  }
+  const int I = fdnn_input_dim(model), O = fdnn_output_dim(model);
+  if (I <= 0 || O <= 0) {
+    set_error("bad model handle");
+    return FDNN_EINVAL;
+  }
+
+  // ---- headers, on the calling thread: a bad file fails before anything is allocated or written ----
+  FileCloser in, out;
+  in.f = std::fopen(feature_bin_path, "rb");
+  if (!in.f) {
+    set_error(std::string("cannot open feature file: ") + feature_bin_path);
+    return FDNN_EIO;
+  }
+  uint8_t hdr[8];
+  if (std::fread(hdr, 1, 8, in.f) != 8) {
+    set_error(std::string("feature file shorter than its header: ") + feature_bin_path);
+    return FDNN_EIO;
+  }
+  const long long n = (long long) int32_t(be32(hdr));
+  const int d = int(int32_t(be32(hdr + 4)));
+  if (n < 0 || d <= 0) {
+    set_error(std::string("not a usable feature file: ") + feature_bin_path);
+    return FDNN_EFORMAT;
+  }
+  // The network's input width is the file's padded to a multiple of four with zero weights (float_dnn.cc:32-33, 61-66);
+  // features may come either way: already padded, or as wide as the unpadded network (missing columns are zeros).
+  if (d > I || I - d >= 4) {
+    set_error("feature dimension " + std::to_string(d) + " does not match the network's input dimension " + std::to_string(I));
+    return FDNN_EINVAL;
+  }
+  if (std::fseek(in.f, 0, SEEK_END) == 0) {  // (not seekable, e.g. a pipe: a short file shows up as a short read below)
+    const long long size = (long long) std::ftell(in.f);
+    if (size >= 0 && size - 8 < n * (long long) d * 4) {
+      set_error(std::string("feature file is shorter than its header announces: ") + feature_bin_path);
+      return FDNN_EIO;
+    }
+    std::fseek(in.f, 8, SEEK_SET);
+  }
+  const int n_dev = fdnn_device_count(model);
+  const int chunk = chunk_frames > 0 ? chunk_frames : 2048 * (n_dev > 0 ? n_dev : 1);
+
+  constexpr int kSlots = 3;  // one being read, one on the GPU, one being written
+  Slot slot[kSlots];
+  struct Buffers {  // page-locked transfer buffers; released on every path out
+    Slot *s;
+    ~Buffers() {
+      for (int i = 0; i < kSlots; ++i) {
+        fdnn_host_free(s[i].in);
+        fdnn_host_free(s[i].out);
+      }
+    }
+  } buffers{slot};
+  const int n_slots = int(std::min<long long>(kSlots, std::max<long long>(1, (n + chunk - 1) / chunk)));
+  for (int i = 0; i < n_slots; ++i) {
+    if (int rc = fdnn_host_alloc(reinterpret_cast<void **>(&slot[i].in), size_t(chunk) * size_t(I) * 4)) return rc;
+    if (int rc = fdnn_host_alloc(reinterpret_cast<void **>(&slot[i].out), size_t(chunk) * size_t(O) * 4)) return rc;
+  }
+  out.f = std::fopen(out_path, "wb");
+  if (!out.f) {
+    set_error(std::string("cannot open for writing: ") + out_path);
+    return FDNN_EIO;
+  }
+  if (!write_header(out.f, out_format, n, O)) {
+    set_error(std::string("short write: ") + out_path);
+    return FDNN_EIO;
+  }
+
+  // ---- reader → (this thread: GPU) → writer ----
+  Channel to_reader, to_compute, to_writer;
+  Failure failure;
+  std::atomic<long long> written{0};
+  for (int i = 0; i < n_slots; ++i) to_reader.push(i);
+
+  std::thread reader([&] {
+    std::vector<uint8_t> raw(size_t(chunk) * size_t(d) * 4);
+    long long done = 0;
+    int s = 0;
+    while (done < n && !failure.any.load(std::memory_order_acquire) && to_reader.pop(&s)) {
+      const int frames = int(std::min<long long>(chunk, n - done));
+      const size_t words = size_t(frames) * size_t(d);
+      if (std::fread(raw.data(), 4, words, in.f) != words) {
+        failure.set(FDNN_EIO, std::string("short read: ") + feature_bin_path);
+        break;
+      }
+      float *dst = slot[s].in;
+      const uint8_t *src = raw.data();
+      for (int r = 0; r < frames; ++r) {
+        uint32_t *row = reinterpret_cast<uint32_t *>(dst + size_t(r) * size_t(I));
+        for (int k = 0; k < d; ++k, src += 4) row[k] = be32(src);
+        for (int k = d; k < I; ++k) row[k] = 0u;
+      }
+      slot[s].frames = frames;
+      done += frames;
+      to_compute.push(s);
+    }
+    to_compute.close();
+  });
+
+  std::thread writer([&] {
+    std::string scratch;
+    int s = 0;
+    while (to_writer.pop(&s)) {
+      if (!failure.any.load(std::memory_order_acquire)) {
+        if (write_rows(out.f, out_format, slot[s].out, slot[s].frames, O, scratch))
+          written.fetch_add(slot[s].frames, std::memory_order_relaxed);
+        else
+          failure.set(FDNN_EIO, std::string("short write: ") + out_path);
+      }
+      to_reader.push(s);
+    }
+  });
+
+  {
+    int s = 0;
+    while (to_compute.pop(&s)) {
+      if (!failure.any.load(std::memory_order_acquire)) {
+        const int rc = fdnn_calculate(model, slot[s].in, slot[s].frames, I, 0, slot[s].out);
+        if (rc != FDNN_OK) failure.set(rc, fdnn_last_error());
+      }
+      if (failure.any.load(std::memory_order_acquire)) {
+        to_reader.close();  // the reader may be waiting for a free slot
+        continue;           // keep draining so that the reader's pushes are consumed and it can finish
+      }
+      to_writer.push(s);
+    }
+    to_writer.close();
+  }
+  reader.join();
+  writer.join();
+  to_reader.close();
+
+  const bool closed = std::fclose(out.f) == 0;
+  out.f = nullptr;
+  if (frames_done) *frames_done = written.load(std::memory_order_relaxed);
+  if (failure.rc != FDNN_OK) {
+    set_error(failure.text);
+    return failure.rc;
+  }
+  if (!closed) {
+    set_error(std::string("short write: ") + out_path);
+    return FDNN_EIO;
+  }
+  return FDNN_OK;
+}
+
+}  // extern "C"

@@ -19,6 +19,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libfast-dnn.so")
 
 FDNN_OK, FDNN_EINVAL, FDNN_EIO, FDNN_EFORMAT, FDNN_ENOGPU, FDNN_ECUDA, FDNN_ENOMEM = 0, -1, -2, -3, -4, -5, -6
+FDNN_DUMP_BIN, FDNN_DUMP_TXT = 1, 0
 
 
 class FdnnError(RuntimeError):
@@ -52,6 +53,7 @@ SIGNATURES = {
     "fdnn_feature_bin_read": (_I, [C.c_char_p, C.POINTER(_I), C.POINTER(_I), C.POINTER(_P)]),
     "fdnn_feature_bin_write": (_I, [C.c_char_p, _P, _I, _I]),
     "fdnn_output_dump_write": (_I, [C.c_char_p, _P, _I, _I]),
+    "fdnn_output_dump_write_txt": (_I, [C.c_char_p, _P, _I, _I]),
     "fdnn_free": (_I, [_P]),
     "fdnn_input_dim": (_I, [_P]),
     "fdnn_output_dim": (_I, [_P]),
@@ -62,6 +64,7 @@ SIGNATURES = {
     "fdnn_device": (_I, [_P]),
     "fdnn_calculate": (_I, [_P, _P, _I, _I, _I, _P]),
     "fdnn_calculate_sink": (_I, [_P, _P, _I, _I, _P, _P]),
+    "fdnn_calculate_file": (_I, [_P, C.c_char_p, C.c_char_p, _I, _I, C.POINTER(_LL)]),
     "fdnn_ctx_new": (_I, [_P, _I, _I, C.POINTER(_P)]),
     "fdnn_ctx_free": (_I, [_P]),
     "fdnn_ctx_frames": (_I, [_P]),
@@ -175,9 +178,18 @@ def write_feature_bin(path, frames) -> None:
     _check(lib().fdnn_feature_bin_write(os.fsencode(path), _ptr(x), x.shape[0], x.shape[1]))
 
 
-def write_output_dump(path, rows) -> None:
+def write_output_dump(path, rows, binary: bool = True) -> None:
+    """BatchData::dumpToFile(path, binary) — float_dnn.cc:128-164 (host only)."""
     x = np.ascontiguousarray(rows, dtype=np.float32)
-    _check(lib().fdnn_output_dump_write(os.fsencode(path), _ptr(x), x.shape[0], x.shape[1]))
+    fn = lib().fdnn_output_dump_write if binary else lib().fdnn_output_dump_write_txt
+    _check(fn(os.fsencode(path), _ptr(x), x.shape[0], x.shape[1]))
+
+
+def read_output_dump(path) -> np.ndarray:
+    """The binary dump back as [frames][dim] fp32 (native-endian uint32 frames, uint32 dim, fp32 rows)."""
+    with open(path, "rb") as f:
+        n, d = np.frombuffer(f.read(8), dtype=np.uint32)
+        return np.fromfile(f, dtype=np.float32, count=int(n) * int(d)).reshape(int(n), int(d))
 
 
 class PinnedArray:
@@ -304,6 +316,14 @@ class QuantizedDnn:
         assert out.dtype == np.float32 and out.flags.c_contiguous and out.shape == (x.shape[0], self._output_dimension)
         _check(lib().fdnn_calculate(self._h, _ptr(x), x.shape[0], x.shape[1], batch_size, _ptr(out)))
         return out
+
+    def calculate_file(self, feature_bin_path, out_path, binary: bool = True, chunk_frames: int = 0) -> int:
+        """The reference's command-line data path (dnn.cc:55-78: BatchData(file) → Calculate → dumpToFile) file to file,
+        streamed in chunks so that neither file is ever held in memory; returns the number of rows written."""
+        done = C.c_longlong()
+        _check(lib().fdnn_calculate_file(self._h, os.fsencode(os.fspath(feature_bin_path)), os.fsencode(os.fspath(out_path)),
+                                         FDNN_DUMP_BIN if binary else FDNN_DUMP_TXT, chunk_frames, C.byref(done)))
+        return int(done.value)
 
     def get_new_lazy_context(self, input_vector_count: int, batch_size: int = 8) -> "LazyContext":
         """getNewLazyContext(int[, int]) — QuantizedDnn.java:100-107."""

@@ -90,6 +90,8 @@ int fdnn_feature_bin_read(const char *path, int *frames, int *dim, float **data)
 int fdnn_feature_bin_write(const char *path, const float *data, int frames, int dim);
 /* BatchData::dumpToFile(..., binary) (float_dnn.cc:128-164): native-endian uint32 n, uint32 d, fp32 rows */
 int fdnn_output_dump_write(const char *path, const float *data, int frames, int dim);
+/* BatchData::dumpToFile(..., binary = false): a row per line, values printed by `ostream << float` ("%g"), one blank between */
+int fdnn_output_dump_write_txt(const char *path, const float *data, int frames, int dim);
 
 /* Java_suskun_nn_QuantizedDnn_delete (jni_dnn.cc:128-133) */
 int fdnn_free(fdnn_model *model);
@@ -130,6 +132,20 @@ int fdnn_calculate(fdnn_model *model, const float *in, int n, int dim, int batch
  * malloc + copy + copy (jni_dnn.cc:49-58). */
 typedef int (*fdnn_sink_fn)(void *user, int first_frame, int n_frames, const float *rows);
 int fdnn_calculate_sink(fdnn_model *model, const float *in, int n, int dim, fdnn_sink_fn sink, void *user);
+
+/* File to file: the data path of the reference's command-line driver (src/cpp/dnn.cc:55-78: BatchData(input_path) →
+ * CalculationContext::Calculate → BatchData::dumpToFile) without holding either file in memory (BASELINE
+ * config 4 is 1.76 GB of features and 32 GB of scores).  The feature file (big-endian int32 frames, int32 dim, fp32 rows,
+ * float_dnn.cc:85-105) is read in chunks of chunk_frames (0 = 2048 per device) by a reader thread, each chunk goes through
+ * fdnn_calculate on the calling thread, a writer thread appends the scores to out_path as the reference's binary dump
+ * (FDNN_DUMP_BIN: native-endian uint32 frames, uint32 dim, fp32 rows) or text dump (FDNN_DUMP_TXT: a row per line, values as
+ * printed by `ostream << float`), float_dnn.cc:128-164.  The file's dim must be the network's input width or its unpadded
+ * width (at most 3 columns fewer, float_dnn.cc:32-33; the missing columns are zeros).  *frames_done (may be NULL) = rows
+ * written, also on failure. */
+#define FDNN_DUMP_BIN 1
+#define FDNN_DUMP_TXT 0
+int fdnn_calculate_file(fdnn_model *model, const char *feature_bin_path, const char *out_path, int out_format, int chunk_frames,
+                        long long *frames_done);
 
 /* ---- contexts: lazy output + device-resident pipelines --------------------------------------
  * Java_suskun_nn_QuantizedDnn_getContext (jni_dnn.cc:64-77): workspace for exactly n frames. */

@@ -11,6 +11,7 @@ from __future__ import annotations
 import ctypes as C
 import os
 import subprocess
+import sys
 
 import numpy as np
 
@@ -233,8 +234,26 @@ class Ref:
                 getattr(L, name).restype = C.c_int
             L.ref_float_layer.argtypes = [C.c_void_p, C.c_int, _f32p, _f32p]
             L.ref_float_shift_scale.argtypes = [C.c_void_p, _f32p, _f32p]
+            L.ref_cli.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p]
+            L.ref_cli.restype = C.c_int
             cls._lib = L
         return cls._lib
+
+    @classmethod
+    def cli(cls, model_path: str, input_path: str, out_path: str, binary: bool = True) -> None:
+        """The reference's own command-line driver (dnn.cc:20-83): feature file in, score dump out (BIN or TXT).
+        Runs in a child process that loads nothing but the reference library: the driver prints numbers through
+        std::cout, which crashes inside a process where numpy/torch have brought their own C++ runtime pieces along."""
+        for p in (model_path, input_path):
+            if not os.path.exists(p):  # the reference dereferences a null FILE* (float_dnn.cc:171-174)
+                raise IOError(p)
+        cls.lib()  # builds it if need be
+        code = ("import ctypes, sys; L = ctypes.CDLL(sys.argv[1]); L.ref_cli.argtypes = [ctypes.c_char_p] * 4; "
+                "sys.exit(L.ref_cli(*[a.encode() for a in sys.argv[2:6]]))")
+        r = subprocess.run([sys.executable, "-c", code, REF_SO, model_path, input_path, out_path, "BIN" if binary else "TXT"],
+                           stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=600)
+        if r.returncode != 0:
+            raise RuntimeError(f"reference CLI returned {r.returncode}: {r.stdout.decode(errors='replace')[-400:]}")
 
     @classmethod
     def load_float_network(cls, path: str):

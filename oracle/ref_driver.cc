@@ -37,6 +37,7 @@
 namespace dnn {
 extern QuantizedSigmoid *qSigmoid;  // defined at dnn.cc:88
 }
+int ref_main(int argc, char *argv[]);  // dnn.cc:20 `main`, renamed by oracle/Makefile
 
 namespace {
 
@@ -264,6 +265,15 @@ double ref_time_lazy(void *h, const float *in, int n, int dim, int batch, const 
   for (auto &th : pool) th.join();
   auto t1 = std::chrono::steady_clock::now();
   return std::chrono::duration<double>(t1 - t0).count();
+}
+
+// The reference's command-line driver itself (dnn.cc:20-83, compiled with -Dmain=ref_main): model file, feature file →
+// BatchData(input) → CalculationContext::Calculate → BatchData::dumpToFile(out, out_type == "BIN").  The file-to-file
+// front end of the product (csrc/stream_file.cc) is checked against the files this writes.
+int ref_cli(const char *model_path, const char *input_path, const char *out_path, const char *out_type) {
+  std::string a0 = "fast-dnn", a1 = model_path, a2 = input_path, a3 = out_path, a4 = out_type;
+  char *argv[5] = {&a0[0], &a1[0], &a2[0], &a3[0], &a4[0]};
+  return ref_main(5, argv);
 }
 
 }  // extern "C"

@@ -86,6 +86,11 @@ def test_bad_arguments_are_refused_not_crashed_on(net_file):
     assert L.fdnn_calculate_sink(None, None, 4, 12, None, None) == qd.FDNN_EINVAL
     assert L.fdnn_ctx_hidden_digest(None, 0, 0, None) == qd.FDNN_EINVAL
     assert L.fdnn_ctx_profile_pass(None, None, 1, None, 1, None, None) == qd.FDNN_EINVAL
+    done = C.c_longlong(7)
+    assert L.fdnn_calculate_file(None, b"/tmp/in.bin", b"/tmp/out.bin", qd.FDNN_DUMP_BIN, 0, C.byref(done)) == qd.FDNN_EINVAL
+    assert done.value == 0  # nothing was written
+    assert L.fdnn_output_dump_write_txt(None, None, 1, 1) == qd.FDNN_EINVAL
+    assert L.fdnn_output_dump_write_txt(b"/nonexistent-dir/x.txt", (C.c_float * 1)(1.0), 1, 1) == qd.FDNN_EIO
 
 
 def test_cutoff_must_be_positive(net_file):

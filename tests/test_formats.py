@@ -48,6 +48,39 @@ def test_feature_bin_round_trip_and_dump(tmp_path):
     assert tuple(raw) == (37, 24)
 
 
+def test_text_dump_format():
+    """`ostream << float` (float_dnn.cc:149): %g with six significant digits, one blank between values, a line per row"""
+    rows = np.array([[1.0, 0.5, 0.000125, 1e-5, 1.234567e-7], [123456.7, 0.1, 2.5e10, 0.0, -0.0]], dtype=np.float32)
+    import tempfile
+    with tempfile.TemporaryDirectory() as d:
+        path = os.path.join(d, "out.txt")
+        qd.write_output_dump(path, rows, binary=False)
+        text = open(path).read()
+    assert text == "1 0.5 0.000125 1e-05 1.23457e-07\n123457 0.1 2.5e+10 0 -0\n"
+
+
+@pytest.mark.skipif(not oracle_py.have_ref(), reason="needs the compiled reference (oracle/_ref)")
+def test_dump_writers_equal_the_reference_cli(tmp_path, net_file):
+    """The reference's own command-line driver (dnn.cc:20-83, `main` compiled as ref_main) writes a BIN and a TXT dump of
+    a small feature file; our writers (the ones the file-to-file front end csrc/stream_file.cc uses) given the same
+    scores produce the same bytes; the feature file it read was written by our writer."""
+    frames = synth.make_frames(37, 432, seed=21)
+    feats, ref_bin, ref_txt, our_bin, our_txt = (str(tmp_path / n) for n in ("f.bin", "ref.bin", "ref.txt", "our.bin", "our.txt"))
+    qd.write_feature_bin(feats, frames)
+    model = net_file("P")
+    oracle_py.Ref.cli(model, feats, ref_bin, binary=True)
+    oracle_py.Ref.cli(model, feats, ref_txt, binary=False)
+    scores = qd.read_output_dump(ref_bin)
+    assert scores.shape == (37, 2000) and np.allclose(scores.sum(axis=1), 1.0, atol=1e-4)
+    # the CLI computes with batch 8 (dnn.cc:66); the result does not depend on the batch size
+    ref = oracle_py.Ref(model)
+    assert np.array_equal(scores, ref.calculate(frames, batch=10))
+    qd.write_output_dump(our_bin, scores, binary=True)
+    qd.write_output_dump(our_txt, scores, binary=False)
+    assert open(our_bin, "rb").read() == open(ref_bin, "rb").read()
+    assert open(our_txt, "rb").read() == open(ref_txt, "rb").read()
+
+
 @pytest.mark.skipif(not os.path.isdir(REFERENCE_ROOT), reason="shipped fixtures live in /root/reference")
 def test_reads_shipped_feature_files():
     x = qd.read_feature_bin(os.path.join(REFERENCE_ROOT, "data", "8khz.aligned.bin"))
