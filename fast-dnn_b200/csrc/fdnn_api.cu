@@ -1226,6 +1226,7 @@ int fdnn_ctx_free(fdnn_ctx *ctx) {
 
 int fdnn_ctx_frames(const fdnn_ctx *ctx) { return ctx ? ctx->cap : FDNN_EINVAL; }
 int fdnn_ctx_output_dim(const fdnn_ctx *ctx) { return ctx ? ctx->model->hdr.out_dim : FDNN_EINVAL; }
+int fdnn_ctx_input_dim(const fdnn_ctx *ctx) { return ctx ? ctx->model->hdr.in_dim : FDNN_EINVAL; }
 
 // Profiling aid: per-CTA phase timestamps (SM clocks) of the tensor-core layer kernels of the NEXT
 // forward pass.  out = [n_qlayers][1024][8] uint64 (host); slots: 0 entry, 1 setup done, 2 first

@@ -44,6 +44,7 @@ FDNN_JNIEXPORT jlong Java_suskun_nn_QuantizedDnn_initialize(JNIEnvPtr env, jobje
   auto get = slot<const char *(*) (JNIEnvPtr, jstring, jboolean *)>(env, kJniGetStringUTFChars);
   auto rel = slot<void (*)(JNIEnvPtr, jstring, const char *)>(env, kJniReleaseStringUTFChars);
   const char *chars = get(env, path, nullptr);
+  if (!chars) return 0;  // OutOfMemoryError is already pending
   fdnn_model *model = nullptr;
   int rc = fdnn_load(chars, cutoff, -1, &model);
   rel(env, path, chars);
@@ -87,11 +88,16 @@ FDNN_JNIEXPORT jfloatArray Java_suskun_nn_QuantizedDnn_calculate(JNIEnvPtr env, 
   auto get = slot<jfloat *(*) (JNIEnvPtr, jfloatArray, jboolean *)>(env, kJniGetFloatArrayElements);
   auto rel = slot<void (*)(JNIEnvPtr, jfloatArray, jfloat *, jint)>(env, kJniReleaseFloatArrayElements);
   auto mk = slot<jfloatArray (*)(JNIEnvPtr, jsize)>(env, kJniNewFloatArray);
+  auto length = slot<jsize (*)(JNIEnvPtr, jarray)>(env, kJniGetArrayLength);
   (void) batch;  // the reference's CPU cache-blocking batch size
   fdnn_model *model = reinterpret_cast<fdnn_model *>(handle);
   const int O = fdnn_output_dim(model);
-  if (count < 0 || O <= 0) {
-    throw_state(env, "bad handle or frame count");
+  if (count < 0 || dim < 0 || O <= 0) {
+    throw_state(env, "bad handle, frame count or dimension");
+    return nullptr;
+  }
+  if (double(length(env, input)) < double(count) * double(dim)) {  // the reference reads count × dim floats whatever the array holds
+    throw_state(env, "input array is shorter than count x dimension");
     return nullptr;
   }
   if (double(count) * double(O) > 2147483647.0) {  // a Java array holds at most 2^31 − 1 elements
@@ -101,6 +107,7 @@ FDNN_JNIEXPORT jfloatArray Java_suskun_nn_QuantizedDnn_calculate(JNIEnvPtr env, 
   jfloatArray result = mk(env, jsize(count) * jsize(O));
   if (!result) return nullptr;  // OutOfMemoryError is already pending
   jfloat *elements = get(env, input, nullptr);
+  if (!elements) return nullptr;  // OutOfMemoryError is already pending
   JavaSink sink{env, result, O};
   const int rc = count == 0 ? FDNN_OK : fdnn_calculate_sink(model, elements, count, dim, java_sink, &sink);
   rel(env, input, elements, JNI_ABORT_MODE);
@@ -125,8 +132,16 @@ FDNN_JNIEXPORT jlong Java_suskun_nn_QuantizedDnn_getContext(JNIEnvPtr env, jobje
 FDNN_JNIEXPORT void Java_suskun_nn_QuantizedDnn_calculateUntilOutput(JNIEnvPtr env, jobject, jlong handle, jfloatArray input) {
   auto get = slot<jfloat *(*) (JNIEnvPtr, jfloatArray, jboolean *)>(env, kJniGetFloatArrayElements);
   auto rel = slot<void (*)(JNIEnvPtr, jfloatArray, jfloat *, jint)>(env, kJniReleaseFloatArrayElements);
+  auto length = slot<jsize (*)(JNIEnvPtr, jarray)>(env, kJniGetArrayLength);
+  fdnn_ctx *ctx = reinterpret_cast<fdnn_ctx *>(handle);
+  // the reference assumes ctx.n × inputDimension floats (jni_dnn.cc:89-91) and reads past a shorter array
+  if (double(length(env, input)) < double(fdnn_ctx_frames(ctx)) * double(fdnn_ctx_input_dim(ctx))) {
+    throw_state(env, "input array is shorter than the context's frames x input dimension");
+    return;
+  }
   jfloat *elements = get(env, input, nullptr);
-  int rc = fdnn_ctx_until_output(reinterpret_cast<fdnn_ctx *>(handle), elements);
+  if (!elements) return;  // OutOfMemoryError is already pending
+  int rc = fdnn_ctx_until_output(ctx, elements);
   rel(env, input, elements, JNI_ABORT_MODE);
   if (rc != FDNN_OK) throw_state(env, fdnn_last_error());
 }
@@ -148,6 +163,10 @@ FDNN_JNIEXPORT jfloatArray Java_suskun_nn_QuantizedDnn_calculateLazy(JNIEnvPtr e
     return nullptr;
   }
   jbyte *bytes = get(env, mask, nullptr);
+  if (!bytes) {  // OutOfMemoryError is already pending
+    std::free(out);
+    return nullptr;
+  }
   int rc = fdnn_ctx_lazy(ctx, index, bytes, out);
   rel(env, mask, bytes, JNI_ABORT_MODE);
   jfloatArray result = nullptr;

@@ -69,6 +69,7 @@ SIGNATURES = {
     "fdnn_ctx_free": (_I, [_P]),
     "fdnn_ctx_frames": (_I, [_P]),
     "fdnn_ctx_output_dim": (_I, [_P]),
+    "fdnn_ctx_input_dim": (_I, [_P]),
     "fdnn_ctx_until_output": (_I, [_P, _P]),
     "fdnn_ctx_lazy": (_I, [_P, _I, _P, _P]),
     "fdnn_ctx_lazy_batch": (_I, [_P, _P, _P]),

@@ -154,6 +154,7 @@ int fdnn_ctx_new(fdnn_model *model, int n, int batch_hint, fdnn_ctx **out);
 int fdnn_ctx_free(fdnn_ctx *ctx);
 int fdnn_ctx_frames(const fdnn_ctx *ctx);
 int fdnn_ctx_output_dim(const fdnn_ctx *ctx);
+int fdnn_ctx_input_dim(const fdnn_ctx *ctx);
 
 /* calculateUntilOutput (jni_dnn.cc:79-95) = CalculateUntilLastHiddenLayer (dnn.cc:402-424).
  * in: host [ctx.n × input_dim].  Also computes the dense output-layer logits on the device so

@@ -87,6 +87,14 @@ def test_full_java_call_sequence(net_file):
     # a mask of the wrong length is refused instead of being read past its end (jni_dnn.cc:97-117 trusts it)
     assert not fn["calculateLazy"](jvm.env, None, ctx, 0, jvm.new_array(np.ones(10, np.int8)))
     assert jvm.thrown and "mask length" in jvm.thrown[-1][1]
+    # arrays shorter than what the call announces are refused as well (jni_dnn.cc:44-47, 89-91 read count × dim floats regardless)
+    jvm.thrown.clear()
+    j_short = jvm.new_array(frames.reshape(-1)[: 440 * (n - 1)].copy())
+    assert not fn["calculate"](jvm.env, None, h, j_short, n, 440, 10)
+    assert jvm.thrown and "shorter" in jvm.thrown[-1][1]
+    jvm.thrown.clear()
+    fn["calculateUntilOutput"](jvm.env, None, ctx, j_short)
+    assert jvm.thrown and "shorter" in jvm.thrown[-1][1]
     # wrong input dimension → exception, no crash
     jvm.thrown.clear()
     assert not fn["calculate"](jvm.env, None, h, j_in, n, 436, 10)
