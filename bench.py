@@ -660,7 +660,7 @@ class Bench:
                                 "process; wall clock, max over ranks"}}
 
 
-def file_stream_leg(dnn, qd, synth, i_dim, o_dim, frames=32768):
+def file_stream_leg(dnn, qd, synth, i_dim, o_dim, frames=65536):
     """The file-to-file front end (fdnn_calculate_file, csrc/stream_file.cc = the data path of the reference's command-line
     driver, dnn.cc:55-78): a big-endian feature file through the GPU into /dev/null — reader thread, byte swap, PCIe both
     ways and the kernels; what a real dump adds is the storage's write rate (32 000 B per frame)."""
@@ -673,13 +673,13 @@ def file_stream_leg(dnn, qd, synth, i_dim, o_dim, frames=32768):
                 f.write(np.array([frames, i_dim], dtype=">i4").tobytes())
                 for _ in range(frames // 4096):
                     f.write(block)
-            dnn.calculate_file(path, "/dev/null", chunk_frames=2048)
+            dnn.calculate_file(path, "/dev/null")
             t0 = time.perf_counter()
-            n = dnn.calculate_file(path, "/dev/null", chunk_frames=2048)
+            n = dnn.calculate_file(path, "/dev/null")
             secs = time.perf_counter() - t0
-        return {"value": n / secs, "unit": "frames/s", "frames": n, "wall_s": secs, "chunk_frames": 2048,
-                "what": "QuantizedDnn.calculate_file: big-endian feature file -> reader thread -> fdnn_calculate on page-locked chunks -> "
-                        "writer thread -> binary dump to /dev/null (wall clock, one pass after a warm-up pass)"}
+        return {"value": n / secs, "unit": "frames/s", "frames": n, "wall_s": secs,
+                "what": "QuantizedDnn.calculate_file: big-endian feature file -> reader thread (4096-frame chunks) -> fdnn_calculate_sink "
+                        "through the model's page-locked staging -> binary dump to /dev/null (wall clock, one pass after a warm-up pass)"}
     except Exception as e:  # a bench line without this leg is better than no bench line
         return {"error": repr(e)}
 

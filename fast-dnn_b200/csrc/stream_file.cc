@@ -5,11 +5,11 @@
 // — holds the whole feature matrix and the whole score matrix in memory (float_dnn.cc:85-105 reads every
 // float of the file into one array, dnn.cc:451 allocates n × outputs floats).  For BASELINE config 4
 // (one million frames: 1.76 GB of features, 32 GB of scores) that is not an option, so here the
-// two files are streamed: a reader thread fills page-locked chunks from the big-endian feature file,
-// the CALLING thread pushes each chunk through fdnn_calculate (host → device, kernels, device → host),
-// a writer thread appends the scores to the dump, and the three overlap over a small ring of chunks.
-// Only the public C ABI is used below (include/fdnn.h): without a usable GPU fdnn_host_alloc fails
-// with FDNN_ENOGPU and so does this — there is no CPU path.
+// two files are streamed: a reader thread fills chunks from the big-endian feature file, the CALLING
+// thread pushes each chunk through fdnn_calculate_sink (host → device, kernels, device → host through the
+// model's pooled page-locked staging) and appends the scores to the dump piece by piece as they land.
+// Only the public C ABI is used below (include/fdnn.h); all arithmetic is the library's GPU path — a
+// model handle cannot even exist without a usable GPU, and there is no CPU path.
 //
 // File formats (both follow the reference exactly):
 //   features   big-endian int32 frames, int32 dim, fp32 rows       float_dnn.cc:85-105, BatchData.java:80-91
@@ -19,8 +19,10 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <deque>
 #include <mutex>
@@ -69,12 +71,6 @@ class Channel {
   bool closed_ = false;
 };
 
-struct Slot {
-  float *in = nullptr;   // [chunk][I] page-locked
-  float *out = nullptr;  // [chunk][O] page-locked
-  int frames = 0;
-};
-
 // the first failure of any stage; its text reaches fdnn_last_error() of the calling thread at the end
 struct Failure {
   std::mutex mu;
@@ -119,6 +115,8 @@ bool write_header(std::FILE *f, int format, long long frames, int dim) {
   const uint32_t hdr[2] = {uint32_t(frames), uint32_t(dim)};
   return std::fwrite(hdr, sizeof hdr, 1, f) == 1;
 }
+
+double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
 struct FileCloser {
   std::FILE *f = nullptr;
@@ -166,7 +164,7 @@ int fdnn_calculate_file(fdnn_model *model, const char *feature_bin_path, const c
     return FDNN_EINVAL;
   }
 
-  // ---- headers, on the calling thread: a bad file fails before anything is allocated or written ----
+  // ---- headers, on the calling thread: a bad file fails before anything is written ----
   FileCloser in, out;
   in.f = std::fopen(feature_bin_path, "rb");
   if (!in.f) {
@@ -199,24 +197,7 @@ int fdnn_calculate_file(fdnn_model *model, const char *feature_bin_path, const c
     std::fseek(in.f, 8, SEEK_SET);
   }
   const int n_dev = fdnn_device_count(model);
-  const int chunk = chunk_frames > 0 ? chunk_frames : 2048 * (n_dev > 0 ? n_dev : 1);
-
-  constexpr int kSlots = 3;  // one being read, one on the GPU, one being written
-  Slot slot[kSlots];
-  struct Buffers {  // page-locked transfer buffers; released on every path out
-    Slot *s;
-    ~Buffers() {
-      for (int i = 0; i < kSlots; ++i) {
-        fdnn_host_free(s[i].in);
-        fdnn_host_free(s[i].out);
-      }
-    }
-  } buffers{slot};
-  const int n_slots = int(std::min<long long>(kSlots, std::max<long long>(1, (n + chunk - 1) / chunk)));
-  for (int i = 0; i < n_slots; ++i) {
-    if (int rc = fdnn_host_alloc(reinterpret_cast<void **>(&slot[i].in), size_t(chunk) * size_t(I) * 4)) return rc;
-    if (int rc = fdnn_host_alloc(reinterpret_cast<void **>(&slot[i].out), size_t(chunk) * size_t(O) * 4)) return rc;
-  }
+  const int chunk = chunk_frames > 0 ? chunk_frames : 4096 * (n_dev > 0 ? n_dev : 1);
   out.f = std::fopen(out_path, "wb");
   if (!out.f) {
     set_error(std::string("cannot open for writing: ") + out_path);
@@ -227,30 +208,51 @@ int fdnn_calculate_file(fdnn_model *model, const char *feature_bin_path, const c
     return FDNN_EIO;
   }
 
-  // ---- reader → (this thread: GPU) → writer ----
-  Channel to_reader, to_compute, to_writer;
+  // FDNN_FILE_DEBUG=1: where the time of a call goes (stderr), per stage the time spent working, not waiting
+  const char *dbg_env = std::getenv("FDNN_FILE_DEBUG");
+  const bool dbg = dbg_env && dbg_env[0] == '1';
+  const double t_begin = now_ms();
+  double ms_read = 0.0, ms_swap = 0.0, ms_gpu = 0.0, ms_write = 0.0;
+
+  // ---- reader thread → this thread (GPU + dump) ----
+  // Two plain chunk buffers: while one is on its way through the GPU the reader fills the other.  The library's own pooled
+  // page-locked staging does the rest (fdnn_calculate_sink: upload, kernels and download of 512-frame passes overlap, and the
+  // scores are written to the dump straight out of the transfer buffer, 128 frames at a time, while later ones are still
+  // crossing PCIe) — buffers of our own would have to be page-locked per call, which costs more than a short file takes
+  // (measured on the B200 host: 120-460 ms to lock 207 MB, as much again to release them).
+  constexpr int kSlots = 2;
+  struct Slot {
+    std::vector<float> in;  // [chunk][I]
+    int frames = 0;
+  } slot[kSlots];
+  const int n_slots = int(std::min<long long>(kSlots, std::max<long long>(1, (n + chunk - 1) / chunk)));
+  for (int i = 0; i < n_slots; ++i) slot[i].in.resize(size_t(std::min<long long>(chunk, std::max<long long>(n, 1))) * size_t(I));
+  Channel to_reader, to_compute;
   Failure failure;
-  std::atomic<long long> written{0};
   for (int i = 0; i < n_slots; ++i) to_reader.push(i);
 
   std::thread reader([&] {
-    std::vector<uint8_t> raw(size_t(chunk) * size_t(d) * 4);
+    std::vector<uint8_t> raw(slot[0].in.size() / size_t(I) * size_t(d) * 4);
     long long done = 0;
     int s = 0;
     while (done < n && !failure.any.load(std::memory_order_acquire) && to_reader.pop(&s)) {
       const int frames = int(std::min<long long>(chunk, n - done));
       const size_t words = size_t(frames) * size_t(d);
+      const double t0 = now_ms();
       if (std::fread(raw.data(), 4, words, in.f) != words) {
         failure.set(FDNN_EIO, std::string("short read: ") + feature_bin_path);
         break;
       }
-      float *dst = slot[s].in;
+      const double t1 = now_ms();
+      float *dst = slot[s].in.data();
       const uint8_t *src = raw.data();
       for (int r = 0; r < frames; ++r) {
         uint32_t *row = reinterpret_cast<uint32_t *>(dst + size_t(r) * size_t(I));
         for (int k = 0; k < d; ++k, src += 4) row[k] = be32(src);
         for (int k = d; k < I; ++k) row[k] = 0u;
       }
+      ms_read += t1 - t0;
+      ms_swap += now_ms() - t1;
       slot[s].frames = frames;
       done += frames;
       to_compute.push(s);
@@ -258,42 +260,53 @@ int fdnn_calculate_file(fdnn_model *model, const char *feature_bin_path, const c
     to_compute.close();
   });
 
-  std::thread writer([&] {
+  struct DumpSink {
+    std::FILE *f;
+    int format, dim;
+    long long written = 0;
+    double ms = 0.0;
     std::string scratch;
-    int s = 0;
-    while (to_writer.pop(&s)) {
-      if (!failure.any.load(std::memory_order_acquire)) {
-        if (write_rows(out.f, out_format, slot[s].out, slot[s].frames, O, scratch))
-          written.fetch_add(slot[s].frames, std::memory_order_relaxed);
-        else
-          failure.set(FDNN_EIO, std::string("short write: ") + out_path);
-      }
-      to_reader.push(s);
-    }
-  });
-
+  } sink{out.f, out_format, O, 0, 0.0, std::string()};
+  const fdnn_sink_fn write_piece = [](void *user, int, int n_frames, const float *rows) -> int {
+    auto *ds = static_cast<DumpSink *>(user);  // called on this thread, in frame order
+    const double t0 = now_ms();
+    const bool ok = write_rows(ds->f, ds->format, rows, n_frames, ds->dim, ds->scratch);
+    ds->ms += now_ms() - t0;
+    if (ok) ds->written += n_frames;
+    return ok ? 0 : 1;
+  };
   {
     int s = 0;
     while (to_compute.pop(&s)) {
       if (!failure.any.load(std::memory_order_acquire)) {
-        const int rc = fdnn_calculate(model, slot[s].in, slot[s].frames, I, 0, slot[s].out);
-        if (rc != FDNN_OK) failure.set(rc, fdnn_last_error());
+        const double t0 = now_ms();
+        const int rc = fdnn_calculate_sink(model, slot[s].in.data(), slot[s].frames, I, write_piece, &sink);
+        ms_gpu += now_ms() - t0;
+        if (rc != FDNN_OK) {
+          if (std::ferror(out.f))  // the sink gave up
+            failure.set(FDNN_EIO, std::string("short write: ") + out_path);
+          else
+            failure.set(rc, fdnn_last_error());
+        }
       }
       if (failure.any.load(std::memory_order_acquire)) {
-        to_reader.close();  // the reader may be waiting for a free slot
+        to_reader.close();  // the reader may be waiting for a free buffer
         continue;           // keep draining so that the reader's pushes are consumed and it can finish
       }
-      to_writer.push(s);
+      to_reader.push(s);
     }
-    to_writer.close();
   }
   reader.join();
-  writer.join();
   to_reader.close();
+  ms_write = sink.ms;
 
   const bool closed = std::fclose(out.f) == 0;
   out.f = nullptr;
-  if (frames_done) *frames_done = written.load(std::memory_order_relaxed);
+  if (frames_done) *frames_done = sink.written;
+  if (dbg)
+    std::fprintf(stderr, "fdnn_calculate_file: %lld frames, chunks of %d: %.1f ms (reader: fread %.1f + byte swap %.1f ms busy; this thread: "
+                         "fdnn_calculate_sink %.1f ms, of which writing the dump %.1f)\n",
+                 n, chunk, now_ms() - t_begin, ms_read, ms_swap, ms_gpu, ms_write);
   if (failure.rc != FDNN_OK) {
     set_error(failure.text);
     return failure.rc;

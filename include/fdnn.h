@@ -136,11 +136,11 @@ int fdnn_calculate_sink(fdnn_model *model, const float *in, int n, int dim, fdnn
 /* File to file: the data path of the reference's command-line driver (src/cpp/dnn.cc:55-78: BatchData(input_path) →
  * CalculationContext::Calculate → BatchData::dumpToFile) without holding either file in memory (BASELINE
  * config 4 is 1.76 GB of features and 32 GB of scores).  The feature file (big-endian int32 frames, int32 dim, fp32 rows,
- * float_dnn.cc:85-105) is read in chunks of chunk_frames (0 = 2048 per device) by a reader thread, each chunk goes through
- * fdnn_calculate on the calling thread, a writer thread appends the scores to out_path as the reference's binary dump
- * (FDNN_DUMP_BIN: native-endian uint32 frames, uint32 dim, fp32 rows) or text dump (FDNN_DUMP_TXT: a row per line, values as
- * printed by `ostream << float`), float_dnn.cc:128-164.  The file's dim must be the network's input width or its unpadded
- * width (at most 3 columns fewer, float_dnn.cc:32-33; the missing columns are zeros).  *frames_done (may be NULL) = rows
+ * float_dnn.cc:85-105) is read in chunks of chunk_frames (0 = 4096 per device) by a reader thread; the calling thread sends each
+ * chunk through fdnn_calculate_sink and appends the scores, piece by piece as they come off the GPU, to out_path as the reference's
+ * binary dump (FDNN_DUMP_BIN: native-endian uint32 frames, uint32 dim, fp32 rows) or text dump (FDNN_DUMP_TXT: a row per line,
+ * values as printed by `ostream << float`), float_dnn.cc:128-164.  The file's dim must be the network's input width or its
+ * unpadded width (at most 3 columns fewer, float_dnn.cc:32-33; the missing columns are zeros).  *frames_done (may be NULL) = rows
  * written, also on failure. */
 #define FDNN_DUMP_BIN 1
 #define FDNN_DUMP_TXT 0

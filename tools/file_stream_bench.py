@@ -2,7 +2,7 @@
 """File-to-file front end (fdnn_calculate_file, csrc/stream_file.cc) on the headline network: frames/s from a big-endian
 feature file to (a) /dev/null — reader, byte swap, PCIe and GPU only — and (b) a real binary dump on local storage.
 
-  python tools/file_stream_bench.py [frames] [out_dir]     → one JSON line
+  python tools/file_stream_bench.py [frames] [out_dir] [nodump]     → one JSON line   (FDNN_FILE_DEBUG=1: stage times on stderr)
 """
 import json
 import os
@@ -31,7 +31,10 @@ with open(feats, "wb") as f:
 dnn = qd.QuantizedDnn.load_from_file(synth.network_file("L"), device=0)
 res = {"tool": "file_stream_bench", "network": "440-7x2048-8000", "frames": frames, "feature_file_mb": round(os.path.getsize(feats) / 1e6, 1)}
 dnn.calculate_file(feats, "/dev/null", chunk_frames=2048)  # warm-up: workspaces, graphs, page cache of the feature file
-for name, target, chunk in (("dev_null", "/dev/null", 2048), ("dev_null_chunk4096", "/dev/null", 4096), ("local_file", dump, 2048)):
+legs = [("dev_null", "/dev/null", 2048), ("dev_null_chunk4096", "/dev/null", 4096), ("dev_null_chunk512", "/dev/null", 512)]
+if "nodump" not in sys.argv[3:]:
+    legs.append(("local_file", dump, 2048))
+for name, target, chunk in legs:
     t0 = time.perf_counter()
     n = dnn.calculate_file(feats, target, chunk_frames=chunk)
     dt = time.perf_counter() - t0
