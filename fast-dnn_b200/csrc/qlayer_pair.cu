@@ -140,6 +140,13 @@ qlayer_pair_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_co
 
   const int warp = int(threadIdx.x) / 32, lane = int(threadIdx.x) % 32;
   auto tstamp = [&](int slot) { stamp(args.timeline, slot); };
+  // Stage-level stamps of the first pair (profiling aid, tools/pair_stage_timeline.py): event `ev` of this CTA's g-th pipeline turn
+  // goes to timeline[2048 + ((cta · 8 + ev) · 256 + g)], beyond the per-CTA slots the grid uses; SM clocks, so only stamps of one
+  // CTA compare.  Events: 0 producer starts waiting for the slot, 1 its TMA boxes are issued, 2 MMA warp sees the stage full
+  // (leader), 3 its MMAs and the commit are issued (leader), 4 a scan set sees the commit, 5 the set has released the stage.
+  auto sstamp = [&](int ev, uint32_t g) {
+    if (args.timeline != nullptr && blockIdx.x < 2 && g < 256u) args.timeline[2048 + ((size_t(blockIdx.x) * 8 + size_t(ev)) * 256 + g)] = clock64();
+  };
   if (threadIdx.x == 0) tstamp(0);
   const int M = args.M, N = args.N, K = args.K;  // rows [args.row0, M) of the activation / output buffers
   const int row0 = args.row0;
@@ -194,11 +201,13 @@ qlayer_pair_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_co
     if (lane < 2) {
       int stage = 0;
       uint32_t phase = 0;
+      uint32_t g = 0;
       for (int ct = first_ct; ct < tiles_total; ct += ct_step) {
         int m_blk, n_blk;
         decode(ct, m_blk, n_blk);
         int kb = first_k_block(ct);
-        for (int i = 0; i < k_blocks; ++i, kb = (kb + 1 == k_blocks ? 0 : kb + 1)) {
+        for (int i = 0; i < k_blocks; ++i, ++g, kb = (kb + 1 == k_blocks ? 0 : kb + 1)) {
+          if (lane == 0) sstamp(0, g);
           ptx::mbar_wait_parked(empty_bar + stage, phase ^ 1);
           uint8_t *sa = tiles + stage * Cfg::kStageBytes;
           uint8_t *sb = sa + Cfg::kABytes;
@@ -207,6 +216,7 @@ qlayer_pair_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_co
           // one instruction, two boxes: per-lane tensor map, destination and row coordinate
           ptx::tma_load_2d_pair(lane == 0 ? &tmap_act : &tmap_w, bar, lane == 0 ? sa : sb, kb * kBlockK,
                                 lane == 0 ? row0 + m_blk * kBlockM : n_blk * BN + int(rank) * (BN / 2));
+          if (lane == 0) sstamp(1, g);
           if (++stage == Cfg::kStages) {
             stage = 0;
             phase ^= 1;
@@ -220,14 +230,16 @@ qlayer_pair_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_co
       constexpr uint32_t idesc = ptx::idesc_i8_u8s8_pair(BN);
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
+      uint32_t g = 0;
       for (int ct = first_ct; ct < tiles_total; ct += ct_step) {
         ptx::mbar_wait_cluster(acc_free_bar + acc, acc_phase ^ 1);
         ptx::tc_fence_after_sync();
         const uint32_t d_tmem = tmem_base + uint32_t(acc * BN);
-        for (int kb = 0; kb < k_blocks; ++kb) {
+        for (int kb = 0; kb < k_blocks; ++kb, ++g) {
           ptx::mbar_wait(full_bar + stage, phase);
           ptx::tc_fence_after_sync();
           if (lane == 0) {
+            sstamp(2, g);
             if (kb == 0) tstamp(2);
             const uint32_t a_addr = ptx::smem_u32(tiles + stage * Cfg::kStageBytes);
             const uint64_t da = ptx::smem_desc_k_sw128(a_addr), db = ptx::smem_desc_k_sw128(a_addr + Cfg::kABytes);
@@ -236,6 +248,7 @@ qlayer_pair_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_co
               ptx::mma_i8_ss_pair(d_tmem, da + uint64_t(k * (kUmmaK / 16)), db + uint64_t(k * (kUmmaK / 16)), idesc, uint32_t((kb | k) != 0));
             }
             ptx::mma_commit_pair(done_bar + stage);
+            sstamp(3, g);
             if (kb == k_blocks - 1) {
               ptx::mma_commit_pair(tmem_full_bar + acc);
               tstamp(3);
@@ -324,7 +337,10 @@ qlayer_pair_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_co
         const int stage = int(g % uint32_t(Cfg::kStages));
         // one warp of the set polls the stage's barrier, the other three wait for it in a hardware barrier: a
         // set idles three turns out of four, and sixteen polling warps would take a third of the issue slots
-        if ((sw & 3) == 0) ptx::mbar_wait_parked(done_bar + stage, (g / uint32_t(Cfg::kStages)) & 1u);
+        if ((sw & 3) == 0) {
+          ptx::mbar_wait_parked(done_bar + stage, (g / uint32_t(Cfg::kStages)) & 1u);
+          if (lane == 0) sstamp(4, g);
+        }
         ptx::named_bar_sync(2 + uint32_t(sset), 128);
         // rows are 128-byte aligned: address = row base | (entry's byte offset with its 16-byte chunk index XORed by row%8)
         const uint32_t a_rows = ptx::smem_u32(tiles + stage * Cfg::kStageBytes) + uint32_t(row_base) * 128u;
@@ -365,7 +381,10 @@ qlayer_pair_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_co
           }
         }
         __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(empty_bar + stage);
+        if (lane == 0) {
+          ptx::mbar_arrive(empty_bar + stage);
+          if ((sw & 3) == 3) sstamp(5, g);
+        }
         if (kb + kScanSets < k_blocks) {
           r0 = P[k_block_of(kb + kScanSets)];
           r1 = P[k_block_of(kb + kScanSets) + 1];
