@@ -27,6 +27,7 @@
 #include <deque>
 #include <mutex>
 #include <string>
+#include <sys/types.h>
 #include <thread>
 #include <vector>
 
@@ -197,7 +198,7 @@ int fdnn_calculate_file(fdnn_model *model, const char *feature_bin_path, const c
     std::fseek(in.f, 8, SEEK_SET);
   }
   const int n_dev = fdnn_device_count(model);
-  const int chunk = chunk_frames > 0 ? chunk_frames : 4096 * (n_dev > 0 ? n_dev : 1);
+  const int chunk = chunk_frames > 0 ? chunk_frames : (out_format == FDNN_DUMP_BIN ? 4096 : 1024) * (n_dev > 0 ? n_dev : 1);
   out.f = std::fopen(out_path, "wb");
   if (!out.f) {
     set_error(std::string("cannot open for writing: ") + out_path);
@@ -260,19 +261,37 @@ int fdnn_calculate_file(fdnn_model *model, const char *feature_bin_path, const c
     to_compute.close();
   });
 
+  // The sink sees the pieces of ONE device in frame order; the devices of a group deliver their shards of a call interleaved
+  // (fdnn_api.cu: calculate_impl collects round-robin).  Binary dump: a piece that is not the continuation of the previous one
+  // is written at its own offset.  Text dump (rows have no fixed length): the rows of a chunk are collected and formatted in
+  // order once the call has returned.
   struct DumpSink {
     std::FILE *f;
     int format, dim;
+    long long base = 0;      // frames of the chunks before this one
+    long long cursor = 0;    // frame the file position stands at (binary)
     long long written = 0;
     double ms = 0.0;
+    bool io_error = false;
+    std::vector<float> rows;  // text: this chunk's scores
     std::string scratch;
-  } sink{out.f, out_format, O, 0, 0.0, std::string()};
-  const fdnn_sink_fn write_piece = [](void *user, int, int n_frames, const float *rows) -> int {
-    auto *ds = static_cast<DumpSink *>(user);  // called on this thread, in frame order
+  } sink{out.f, out_format, O, 0, 0, 0, 0.0, false, {}, std::string()};
+  if (out_format == FDNN_DUMP_TXT) sink.rows.resize(slot[0].in.size() / size_t(I) * size_t(O));
+  const fdnn_sink_fn take_piece = [](void *user, int first_frame, int n_frames, const float *rows) -> int {
+    auto *ds = static_cast<DumpSink *>(user);  // called on this thread
     const double t0 = now_ms();
-    const bool ok = write_rows(ds->f, ds->format, rows, n_frames, ds->dim, ds->scratch);
+    bool ok = true;
+    if (ds->format == FDNN_DUMP_BIN) {
+      const long long at = ds->base + first_frame;
+      if (at != ds->cursor) ok = fseeko(ds->f, off_t(8 + at * (long long) ds->dim * 4), SEEK_SET) == 0;
+      ok = ok && write_rows(ds->f, FDNN_DUMP_BIN, rows, n_frames, ds->dim, ds->scratch);
+      ds->cursor = at + n_frames;
+      if (ok) ds->written += n_frames;
+    } else {
+      std::memcpy(ds->rows.data() + size_t(first_frame) * size_t(ds->dim), rows, size_t(n_frames) * size_t(ds->dim) * sizeof(float));
+    }
     ds->ms += now_ms() - t0;
-    if (ok) ds->written += n_frames;
+    if (!ok) ds->io_error = true;
     return ok ? 0 : 1;
   };
   {
@@ -280,14 +299,21 @@ int fdnn_calculate_file(fdnn_model *model, const char *feature_bin_path, const c
     while (to_compute.pop(&s)) {
       if (!failure.any.load(std::memory_order_acquire)) {
         const double t0 = now_ms();
-        const int rc = fdnn_calculate_sink(model, slot[s].in.data(), slot[s].frames, I, write_piece, &sink);
-        ms_gpu += now_ms() - t0;
-        if (rc != FDNN_OK) {
-          if (std::ferror(out.f))  // the sink gave up
-            failure.set(FDNN_EIO, std::string("short write: ") + out_path);
+        const int rc = fdnn_calculate_sink(model, slot[s].in.data(), slot[s].frames, I, take_piece, &sink);
+        if (rc == FDNN_OK && out_format == FDNN_DUMP_TXT) {
+          const double t1 = now_ms();
+          if (write_rows(out.f, FDNN_DUMP_TXT, sink.rows.data(), slot[s].frames, O, sink.scratch))
+            sink.written += slot[s].frames;
           else
-            failure.set(rc, fdnn_last_error());
+            sink.io_error = true;
+          sink.ms += now_ms() - t1;
         }
+        sink.base += slot[s].frames;
+        ms_gpu += now_ms() - t0;
+        if (sink.io_error)
+          failure.set(FDNN_EIO, std::string("short write: ") + out_path);
+        else if (rc != FDNN_OK)
+          failure.set(rc, fdnn_last_error());
       }
       if (failure.any.load(std::memory_order_acquire)) {
         to_reader.close();  // the reader may be waiting for a free buffer

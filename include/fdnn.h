@@ -125,9 +125,9 @@ int fdnn_set_tile_policy(fdnn_model *model, int policy);
  * reference's CPU cache-blocking batchSize; results do not depend on it and it is ignored.
  * Re-entrant: concurrent calls on one model each use a private workspace. n == 0 is a no-op. */
 int fdnn_calculate(fdnn_model *model, const float *in, int n, int dim, int batch_hint, float *out);
-/* Same computation, results delivered piecewise: `sink` is called on the CALLING thread, in frame order, with
- * rows [first_frame, first_frame + n_frames) in page-locked memory that is only valid during the call; a non-zero return
- * aborts.  This is what Java_suskun_nn_QuantizedDnn_calculate uses to move scores from the transfer buffer straight into
+/* Same computation, results delivered piecewise: `sink` is called on the CALLING thread with rows [first_frame,
+ * first_frame + n_frames) in page-locked memory that is only valid during the call — in frame order on one device, the
+ * shards of a device group interleaved (each in order); every frame exactly once; a non-zero return aborts.  This is what Java_suskun_nn_QuantizedDnn_calculate uses to move scores from the transfer buffer straight into
  * the Java array (SetFloatArrayRegion) while the next sub-chunk is still crossing PCIe, instead of the reference's
  * malloc + copy + copy (jni_dnn.cc:49-58). */
 typedef int (*fdnn_sink_fn)(void *user, int first_frame, int n_frames, const float *rows);
@@ -136,7 +136,7 @@ int fdnn_calculate_sink(fdnn_model *model, const float *in, int n, int dim, fdnn
 /* File to file: the data path of the reference's command-line driver (src/cpp/dnn.cc:55-78: BatchData(input_path) →
  * CalculationContext::Calculate → BatchData::dumpToFile) without holding either file in memory (BASELINE
  * config 4 is 1.76 GB of features and 32 GB of scores).  The feature file (big-endian int32 frames, int32 dim, fp32 rows,
- * float_dnn.cc:85-105) is read in chunks of chunk_frames (0 = 4096 per device) by a reader thread; the calling thread sends each
+ * float_dnn.cc:85-105) is read in chunks of chunk_frames (0 = 4096 per device; 1024 for the text dump) by a reader thread; the calling thread sends each
  * chunk through fdnn_calculate_sink and appends the scores, piece by piece as they come off the GPU, to out_path as the reference's
  * binary dump (FDNN_DUMP_BIN: native-endian uint32 frames, uint32 dim, fp32 rows) or text dump (FDNN_DUMP_TXT: a row per line,
  * values as printed by `ostream << float`), float_dnn.cc:128-164.  The file's dim must be the network's input width or its

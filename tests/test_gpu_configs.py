@@ -422,6 +422,14 @@ def test_device_group_behind_one_handle(net_file):
         for n in (1, 100, 129, 512, 3000, 9001):
             frames = synth.make_frames(n, 440, seed=50 + n)
             assert np.array_equal(group.calculate(frames), single.calculate(frames)), n
+        # the file-to-file front end on the group handle: every chunk of the feature file is sharded over the devices
+        import tempfile
+        with tempfile.TemporaryDirectory() as d:
+            frames = synth.make_frames(7000, 440, seed=77)
+            feats, dump = os.path.join(d, "f.bin"), os.path.join(d, "o.bin")
+            qd.write_feature_bin(feats, frames)
+            assert group.calculate_file(feats, dump, chunk_frames=1500) == 7000
+            assert np.array_equal(qd.read_output_dump(dump), single.calculate(frames))
         frames = synth.make_frames(64, 440, seed=9)
         masks = synth.make_masks(64, 2000, seed=4)
         want_ctx = single.get_new_lazy_context(64)
