@@ -144,8 +144,15 @@ qlayer_pair_kernel(const __grid_constant__ CUtensorMap tmap_act, const __grid_co
   // goes to timeline[2048 + ((cta · 8 + ev) · 256 + g)], beyond the per-CTA slots the grid uses; SM clocks, so only stamps of one
   // CTA compare.  Events: 0 producer starts waiting for the slot, 1 its TMA boxes are issued, 2 MMA warp sees the stage full
   // (leader), 3 its MMAs and the commit are issued (leader), 4 a scan set sees the commit, 5 the set has released the stage.
+  // Compiled in only with -DFDNN_STAGE_STAMPS (make NVFLAGS_EXTRA=-DFDNN_STAGE_STAMPS): the MMA-issuing thread is bound by its own
+  // instruction stream, and even stamps that are switched off cost it a compare and a branch per stage.
   auto sstamp = [&](int ev, uint32_t g) {
+#ifdef FDNN_STAGE_STAMPS
     if (args.timeline != nullptr && blockIdx.x < 2 && g < 256u) args.timeline[2048 + ((size_t(blockIdx.x) * 8 + size_t(ev)) * 256 + g)] = clock64();
+#else
+    (void) ev;
+    (void) g;
+#endif
   };
   if (threadIdx.x == 0) tstamp(0);
   const int M = args.M, N = args.N, K = args.K;  // rows [args.row0, M) of the activation / output buffers

@@ -5,7 +5,10 @@ qlayer_pair.cu stamps, for the first 256 pipeline turns of its first pair, when 
 issued its TMA boxes (1), the MMA warp sees the stage full (2, leader), has issued MMAs + commit (3, leader), a scan set sees the
 commit (4) and has released the stage (5).  SM clocks: only stamps of one CTA compare.
 
+The stamps are compiled in only on request (the MMA-issuing thread pays for every instruction in its loop):
+  touch fast-dnn_b200/csrc/qlayer_pair.cu && make -C fast-dnn_b200/csrc NVFLAGS_EXTRA=-DFDNN_STAGE_STAMPS
   python tools/pair_stage_timeline.py [frames] [layer]
+  touch fast-dnn_b200/csrc/qlayer_pair.cu && make -C fast-dnn_b200/csrc        # back to the production kernel
 """
 import os
 import sys
