@@ -26,7 +26,9 @@
 #include <cstring>
 #include <deque>
 #include <mutex>
+#include <new>
 #include <string>
+#include <system_error>
 #include <sys/types.h>
 #include <thread>
 #include <vector>
@@ -227,13 +229,22 @@ int fdnn_calculate_file(fdnn_model *model, const char *feature_bin_path, const c
     int frames = 0;
   } slot[kSlots];
   const int n_slots = int(std::min<long long>(kSlots, std::max<long long>(1, (n + chunk - 1) / chunk)));
-  for (int i = 0; i < n_slots; ++i) slot[i].in.resize(size_t(std::min<long long>(chunk, std::max<long long>(n, 1))) * size_t(I));
+  const size_t cap_frames = size_t(std::min<long long>(chunk, std::max<long long>(n, 1)));
+  std::vector<uint8_t> raw;       // the reader's view of the file: big-endian rows of d floats
+  std::vector<float> text_rows;   // text dump: the scores of the chunk on the GPU
+  try {  // everything is allocated before the reader thread exists; nothing may throw across the C ABI
+    for (int i = 0; i < n_slots; ++i) slot[i].in.resize(cap_frames * size_t(I));
+    raw.resize(cap_frames * size_t(d) * 4);
+    if (out_format == FDNN_DUMP_TXT) text_rows.resize(cap_frames * size_t(O));
+  } catch (const std::bad_alloc &) {
+    set_error("out of host memory for chunks of " + std::to_string(cap_frames) + " frames");
+    return FDNN_ENOMEM;
+  }
   Channel to_reader, to_compute;
   Failure failure;
   for (int i = 0; i < n_slots; ++i) to_reader.push(i);
 
-  std::thread reader([&] {
-    std::vector<uint8_t> raw(slot[0].in.size() / size_t(I) * size_t(d) * 4);
+  auto read_chunks = [&] {
     long long done = 0;
     int s = 0;
     while (done < n && !failure.any.load(std::memory_order_acquire) && to_reader.pop(&s)) {
@@ -259,7 +270,14 @@ int fdnn_calculate_file(fdnn_model *model, const char *feature_bin_path, const c
       to_compute.push(s);
     }
     to_compute.close();
-  });
+  };
+  std::thread reader;
+  try {
+    reader = std::thread(read_chunks);
+  } catch (const std::system_error &) {
+    set_error("cannot start the reader thread");
+    return FDNN_ENOMEM;
+  }
 
   // The sink sees the pieces of ONE device in frame order; the devices of a group deliver their shards of a call interleaved
   // (fdnn_api.cu: calculate_impl collects round-robin).  Binary dump: a piece that is not the continuation of the previous one
@@ -273,10 +291,9 @@ int fdnn_calculate_file(fdnn_model *model, const char *feature_bin_path, const c
     long long written = 0;
     double ms = 0.0;
     bool io_error = false;
-    std::vector<float> rows;  // text: this chunk's scores
+    float *rows;  // text: this chunk's scores
     std::string scratch;
-  } sink{out.f, out_format, O, 0, 0, 0, 0.0, false, {}, std::string()};
-  if (out_format == FDNN_DUMP_TXT) sink.rows.resize(slot[0].in.size() / size_t(I) * size_t(O));
+  } sink{out.f, out_format, O, 0, 0, 0, 0.0, false, text_rows.data(), std::string()};
   const fdnn_sink_fn take_piece = [](void *user, int first_frame, int n_frames, const float *rows) -> int {
     auto *ds = static_cast<DumpSink *>(user);  // called on this thread
     const double t0 = now_ms();
@@ -288,7 +305,7 @@ int fdnn_calculate_file(fdnn_model *model, const char *feature_bin_path, const c
       ds->cursor = at + n_frames;
       if (ok) ds->written += n_frames;
     } else {
-      std::memcpy(ds->rows.data() + size_t(first_frame) * size_t(ds->dim), rows, size_t(n_frames) * size_t(ds->dim) * sizeof(float));
+      std::memcpy(ds->rows + size_t(first_frame) * size_t(ds->dim), rows, size_t(n_frames) * size_t(ds->dim) * sizeof(float));
     }
     ds->ms += now_ms() - t0;
     if (!ok) ds->io_error = true;
@@ -302,7 +319,7 @@ int fdnn_calculate_file(fdnn_model *model, const char *feature_bin_path, const c
         const int rc = fdnn_calculate_sink(model, slot[s].in.data(), slot[s].frames, I, take_piece, &sink);
         if (rc == FDNN_OK && out_format == FDNN_DUMP_TXT) {
           const double t1 = now_ms();
-          if (write_rows(out.f, FDNN_DUMP_TXT, sink.rows.data(), slot[s].frames, O, sink.scratch))
+          if (write_rows(out.f, FDNN_DUMP_TXT, sink.rows, slot[s].frames, O, sink.scratch))
             sink.written += slot[s].frames;
           else
             sink.io_error = true;
