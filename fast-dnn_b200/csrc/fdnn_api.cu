@@ -24,6 +24,7 @@
 #include <functional>
 #include <memory>
 #include <mutex>
+#include <new>
 #include <string>
 #include <vector>
 
@@ -45,6 +46,17 @@ std::atomic<long long> g_launches{0};
       return FDNN_ECUDA;                                                                    \
     }                                                                                       \
   } while (0)
+
+// Nothing may propagate out of an extern "C" entry point: the ones that allocate are function-try-blocks ending in this.
+#define FDNN_CATCH                                                           \
+  catch (const std::bad_alloc &) {                                           \
+    set_error("out of host memory");                                         \
+    return FDNN_ENOMEM;                                                      \
+  }                                                                          \
+  catch (const std::exception &e_) {                                         \
+    set_error(std::string("internal error: ") + e_.what());                  \
+    return FDNN_ECUDA;                                                       \
+  }
 
 int round_up(int v, int m) { return (v + m - 1) / m * m; }
 
@@ -847,7 +859,7 @@ extern "C" {
 const char *fdnn_last_error(void) { return get_error(); }
 const char *fdnn_version(void) { return "fast-dnn-b200 0.1 (sm_100a)"; }
 
-int fdnn_pack(const char *path, float cutoff, void **blob, size_t *size) {
+int fdnn_pack(const char *path, float cutoff, void **blob, size_t *size) try {
   if (!blob || !size) {
     set_error("null output pointer");
     return FDNN_EINVAL;
@@ -863,19 +875,19 @@ int fdnn_pack(const char *path, float cutoff, void **blob, size_t *size) {
   *blob = p;
   *size = v.size();
   return FDNN_OK;
-}
+} FDNN_CATCH
 
 void fdnn_blob_free(void *blob) { std::free(blob); }
 
-int fdnn_align_dnn_bin(const char *in_path, const char *out_path, int input_alignment, int hidden_alignment) {
+int fdnn_align_dnn_bin(const char *in_path, const char *out_path, int input_alignment, int hidden_alignment) try {
   return align_dnn_bin(in_path, out_path, input_alignment, hidden_alignment);
-}
+} FDNN_CATCH
 
-int fdnn_import_kaldi_nnet1(const char *nnet_txt_path, const char *transform_txt_path, const char *out_dnn_bin_path) {
+int fdnn_import_kaldi_nnet1(const char *nnet_txt_path, const char *transform_txt_path, const char *out_dnn_bin_path) try {
   return import_kaldi_nnet1(nnet_txt_path, transform_txt_path, out_dnn_bin_path);
-}
+} FDNN_CATCH
 
-int fdnn_feature_bin_read(const char *path, int *frames, int *dim, float **data) {
+int fdnn_feature_bin_read(const char *path, int *frames, int *dim, float **data) try {
   if (!path || !frames || !dim || !data) {
     set_error("null argument");
     return FDNN_EINVAL;
@@ -890,12 +902,12 @@ int fdnn_feature_bin_read(const char *path, int *frames, int *dim, float **data)
   if (!v.empty()) std::memcpy(p, v.data(), v.size() * sizeof(float));
   *data = p;
   return FDNN_OK;
-}
+} FDNN_CATCH
 
-int fdnn_feature_bin_write(const char *path, const float *data, int frames, int dim) { return write_feature_bin(path, data, frames, dim); }
-int fdnn_output_dump_write(const char *path, const float *data, int frames, int dim) { return write_output_dump(path, data, frames, dim); }
+int fdnn_feature_bin_write(const char *path, const float *data, int frames, int dim) try { return write_feature_bin(path, data, frames, dim); } FDNN_CATCH
+int fdnn_output_dump_write(const char *path, const float *data, int frames, int dim) try { return write_output_dump(path, data, frames, dim); } FDNN_CATCH
 
-int fdnn_load_blob(const void *blob, size_t size, int device, fdnn_model **out) {
+int fdnn_load_blob(const void *blob, size_t size, int device, fdnn_model **out) try {
   if (!blob || !out) {
     set_error("null argument");
     return FDNN_EINVAL;
@@ -916,7 +928,7 @@ int fdnn_load_blob(const void *blob, size_t size, int device, fdnn_model **out) 
   }
   if (int rc = validate_blob(view, size)) return rc;
   return upload_model(view, blob, on_device, size, dev, out);
-}
+} FDNN_CATCH
 
 // ---- device groups: one replica per GPU behind ONE handle ----------------------------------------------
 // The host parses and quantizes once, the packed blob goes to the first device, ONE ncclBroadcast (in-process communicator,
@@ -1074,7 +1086,7 @@ void release_group(fdnn_model *model) {
 
 extern "C" {
 
-int fdnn_load_devices(const char *path, float cutoff, const int *devices, int n_devices, fdnn_model **out) {
+int fdnn_load_devices(const char *path, float cutoff, const int *devices, int n_devices, fdnn_model **out) try {
   if (!out || !devices || n_devices <= 0) {
     set_error("bad argument to fdnn_load_devices");
     return FDNN_EINVAL;
@@ -1112,9 +1124,9 @@ int fdnn_load_devices(const char *path, float cutoff, const int *devices, int n_
   reps[0]->group = reps;
   *out = reps[0];
   return FDNN_OK;
-}
+} FDNN_CATCH
 
-int fdnn_load(const char *path, float cutoff, int device, fdnn_model **out) {
+int fdnn_load(const char *path, float cutoff, int device, fdnn_model **out) try {
   if (!out) {
     set_error("null output pointer");
     return FDNN_EINVAL;
@@ -1130,7 +1142,7 @@ int fdnn_load(const char *path, float cutoff, int device, fdnn_model **out) {
   std::vector<uint8_t> v;
   if (int rc = pack_model(path, cutoff, v)) return rc;
   return upload_model(v.data(), v.data(), false, v.size(), dev, out);
-}
+} FDNN_CATCH
 
 int fdnn_free(fdnn_model *model) {
   if (!model) return FDNN_OK;
@@ -1169,7 +1181,7 @@ int fdnn_layer_dim(const fdnn_model *m, int i) {
   return m->q[size_t(i)].nodes;
 }
 
-int fdnn_model_qlayer(const fdnn_model *m, int i, int *nodes, int *inputs, float *multiplier, int8_t *weights, float *bias) {
+int fdnn_model_qlayer(const fdnn_model *m, int i, int *nodes, int *inputs, float *multiplier, int8_t *weights, float *bias) try {
   if (!m || i < 0 || i >= m->hdr.n_qlayers) {
     set_error("bad layer index");
     return FDNN_EINVAL;
@@ -1183,7 +1195,7 @@ int fdnn_model_qlayer(const fdnn_model *m, int i, int *nodes, int *inputs, float
   if (weights) CUDA_TRY(cudaMemcpy(weights, m->d_blob + q.off_w, size_t(q.nodes) * size_t(q.inputs), cudaMemcpyDeviceToHost));
   if (bias) CUDA_TRY(cudaMemcpy(bias, m->d_blob + q.off_bias, size_t(q.nodes) * 4, cudaMemcpyDeviceToHost));
   return FDNN_OK;
-}
+} FDNN_CATCH
 
 int fdnn_model_fixup_count(const fdnn_model *m, int i) {
   if (!m || i < 0 || i >= m->hdr.n_qlayers) return FDNN_EINVAL;
@@ -1208,7 +1220,7 @@ int fdnn_sigmoid_lut(uint8_t out[1280]) {
 
 // ---- contexts -----------------------------------------------------------------------------------------
 
-int fdnn_ctx_new(fdnn_model *model, int n, int batch_hint, fdnn_ctx **out) {
+int fdnn_ctx_new(fdnn_model *model, int n, int batch_hint, fdnn_ctx **out) try {
   (void) batch_hint;
   if (!model || !out) {
     set_error("null argument");
@@ -1217,7 +1229,7 @@ int fdnn_ctx_new(fdnn_model *model, int n, int batch_hint, fdnn_ctx **out) {
   // a device group hands its contexts out round-robin: one context lives on one GPU
   fdnn_model *home = model->group.empty() ? model : model->group[model->next_ctx.fetch_add(1, std::memory_order_relaxed) % model->group.size()];
   return create_ctx(home, n, out);
-}
+} FDNN_CATCH
 
 int fdnn_ctx_free(fdnn_ctx *ctx) {
   destroy_ctx(ctx);
@@ -1260,7 +1272,7 @@ int fdnn_ctx_set_trace(fdnn_ctx *ctx, int enable) {
   return FDNN_OK;
 }
 
-int fdnn_ctx_until_output_device(fdnn_ctx *ctx, const float *d_in, int n_frames, void *stream) {
+int fdnn_ctx_until_output_device(fdnn_ctx *ctx, const float *d_in, int n_frames, void *stream) try {
   if (!ctx || !d_in || n_frames < 0 || n_frames > ctx->cap) {
     set_error("bad argument to fdnn_ctx_until_output_device");
     return FDNN_EINVAL;
@@ -1269,9 +1281,9 @@ int fdnn_ctx_until_output_device(fdnn_ctx *ctx, const float *d_in, int n_frames,
   if (int rc = run_pass(ctx, d_in, n_frames, ctx->d_logits, false, static_cast<cudaStream_t>(stream))) return rc;
   ctx->have_logits = true;
   return FDNN_OK;
-}
+} FDNN_CATCH
 
-int fdnn_ctx_forward_device(fdnn_ctx *ctx, const float *d_in, int n_frames, float *d_out, void *stream) {
+int fdnn_ctx_forward_device(fdnn_ctx *ctx, const float *d_in, int n_frames, float *d_out, void *stream) try {
   if (!ctx || !d_in || !d_out || n_frames < 0 || n_frames > ctx->cap) {
     set_error("bad argument to fdnn_ctx_forward_device");
     return FDNN_EINVAL;
@@ -1279,7 +1291,7 @@ int fdnn_ctx_forward_device(fdnn_ctx *ctx, const float *d_in, int n_frames, floa
   DeviceGuard g(ctx->model->device);
   ctx->have_logits = false;  // logits are produced straight into the caller's buffer and normalised in place
   return run_pass(ctx, d_in, n_frames, d_out, true, static_cast<cudaStream_t>(stream));
-}
+} FDNN_CATCH
 
 int fdnn_ctx_lazy_batch_device(fdnn_ctx *ctx, const int8_t *d_masks, int n_frames, float *d_out, void *stream) {
   if (!ctx || !d_masks || !d_out || n_frames < 0 || n_frames > ctx->last_frames) {
@@ -1294,7 +1306,7 @@ int fdnn_ctx_lazy_batch_device(fdnn_ctx *ctx, const int8_t *d_masks, int n_frame
   return enqueue_softmax(ctx, ctx->d_logits, d_masks, n_frames, d_out, static_cast<cudaStream_t>(stream));
 }
 
-int fdnn_ctx_until_output(fdnn_ctx *ctx, const float *in) {
+int fdnn_ctx_until_output(fdnn_ctx *ctx, const float *in) try {
   if (!ctx || !in) {
     set_error("null argument");
     return FDNN_EINVAL;
@@ -1306,9 +1318,9 @@ int fdnn_ctx_until_output(fdnn_ctx *ctx, const float *in) {
   CUDA_TRY(cudaStreamSynchronize(ctx->stream));
   ctx->have_logits = true;
   return FDNN_OK;
-}
+} FDNN_CATCH
 
-int fdnn_ctx_lazy(fdnn_ctx *ctx, int idx, const int8_t *mask, float *out) {
+int fdnn_ctx_lazy(fdnn_ctx *ctx, int idx, const int8_t *mask, float *out) try {
   if (!ctx || !mask || !out) {
     set_error("null argument");
     return FDNN_EINVAL;
@@ -1335,7 +1347,7 @@ int fdnn_ctx_lazy(fdnn_ctx *ctx, int idx, const int8_t *mask, float *out) {
   CUDA_TRY(cudaStreamSynchronize(ctx->stream));
   std::memcpy(out, ctx->h_row, size_t(O) * 4);
   return FDNN_OK;
-}
+} FDNN_CATCH
 
 int fdnn_ctx_hidden(fdnn_ctx *ctx, int layer, int n_frames, uint8_t *out) {
   if (!ctx || !out) return FDNN_EINVAL;
@@ -1419,7 +1431,7 @@ int fdnn_ctx_input_undecided(fdnn_ctx *ctx, unsigned *undecided) {
   return FDNN_OK;
 }
 
-int fdnn_ctx_profile_stages(fdnn_ctx *ctx, const float *d_in, int n_frames, float *d_out, int iters, float *ms) {
+int fdnn_ctx_profile_stages(fdnn_ctx *ctx, const float *d_in, int n_frames, float *d_out, int iters, float *ms) try {
   if (!ctx || !d_in || !d_out || !ms || iters <= 0 || n_frames <= 0 || n_frames > ctx->cap) {
     set_error("bad argument to fdnn_ctx_profile_stages");
     return FDNN_EINVAL;
@@ -1450,12 +1462,12 @@ int fdnn_ctx_profile_stages(fdnn_ctx *ctx, const float *d_in, int n_frames, floa
   for (auto &e : ev) cudaEventDestroy(e);
   for (int s = 0; s < stages; ++s) ms[s] = float(total[size_t(s)] / iters);
   return rc;
-}
+} FDNN_CATCH
 
 // Bench/profiling aid: the pass as it normally runs (fused kernel where it applies), `iters` times on the context's stream
 // with CUDA events after the input layer and at the end.  ms[0] = fp32 input layer, ms[1] = everything after it (the fused
 // int8 stack + softmax: ONE kernel when *fused = 1); averages in milliseconds.
-int fdnn_ctx_profile_pass(fdnn_ctx *ctx, const float *d_in, int n_frames, float *d_out, int iters, float *ms, int *fused) {
+int fdnn_ctx_profile_pass(fdnn_ctx *ctx, const float *d_in, int n_frames, float *d_out, int iters, float *ms, int *fused) try {
   if (!ctx || !d_in || !d_out || !ms || iters <= 0 || n_frames <= 0 || n_frames > ctx->cap) {
     set_error("bad argument to fdnn_ctx_profile_pass");
     return FDNN_EINVAL;
@@ -1498,7 +1510,7 @@ int fdnn_ctx_profile_pass(fdnn_ctx *ctx, const float *d_in, int n_frames, float 
   ms[1] = float(total[1] / iters);
   if (fused) *fused = took_fused ? 1 : 0;
   return rc;
-}
+} FDNN_CATCH
 
 // ---- full forward over host buffers -------------------------------------------------------------
 
@@ -1814,7 +1826,7 @@ int calculate_impl(fdnn_model *model, const float *in, int n, int dim, float *ou
 // All frames of the context at once (BASELINE config 3): masks up, one masked-softmax launch, scores down.  With page-locked caller
 // memory all three are asynchronous and the thread naps until they are done; pageable memory goes through the driver's own
 // staging (measured on B200: faster than staging it here — 152 k against 123 k frames/s at batch 512, profiles/r2_experiments.md).
-int fdnn_ctx_lazy_batch(fdnn_ctx *ctx, const int8_t *masks, float *out) {
+int fdnn_ctx_lazy_batch(fdnn_ctx *ctx, const int8_t *masks, float *out) try {
   if (!ctx || !masks || !out) {
     set_error("null argument");
     return FDNN_EINVAL;
@@ -1836,20 +1848,20 @@ int fdnn_ctx_lazy_batch(fdnn_ctx *ctx, const int8_t *masks, float *out) {
   CUDA_TRY(cudaEventRecord(ctx->events[0], ctx->stream));
   CUDA_TRY(wait_event(ctx->events[0]));
   return FDNN_OK;
-}
+} FDNN_CATCH
 
-int fdnn_calculate(fdnn_model *model, const float *in, int n, int dim, int batch_hint, float *out) {
+int fdnn_calculate(fdnn_model *model, const float *in, int n, int dim, int batch_hint, float *out) try {
   (void) batch_hint;
   return calculate_impl(model, in, n, dim, out, nullptr, nullptr);
-}
+} FDNN_CATCH
 
-int fdnn_calculate_sink(fdnn_model *model, const float *in, int n, int dim, fdnn_sink_fn sink, void *user) {
+int fdnn_calculate_sink(fdnn_model *model, const float *in, int n, int dim, fdnn_sink_fn sink, void *user) try {
   if (!sink) {
     set_error("null sink");
     return FDNN_EINVAL;
   }
   return calculate_impl(model, in, n, dim, nullptr, sink, user);
-}
+} FDNN_CATCH
 
 // ---- misc ---------------------------------------------------------------------------------------------
 

@@ -93,6 +93,16 @@ def test_bad_arguments_are_refused_not_crashed_on(net_file):
     assert L.fdnn_output_dump_write_txt(b"/nonexistent-dir/x.txt", (C.c_float * 1)(1.0), 1, 1) == qd.FDNN_EIO
 
 
+def test_allocation_failures_do_not_cross_the_abi():
+    """an impossible request comes back as an error code (function-try-blocks around the allocating entry points), not as
+    a C++ exception unwinding into the caller"""
+    L = qd.lib()
+    one = (C.c_float * 4)(1.0, 2.0, 3.0, 4.0)
+    rc = L.fdnn_feature_bin_write(b"/tmp/fdnn_never_written.bin", one, 2**31 - 1, 2**31 - 1)
+    assert rc in (qd.FDNN_ENOMEM, qd.FDNN_ECUDA) and L.fdnn_last_error()
+    assert not os.path.exists("/tmp/fdnn_never_written.bin")
+
+
 def test_cutoff_must_be_positive(net_file):
     with pytest.raises(ValueError):
         qd.QuantizedDnn.load_from_file(net_file("tiny"), 0.0)
