@@ -485,6 +485,13 @@ int align_dnn_bin(const char *in_path, const char *out_path, int input_alignment
     set_error("bad argument to fdnn_align_dnn_bin");
     return FDNN_EINVAL;
   }
+  // alignments are SIMD / tile widths (the reference uses 4 and 16, FeedForwardNetwork.java:50-58); a huge one would pad a
+  // small network into terabytes of zeros, one push_back at a time
+  constexpr int kMaxAlignment = 4096;
+  if (input_alignment > kMaxAlignment || hidden_alignment > kMaxAlignment) {
+    set_error("alignment above " + std::to_string(kMaxAlignment));
+    return FDNN_EINVAL;
+  }
   FileBytes fb;
   if (int rc = read_file(in_path, fb.data)) return rc;
   const int layer_count = int(fb.word());
@@ -518,7 +525,18 @@ int align_dnn_bin(const char *in_path, const char *out_path, int input_alignment
     set_error("dnn.bin truncated in shift/scale");
     return FDNN_EIO;
   }
+  // size of the aligned file, known before a byte of it is built: an allocation that cannot succeed fails here, at once
+  // (std::bad_alloc → FDNN_ENOMEM at the C ABI)
+  size_t total = 4;
+  for (int j = 0; j < layer_count; ++j) {
+    const FloatLayer &l = layers[size_t(j)];
+    const size_t in_pad = size_t(round_up(l.in, j == 0 ? input_alignment : hidden_alignment));
+    const size_t out_pad = size_t(j == layer_count - 1 ? l.out : round_up(l.out, hidden_alignment));
+    total += 8 + 4 * (in_pad * out_pad + out_pad);
+  }
+  total += 8 * size_t(round_up(in0, input_alignment));
   std::vector<uint8_t> out;
+  out.reserve(total);
   put_be32(out, uint32_t(layer_count));
   for (int j = 0; j < layer_count; ++j) {
     const FloatLayer &l = layers[size_t(j)];

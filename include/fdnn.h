@@ -78,7 +78,8 @@ int fdnn_load_blob(const void *blob, size_t size, int device, fdnn_model **out);
  * FeedForwardNetwork.align + saveBinary (src/java/suskun/nn/FeedForwardNetwork.java:50-58,226-235,
  * 264-281,331-340): read a dnn.bin of any shape, zero-pad the input width to a multiple of
  * input_alignment (4) and every hidden width to a multiple of hidden_alignment (16), write a dnn.bin
- * that fdnn_load accepts.  The reference does this in Java only (README.md:76 lists C++ as a TODO). */
+ * that fdnn_load accepts.  Alignments are 1 … 4096 (FDNN_EINVAL otherwise).  The reference does this in Java only
+ * (README.md:76 lists C++ as a TODO). */
 int fdnn_align_dnn_bin(const char *in_path, const char *out_path, int input_alignment, int hidden_alignment);
 /* FeedForwardNetwork.loadFromTextFile + saveBinary (FeedForwardNetwork.java:86-119,159-207,226-235): Kaldi nnet1
  * text model ("<AffineTransform> out in" blocks) plus the feature-transform text (optional <Splice> block,

@@ -95,3 +95,83 @@ def test_restatement_equals_compiled_reference_on_random_networks(seed, tmp_path
         assert np.array_equal(want[ok].view(np.uint32), got[ok].view(np.uint32)), (dims, cutoff, n)
         ref.close()
         port.close()
+
+
+def _mutate(rng, b, texty):
+    b = b.copy()
+    mode = int(rng.integers(0, 6))
+    if mode == 0:  # header bytes
+        for _ in range(int(rng.integers(1, 8))):
+            b[rng.integers(0, min(len(b), 64))] = rng.integers(0, 256)
+    elif mode == 1:  # bytes anywhere (text: characters that mean something to the parser)
+        alphabet = np.frombuffer(b"[]<> \n0123456789.e-+xA", dtype=np.uint8)
+        for _ in range(int(rng.integers(1, 30))):
+            b[rng.integers(0, len(b))] = rng.choice(alphabet) if texty else rng.integers(0, 256)
+    elif mode == 2:  # truncation
+        b = b[: rng.integers(0, len(b))]
+    elif mode == 3 and not texty:  # an extreme big-endian word among the first forty
+        w = int(rng.integers(0, min(len(b) // 4, 40)))
+        word = np.array([rng.choice([0x7FFFFFFF, 0xFFFFFFFF, 0x80000000, 0x40000000, 0, 1, 0x00FFFFFF, 16, 32])], dtype=">u4")
+        b[4 * w:4 * w + 4] = np.frombuffer(word.tobytes(), dtype=np.uint8)
+    elif mode == 3:  # a run of text removed
+        i = int(rng.integers(0, len(b)))
+        b = np.concatenate([b[:i], b[min(len(b), i + int(rng.integers(1, 400))):]])
+    elif mode == 4:  # trailing garbage
+        b = np.concatenate([b, rng.integers(0, 256, int(rng.integers(1, 100)), dtype=np.uint8)])
+    return b  # mode 5: unchanged
+
+
+def test_host_parsers_under_sanitizers(tmp_path):
+    """csrc/model_host.cc (everything the library does with files and foreign blobs before a byte reaches the GPU) built with
+    -fsanitize=address,undefined and run over mutated dnn.bin, feature, nnet1 and feature-transform files and corrupted blobs:
+    status codes only, no sanitizer report."""
+    import shutil
+    import subprocess
+    from conftest import ROOT
+    import os
+    import test_formats as tf
+
+    if shutil.which("g++") is None:
+        pytest.skip("needs g++")
+    exe = str(tmp_path / "host_fuzz_driver")
+    cmd = ["g++", "-O1", "-g", "-std=c++17", "-fsanitize=address,undefined", "-fno-sanitize-recover=undefined", "-fno-omit-frame-pointer",
+           os.path.join(ROOT, "tests", "host_fuzz_driver.cc"), os.path.join(ROOT, "fast-dnn_b200", "csrc", "model_host.cc"), "-o", exe]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0 and "sanitize" in r.stderr and "cannot find" in r.stderr:
+        pytest.skip("sanitizer runtime not installed")
+    assert r.returncode == 0, r.stderr[-2000:]
+    rng = np.random.default_rng(1)
+    layers, shift, scale = synth.make_network((12, 32, 3, 7), seed=5)
+    d = tmp_path / "corpus"
+    d.mkdir()
+    formats.write_dnn_bin(str(d / "base.bin"), layers, shift, scale)
+    formats.write_feature_bin(str(d / "fbase.bin"), synth.make_frames(9, 12, seed=1))
+    net = np.frombuffer((d / "base.bin").read_bytes(), dtype=np.uint8)
+    feat = np.frombuffer((d / "fbase.bin").read_bytes(), dtype=np.uint8)
+    nnet = np.frombuffer(tf._kaldi_text(layers).encode(), dtype=np.uint8)
+    trans = np.frombuffer(tf._transform_text(shift, scale, True).encode(), dtype=np.uint8)
+    count = 300
+    for i in range(count):
+        (d / f"net_{i}.bin").write_bytes(_mutate(rng, net, False).tobytes())
+        (d / f"feat_{i}.bin").write_bytes(_mutate(rng, feat, False).tobytes())
+        (d / f"nnet_{i}.txt").write_bytes(_mutate(rng, nnet, True).tobytes())
+        (d / f"trans_{i}.txt").write_bytes(_mutate(rng, trans, True).tobytes())
+    r = subprocess.run([exe, str(d), str(count)], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, (r.stdout[-500:], r.stderr[-3000:])
+    assert r.stdout.startswith("accepted: pack "), r.stdout
+    # the corpus is not all rejects: unchanged and lightly damaged files still load
+    assert int(r.stdout.split()[2]) > count // 4
+
+
+def test_aligner_refuses_absurd_alignments(tmp_path):
+    """an alignment of 2^20 would pad a 40-wide layer into 4 TB of zeros (found by the fuzz: the process grew until the host
+    ran out of memory); FeedForwardNetwork.align is only ever called with SIMD widths (FeedForwardNetwork.java:50-58)"""
+    layers, shift, scale = synth.make_network((10, 40, 3, 7), seed=5)
+    raw, out = str(tmp_path / "raw.bin"), str(tmp_path / "out.bin")
+    formats.write_dnn_bin(raw, layers, shift, scale)
+    L = qd.lib()
+    for ia, ha in [(1 << 20, 16), (4, 1 << 20), (4097, 16), (0, 16), (4, -1)]:
+        assert L.fdnn_align_dnn_bin(raw.encode(), out.encode(), ia, ha) == qd.FDNN_EINVAL
+    assert L.fdnn_align_dnn_bin(raw.encode(), out.encode(), 4096, 16) == qd.FDNN_OK  # the cap itself is still taken
+    got, sh, _ = formats.read_dnn_bin(out)
+    assert [w.shape for w, _ in got] == [(48, 4096), (48, 48), (48, 48), (7, 48)] and sh.shape == (4096,)
