@@ -93,6 +93,16 @@ def test_restatement_equals_compiled_reference_on_random_networks(seed, tmp_path
         assert np.array_equal(np.isnan(want), np.isnan(got)), (dims, cutoff, n)
         ok = ~np.isnan(want)
         assert np.array_equal(want[ok].view(np.uint32), got[ok].view(np.uint32)), (dims, cutoff, n)
+        # lazy masked output (dnn.cc:355-392): any non-zero byte is "active", inactive nodes enter the softmax as exp(0)
+        rc = ref.lazy_context(n, batch=int(rng.choice([1, 8, 10])))
+        rc.until_output(frames.copy())
+        hidden = port.until_output(frames.copy())
+        assert np.array_equal(rc.hidden(), hidden), (dims, cutoff, n)
+        for idx in rng.choice(n, size=min(n, 3), replace=False):
+            mask = rng.choice(np.array([0, 0, 1, 7, -1, -128], dtype=np.int8), size=dims[-1])
+            a, b = rc.lazy(int(idx), mask), port.lazy(hidden[int(idx)], mask)
+            assert np.array_equal(np.isnan(a), np.isnan(b)) and np.array_equal(a[~np.isnan(a)].view(np.uint32), b[~np.isnan(b)].view(np.uint32)), (dims, cutoff, n, int(idx))
+        rc.close()
         ref.close()
         port.close()
 
